@@ -1,0 +1,1123 @@
+// api.cu -- C ABI of libdfdb_b200 (include/dfdb_b200.h): runtime, table residency, scan orchestration.
+//
+// Scan driver: stands in for BlocksIterator{DataReader|SizeReader} (/root/reference/src/io/blocksiterator.jl:
+// 20-145).  Where the reference walks one block at a time (read selection columns -> apply -> read
+// projection columns -> project), this driver decodes every needed column block of the shard with one
+// K1 launch and then runs each selection stage / consumer as one kernel over all blocks.
+#include <cuda_runtime.h>
+#include <fcntl.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace dfdb;
+
+namespace {
+
+struct PhaseRec { int phase; cudaEvent_t a, b; int64_t launches, bytes; };
+const char *k_phases[] = {"h2d", "decode", "unpack", "select", "consume", "d2h"};
+enum { PH_H2D = 0, PH_DECODE, PH_UNPACK, PH_SELECT, PH_CONSUME, PH_D2H, PH_COUNT };
+
+struct Runtime {
+    bool inited = false;
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    unsigned int *d_counter = nullptr;
+    int *d_error = nullptr;
+    std::atomic<int64_t> launches{0};
+    // options
+    int64_t lz4_simple = 0;
+    int64_t no_wide = 0;
+    int64_t no_fused = 0;
+    // profiling
+    bool profiling = false;
+    std::vector<PhaseRec> recs;
+    double acc_ms[PH_COUNT] = {0};
+    int64_t acc_launches[PH_COUNT] = {0}, acc_bytes[PH_COUNT] = {0};
+} rt;
+
+#define CUDA_TRY(expr)                                                                                         \
+    do {                                                                                                       \
+        cudaError_t _e = (expr);                                                                               \
+        if (_e != cudaSuccess) return fail(DFDB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));     \
+    } while (0)
+
+#define LAUNCH(expr)                                                                                           \
+    do {                                                                                                       \
+        if ((expr) != 0) return fail(DFDB_ERR_CUDA, "kernel launch failed: %s (%s)", #expr, cudaGetErrorString(cudaGetLastError())); \
+        rt.launches++;                                                                                         \
+    } while (0)
+
+int need_init()
+{
+    if (!rt.inited) return fail(DFDB_ERR_CUDA, "dfdb_init has not been called (or no CUDA device is usable)");
+    return DFDB_OK;
+}
+
+struct PhaseScope {
+    int idx = -1;
+    int64_t l0 = 0;
+    PhaseScope(int phase, int64_t bytes)
+    {
+        if (!rt.profiling) return;
+        PhaseRec r{phase, nullptr, nullptr, 0, bytes};
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, rt.stream);
+        rt.recs.push_back(r);
+        idx = (int)rt.recs.size() - 1;
+        l0 = rt.launches.load();
+    }
+    ~PhaseScope()
+    {
+        if (idx < 0) return;
+        cudaEventRecord(rt.recs[(size_t)idx].b, rt.stream);
+        rt.recs[(size_t)idx].launches = rt.launches.load() - l0;
+    }
+};
+
+void profile_collect()
+{
+    for (auto &r : rt.recs) {
+        cudaEventSynchronize(r.b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        rt.acc_ms[r.phase] += ms;
+        rt.acc_launches[r.phase] += r.launches;
+        rt.acc_bytes[r.phase] += r.bytes;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    rt.recs.clear();
+}
+
+template <typename T>
+int dev_upload(T **dptr, const std::vector<T> &h)
+{
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(dptr), std::max<size_t>(h.size(), 1) * sizeof(T)));
+    if (!h.empty()) CUDA_TRY(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return DFDB_OK;
+}
+
+void column_release(Column &c)
+{
+    if (c.h_comp) cudaFreeHost(c.h_comp);
+    cudaFree(c.d_comp); cudaFree(c.d_decoded); cudaFree(c.d_comp_off); cudaFree(c.d_comp_len); cudaFree(c.d_dec_off);
+    cudaFree(c.d_origin); cudaFree(c.d_status); cudaFree(c.d_str_off);
+    c.h_comp = nullptr; c.d_comp = nullptr; c.d_decoded = nullptr; c.d_comp_off = nullptr; c.d_comp_len = nullptr;
+    c.d_dec_off = nullptr; c.d_origin = nullptr; c.d_status = nullptr; c.d_str_off = nullptr;
+    c.loaded = false; c.decoded_valid = false; c.str_off_valid = false;
+}
+
+Geometry make_geometry(const dfdb_table *t)
+{
+    Geometry g;
+    g.nrows_total = t->nrows;
+    g.block_size = t->block_size;
+    g.blk_lo = t->blk_lo;
+    g.nblocks = (int32_t)(t->blk_hi - t->blk_lo);
+    g.wpb = (int32_t)((t->block_size + 31) / 32);
+    // work units: segments of whole tiles inside a block; a fixed function of the table shape only, so the
+    // floating-point combination order does not depend on the GPU or the shard layout
+    int64_t tiles_per_block = (t->block_size + TILE_ROWS - 1) / TILE_ROWS;
+    int64_t seg_tiles = tiles_per_block;
+    while (seg_tiles > 1 && (int64_t)t->nblocks * ((tiles_per_block + seg_tiles - 1) / seg_tiles) < 8192) seg_tiles = (seg_tiles + 1) / 2;
+    g.seg_rows = (int32_t)(seg_tiles * TILE_ROWS);
+    g.segs_per_block = (int32_t)((t->block_size + g.seg_rows - 1) / g.seg_rows);
+    return g;
+}
+
+ColView make_view(const Column &c)
+{
+    ColView v;
+    v.base = c.d_decoded;
+    v.blk_off = c.d_dec_off;
+    v.str_off = c.d_str_off;
+    v.kind = c.type.kind;
+    v.elsize = c.type.elsize;
+    v.nullable = c.type.nullable ? 1 : 0;
+    v.cls = value_class(c.type.kind);
+    return v;
+}
+
+// 16-byte loads of 8-byte values need 16-byte aligned value areas in every block
+bool wide_ok(const dfdb_table *t, const Column &c)
+{
+    if (rt.no_wide || c.type.elsize != 8) return false;
+    if (value_class(c.type.kind) == VC_NONE || value_class(c.type.kind) == VC_STR) return false;
+    if (!c.type.nullable) return true;
+    for (int64_t b = t->blk_lo; b < t->blk_hi; b++) {
+        int64_t rows = c.blocks[(size_t)b].rows;
+        if ((((rows + 63) / 64) * 8) % 16 != 0) return false;
+    }
+    return true;
+}
+
+// ---- decode ---------------------------------------------------------------------------------------------
+int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids)
+{
+    std::vector<Column *> todo;
+    for (int64_t id : col_ids) {
+        Column *c = t->find(id);
+        if (!c) return fail(DFDB_ERR_KEY, "unknown column id %lld", (long long)id);
+        if (!c->loaded) return fail(DFDB_ERR_STATE, "column %s is not loaded (call dfdb_table_load first)", c->name.c_str());
+        if (!c->decoded_valid && std::find(todo.begin(), todo.end(), c) == todo.end()) todo.push_back(c);
+    }
+    const int nblocks = (int)(t->blk_hi - t->blk_lo);
+    if (todo.empty() || nblocks == 0) return DFDB_OK;
+    {
+        int64_t bytes = 0;
+        for (Column *c : todo) if (c->mode == DFDB_LOAD_HOST) bytes += (int64_t)c->comp_bytes;
+        if (bytes) {
+            PhaseScope ps(PH_H2D, bytes);
+            for (Column *c : todo)
+                if (c->mode == DFDB_LOAD_HOST) CUDA_TRY(cudaMemcpyAsync(c->d_comp, c->h_comp, c->comp_bytes, cudaMemcpyHostToDevice, rt.stream));
+        }
+    }
+    for (size_t i = 0; i < todo.size(); i += DECODE_MAX_COLS) {
+        DecodeArgs a;
+        memset(&a, 0, sizeof a);
+        a.nblocks = nblocks;
+        int64_t bytes = 0;
+        for (size_t k = i; k < todo.size() && k < i + DECODE_MAX_COLS; k++) {
+            Column *c = todo[k];
+            DecodeCol &d = a.col[a.ncols++];
+            d.comp = c->d_comp; d.comp_off = c->d_comp_off; d.comp_len = c->d_comp_len; d.dec_off = c->d_dec_off;
+            d.origin = c->d_origin; d.out = c->d_decoded; d.status = c->d_status;
+            for (int64_t b = t->blk_lo; b < t->blk_hi; b++) bytes += c->blocks[(size_t)b].compressed + c->blocks[(size_t)b].origin;
+        }
+        PhaseScope ps(PH_DECODE, bytes);
+        LAUNCH(launch_lz4_decode(a, rt.d_counter, rt.sm_count, (int)rt.lz4_simple, rt.stream));
+    }
+    const Geometry g = make_geometry(t);
+    for (Column *c : todo)
+        if (c->type.kind == DFDB_STRING) {
+            PhaseScope ps(PH_UNPACK, 0);
+            LAUNCH(launch_str_offsets(g, make_view(*c), c->d_str_off, c->d_status, rt.stream));
+        }
+    // integrity gate (the reference asserts after every block, BlockStreams.jl:112)
+    std::vector<int32_t> st((size_t)nblocks);
+    for (Column *c : todo) {
+        CUDA_TRY(cudaMemcpyAsync(st.data(), c->d_status, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, rt.stream));
+        CUDA_TRY(cudaStreamSynchronize(rt.stream));
+        for (int b = 0; b < nblocks; b++)
+            if (st[(size_t)b] != 0)
+                return fail(DFDB_ERR_CORRUPT, "decompression error in column %s block %lld (code %d)", c->name.c_str(),
+                            (long long)(t->blk_lo + b), st[(size_t)b]);
+        c->decoded_valid = true;
+    }
+    return DFDB_OK;
+}
+
+void invalidate_decoded(dfdb_table *t)
+{
+    for (auto &c : t->cols)
+        if (c.mode != DFDB_LOAD_DECODED) c.decoded_valid = false;
+}
+
+// ---- scan helpers ---------------------------------------------------------------------------------------
+int scan_alloc(dfdb_scan *s)
+{
+    const Geometry g = make_geometry(s->tbl);
+    const int64_t words = (int64_t)g.nblocks * g.wpb;
+    if (!s->d_mask || s->mask_words != words) {
+        cudaFree(s->d_mask);
+        s->d_mask = nullptr;
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&s->d_mask), (size_t)std::max<int64_t>(words, 1) * 4));
+        CUDA_TRY(cudaMemsetAsync(s->d_mask, 0, (size_t)std::max<int64_t>(words, 1) * 4, rt.stream));
+        s->mask_words = words;
+        cudaFree(s->d_blk_counts); cudaFree(s->d_blk_base); cudaFree(s->d_blk_bytes);
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&s->d_blk_counts), (size_t)(g.nblocks + 2) * 8));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&s->d_blk_base), (size_t)(g.nblocks + 2) * 8));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&s->d_blk_bytes), (size_t)(g.nblocks + 2) * 8 * 2));
+        s->mask_valid = false;
+    }
+    const size_t need = (size_t)std::max(1, g.nblocks * g.segs_per_block) * sizeof(AggPartial);
+    if (need > s->partials_cap) {
+        cudaFree(s->d_partials);
+        CUDA_TRY(cudaMalloc(&s->d_partials, need));
+        s->partials_cap = need;
+    }
+    if (!s->d_result) {
+        CUDA_TRY(cudaMalloc(&s->d_result, 256));
+        CUDA_TRY(cudaMallocHost(&s->h_result, 256));
+    }
+    return DFDB_OK;
+}
+
+struct DevProg {
+    VmProgram *d = nullptr;
+    ~DevProg() { cudaFree(d); }
+    int upload(const VmProgram &p)
+    {
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d), sizeof(VmProgram)));
+        CUDA_TRY(cudaMemcpyAsync(d, &p, sizeof(VmProgram), cudaMemcpyHostToDevice, rt.stream));
+        return DFDB_OK;
+    }
+};
+
+int fill_slots(dfdb_scan *s, ColView *slots)
+{
+    for (size_t i = 0; i < s->slots.size(); i++) {
+        Column *c = s->tbl->find(s->slots[i]);
+        if (!c) return fail(DFDB_ERR_KEY, "unknown column id %lld", (long long)s->slots[i]);
+        slots[i] = make_view(*c);
+    }
+    return DFDB_OK;
+}
+
+int check_device_error()
+{
+    int e = 0;
+    CUDA_TRY(cudaMemcpyAsync(&e, rt.d_error, 4, cudaMemcpyDeviceToHost, rt.stream));
+    CUDA_TRY(cudaStreamSynchronize(rt.stream));
+    if (e) {
+        int zero = 0;
+        cudaMemcpyAsync(rt.d_error, &zero, 4, cudaMemcpyHostToDevice, rt.stream);
+        if (e == DFDB_ERR_DIVIDE) return fail(DFDB_ERR_DIVIDE, "DivideError: integer division error");
+        return fail(e, "device-side error %d", e);
+    }
+    return DFDB_OK;
+}
+
+bool fused_terms_wide(dfdb_scan *s, const Expr &e)
+{
+    for (int i = 0; i < e.nterms; i++) {
+        Column *c = s->tbl->find(s->slots[(size_t)e.terms[i].slot]);
+        if (!c || !wide_ok(s->tbl, *c)) return false;
+    }
+    return true;
+}
+
+void fill_terms(dfdb_scan *s, const Expr &e, FusedArgs *a)
+{
+    a->nterms = e.nterms;
+    a->const_false = 0;
+    for (int i = 0; i < e.nterms; i++) {
+        a->term[i] = e.terms[i];
+        a->term_col[i] = make_view(*s->tbl->find(s->slots[(size_t)e.terms[i].slot]));
+        if (e.terms[i].constant_result == 0) a->const_false = 1;
+    }
+}
+
+// Runs every selection stage and leaves the selection bitmask in s->d_mask.
+// The rank of a surviving row for range stages is global (selection.jl:94-111 running offsets).
+int run_selection(dfdb_scan *s)
+{
+    dfdb_table *t = s->tbl;
+    int rc = scan_alloc(s);
+    if (rc) return rc;
+    const Geometry g = make_geometry(t);
+    bool dense = true;   // every row of the shard survives so far and the mask is not materialised
+    bool used_vm = false;
+    for (auto &st : s->stages) {
+        if (st.kind != ST_PRED) {
+            RangeArgs a;
+            memset(&a, 0, sizeof a);
+            a.g = g; a.mask = s->d_mask; a.kind = st.kind; a.start = st.start; a.step = st.step; a.stop = st.stop;
+            if (st.kind == ST_INDEXVEC) {
+                if (!st.d_idx) {
+                    rc = dev_upload(&st.d_idx, st.idx);
+                    if (rc) return rc;
+                }
+                a.idx = st.d_idx;
+                a.nidx = (int64_t)st.idx.size();
+            }
+            PhaseScope ps(PH_SELECT, 0);
+            if (dense) {
+                a.dense = 1;
+            } else {
+                if (t->world > 1)
+                    return fail(DFDB_ERR_UNSUPPORTED, "a range stage after a predicate needs global survivor ranks; not available on a sharded table yet");
+                LAUNCH(launch_block_counts(g, s->d_mask, s->d_blk_counts, rt.stream));
+                LAUNCH(launch_exclusive_scan(s->d_blk_counts, s->d_blk_base, g.nblocks, rt.stream));
+                a.dense = 0;
+                a.blk_base = s->d_blk_base;
+            }
+            LAUNCH(launch_range_stage(a, rt.stream));
+            dense = false;
+        } else {
+            rc = ensure_decoded(t, st.e.col_ids);
+            if (rc) return rc;
+            int64_t bytes = 0;
+            for (int64_t id : st.e.col_ids) for (int64_t b = t->blk_lo; b < t->blk_hi; b++) bytes += t->find(id)->blocks[(size_t)b].origin;
+            PhaseScope ps(PH_SELECT, bytes);
+            if (st.e.simple && !rt.no_fused) {
+                FusedArgs a;
+                memset(&a, 0, sizeof a);
+                a.g = g;
+                fill_terms(s, st.e, &a);
+                a.mask_in = dense ? nullptr : s->d_mask;
+                a.mask_out = s->d_mask;
+                a.partials = static_cast<AggPartial *>(s->d_partials);
+                LAUNCH(launch_fused(a, 0, true, false, rt.sm_count, rt.stream));
+            } else {
+                VmArgs a;
+                memset(&a, 0, sizeof a);
+                a.g = g;
+                rc = fill_slots(s, a.slot);
+                if (rc) return rc;
+                DevProg prog;
+                rc = prog.upload(st.e.prog);
+                if (rc) return rc;
+                a.prog = prog.d;
+                a.mask_in = dense ? nullptr : s->d_mask;
+                a.mask_out = s->d_mask;
+                a.error_flag = rt.d_error;
+                LAUNCH(launch_vm_mask(a, rt.sm_count, rt.stream));
+                CUDA_TRY(cudaStreamSynchronize(rt.stream));   // program buffer is freed on scope exit
+                used_vm = true;
+            }
+            dense = false;
+        }
+    }
+    if (dense) {
+        PhaseScope ps(PH_SELECT, 0);
+        LAUNCH(launch_fill_mask(g, s->d_mask, rt.stream));
+    }
+    if (used_vm) {
+        rc = check_device_error();
+        if (rc) return rc;
+    }
+    s->mask_valid = true;
+    return DFDB_OK;
+}
+
+// per-block selected counts + exclusive scan; total rows -> *total
+int count_mask(dfdb_scan *s, int64_t *total)
+{
+    const Geometry g = make_geometry(s->tbl);
+    {
+        PhaseScope ps(PH_CONSUME, (int64_t)g.nblocks * g.wpb * 4);
+        LAUNCH(launch_block_counts(g, s->d_mask, s->d_blk_counts, rt.stream));
+        LAUNCH(launch_exclusive_scan(s->d_blk_counts, s->d_blk_base, g.nblocks, rt.stream));
+    }
+    PhaseScope ps(PH_D2H, 8);
+    CUDA_TRY(cudaMemcpyAsync(s->h_result, s->d_blk_base + g.nblocks, 8, cudaMemcpyDeviceToHost, rt.stream));
+    CUDA_TRY(cudaStreamSynchronize(rt.stream));
+    *total = *static_cast<int64_t *>(s->h_result);
+    s->selected = *total;
+    return DFDB_OK;
+}
+
+bool single_simple_pred(const dfdb_scan *s)
+{
+    return !rt.no_fused && s->stages.size() == 1 && s->stages[0].kind == ST_PRED && s->stages[0].e.simple;
+}
+
+void agg_to_public(const AggPartial &p, int cls, dfdb_agg *out)
+{
+    memset(out, 0, sizeof *out);
+    out->count = p.count;
+    out->nmissing = p.nmissing;
+    out->sum_i64 = p.sum_i;
+    out->sum_f64 = p.sum_f;
+    out->sum_f64_lo = p.sum_lo;
+    out->min_i64 = p.min_i; out->max_i64 = p.max_i;
+    out->min_f64 = p.min_f; out->max_f64 = p.max_f;
+    out->has_nan = p.has_nan;
+    const bool any = p.has_value || p.has_nan;
+    out->value_class = any ? (cls == VC_FLT ? 3 : cls == VC_UINT ? 2 : cls == VC_BOOL ? 4 : 1) : 0;
+}
+
+int run_aggregate(dfdb_scan *s, int32_t proj_idx, bool count_only, AggPartial *host_out, int *cls_out)
+{
+    dfdb_table *t = s->tbl;
+    int rc = scan_alloc(s);
+    if (rc) return rc;
+    const Geometry g = make_geometry(t);
+    FusedArgs a;
+    memset(&a, 0, sizeof a);
+    a.g = g;
+    a.partials = static_cast<AggPartial *>(s->d_partials);
+    int agg = 0, cls = VC_INT;
+    bool wide = true;
+    std::vector<int64_t> need;
+    Column *ac = nullptr;
+    if (!count_only) {
+        if (proj_idx < 0 || (size_t)proj_idx >= s->projs.size()) return fail(DFDB_ERR_ARGUMENT, "projection index out of range");
+        const Proj &p = s->projs[(size_t)proj_idx];
+        if (p.kind != PJ_COL) return fail(DFDB_ERR_UNSUPPORTED, "aggregates over computed columns are not supported yet");
+        ac = t->find(p.col);
+        cls = value_class(ac->type.kind);
+        if (cls == VC_NONE || cls == VC_STR) return fail(DFDB_ERR_UNSUPPORTED, "aggregate over column %s of type %s", ac->name.c_str(), ac->typestr.c_str());
+        agg = cls == VC_FLT ? 2 : 1;
+        need.push_back(p.col);
+        wide = wide && wide_ok(t, *ac);
+    }
+    const int nunits = g.nblocks * g.segs_per_block;
+    if (s->stages.empty() || single_simple_pred(s)) {
+        if (!s->stages.empty()) for (int64_t id : s->stages[0].e.col_ids) need.push_back(id);
+        rc = ensure_decoded(t, need);
+        if (rc) return rc;
+        if (!s->stages.empty()) {
+            fill_terms(s, s->stages[0].e, &a);
+            wide = wide && fused_terms_wide(s, s->stages[0].e);
+        }
+    } else {
+        rc = run_selection(s);
+        if (rc) return rc;
+        rc = ensure_decoded(t, need);
+        if (rc) return rc;
+        a.mask_in = s->d_mask;
+        wide = false;
+    }
+    if (ac) { a.agg_col = make_view(*ac); a.agg_cls = cls; }
+    {
+        int64_t bytes = 0;
+        for (int64_t id : need) for (int64_t b = t->blk_lo; b < t->blk_hi; b++) bytes += t->find(id)->blocks[(size_t)b].origin;
+        PhaseScope ps(PH_CONSUME, bytes);
+        if (nunits > 0) LAUNCH(launch_fused(a, agg, false, wide, rt.sm_count, rt.stream));
+        LAUNCH(launch_agg_finalize(static_cast<AggPartial *>(s->d_partials), nunits, agg == 2 ? VC_FLT : cls, static_cast<AggPartial *>(s->d_result), rt.stream));
+    }
+    PhaseScope ps(PH_D2H, sizeof(AggPartial));
+    CUDA_TRY(cudaMemcpyAsync(s->h_result, s->d_result, sizeof(AggPartial), cudaMemcpyDeviceToHost, rt.stream));
+    CUDA_TRY(cudaStreamSynchronize(rt.stream));
+    *host_out = *static_cast<AggPartial *>(s->h_result);
+    *cls_out = cls;
+    return DFDB_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char *dfdb_last_error(void) { return dfdb::last_error(); }
+
+int32_t dfdb_init(int32_t device)
+{
+    if (rt.inited) {
+        if (device != rt.device) return fail(DFDB_ERR_STATE, "already initialised on device %d (one process per GPU)", rt.device);
+        return DFDB_OK;
+    }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(DFDB_ERR_CUDA, "no CUDA device available: %s", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(DFDB_ERR_CUDA, "device %d out of range (%d devices)", device, n);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(DFDB_ERR_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+    rt.device = device;
+    rt.sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&rt.own_stream, cudaStreamNonBlocking));
+    rt.stream = rt.own_stream;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&rt.d_counter), 64));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&rt.d_error), 64));
+    CUDA_TRY(cudaMemset(rt.d_error, 0, 64));
+    rt.inited = true;
+    return DFDB_OK;
+}
+
+int32_t dfdb_shutdown(void)
+{
+    if (!rt.inited) return DFDB_OK;
+    cudaStreamSynchronize(rt.stream);
+    profile_collect();
+    cudaFree(rt.d_counter);
+    cudaFree(rt.d_error);
+    cudaStreamDestroy(rt.own_stream);
+    rt.inited = false;
+    return DFDB_OK;
+}
+
+int32_t dfdb_set_stream(void *cuda_stream)
+{
+    int rc = need_init();
+    if (rc) return rc;
+    cudaStreamSynchronize(rt.stream);
+    rt.stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : rt.own_stream;
+    return DFDB_OK;
+}
+
+int32_t dfdb_synchronize(void)
+{
+    int rc = need_init();
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(rt.stream));
+    return DFDB_OK;
+}
+
+int64_t dfdb_kernel_launches(void) { return rt.launches.load(); }
+
+int32_t dfdb_set_option(const char *name, int64_t value)
+{
+    std::string n(name ? name : "");
+    if (n == "lz4_simple") rt.lz4_simple = value;
+    else if (n == "no_wide") rt.no_wide = value;
+    else if (n == "no_fused") rt.no_fused = value;
+    else return fail(DFDB_ERR_ARGUMENT, "unknown option %s", n.c_str());
+    return DFDB_OK;
+}
+
+int32_t dfdb_profile_enable(int32_t on) { rt.profiling = on != 0; return DFDB_OK; }
+int32_t dfdb_profile_reset(void)
+{
+    if (rt.inited) { cudaStreamSynchronize(rt.stream); profile_collect(); }
+    for (int i = 0; i < PH_COUNT; i++) { rt.acc_ms[i] = 0; rt.acc_launches[i] = 0; rt.acc_bytes[i] = 0; }
+    return DFDB_OK;
+}
+int32_t dfdb_profile_get(const char *phase, double *total_ms, int64_t *launches, int64_t *bytes)
+{
+    if (rt.inited) profile_collect();
+    for (int i = 0; i < PH_COUNT; i++)
+        if (strcmp(phase, k_phases[i]) == 0) {
+            if (total_ms) *total_ms = rt.acc_ms[i];
+            if (launches) *launches = rt.acc_launches[i];
+            if (bytes) *bytes = rt.acc_bytes[i];
+            return DFDB_OK;
+        }
+    return fail(DFDB_ERR_ARGUMENT, "unknown phase %s", phase);
+}
+
+// ---- table ------------------------------------------------------------------------------------------
+int32_t dfdb_table_open(const char *path, dfdb_table **out)
+{
+    if (!path || !out) return fail(DFDB_ERR_ARGUMENT, "null argument");
+    return table_open_host(path, out);
+}
+
+int32_t dfdb_table_close(dfdb_table *t)
+{
+    if (!t) return DFDB_OK;
+    if (rt.inited) cudaStreamSynchronize(rt.stream);
+    for (auto &c : t->cols) column_release(c);
+    delete t;
+    return DFDB_OK;
+}
+
+int64_t dfdb_table_nrows(const dfdb_table *t) { return t->nrows; }
+int64_t dfdb_table_ncols(const dfdb_table *t) { return (int64_t)t->cols.size(); }
+int64_t dfdb_table_block_size(const dfdb_table *t) { return t->block_size; }
+int64_t dfdb_table_nblocks(const dfdb_table *t) { return t->nblocks; }
+
+int32_t dfdb_table_column(const dfdb_table *t, int32_t index, int64_t *id, char *name, int32_t name_cap, char *typestring,
+                          int32_t ts_cap, int32_t *kind, int32_t *nullable, int32_t *elsize)
+{
+    if (index < 0 || (size_t)index >= t->cols.size()) return fail(DFDB_ERR_KEY, "column index %d out of range", index);
+    const Column &c = t->cols[(size_t)index];
+    if (id) *id = c.id;
+    if (name && name_cap > 0) snprintf(name, (size_t)name_cap, "%s", c.name.c_str());
+    if (typestring && ts_cap > 0) snprintf(typestring, (size_t)ts_cap, "%s", c.typestr.c_str());
+    if (kind) *kind = c.type.kind;
+    if (nullable) *nullable = c.type.nullable;
+    if (elsize) *elsize = c.type.elsize;
+    return DFDB_OK;
+}
+
+int32_t dfdb_table_column_stats(const dfdb_table *t, int64_t col_id, int64_t *compressed, int64_t *uncompressed)
+{
+    const Column *c = const_cast<dfdb_table *>(t)->find(col_id);
+    if (!c) return fail(DFDB_ERR_KEY, "unknown column id %lld", (long long)col_id);
+    int64_t cs = 0, us = 0;
+    for (int64_t b = t->blk_lo; b < t->blk_hi; b++) { cs += c->blocks[(size_t)b].compressed; us += c->blocks[(size_t)b].origin; }
+    if (compressed) *compressed = cs;
+    if (uncompressed) *uncompressed = us;
+    return DFDB_OK;
+}
+
+int32_t dfdb_table_set_shard(dfdb_table *t, int32_t rank, int32_t world)
+{
+    if (world < 1 || rank < 0 || rank >= world) return fail(DFDB_ERR_ARGUMENT, "bad shard %d of %d", rank, world);
+    for (auto &c : t->cols) if (c.loaded) column_release(c);
+    t->rank = rank;
+    t->world = world;
+    t->blk_lo = t->nblocks * rank / world;
+    t->blk_hi = t->nblocks * (rank + 1) / world;
+    return DFDB_OK;
+}
+
+int32_t dfdb_table_shard_range(const dfdb_table *t, int64_t *block_lo, int64_t *block_hi, int64_t *row_lo, int64_t *row_hi)
+{
+    if (block_lo) *block_lo = t->blk_lo;
+    if (block_hi) *block_hi = t->blk_hi;
+    if (row_lo) *row_lo = std::min(t->nrows, t->blk_lo * t->block_size);
+    if (row_hi) *row_hi = std::min(t->nrows, t->blk_hi * t->block_size);
+    return DFDB_OK;
+}
+
+int32_t dfdb_table_load(dfdb_table *t, const int64_t *col_ids, int32_t n, int32_t mode)
+{
+    int rc = need_init();
+    if (rc) return rc;
+    if (mode < DFDB_LOAD_HOST || mode > DFDB_LOAD_DECODED) return fail(DFDB_ERR_ARGUMENT, "bad residency mode %d", mode);
+    std::vector<Column *> cols;
+    if (n <= 0) for (auto &c : t->cols) cols.push_back(&c);
+    else
+        for (int i = 0; i < n; i++) {
+            Column *c = t->find(col_ids[i]);
+            if (!c) return fail(DFDB_ERR_KEY, "unknown column id %lld", (long long)col_ids[i]);
+            cols.push_back(c);
+        }
+    const int64_t nb = t->blk_hi - t->blk_lo;
+    for (Column *c : cols) {
+        if (c->loaded && c->mode == mode) continue;
+        column_release(*c);
+        std::vector<int64_t> comp_off((size_t)nb), dec_off((size_t)nb);
+        std::vector<int32_t> comp_len((size_t)nb), origin((size_t)nb);
+        int64_t cpos = 0, dpos = 0;
+        for (int64_t b = 0; b < nb; b++) {
+            const BlockInfo &bi = c->blocks[(size_t)(t->blk_lo + b)];
+            if (c->type.kind == DFDB_STRING && bi.origin < 4 + 4 * (int64_t)bi.rows)
+                return fail(DFDB_ERR_CORRUPT, "column %s block %lld: string body smaller than its size table", c->name.c_str(), (long long)(t->blk_lo + b));
+            if (c->type.kind != DFDB_STRING) {
+                int64_t expect = (int64_t)bi.rows * c->type.elsize + (c->type.nullable ? ((bi.rows + 63) / 64) * 8 : 0);
+                if (bi.origin != expect)
+                    return fail(DFDB_ERR_CORRUPT, "column %s block %lld: body is %lld bytes, expected %lld", c->name.c_str(),
+                                (long long)(t->blk_lo + b), (long long)bi.origin, (long long)expect);
+            }
+            comp_off[(size_t)b] = cpos;
+            comp_len[(size_t)b] = (int32_t)bi.compressed;
+            cpos += (bi.compressed + 15) & ~(int64_t)15;
+            dec_off[(size_t)b] = dpos;
+            origin[(size_t)b] = (int32_t)bi.origin;
+            dpos += (bi.origin + 255) & ~(int64_t)255;
+        }
+        c->comp_bytes = (size_t)cpos + 4096;       // slack for the decoder's aligned window over-read
+        c->decoded_bytes = (size_t)dpos + 256;
+        c->h_dec_off = dec_off;
+        CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&c->h_comp), c->comp_bytes));
+        memset(c->h_comp + cpos, 0, 4096);
+        {
+            std::string p = t->path + "/" + std::to_string(c->id) + ".bin";
+            int fd = open(p.c_str(), O_RDONLY);
+            if (fd < 0) return fail(DFDB_ERR_IO, "cannot open %s", p.c_str());
+            for (int64_t b = 0; b < nb; b++) {
+                const BlockInfo &bi = c->blocks[(size_t)(t->blk_lo + b)];
+                int64_t got = 0;
+                while (got < bi.compressed) {
+                    ssize_t r = pread(fd, c->h_comp + comp_off[(size_t)b] + got, (size_t)(bi.compressed - got), bi.file_off + got);
+                    if (r <= 0) { close(fd); return fail(DFDB_ERR_IO, "short read in %s", p.c_str()); }
+                    got += r;
+                }
+                int64_t pad = ((bi.compressed + 15) & ~(int64_t)15) - bi.compressed;
+                if (pad) memset(c->h_comp + comp_off[(size_t)b] + bi.compressed, 0, (size_t)pad);
+            }
+            close(fd);
+        }
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&c->d_comp), c->comp_bytes));
+        if ((rc = dev_upload(&c->d_comp_off, comp_off))) return rc;
+        if ((rc = dev_upload(&c->d_comp_len, comp_len))) return rc;
+        if ((rc = dev_upload(&c->d_dec_off, dec_off))) return rc;
+        if ((rc = dev_upload(&c->d_origin, origin))) return rc;
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&c->d_status), (size_t)std::max<int64_t>(nb, 1) * 4));
+        CUDA_TRY(cudaMemset(c->d_status, 0, (size_t)std::max<int64_t>(nb, 1) * 4));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&c->d_decoded), c->decoded_bytes));
+        if (c->type.kind == DFDB_STRING)
+            CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&c->d_str_off), (size_t)std::max<int64_t>(nb, 1) * (size_t)t->block_size * 4));
+        if (mode != DFDB_LOAD_HOST) {
+            CUDA_TRY(cudaMemcpy(c->d_comp, c->h_comp, c->comp_bytes, cudaMemcpyHostToDevice));
+            cudaFreeHost(c->h_comp);
+            c->h_comp = nullptr;
+        }
+        c->mode = mode;
+        c->loaded = true;
+        c->decoded_valid = false;
+    }
+    return DFDB_OK;
+}
+
+int32_t dfdb_table_drop_decoded(dfdb_table *t)
+{
+    for (auto &c : t->cols) c.decoded_valid = false;
+    return DFDB_OK;
+}
+
+// ---- scan ---------------------------------------------------------------------------------------------
+int32_t dfdb_scan_prepare(dfdb_table *t, const uint8_t *plan, int64_t plan_len, dfdb_scan **out)
+{
+    if (!t || !plan || !out) return fail(DFDB_ERR_ARGUMENT, "null argument");
+    auto *s = new dfdb_scan();
+    s->tbl = t;
+    int rc = plan_parse(t, plan, plan_len, s);
+    if (rc) { delete s; return rc; }
+    *out = s;
+    return DFDB_OK;
+}
+
+int32_t dfdb_scan_free(dfdb_scan *s)
+{
+    if (!s) return DFDB_OK;
+    if (rt.inited) cudaStreamSynchronize(rt.stream);
+    cudaFree(s->d_mask); cudaFree(s->d_blk_counts); cudaFree(s->d_blk_base); cudaFree(s->d_blk_bytes);
+    cudaFree(s->d_partials); cudaFree(s->d_result);
+    if (s->h_result) cudaFreeHost(s->h_result);
+    for (auto &st : s->stages) cudaFree(st.d_idx);
+    delete s;
+    return DFDB_OK;
+}
+
+int32_t dfdb_scan_nproj(const dfdb_scan *s) { return (int32_t)s->projs.size(); }
+
+int32_t dfdb_scan_proj_type(const dfdb_scan *s, int32_t proj_idx, int32_t *kind, int32_t *nullable, int32_t *elsize)
+{
+    if (proj_idx < 0 || (size_t)proj_idx >= s->projs.size()) return fail(DFDB_ERR_ARGUMENT, "projection index out of range");
+    const ColType &t = s->projs[(size_t)proj_idx].type;
+    if (kind) *kind = t.kind;
+    if (nullable) *nullable = t.nullable;
+    if (elsize) *elsize = t.elsize;
+    return DFDB_OK;
+}
+
+int32_t dfdb_scan_count(dfdb_scan *s, int64_t *n)
+{
+    int rc = need_init();
+    if (rc) return rc;
+    dfdb_table *t = s->tbl;
+    invalidate_decoded(t);
+    if (s->stages.empty()) {
+        // isonly_range with an empty queue: header-only count (blocksiterator.jl:135)
+        *n = std::min(t->nrows, t->blk_hi * t->block_size) - std::min(t->nrows, t->blk_lo * t->block_size);
+        return DFDB_OK;
+    }
+    if (single_simple_pred(s)) {
+        AggPartial p;
+        int cls;
+        rc = run_aggregate(s, -1, true, &p, &cls);
+        if (rc) return rc;
+        *n = p.count;
+        return DFDB_OK;
+    }
+    rc = run_selection(s);
+    if (rc) return rc;
+    return count_mask(s, n);
+}
+
+int32_t dfdb_scan_aggregate(dfdb_scan *s, int32_t proj_idx, dfdb_agg *out)
+{
+    int rc = need_init();
+    if (rc) return rc;
+    invalidate_decoded(s->tbl);
+    AggPartial p;
+    int cls;
+    rc = run_aggregate(s, proj_idx, false, &p, &cls);
+    if (rc) return rc;
+    agg_to_public(p, cls, out);
+    return DFDB_OK;
+}
+
+int32_t dfdb_scan_aggregate_device(dfdb_scan *s, int32_t proj_idx, void *device_out)
+{
+    dfdb_agg a;
+    int rc = dfdb_scan_aggregate(s, proj_idx, &a);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(device_out, &a, sizeof a, cudaMemcpyHostToDevice, rt.stream));
+    CUDA_TRY(cudaStreamSynchronize(rt.stream));
+    return DFDB_OK;
+}
+
+int32_t dfdb_agg_fold(const dfdb_agg *partials, int32_t n, dfdb_agg *out)
+{
+    // fixed rank-order fold; floating sums combined with two-sum so the result does not depend on how the
+    // blocks were split over ranks beyond the last bit of the compensated pair
+    dfdb_agg r;
+    memset(&r, 0, sizeof r);
+    for (int i = 0; i < n; i++) {
+        const dfdb_agg &p = partials[i];
+        r.count += p.count;
+        r.nmissing += p.nmissing;
+        r.sum_i64 = (int64_t)((uint64_t)r.sum_i64 + (uint64_t)p.sum_i64);
+        {
+            double t = r.sum_f64 + p.sum_f64;
+            double bb = t - r.sum_f64;
+            r.sum_f64_lo += (r.sum_f64 - (t - bb)) + (p.sum_f64 - bb);
+            r.sum_f64_lo += p.sum_f64_lo;
+            r.sum_f64 = t;
+        }
+        r.has_nan |= p.has_nan;
+        if (p.value_class) {
+            if (!r.value_class) {
+                r.min_i64 = p.min_i64; r.max_i64 = p.max_i64; r.min_f64 = p.min_f64; r.max_f64 = p.max_f64;
+                r.value_class = p.value_class;
+            } else if (p.value_class == 3) {
+                auto mn = [](double a, double b) { return (a != a) ? a : (b != b) ? b : ((a < b || (a == b && std::signbit(a))) ? a : b); };
+                auto mx = [](double a, double b) { return (a != a) ? a : (b != b) ? b : ((a > b || (a == b && !std::signbit(a))) ? a : b); };
+                r.min_f64 = mn(r.min_f64, p.min_f64);
+                r.max_f64 = mx(r.max_f64, p.max_f64);
+            } else if (p.value_class == 2) {
+                if ((uint64_t)p.min_i64 < (uint64_t)r.min_i64) r.min_i64 = p.min_i64;
+                if ((uint64_t)p.max_i64 > (uint64_t)r.max_i64) r.max_i64 = p.max_i64;
+            } else {
+                if (p.min_i64 < r.min_i64) r.min_i64 = p.min_i64;
+                if (p.max_i64 > r.max_i64) r.max_i64 = p.max_i64;
+            }
+        }
+    }
+    double s = r.sum_f64 + r.sum_f64_lo;
+    r.sum_f64_lo = (r.sum_f64 - s) + r.sum_f64_lo;
+    r.sum_f64 = s;
+    *out = r;
+    return DFDB_OK;
+}
+
+int32_t dfdb_scan_mask(dfdb_scan *s, uint64_t *words, int64_t nwords)
+{
+    int rc = need_init();
+    if (rc) return rc;
+    dfdb_table *t = s->tbl;
+    invalidate_decoded(t);
+    rc = run_selection(s);
+    if (rc) return rc;
+    const Geometry g = make_geometry(t);
+    std::vector<uint32_t> h((size_t)std::max<int64_t>(s->mask_words, 1));
+    {
+        PhaseScope ps(PH_D2H, s->mask_words * 4);
+        CUDA_TRY(cudaMemcpyAsync(h.data(), s->d_mask, (size_t)s->mask_words * 4, cudaMemcpyDeviceToHost, rt.stream));
+        CUDA_TRY(cudaStreamSynchronize(rt.stream));
+    }
+    if (nwords < (t->nrows + 63) / 64) return fail(DFDB_ERR_ARGUMENT, "mask buffer too small: need %lld words", (long long)((t->nrows + 63) / 64));
+    memset(words, 0, (size_t)nwords * 8);
+    for (int lb = 0; lb < g.nblocks; lb++) {
+        const int64_t row0 = (g.blk_lo + lb) * g.block_size;
+        const int64_t rows = block_rows(g, lb);
+        if ((row0 & 31) == 0) {
+            // word-aligned block: copy 32-bit words straight into the little-endian 64-bit layout
+            uint32_t *w32 = reinterpret_cast<uint32_t *>(words);
+            for (int64_t w = 0; w * 32 < rows; w++) w32[(row0 >> 5) + w] = h[(size_t)((int64_t)lb * g.wpb + w)];
+        } else {
+            for (int64_t r = 0; r < rows; r++)
+                if ((h[(size_t)((int64_t)lb * g.wpb + (r >> 5))] >> (r & 31)) & 1u) words[(row0 + r) >> 6] |= 1ull << ((row0 + r) & 63);
+        }
+    }
+    return DFDB_OK;
+}
+
+int32_t dfdb_scan_indices(dfdb_scan *s, int64_t *idx, int64_t cap, int64_t *n)
+{
+    int rc = need_init();
+    if (rc) return rc;
+    invalidate_decoded(s->tbl);
+    rc = run_selection(s);
+    if (rc) return rc;
+    int64_t total = 0;
+    rc = count_mask(s, &total);
+    if (rc) return rc;
+    if (n) *n = total;
+    if (total > cap) return fail(DFDB_ERR_ARGUMENT, "index buffer too small: need %lld", (long long)total);
+    if (total == 0) return DFDB_OK;
+    int64_t *d_out = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d_out), (size_t)total * 8));
+    GatherArgs a;
+    memset(&a, 0, sizeof a);
+    a.g = make_geometry(s->tbl);
+    a.mask = s->d_mask;
+    a.blk_base = s->d_blk_base;
+    a.out_indices = d_out;
+    if (launch_gather_indices(a, rt.stream) != 0) { cudaFree(d_out); return fail(DFDB_ERR_CUDA, "gather_indices launch failed"); }
+    rt.launches++;
+    cudaError_t e = cudaMemcpyAsync(idx, d_out, (size_t)total * 8, cudaMemcpyDeviceToHost, rt.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(rt.stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(DFDB_ERR_CUDA, "indices copy failed: %s", cudaGetErrorString(e));
+    return DFDB_OK;
+}
+
+int32_t dfdb_scan_materialize_sizes(dfdb_scan *s, int64_t *nrows, int64_t *str_bytes_per_col)
+{
+    int rc = need_init();
+    if (rc) return rc;
+    dfdb_table *t = s->tbl;
+    invalidate_decoded(t);
+    rc = run_selection(s);
+    if (rc) return rc;
+    int64_t total = 0;
+    rc = count_mask(s, &total);
+    if (rc) return rc;
+    if (nrows) *nrows = total;
+    s->str_bytes.assign(s->projs.size(), 0);
+    const Geometry g = make_geometry(t);
+    for (size_t i = 0; i < s->projs.size(); i++) {
+        const Proj &p = s->projs[i];
+        if (p.kind == PJ_COL && p.type.kind == DFDB_STRING && total > 0) {
+            rc = ensure_decoded(t, {p.col});
+            if (rc) return rc;
+            GatherArgs a;
+            memset(&a, 0, sizeof a);
+            a.g = g;
+            a.mask = s->d_mask;
+            a.col = make_view(*t->find(p.col));
+            PhaseScope ps(PH_CONSUME, 0);
+            LAUNCH(launch_str_block_bytes(a, s->d_blk_bytes, rt.stream));
+            LAUNCH(launch_exclusive_scan(s->d_blk_bytes, s->d_blk_bytes + g.nblocks + 1, g.nblocks, rt.stream));
+            CUDA_TRY(cudaMemcpyAsync(s->h_result, s->d_blk_bytes + g.nblocks + 1 + g.nblocks, 8, cudaMemcpyDeviceToHost, rt.stream));
+            CUDA_TRY(cudaStreamSynchronize(rt.stream));
+            s->str_bytes[i] = *static_cast<int64_t *>(s->h_result);
+        }
+        if (str_bytes_per_col) str_bytes_per_col[i] = s->str_bytes[i];
+    }
+    return DFDB_OK;
+}
+
+int32_t dfdb_scan_materialize(dfdb_scan *s, dfdb_outcol *cols, int32_t ncols)
+{
+    int rc = need_init();
+    if (rc) return rc;
+    dfdb_table *t = s->tbl;
+    if ((size_t)ncols != s->projs.size()) return fail(DFDB_ERR_ARGUMENT, "expected %zu output columns, got %d", s->projs.size(), ncols);
+    if (!s->mask_valid || s->selected < 0) {
+        rc = dfdb_scan_materialize_sizes(s, nullptr, nullptr);
+        if (rc) return rc;
+    }
+    const int64_t total = s->selected;
+    const Geometry g = make_geometry(t);
+    if (total == 0) return DFDB_OK;
+    for (size_t i = 0; i < s->projs.size(); i++) {
+        const Proj &p = s->projs[i];
+        dfdb_outcol &oc = cols[i];
+        uint8_t *d_vals = nullptr, *d_miss = nullptr, *d_chars = nullptr;
+        int32_t *d_sizes = nullptr;
+        auto cleanup = [&]() { cudaFree(d_vals); cudaFree(d_miss); cudaFree(d_chars); cudaFree(d_sizes); };
+        if (p.kind == PJ_COL) {
+            rc = ensure_decoded(t, {p.col});
+            if (rc) return rc;
+            Column *c = t->find(p.col);
+            GatherArgs a;
+            memset(&a, 0, sizeof a);
+            a.g = g;
+            a.mask = s->d_mask;
+            a.blk_base = s->d_blk_base;
+            a.col = make_view(*c);
+            if (c->type.kind == DFDB_STRING) {
+                if (!oc.str_sizes) return fail(DFDB_ERR_ARGUMENT, "output column %zu needs str_sizes", i);
+                // per-block char bases for this column
+                PhaseScope ps(PH_CONSUME, c->total_origin);
+                LAUNCH(launch_str_block_bytes(a, s->d_blk_bytes, rt.stream));
+                LAUNCH(launch_exclusive_scan(s->d_blk_bytes, s->d_blk_bytes + g.nblocks + 1, g.nblocks, rt.stream));
+                a.blk_char_base = s->d_blk_bytes + g.nblocks + 1;
+                const int64_t nbytes = s->str_bytes[i];
+                if (cudaMalloc(reinterpret_cast<void **>(&d_sizes), (size_t)total * 4) != cudaSuccess ||
+                    cudaMalloc(reinterpret_cast<void **>(&d_chars), (size_t)std::max<int64_t>(nbytes, 1)) != cudaSuccess) {
+                    cleanup();
+                    return fail(DFDB_ERR_NOMEM, "out of device memory for string gather");
+                }
+                a.out_sizes = d_sizes;
+                a.out_chars = d_chars;
+                if (launch_gather_strings(a, rt.stream) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "gather_strings launch failed"); }
+                rt.launches++;
+                cudaMemcpyAsync(oc.str_sizes, d_sizes, (size_t)total * 4, cudaMemcpyDeviceToHost, rt.stream);
+                if (nbytes > 0 && oc.str_chars) cudaMemcpyAsync(oc.str_chars, d_chars, (size_t)nbytes, cudaMemcpyDeviceToHost, rt.stream);
+            } else {
+                if (!oc.values) return fail(DFDB_ERR_ARGUMENT, "output column %zu needs a values buffer", i);
+                const int es = c->type.elsize;
+                if (cudaMalloc(reinterpret_cast<void **>(&d_vals), (size_t)total * es) != cudaSuccess ||
+                    (c->type.nullable && cudaMalloc(reinterpret_cast<void **>(&d_miss), (size_t)total) != cudaSuccess)) {
+                    cleanup();
+                    return fail(DFDB_ERR_NOMEM, "out of device memory for gather");
+                }
+                a.out_values = d_vals;
+                a.out_missing = d_miss;
+                {
+                    PhaseScope ps(PH_CONSUME, c->total_origin + total * es);
+                    if (launch_gather_fixed(a, rt.stream) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "gather launch failed"); }
+                    rt.launches++;
+                }
+                PhaseScope ps(PH_D2H, total * es);
+                cudaMemcpyAsync(oc.values, d_vals, (size_t)total * es, cudaMemcpyDeviceToHost, rt.stream);
+                if (c->type.nullable && oc.missing) cudaMemcpyAsync(oc.missing, d_miss, (size_t)total, cudaMemcpyDeviceToHost, rt.stream);
+            }
+        } else {
+            rc = ensure_decoded(t, p.e.col_ids);
+            if (rc) return rc;
+            if (!oc.values) return fail(DFDB_ERR_ARGUMENT, "output column %zu needs a values buffer", i);
+            ProjVmArgs a;
+            memset(&a, 0, sizeof a);
+            a.g = g;
+            rc = fill_slots(s, a.slot);
+            if (rc) return rc;
+            DevProg prog;
+            rc = prog.upload(p.e.prog);
+            if (rc) return rc;
+            const int es = p.type.elsize;
+            if (cudaMalloc(reinterpret_cast<void **>(&d_vals), (size_t)total * es) != cudaSuccess ||
+                (p.type.nullable && cudaMalloc(reinterpret_cast<void **>(&d_miss), (size_t)total) != cudaSuccess)) {
+                cleanup();
+                return fail(DFDB_ERR_NOMEM, "out of device memory for computed column");
+            }
+            a.prog = prog.d;
+            a.mask = s->d_mask;
+            a.blk_base = s->d_blk_base;
+            a.out_values = d_vals;
+            a.out_missing = d_miss;
+            a.elsize = es;
+            a.error_flag = rt.d_error;
+            if (launch_proj_vm(a, rt.stream) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "proj_vm launch failed"); }
+            rt.launches++;
+            cudaMemcpyAsync(oc.values, d_vals, (size_t)total * es, cudaMemcpyDeviceToHost, rt.stream);
+            if (p.type.nullable && oc.missing) cudaMemcpyAsync(oc.missing, d_miss, (size_t)total, cudaMemcpyDeviceToHost, rt.stream);
+            cudaStreamSynchronize(rt.stream);
+            rc = check_device_error();
+            if (rc) { cleanup(); return rc; }
+        }
+        cudaError_t e = cudaStreamSynchronize(rt.stream);
+        cleanup();
+        if (e != cudaSuccess) return fail(DFDB_ERR_CUDA, "materialize failed: %s", cudaGetErrorString(e));
+    }
+    return DFDB_OK;
+}
+
+// ---- codec hook ---------------------------------------------------------------------------------------
+int32_t dfdb_lz4_decode_blocks(const uint8_t *comp, const int64_t *comp_off, const int64_t *comp_len, uint8_t *out,
+                               const int64_t *out_off, const int64_t *origin, int32_t n, int32_t *status)
+{
+    int rc = need_init();
+    if (rc) return rc;
+    if (n <= 0) return DFDB_OK;
+    std::vector<int64_t> coff((size_t)n), doff((size_t)n);
+    std::vector<int32_t> clen((size_t)n), orig((size_t)n);
+    int64_t cpos = 0, dpos = 0;
+    for (int i = 0; i < n; i++) {
+        if (comp_len[i] < 0 || origin[i] < 0 || comp_len[i] > 0x7F000000LL || origin[i] > 0x7E000000LL) return fail(DFDB_ERR_ARGUMENT, "bad block sizes");
+        coff[(size_t)i] = cpos; clen[(size_t)i] = (int32_t)comp_len[i]; cpos += (comp_len[i] + 15) & ~(int64_t)15;
+        doff[(size_t)i] = dpos; orig[(size_t)i] = (int32_t)origin[i]; dpos += (origin[i] + 255) & ~(int64_t)255;
+    }
+    std::vector<uint8_t> packed((size_t)cpos + 4096, 0);
+    for (int i = 0; i < n; i++) memcpy(packed.data() + coff[(size_t)i], comp + comp_off[i], (size_t)comp_len[i]);
+    uint8_t *d_comp = nullptr, *d_out = nullptr;
+    int64_t *d_coff = nullptr, *d_doff = nullptr;
+    int32_t *d_clen = nullptr, *d_orig = nullptr, *d_status = nullptr;
+    auto cleanup = [&]() { cudaFree(d_comp); cudaFree(d_out); cudaFree(d_coff); cudaFree(d_doff); cudaFree(d_clen); cudaFree(d_orig); cudaFree(d_status); };
+    rc = DFDB_OK;
+    if (cudaMalloc(reinterpret_cast<void **>(&d_comp), packed.size()) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void **>(&d_out), (size_t)dpos + 256) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void **>(&d_status), (size_t)n * 4) != cudaSuccess) {
+        cleanup();
+        return fail(DFDB_ERR_NOMEM, "out of device memory");
+    }
+    if ((rc = dev_upload(&d_coff, coff)) || (rc = dev_upload(&d_doff, doff)) || (rc = dev_upload(&d_clen, clen)) || (rc = dev_upload(&d_orig, orig))) {
+        cleanup();
+        return rc;
+    }
+    cudaMemcpyAsync(d_comp, packed.data(), packed.size(), cudaMemcpyHostToDevice, rt.stream);
+    cudaMemsetAsync(d_status, 0xff, (size_t)n * 4, rt.stream);
+    DecodeArgs a;
+    memset(&a, 0, sizeof a);
+    a.ncols = 1;
+    a.nblocks = n;
+    a.col[0] = DecodeCol{d_comp, d_coff, d_clen, d_doff, d_orig, d_out, d_status};
+    if (launch_lz4_decode(a, rt.d_counter, rt.sm_count, (int)rt.lz4_simple, rt.stream) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "decode launch failed"); }
+    rt.launches++;
+    std::vector<uint8_t> hout((size_t)dpos + 256);
+    cudaMemcpyAsync(hout.data(), d_out, hout.size(), cudaMemcpyDeviceToHost, rt.stream);
+    cudaMemcpyAsync(status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, rt.stream);
+    cudaError_t e = cudaStreamSynchronize(rt.stream);
+    cleanup();
+    if (e != cudaSuccess) return fail(DFDB_ERR_CUDA, "decode failed: %s", cudaGetErrorString(e));
+    for (int i = 0; i < n; i++) {
+        if (status[i] == 0) memcpy(out + out_off[i], hout.data() + doff[(size_t)i], (size_t)origin[i]);
+        else status[i] = DFDB_ERR_CORRUPT;
+    }
+    return DFDB_OK;
+}
+
+}  // extern "C"

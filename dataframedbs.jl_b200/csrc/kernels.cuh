@@ -1,0 +1,136 @@
+// kernels.cuh -- kernel argument PODs and launch wrappers shared by the .cu translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "internal.hpp"
+
+namespace dfdb {
+
+// ---- K1: LZ4 block decode ------------------------------------------------------------------------
+constexpr int DECODE_MAX_COLS = 16;
+struct DecodeCol {
+    const uint8_t *comp;        // packed compressed payloads (16-byte aligned, 16-byte padded slots)
+    const int64_t *comp_off;    // per local block
+    const int32_t *comp_len;
+    const int64_t *dec_off;     // per local block: offset of the 256-byte aligned body slot
+    const int32_t *origin;
+    uint8_t *out;
+    int32_t *status;
+};
+struct DecodeArgs {
+    DecodeCol col[DECODE_MAX_COLS];
+    int ncols;
+    int nblocks;
+};
+int launch_lz4_decode(const DecodeArgs &args, unsigned int *d_counter, int sm_count, int simple_mode, cudaStream_t stream);
+
+// ---- scan geometry -------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int ROWS_PER_THREAD = 8;
+constexpr int TILE_ROWS = SCAN_THREADS * ROWS_PER_THREAD;   // 2048 rows per CTA iteration
+
+struct Geometry {
+    int64_t nrows_total;     // rows of the whole table
+    int64_t block_size;      // rows per column block
+    int64_t blk_lo;          // first table block of this shard
+    int32_t nblocks;         // local blocks
+    int32_t wpb;             // mask words (32 rows each) per block
+    int32_t segs_per_block;  // work units per block
+    int32_t seg_rows;        // rows per work unit (multiple of TILE_ROWS)
+};
+
+__host__ __device__ inline int64_t block_rows(const Geometry &g, int lb)
+{
+    int64_t r = g.nrows_total - (g.blk_lo + lb) * g.block_size;
+    return r < g.block_size ? (r < 0 ? 0 : r) : g.block_size;
+}
+
+// per-unit aggregate partial (also the final result layout on device)
+struct AggPartial {
+    long long count, nmissing, sum_i;
+    double sum_f, sum_lo;
+    long long min_i, max_i;
+    double min_f, max_f;
+    int has_nan, has_value;
+};
+
+// ---- K3/K7 fused: conjunction of terms (or a precomputed mask) -> count / aggregate / mask -----------
+struct FusedArgs {
+    Geometry g;
+    ColView term_col[MAX_TERMS];
+    Term term[MAX_TERMS];
+    int nterms;
+    int const_false;              // some term folded to `false`
+    const uint32_t *mask_in;      // selection comes from this mask instead of the terms (may be null)
+    uint32_t *mask_out;           // EMIT: write the selection mask (AND with mask_in when given)
+    ColView agg_col;              // aggregated column (AGG != 0)
+    int agg_cls;                  // VC_INT / VC_UINT / VC_FLT / VC_BOOL
+    AggPartial *partials;         // one per unit
+};
+int launch_fused(const FusedArgs &a, int agg, bool emit_mask, bool wide, int sm_count, cudaStream_t stream);
+int launch_agg_finalize(const AggPartial *partials, int nunits, int cls, AggPartial *result, cudaStream_t stream);
+
+// ---- K3 generic: VM predicate -> mask ------------------------------------------------------------------
+struct VmArgs {
+    Geometry g;
+    ColView slot[MAX_SLOTS];
+    const VmProgram *prog;        // device copy
+    const uint32_t *mask_in;      // rows to evaluate (null = all rows)
+    uint32_t *mask_out;
+    int *error_flag;              // DivideError etc.
+};
+int launch_vm_mask(const VmArgs &a, int sm_count, cudaStream_t stream);
+
+// ---- K4: range / index-vector stages on running survivor ranks ----------------------------------------
+struct RangeArgs {
+    Geometry g;
+    uint32_t *mask;               // in/out
+    int dense;                    // 1: every row of the shard survives so far -> rank = global row number
+    const int64_t *blk_base;      // exclusive scan of per-block survivor counts (when !dense)
+    int64_t rank_offset;          // survivors before this shard (multi-GPU) -- added to every rank
+    int kind;                     // ST_RANGE / ST_INDEXVEC
+    int64_t start, step, stop;
+    const int64_t *idx;
+    int64_t nidx;
+};
+int launch_block_counts(const Geometry &g, const uint32_t *mask, int64_t *counts, cudaStream_t stream);
+int launch_exclusive_scan(const int64_t *in, int64_t *out, int n, cudaStream_t stream);   // out[n] = total
+int launch_range_stage(const RangeArgs &a, cudaStream_t stream);
+int launch_fill_mask(const Geometry &g, uint32_t *mask, cudaStream_t stream);
+
+// ---- K2: String bodies: per-row char offsets (unsafe_remake_offsets!) --------------------------------
+int launch_str_offsets(const Geometry &g, const ColView &col, int32_t *str_off, int32_t *status, cudaStream_t stream);
+
+// ---- K5/K6: stream compaction / gathers ---------------------------------------------------------------
+struct GatherArgs {
+    Geometry g;
+    const uint32_t *mask;
+    const int64_t *blk_base;      // exclusive scan of per-block selected counts
+    ColView col;
+    uint8_t *out_values;          // fixed width
+    uint8_t *out_missing;         // 1 byte per row (nullable), may be null
+    int32_t *out_sizes;           // strings
+    uint8_t *out_chars;
+    const int64_t *blk_char_base; // exclusive scan of per-block selected string bytes
+    int64_t *out_indices;         // row numbers (1-based, table order) when non-null
+};
+int launch_gather_fixed(const GatherArgs &a, cudaStream_t stream);
+int launch_gather_indices(const GatherArgs &a, cudaStream_t stream);
+int launch_str_block_bytes(const GatherArgs &a, int64_t *blk_bytes, cudaStream_t stream);
+int launch_gather_strings(const GatherArgs &a, cudaStream_t stream);
+
+// computed projection columns: VM value per selected row
+struct ProjVmArgs {
+    Geometry g;
+    ColView slot[MAX_SLOTS];
+    const VmProgram *prog;
+    const uint32_t *mask;
+    const int64_t *blk_base;
+    uint8_t *out_values;
+    uint8_t *out_missing;
+    int elsize;
+    int *error_flag;
+};
+int launch_proj_vm(const ProjVmArgs &a, cudaStream_t stream);
+
+}  // namespace dfdb

@@ -1,0 +1,351 @@
+// lz4_decode.cu -- K1: raw LZ4 block decode on sm_100a, one warp per compressed column block.
+//
+// Replaces read_block's LZ4_decompress_safe call (/root/reference/src/io/BlockStreams.jl:101-119,
+// liblz4 through CodecLz4) for whole batches of independent column blocks.  Like the _safe decoder it
+// never reads outside the compressed payload nor writes outside `origin` bytes, and it reports a
+// per-block status instead of the reference's `@assert size == sizes.origin "decompression error"`.
+//
+// Algorithm (decode_batched): the serial part of LZ4 is only the *position* of each token.  A warp
+//   A. walks 32 tokens of the smem-staged compressed stream with a 3-instruction dependent chain
+//      (LDS token, shift, add) and records the 32 token positions;
+//   B. then handles the 32 sequences lane-parallel: every lane reads its own token/offset, a warp
+//      prefix sum of (literals + match) lengths gives every lane its output position, literals are
+//      copied from the staged stream into an smem output staging area, matches are copied in
+//      dependency waves (a lane whose source bytes are already final runs immediately; sources inside
+//      the current batch wait for the frontier of completed lanes);
+//   C. the staged output is flushed to HBM with coalesced 16-byte stores.
+// Sequences with length extensions (literal or match nibble == 15) and the last sequence of a block
+// take the warp-cooperative path decode_one_sequence, whose literal copy is a 16-byte vectorised,
+// re-aligning warp memcpy -- that path is what incompressible Float64 blocks (one giant literal run)
+// exercise, so it has to run at copy bandwidth.
+//
+// Algorithmic bytes per block (roofline): compressed bytes read + origin bytes written.
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+
+namespace dfdb {
+
+namespace {
+
+constexpr int WARPS_PER_CTA = 8;
+constexpr int WIN = 2048;              // bytes of compressed stream staged per warp
+constexpr int WIN_PAD = 64;
+constexpr int BATCH_IN_MAX = 32 * 17;  // 32 sequences * (token + 14 literals + offset)
+constexpr int STG = 1280;              // output staging: 15 carried bytes + 32 * (14 + 18) bytes, rounded up
+
+enum { E_OK = 0, E_TRUNCATED = 1, E_OFFSET = 2, E_OVERFLOW = 3, E_SIZE = 4 };
+
+struct WarpSmem {
+    __align__(16) uint8_t win[WIN + WIN_PAD];
+    __align__(16) uint8_t stg[STG];
+    uint16_t pos[32];
+};
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+// ---- warp memcpy global -> global, arbitrary alignment, vectorised on the destination -----------
+__device__ __forceinline__ uint4 shift_combine(const uint4 lo, const uint4 hi, int q, int r8)
+{
+    uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    uint4 o;
+    switch (q) {   // q is uniform over the whole copy
+    case 0: o.x = __funnelshift_r(w[0], w[1], r8); o.y = __funnelshift_r(w[1], w[2], r8); o.z = __funnelshift_r(w[2], w[3], r8); o.w = __funnelshift_r(w[3], w[4], r8); break;
+    case 1: o.x = __funnelshift_r(w[1], w[2], r8); o.y = __funnelshift_r(w[2], w[3], r8); o.z = __funnelshift_r(w[3], w[4], r8); o.w = __funnelshift_r(w[4], w[5], r8); break;
+    case 2: o.x = __funnelshift_r(w[2], w[3], r8); o.y = __funnelshift_r(w[3], w[4], r8); o.z = __funnelshift_r(w[4], w[5], r8); o.w = __funnelshift_r(w[5], w[6], r8); break;
+    default: o.x = __funnelshift_r(w[3], w[4], r8); o.y = __funnelshift_r(w[4], w[5], r8); o.z = __funnelshift_r(w[5], w[6], r8); o.w = __funnelshift_r(w[6], w[7], r8); break;
+    }
+    return o;
+}
+
+// `src_limit` = one past the last readable byte of the source buffer rounded up to 16 (payload slots are
+// 16-byte padded), so the aligned over-read of the last chunk stays inside the slot.
+__device__ void warp_copy(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int64_t n)
+{
+    const uint32_t lane = lane_id();
+    int64_t head = (int64_t)((16 - ((uintptr_t)dst & 15)) & 15);
+    if (head > n) head = n;
+    if ((int64_t)lane < head) dst[lane] = src[lane];
+    dst += head; src += head; n -= head;
+    const int64_t nchunks = n >> 4;
+    if (nchunks > 0) {
+        uint4 *d16 = reinterpret_cast<uint4 *>(dst);
+        const int s = (int)((uintptr_t)src & 15);
+        if (s == 0) {
+            const uint4 *s16 = reinterpret_cast<const uint4 *>(src);
+            int64_t c = lane;
+            for (; c + 96 < nchunks; c += 128) {
+                uint4 v0 = __ldg(s16 + c), v1 = __ldg(s16 + c + 32), v2 = __ldg(s16 + c + 64), v3 = __ldg(s16 + c + 96);
+                d16[c] = v0; d16[c + 32] = v1; d16[c + 64] = v2; d16[c + 96] = v3;
+            }
+            for (; c < nchunks; c += 32) d16[c] = __ldg(s16 + c);
+        } else {
+            const uint4 *s16 = reinterpret_cast<const uint4 *>(src - s);   // aligned base; chunk c needs s16[c], s16[c+1]
+            const int q = s >> 2, r8 = (s & 3) * 8;
+            int64_t c = lane;
+            for (; c + 96 < nchunks; c += 128) {
+                uint4 a0 = __ldg(s16 + c), b0 = __ldg(s16 + c + 1);
+                uint4 a1 = __ldg(s16 + c + 32), b1 = __ldg(s16 + c + 33);
+                uint4 a2 = __ldg(s16 + c + 64), b2 = __ldg(s16 + c + 65);
+                uint4 a3 = __ldg(s16 + c + 96), b3 = __ldg(s16 + c + 97);
+                d16[c] = shift_combine(a0, b0, q, r8);
+                d16[c + 32] = shift_combine(a1, b1, q, r8);
+                d16[c + 64] = shift_combine(a2, b2, q, r8);
+                d16[c + 96] = shift_combine(a3, b3, q, r8);
+            }
+            for (; c < nchunks; c += 32) d16[c] = shift_combine(__ldg(s16 + c), __ldg(s16 + c + 1), q, r8);
+        }
+    }
+    const int64_t done = nchunks << 4;
+    const int64_t tail = n - done;
+    if ((int64_t)lane < tail) dst[done + lane] = src[done + lane];
+}
+
+// length extension bytes (LZ4: add bytes while they are 255); cooperative over the warp.
+// returns false when the stream ends inside the extension.
+__device__ __forceinline__ bool read_length_ext(const uint8_t *__restrict__ src, int64_t &ip, int64_t comp_len, int64_t &len)
+{
+    const uint32_t lane = lane_id();
+    for (;;) {
+        int64_t p = ip + lane;
+        uint32_t b = p < comp_len ? src[p] : 0u;     // past the end reads as a terminator and is caught below
+        uint32_t stop = __ballot_sync(0xffffffffu, b != 255u);
+        if (stop == 0) { len += 255 * 32; ip += 32; if (ip >= comp_len) return false; continue; }
+        int f = __ffs(stop) - 1;
+        uint32_t last = __shfl_sync(0xffffffffu, b, f);
+        if (ip + f >= comp_len) return false;
+        len += 255 * f + last;
+        ip += f + 1;
+        return true;
+    }
+}
+
+// One sequence, whole warp cooperating, direct global I/O.  All bytes < op are final in global memory
+// on entry and on exit.  Returns E_* ; sets done when the block's last sequence was consumed.
+__device__ int decode_one_sequence(const uint8_t *__restrict__ src, int64_t comp_len, uint8_t *dst, int64_t origin,
+                                   int64_t &ip, int64_t &op, bool &done)
+{
+    const uint32_t lane = lane_id();
+    if (ip >= comp_len) return E_TRUNCATED;
+    const uint32_t token = src[ip];
+    ip += 1;
+    int64_t L = token >> 4;
+    if (L == 15 && !read_length_ext(src, ip, comp_len, L)) return E_TRUNCATED;
+    if (ip + L > comp_len) return E_TRUNCATED;
+    if (op + L > origin) return E_OVERFLOW;
+    if (L > 0) warp_copy(dst + op, src + ip, L);
+    ip += L;
+    op += L;
+    if (ip == comp_len) { done = true; return E_OK; }   // last sequence: literals only
+    if (ip + 2 > comp_len) return E_TRUNCATED;
+    const uint32_t off = (uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8);
+    ip += 2;
+    int64_t M = token & 15;
+    if (M == 15 && !read_length_ext(src, ip, comp_len, M)) return E_TRUNCATED;
+    M += 4;
+    if (off == 0 || (int64_t)off > op) return E_OFFSET;
+    if (op + M > origin) return E_OVERFLOW;
+    __syncwarp();                                       // literal bytes visible to the whole warp
+    // every source byte is < op, i.e. already final: the copy is fully parallel even when it overlaps
+    uint8_t *m_dst = dst + op;
+    const uint8_t *m_src = dst + op - off;
+    if ((int64_t)off >= M) {
+        for (int64_t i = lane; i < M; i += 32) m_dst[i] = __ldcg(m_src + i);
+    } else {
+        for (int64_t i = lane; i < M; i += 32) m_dst[i] = __ldcg(m_src + ((uint32_t)i % off));
+    }
+    op += M;
+    __syncwarp();
+    return E_OK;
+}
+
+// ---- baseline decoder: one sequence at a time (kept for A/B checks, option "lz4_simple") ---------
+__device__ int decode_simple(const uint8_t *__restrict__ src, int64_t comp_len, uint8_t *dst, int64_t origin)
+{
+    int64_t ip = 0, op = 0;
+    bool done = false;
+    while (!done) {
+        int e = decode_one_sequence(src, comp_len, dst, origin, ip, op, done);
+        if (e) return e;
+    }
+    return (op == origin && ip == comp_len) ? E_OK : E_SIZE;
+}
+
+__device__ __forceinline__ uint8_t stg_or_global(const WarpSmem &sm, const uint8_t *dst, int64_t stg_base, int64_t x)
+{
+    return x >= stg_base ? sm.stg[x - stg_base] : __ldcg(dst + x);
+}
+
+// ---- batched decoder ----------------------------------------------------------------------------
+__device__ int decode_batched(WarpSmem &sm, const uint8_t *__restrict__ src, int64_t comp_len, uint8_t *dst, int64_t origin)
+{
+    const uint32_t lane = lane_id();
+    const int64_t comp_pad = (comp_len + 15) & ~(int64_t)15;
+    int64_t ip = 0, op = 0;
+    int64_t win_base = -(int64_t)WIN * 2;   // forces the first refill
+    int64_t stg_base = 0;                   // 16-aligned; staging holds out bytes [stg_base, op)
+    bool done = false;
+
+    while (!done) {
+        // ---- input window -------------------------------------------------------------------
+        if (ip < win_base || ip + BATCH_IN_MAX > win_base + WIN) {
+            win_base = ip & ~(int64_t)15;
+            const uint4 *s16 = reinterpret_cast<const uint4 *>(src + win_base);
+            uint4 *w16 = reinterpret_cast<uint4 *>(sm.win);
+#pragma unroll
+            for (int c = 0; c < (WIN + WIN_PAD) / 16 / 32 + 1; c++) {
+                int ch = c * 32 + lane;
+                if (ch < (WIN + WIN_PAD) / 16) {
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (win_base + (int64_t)ch * 16 < comp_pad) v = __ldg(s16 + ch);
+                    w16[ch] = v;
+                }
+            }
+            __syncwarp();
+        }
+        // ---- A: token chain -----------------------------------------------------------------
+        uint32_t p = (uint32_t)(ip - win_base);
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            uint32_t t = sm.win[p];
+            sm.pos[k] = (uint16_t)p;
+            p += 3 + (t >> 4);
+        }
+        __syncwarp();
+        // ---- B: lane-parallel sequences -----------------------------------------------------
+        const uint32_t mypos = sm.pos[lane];
+        const uint32_t tok = sm.win[mypos];
+        const uint32_t L = tok >> 4, Mn = tok & 15;
+        const int64_t seq_end_in = win_base + mypos + 3 + L;
+        const bool simple = (L < 15) && (Mn < 15) && (seq_end_in < comp_len);
+        const uint32_t bs = __ballot_sync(0xffffffffu, simple);
+        const int nvalid = (bs == 0xffffffffu) ? 32 : (__ffs(~bs) - 1);
+        if (nvalid == 0) {
+            // make global memory complete up to op, run one cooperative sequence, re-seed the staging
+            const int carried = (int)(op - stg_base);
+            if ((int)lane < carried) dst[stg_base + lane] = sm.stg[lane];
+            __syncwarp();
+            int e = decode_one_sequence(src, comp_len, dst, origin, ip, op, done);
+            if (e) return e;
+            stg_base = op & ~(int64_t)15;
+            const int tail = (int)(op - stg_base);
+            if ((int)lane < tail) sm.stg[lane] = __ldcg(dst + stg_base + lane);
+            __syncwarp();
+            continue;
+        }
+        const bool active = (int)lane < nvalid;
+        const uint32_t off = active ? ((uint32_t)sm.win[mypos + 1 + L] | ((uint32_t)sm.win[mypos + 2 + L] << 8)) : 1u;
+        const uint32_t M = Mn + 4;
+        const uint32_t len = active ? L + M : 0u;
+        uint32_t incl = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const int64_t o = op + (incl - len);          // my literals start here
+        const int64_t m_dst = o + L;                  // my match starts here
+        const int64_t m_src = m_dst - (int64_t)off;
+        const bool bad = active && (off == 0 || m_src < 0);
+        if (__any_sync(0xffffffffu, bad)) return E_OFFSET;
+        if (op + total > origin) return E_OVERFLOW;
+        // literals: compressed stream (smem window) -> staging
+        if (active) {
+            for (uint32_t i = 0; i < L; i++) sm.stg[o - stg_base + i] = sm.win[mypos + 1 + i];
+        }
+        __syncwarp();
+        // matches in dependency waves.  Frontier F: every output byte < F is final.
+        {
+            const int64_t src_end = (m_src + (int64_t)M < m_dst) ? m_src + M : m_dst;   // bytes needed from other producers end here
+            uint32_t pending = __ballot_sync(0xffffffffu, active);
+            int64_t F = op;
+            int P = 0;                                                                 // first lane whose match is not done
+            while (pending) {
+                const bool mine = (pending >> lane) & 1u;
+                const bool ready = mine && (src_end <= F || (int)lane == P);
+                if (ready) {
+                    const int64_t sd = m_dst - stg_base;
+                    if (off >= 8 && ((m_dst | m_src) & 7) == 0 && M == 8) {
+                        unsigned long long v;
+                        if (m_src >= stg_base) v = *reinterpret_cast<const unsigned long long *>(sm.stg + (m_src - stg_base));
+                        else v = __ldcg(reinterpret_cast<const unsigned long long *>(dst + m_src));
+                        *reinterpret_cast<unsigned long long *>(sm.stg + sd) = v;
+                    } else {
+                        // byte-serial per lane: correct for self-overlapping matches (off < M) as well
+                        for (uint32_t i = 0; i < M; i++) sm.stg[sd + i] = stg_or_global(sm, dst, stg_base, m_src + i);
+                    }
+                }
+                __syncwarp();
+                pending &= ~__ballot_sync(0xffffffffu, ready);
+                if (pending) {
+                    P = __ffs(pending) - 1;
+                    F = __shfl_sync(0xffffffffu, m_dst, P);
+                }
+            }
+        }
+        // ---- C: flush whole 16-byte chunks, carry the partial tail ---------------------------
+        const int64_t new_op = op + total;
+        const int nchunks = (int)((new_op >> 4) - (stg_base >> 4));
+        {
+            uint4 *d16 = reinterpret_cast<uint4 *>(dst + stg_base);
+            const uint4 *g16 = reinterpret_cast<const uint4 *>(sm.stg);
+            for (int c = lane; c < nchunks; c += 32) d16[c] = g16[c];
+        }
+        const int tail = (int)(new_op & 15);
+        uint8_t tb = 0;
+        if (nchunks > 0 && (int)lane < tail) tb = sm.stg[nchunks * 16 + lane];
+        __syncwarp();
+        if (nchunks > 0 && (int)lane < tail) sm.stg[lane] = tb;
+        stg_base += (int64_t)nchunks * 16;
+        op = new_op;
+        ip = __shfl_sync(0xffffffffu, seq_end_in, nvalid - 1);
+        __syncwarp();
+    }
+    // block finished inside decode_one_sequence (which leaves everything < op in global memory)
+    return (op == origin && ip == comp_len) ? E_OK : E_SIZE;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) lz4_decode_kernel(DecodeArgs args, unsigned int *counter, int simple_mode)
+{
+    __shared__ WarpSmem smem[WARPS_PER_CTA];
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    const unsigned int njobs = (unsigned int)args.ncols * (unsigned int)args.nblocks;
+    for (;;) {
+        unsigned int job = 0;
+        if (lane == 0) job = atomicAdd(counter, 1u);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= njobs) break;
+        const int c = (int)(job % (unsigned int)args.ncols);
+        const int b = (int)(job / (unsigned int)args.ncols);
+        const DecodeCol &col = args.col[c];
+        const uint8_t *src = col.comp + col.comp_off[b];
+        uint8_t *dst = col.out + col.dec_off[b];
+        const int64_t comp_len = col.comp_len[b], origin = col.origin[b];
+        int e = simple_mode ? decode_simple(src, comp_len, dst, origin) : decode_batched(smem[warp], src, comp_len, dst, origin);
+        if (lane == 0) col.status[b] = e;
+        __syncwarp();
+    }
+}
+
+int launch_lz4_decode(const DecodeArgs &args, unsigned int *d_counter, int sm_count, int simple_mode, cudaStream_t stream)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(lz4_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream);
+    const long long njobs = (long long)args.ncols * args.nblocks;
+    long long ctas = (njobs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const long long max_ctas = (long long)sm_count * 4;     // 32 resident warps per SM, persistent over the job queue
+    if (ctas > max_ctas) ctas = max_ctas;
+    if (ctas < 1) ctas = 1;
+    lz4_decode_kernel<<<(unsigned int)ctas, WARPS_PER_CTA * 32, 0, stream>>>(args, d_counter, simple_mode);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace dfdb

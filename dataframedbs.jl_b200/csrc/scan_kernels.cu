@@ -1,0 +1,1056 @@
+// scan_kernels.cu -- K2..K7: everything that runs over decoded column blocks.
+//
+//   K3+K7 fused_scan_kernel   predicate terms -> selection bits -> count / sum / min / max (or mask)
+//                             replaces apply(::SelectionExecutor) + eval_on_range + the Base folds over
+//                             iterate(::DFColumn): /root/reference/src/tables/selection.jl:133-167,
+//                             broadcast.jl:96-133, column.jl:102-126, view.jl:192-206 (nrow)
+//   K3    vm_mask_kernel      generic typed VM for arbitrary BlockBroadcasting predicates (broadcast.jl:6-17)
+//   K4    range_stage_kernel  range / index-vector stages on running survivor ranks (selection.jl:94-111)
+//   K2    str_offsets_kernel  unsafe_remake_offsets! (/root/reference/src/FlatStringsVectors.jl:61-70)
+//   K5/K6 gather_* kernels    ColProjExec `buffer .= data[name][range]` + append! (projection.jl:130-133,
+//                             materialization.jl:27-40) and the FlatStringsVector gather
+//                             (FlatStringsVectors.jl:136-157): warp-aggregated prefix-sum compaction
+//
+// Decoded bodies keep the reference's block-body layouts (src/io/blocks.jl:2-33); every kernel addresses
+// rows as (local block, row in block).  All kernels are HBM-bound streaming kernels: algorithmic bytes
+// per row are listed in DESIGN.md.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "kernels.cuh"
+
+namespace dfdb {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+// ---- column access -----------------------------------------------------------------------------------
+__device__ __forceinline__ const uint8_t *col_body(const ColView &c, int lb) { return c.base + c.blk_off[lb]; }
+__device__ __forceinline__ const uint8_t *col_values(const ColView &c, int lb, int64_t rows_b)
+{
+    const uint8_t *body = col_body(c, lb);
+    return c.nullable ? body + ((rows_b + 63) >> 6) * 8 : body;
+}
+__device__ __forceinline__ bool col_missing(const ColView &c, int lb, int64_t r)
+{
+    if (!c.nullable) return false;
+    const unsigned long long *w = reinterpret_cast<const unsigned long long *>(col_body(c, lb));
+    return (w[r >> 6] >> (r & 63)) & 1ull;
+}
+
+// 64-bit payload of a fixed-width value: integers sign/zero extended, floats as double bits, Bool 0/1
+__device__ __forceinline__ unsigned long long load_widen(const uint8_t *p, int kind)
+{
+    switch (kind) {
+    case DFDB_I8: return (unsigned long long)(long long)*reinterpret_cast<const int8_t *>(p);
+    case DFDB_I16: return (unsigned long long)(long long)*reinterpret_cast<const int16_t *>(p);
+    case DFDB_I32: return (unsigned long long)(long long)*reinterpret_cast<const int32_t *>(p);
+    case DFDB_U8: case DFDB_BOOL: return *p;
+    case DFDB_U16: return *reinterpret_cast<const uint16_t *>(p);
+    case DFDB_U32: return *reinterpret_cast<const uint32_t *>(p);
+    case DFDB_F32: return (unsigned long long)__double_as_longlong((double)*reinterpret_cast<const float *>(p));
+    default: return *reinterpret_cast<const unsigned long long *>(p);   // 8-byte kinds
+    }
+}
+
+template <bool WIDE>
+__device__ __forceinline__ int64_t row_of(int64_t tile0, int k, int tid)
+{
+    if (WIDE) return tile0 + (k >> 1) * (2 * SCAN_THREADS) + 2 * tid + (k & 1);
+    return tile0 + (int64_t)k * SCAN_THREADS + tid;
+}
+
+// values of this thread's 8 rows of one tile; `miss` gets bit k set when row k is missing
+template <bool WIDE>
+__device__ __forceinline__ void load8(const ColView &c, int lb, int64_t rows_b, int64_t tile0, int tid, unsigned long long (&v)[8],
+                                      unsigned &miss)
+{
+    const uint8_t *vals = col_values(c, lb, rows_b);
+    if (WIDE) {
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const int64_t r = tile0 + s * (2 * SCAN_THREADS) + 2 * tid;
+            if (r + 1 < rows_b) {
+                const ulonglong2 x = __ldcs(reinterpret_cast<const ulonglong2 *>(vals + r * 8));
+                v[2 * s] = x.x;
+                v[2 * s + 1] = x.y;
+            } else {
+                v[2 * s] = r < rows_b ? __ldcs(reinterpret_cast<const unsigned long long *>(vals + r * 8)) : 0ull;
+                v[2 * s + 1] = 0ull;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int64_t r = tile0 + (int64_t)k * SCAN_THREADS + tid;
+            v[k] = r < rows_b ? load_widen(vals + r * c.elsize, c.kind) : 0ull;
+        }
+    }
+    miss = 0;
+    if (c.nullable) {
+        const unsigned long long *w = reinterpret_cast<const unsigned long long *>(col_body(c, lb));
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int64_t r = row_of<WIDE>(tile0, k, tid);
+            if (r < rows_b) miss |= (unsigned)((__ldg(w + (r >> 6)) >> (r & 63)) & 1ull) << k;
+        }
+    }
+}
+
+__device__ __forceinline__ bool cmp_code(int code, int c3)   // c3: -1,0,1 or 2 = unordered
+{
+    if (c3 == 2) return code == 1;
+    switch (code) {
+    case 0: return c3 == 0;
+    case 1: return c3 != 0;
+    case 2: return c3 < 0;
+    case 3: return c3 <= 0;
+    case 4: return c3 > 0;
+    default: return c3 >= 0;
+    }
+}
+
+__device__ __forceinline__ unsigned term_bits(const Term &t, const unsigned long long (&v)[8])
+{
+    unsigned b = 0;
+    if (t.cls == VC_INT) {
+        const long long c = t.ci;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const long long x = (long long)v[k];
+            b |= (unsigned)cmp_code(t.code, x < c ? -1 : (x > c ? 1 : 0)) << k;
+        }
+    } else if (t.cls == VC_UINT) {
+        const unsigned long long c = (unsigned long long)t.ci;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const unsigned long long x = v[k];
+            b |= (unsigned)cmp_code(t.code, x < c ? -1 : (x > c ? 1 : 0)) << k;
+        }
+    } else {
+        const double c = t.cf;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const double x = __longlong_as_double((long long)v[k]);
+            const int c3 = (x != x || c != c) ? 2 : (x < c ? -1 : (x > c ? 1 : 0));
+            b |= (unsigned)cmp_code(t.code, c3) << k;
+        }
+    }
+    return b;
+}
+
+// ---- aggregate accumulators ------------------------------------------------------------------------------
+__device__ __forceinline__ void two_sum_add(double &hi, double &lo, double x)
+{
+    const double t = hi + x;
+    const double bb = t - hi;
+    lo += (hi - (t - bb)) + (x - bb);   // Knuth two-sum: exact error of hi + x
+    hi = t;
+}
+__device__ __forceinline__ double jl_min(double a, double b) { return (a < b || (a == b && signbit(a))) ? a : b; }
+__device__ __forceinline__ double jl_max(double a, double b) { return (a > b || (a == b && !signbit(a))) ? a : b; }
+
+__device__ __forceinline__ void agg_init(AggPartial &a)
+{
+    a.count = 0; a.nmissing = 0; a.sum_i = 0; a.sum_f = 0.0; a.sum_lo = 0.0;
+    a.min_i = 0; a.max_i = 0; a.min_f = 0.0; a.max_f = 0.0; a.has_nan = 0; a.has_value = 0;
+}
+
+// fixed-order merge (b follows a in row order)
+__device__ __forceinline__ void agg_merge(AggPartial &a, const AggPartial &b, int cls)
+{
+    a.count += b.count;
+    a.nmissing += b.nmissing;
+    a.sum_i = (long long)((unsigned long long)a.sum_i + (unsigned long long)b.sum_i);
+    two_sum_add(a.sum_f, a.sum_lo, b.sum_f);
+    a.sum_lo += b.sum_lo;
+    a.has_nan |= b.has_nan;
+    if (b.has_value) {
+        if (!a.has_value) {
+            a.min_i = b.min_i; a.max_i = b.max_i; a.min_f = b.min_f; a.max_f = b.max_f;
+        } else if (cls == VC_FLT) {
+            a.min_f = jl_min(a.min_f, b.min_f);
+            a.max_f = jl_max(a.max_f, b.max_f);
+        } else if (cls == VC_UINT) {
+            if ((unsigned long long)b.min_i < (unsigned long long)a.min_i) a.min_i = b.min_i;
+            if ((unsigned long long)b.max_i > (unsigned long long)a.max_i) a.max_i = b.max_i;
+        } else {
+            if (b.min_i < a.min_i) a.min_i = b.min_i;
+            if (b.max_i > a.max_i) a.max_i = b.max_i;
+        }
+        a.has_value = 1;
+    }
+}
+
+__device__ __forceinline__ AggPartial agg_shfl_down(const AggPartial &a, int d)
+{
+    AggPartial b;
+    b.count = __shfl_down_sync(FULL, a.count, d);
+    b.nmissing = __shfl_down_sync(FULL, a.nmissing, d);
+    b.sum_i = __shfl_down_sync(FULL, a.sum_i, d);
+    b.sum_f = __shfl_down_sync(FULL, a.sum_f, d);
+    b.sum_lo = __shfl_down_sync(FULL, a.sum_lo, d);
+    b.min_i = __shfl_down_sync(FULL, a.min_i, d);
+    b.max_i = __shfl_down_sync(FULL, a.max_i, d);
+    b.min_f = __shfl_down_sync(FULL, a.min_f, d);
+    b.max_f = __shfl_down_sync(FULL, a.max_f, d);
+    b.has_nan = __shfl_down_sync(FULL, a.has_nan, d);
+    b.has_value = __shfl_down_sync(FULL, a.has_value, d);
+    return b;
+}
+
+// warp-shuffle tree then a sequential fold over the warps of the CTA: the combination order is a fixed
+// function of the thread index, so floating-point results are reproducible run to run
+__device__ void agg_block_reduce(AggPartial &a, int cls, AggPartial *smem /* [SCAN_THREADS/32] */)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        AggPartial b = agg_shfl_down(a, d);
+        if (lane_id() + d < 32) agg_merge(a, b, cls);
+    }
+    if (lane_id() == 0) smem[warp_id()] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        AggPartial r = smem[0];
+        for (int w = 1; w < SCAN_THREADS / 32; w++) agg_merge(r, smem[w], cls);
+        a = r;
+    }
+    __syncthreads();
+}
+
+// ---- K3+K7 fused ---------------------------------------------------------------------------------------
+// AGG: 0 = count only, 1 = integer/Bool values, 2 = floating values
+template <int AGG, bool WIDE, bool EMIT>
+__global__ void __launch_bounds__(SCAN_THREADS) fused_scan_kernel(const FusedArgs A)
+{
+    __shared__ AggPartial red[SCAN_THREADS / 32];
+    const int tid = threadIdx.x;
+    const Geometry g = A.g;
+    const int nunits = g.nblocks * g.segs_per_block;
+    for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        const int lb = unit / g.segs_per_block;
+        const int seg = unit - lb * g.segs_per_block;
+        const int64_t rows_b = block_rows(g, lb);
+        const int64_t row0 = (int64_t)seg * g.seg_rows;
+        int64_t row1 = row0 + g.seg_rows;
+        if (row1 > rows_b) row1 = rows_b;
+        AggPartial acc;
+        agg_init(acc);
+        for (int64_t tile0 = row0; tile0 < row1; tile0 += TILE_ROWS) {
+            unsigned long long av[8];
+            unsigned amiss = 0;
+            if (AGG) load8<WIDE>(A.agg_col, lb, rows_b, tile0, tid, av, amiss);
+            // valid rows of this thread
+            unsigned m = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) m |= (unsigned)(row_of<WIDE>(tile0, k, tid) < row1) << k;
+            if (A.const_false) m = 0;
+            if (A.mask_in) {
+                // non-wide mapping only: row k of this thread is bit `lane` of word (tile0 + k*256 + warp*32) / 32
+                unsigned sel = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int64_t r0 = tile0 + (int64_t)k * SCAN_THREADS + warp_id() * 32;
+                    if (r0 < rows_b) sel |= ((__ldg(A.mask_in + (int64_t)lb * g.wpb + (r0 >> 5)) >> lane_id()) & 1u) << k;
+                }
+                m &= sel;
+            }
+            for (int t = 0; t < A.nterms; t++) {
+                const Term &term = A.term[t];
+                if (term.constant_result >= 0) continue;   // folded (a false one sets const_false)
+                unsigned long long v[8];
+                unsigned miss;
+                load8<WIDE>(A.term_col[t], lb, rows_b, tile0, tid, v, miss);
+                m &= term_bits(term, v) & ~miss;           // missing compares as false under coalesce(..., false)
+            }
+            if (EMIT) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const unsigned word = __ballot_sync(FULL, (m >> k) & 1u);
+                    const int64_t r0 = tile0 + (int64_t)k * SCAN_THREADS + warp_id() * 32;
+                    if (lane_id() == 0 && r0 < rows_b) A.mask_out[(int64_t)lb * g.wpb + (r0 >> 5)] = word;
+                }
+            }
+            acc.count += __popc(m);
+            if (AGG) {
+                acc.nmissing += __popc(m & amiss);
+                const unsigned use = m & ~amiss;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if ((use >> k) & 1u) {
+                        if (AGG == 2) {
+                            const double x = __longlong_as_double((long long)av[k]);
+                            if (x != x) acc.has_nan = 1;
+                            else {
+                                two_sum_add(acc.sum_f, acc.sum_lo, x);
+                                if (!acc.has_value) { acc.min_f = x; acc.max_f = x; acc.has_value = 1; }
+                                else { acc.min_f = jl_min(acc.min_f, x); acc.max_f = jl_max(acc.max_f, x); }
+                            }
+                        } else {
+                            const long long x = (long long)av[k];
+                            acc.sum_i = (long long)((unsigned long long)acc.sum_i + (unsigned long long)x);
+                            if (!acc.has_value) { acc.min_i = x; acc.max_i = x; acc.has_value = 1; }
+                            else if (A.agg_cls == VC_UINT) {
+                                if ((unsigned long long)x < (unsigned long long)acc.min_i) acc.min_i = x;
+                                if ((unsigned long long)x > (unsigned long long)acc.max_i) acc.max_i = x;
+                            } else {
+                                if (x < acc.min_i) acc.min_i = x;
+                                if (x > acc.max_i) acc.max_i = x;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        agg_block_reduce(acc, AGG == 2 ? VC_FLT : A.agg_cls, red);
+        if (tid == 0) A.partials[unit] = acc;
+    }
+}
+
+// final fold of the per-unit partials: thread t folds units t, t+256, ... in order, then the fixed tree
+__global__ void __launch_bounds__(SCAN_THREADS) agg_finalize_kernel(const AggPartial *partials, int nunits, int cls, AggPartial *result)
+{
+    __shared__ AggPartial red[SCAN_THREADS / 32];
+    AggPartial acc;
+    agg_init(acc);
+    // contiguous chunk per thread keeps row order: thread t owns units [t*per, (t+1)*per)
+    const int per = (nunits + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int lo = threadIdx.x * per;
+    int hi = lo + per;
+    if (hi > nunits) hi = nunits;
+    for (int u = lo; u < hi; u++) agg_merge(acc, partials[u], cls);
+    agg_block_reduce(acc, cls, red);
+    if (threadIdx.x == 0) {
+        // renormalise the compensated sum; NaN anywhere makes sum / min / max NaN (Julia propagates)
+        double s = acc.sum_f + acc.sum_lo;
+        acc.sum_lo = (acc.sum_f - s) + acc.sum_lo;
+        acc.sum_f = s;
+        if (acc.has_nan) { acc.sum_f = CUDART_NAN; acc.sum_lo = 0.0; acc.min_f = CUDART_NAN; acc.max_f = CUDART_NAN; }
+        *result = acc;
+    }
+}
+
+// ---- typed VM ---------------------------------------------------------------------------------------------
+struct VmStack {
+    unsigned long long v[VM_MAX_STACK];
+    int len[VM_MAX_STACK];   // strings: byte length
+    unsigned miss;           // bit i = entry i is missing
+};
+
+__device__ __forceinline__ int cmp_int_flt(long long a, bool uns, double b)
+{
+    if (b != b) return 2;
+    if (uns) {
+        const unsigned long long ua = (unsigned long long)a;
+        if (b < 0.0) return 1;
+        if (b >= 18446744073709551616.0) return -1;
+        const unsigned long long tb = (unsigned long long)b;
+        if (ua < tb) return -1;
+        if (ua > tb) return 1;
+        return (double)tb < b ? -1 : 0;
+    }
+    if (b >= 9223372036854775808.0) return -1;
+    if (b < -9223372036854775808.0) return 1;
+    const long long tb = (long long)b;
+    if (a < tb) return -1;
+    if (a > tb) return 1;
+    const double frac = b - (double)tb;
+    return frac > 0.0 ? -1 : (frac < 0.0 ? 1 : 0);
+}
+__device__ __forceinline__ int cmp_u(unsigned long long a, unsigned long long b) { return a < b ? -1 : (a > b ? 1 : 0); }
+__device__ __forceinline__ int cmp_s(long long a, long long b) { return a < b ? -1 : (a > b ? 1 : 0); }
+
+__device__ __forceinline__ int cmp3_pair(int cp, unsigned long long a, unsigned long long b)
+{
+    switch (cp) {
+    case CP_II: return cmp_s((long long)a, (long long)b);
+    case CP_UU: return cmp_u(a, b);
+    case CP_IU: return (long long)a < 0 ? -1 : cmp_u(a, b);
+    case CP_UI: return (long long)b < 0 ? 1 : cmp_u(a, b);
+    case CP_IF: return cmp_int_flt((long long)a, false, __longlong_as_double((long long)b));
+    case CP_UF: return cmp_int_flt((long long)a, true, __longlong_as_double((long long)b));
+    case CP_FI: { int c = cmp_int_flt((long long)b, false, __longlong_as_double((long long)a)); return c == 2 ? 2 : -c; }
+    case CP_FU: { int c = cmp_int_flt((long long)b, true, __longlong_as_double((long long)a)); return c == 2 ? 2 : -c; }
+    default: {
+        const double x = __longlong_as_double((long long)a), y = __longlong_as_double((long long)b);
+        return (x != x || y != y) ? 2 : (x < y ? -1 : (x > y ? 1 : 0));
+    }
+    }
+}
+
+__device__ __forceinline__ int str_cmp(const uint8_t *a, int la, const uint8_t *b, int lb)
+{
+    const int m = la < lb ? la : lb;
+    for (int i = 0; i < m; i++) {
+        const int x = a[i], y = b[i];
+        if (x != y) return x < y ? -1 : 1;
+    }
+    return la < lb ? -1 : (la > lb ? 1 : 0);
+}
+
+__device__ __forceinline__ long long wrap_int(long long v, int bytes, bool uns)
+{
+    if (bytes >= 8) return v;
+    const int bits = bytes * 8;
+    const unsigned long long m = (1ull << bits) - 1ull;
+    unsigned long long u = (unsigned long long)v & m;
+    if (!uns && (u >> (bits - 1))) u |= ~m;
+    return (long long)u;
+}
+
+__device__ __forceinline__ double to_double(unsigned long long v, int cls)
+{
+    switch (cls) {
+    case 3: return __longlong_as_double((long long)v);
+    case 2: return (double)v;
+    default: return (double)(long long)v;   // signed / Bool
+    }
+}
+
+// evaluates the program for row r of local block lb; returns payload + missing flag of the result
+__device__ void vm_eval(const VmProgram *__restrict__ P, const ColView *slots, const Geometry &g, int lb, int64_t rows_b, int64_t r,
+                        unsigned long long &out, bool &out_miss, int *error_flag)
+{
+    VmStack S;
+    S.miss = 0;
+    int sp = 0;
+    const int n = P->ninstr;
+    for (int pc = 0; pc < n; pc++) {
+        const VmInstr I = P->instr[pc];
+        switch (I.op) {
+        case V_LOAD: {
+            const ColView &c = slots[I.a];
+            S.miss &= ~(1u << sp);
+            if (c.cls == VC_STR) {
+                const uint8_t *body = col_body(c, lb);
+                const int sz = reinterpret_cast<const int32_t *>(body + 4)[r];
+                S.v[sp] = (unsigned long long)(uintptr_t)(body + 4 + 4 * rows_b + c.str_off[(int64_t)lb * g.block_size + r]);
+                S.len[sp] = sz;
+                if (sz < 0) { S.miss |= 1u << sp; S.len[sp] = 0; }
+            } else {
+                const bool ms = col_missing(c, lb, r);
+                S.v[sp] = ms ? 0ull : load_widen(col_values(c, lb, rows_b) + r * c.elsize, c.kind);
+                if (ms) S.miss |= 1u << sp;
+            }
+            sp++;
+            break;
+        }
+        case V_CONST:
+            S.v[sp] = (unsigned long long)P->consts[I.imm];
+            S.miss &= ~(1u << sp);
+            sp++;
+            break;
+        case V_CONSTSTR:
+            S.v[sp] = (unsigned long long)(uintptr_t)(P->strpool + I.imm);
+            S.len[sp] = (int)I.a | ((int)I.b << 8);
+            S.miss &= ~(1u << sp);
+            sp++;
+            break;
+        case V_CMP: case V_STRCMP: case V_STRNUM: case V_STARTSWITH: case V_ENDSWITH: {
+            const int ia = sp - 2, ib = sp - 1;
+            const bool ms = ((S.miss >> ia) | (S.miss >> ib)) & 1u;
+            bool res = false;
+            if (!ms) {
+                if (I.op == V_CMP) res = cmp_code(I.a, cmp3_pair(I.b, S.v[ia], S.v[ib]));
+                else if (I.op == V_STRNUM) res = I.a == 1;
+                else {
+                    const uint8_t *pa = reinterpret_cast<const uint8_t *>((uintptr_t)S.v[ia]);
+                    const uint8_t *pb = reinterpret_cast<const uint8_t *>((uintptr_t)S.v[ib]);
+                    const int la = S.len[ia], lb2 = S.len[ib];
+                    if (I.op == V_STRCMP) res = cmp_code(I.a, str_cmp(pa, la, pb, lb2));
+                    else if (lb2 > la) res = false;
+                    else {
+                        const uint8_t *q = I.op == V_STARTSWITH ? pa : pa + (la - lb2);
+                        res = true;
+                        for (int i = 0; i < lb2; i++) if (q[i] != pb[i]) { res = false; break; }
+                    }
+                }
+            }
+            sp--;
+            S.v[ia] = res ? 1ull : 0ull;
+            S.miss = (S.miss & ~(3u << ia)) | ((unsigned)ms << ia);
+            break;
+        }
+        case V_AND: case V_OR: case V_XOR: {
+            const int ia = sp - 2, ib = sp - 1;
+            const bool ma = (S.miss >> ia) & 1u, mb = (S.miss >> ib) & 1u;
+            const bool va = S.v[ia] != 0, vb = S.v[ib] != 0;
+            bool res, ms;
+            if (I.op == V_AND) {
+                if ((!ma && !va) || (!mb && !vb)) { res = false; ms = false; }
+                else if (ma || mb) { res = false; ms = true; }
+                else { res = true; ms = false; }
+            } else if (I.op == V_OR) {
+                if ((!ma && va) || (!mb && vb)) { res = true; ms = false; }
+                else if (ma || mb) { res = false; ms = true; }
+                else { res = false; ms = false; }
+            } else {
+                ms = ma || mb;
+                res = !ms && (va != vb);
+            }
+            sp--;
+            S.v[ia] = res ? 1ull : 0ull;
+            S.miss = (S.miss & ~(3u << ia)) | ((unsigned)ms << ia);
+            break;
+        }
+        case V_NOT: {
+            const int ia = sp - 1;
+            if (!((S.miss >> ia) & 1u)) S.v[ia] = S.v[ia] ? 0ull : 1ull;
+            break;
+        }
+        case V_ISMISSING: {
+            const int ia = sp - 1;
+            S.v[ia] = (S.miss >> ia) & 1u;
+            S.miss &= ~(1u << ia);
+            break;
+        }
+        case V_COALESCE: {
+            const int ia = sp - 2, ib = sp - 1;
+            if ((S.miss >> ia) & 1u) { S.v[ia] = S.v[ib]; S.len[ia] = S.len[ib]; }
+            sp--;
+            S.miss &= ~(3u << ia);
+            break;
+        }
+        case V_IN: {
+            const int ia = sp - 1;
+            if (!((S.miss >> ia) & 1u)) {
+                const int cnt = (int)I.a | ((int)I.b << 8);
+                const unsigned long long x = S.v[ia];
+                bool hit = false;
+                for (int q = 0; q < cnt && !hit; q++) {
+                    const long long sv = P->consts[I.imm + q];
+                    hit = I.c ? (sv >= 0 && x == (unsigned long long)sv) : ((long long)x == sv);
+                }
+                S.v[ia] = hit ? 1ull : 0ull;
+            }
+            break;
+        }
+        case V_ARITH: {
+            const bool unary = I.a == 5;
+            const int ia = unary ? sp - 1 : sp - 2, ib = sp - 1;
+            const bool ms = unary ? ((S.miss >> ia) & 1u) : (((S.miss >> ia) | (S.miss >> ib)) & 1u);
+            const int ca = I.b & 15, cb = I.b >> 4;
+            unsigned long long res = 0;
+            if (!ms) {
+                if (I.c & 0x40) {
+                    double x = to_double(S.v[ia], ca), y = unary ? 0.0 : to_double(S.v[ib], cb);
+                    const bool f32 = (I.c & 15) == 4;
+                    if (f32) { x = (double)(float)x; y = (double)(float)y; }
+                    double z;
+                    switch (I.a) {
+                    case 0: z = x + y; break;
+                    case 1: z = x - y; break;
+                    case 2: z = x * y; break;
+                    case 3: z = x / y; break;
+                    case 4: z = fmod(x, y); break;
+                    default: z = -x; break;
+                    }
+                    if (f32) z = (double)(float)z;
+                    res = (unsigned long long)__double_as_longlong(z);
+                } else {
+                    const bool uns = I.c & 0x80;
+                    const unsigned long long ux = S.v[ia], uy = unary ? 0ull : S.v[ib];
+                    unsigned long long z;
+                    switch (I.a) {
+                    case 0: z = ux + uy; break;
+                    case 1: z = ux - uy; break;
+                    case 2: z = ux * uy; break;
+                    case 4:
+                        if (uy == 0ull) { atomicExch(error_flag, DFDB_ERR_DIVIDE); z = 0ull; }
+                        else if (uns) z = ux % uy;
+                        else z = ((long long)uy == -1ll) ? 0ull : (unsigned long long)((long long)ux % (long long)uy);
+                        break;
+                    default: z = 0ull - ux; break;
+                    }
+                    res = (unsigned long long)wrap_int((long long)z, I.c & 15, uns);
+                }
+            }
+            if (!unary) sp--;
+            S.v[ia] = res;
+            S.miss = (S.miss & ~((unary ? 1u : 3u) << ia)) | ((unsigned)ms << ia);
+            break;
+        }
+        default: break;
+        }
+    }
+    out = S.v[0];
+    out_miss = S.miss & 1u;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) vm_mask_kernel(const VmArgs A)
+{
+    const Geometry g = A.g;
+    const int tiles_per_block = (int)((g.block_size + TILE_ROWS - 1) / TILE_ROWS);
+    const int64_t ntiles = (int64_t)g.nblocks * tiles_per_block;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int lb = (int)(tile / tiles_per_block);
+        const int64_t tile0 = (tile - (int64_t)lb * tiles_per_block) * TILE_ROWS;
+        const int64_t rows_b = block_rows(g, lb);
+#pragma unroll 1
+        for (int k = 0; k < ROWS_PER_THREAD; k++) {
+            const int64_t r0 = tile0 + (int64_t)k * SCAN_THREADS + warp_id() * 32;
+            if (r0 >= rows_b) continue;                                  // warp-uniform
+            const int64_t r = r0 + lane_id();
+            const int64_t widx = (int64_t)lb * g.wpb + (r0 >> 5);
+            bool sel = r < rows_b;
+            if (A.mask_in) sel = sel && ((A.mask_in[widx] >> lane_id()) & 1u);
+            bool res = false;
+            if (sel) {
+                unsigned long long v;
+                bool ms;
+                vm_eval(A.prog, A.slot, g, lb, rows_b, r, v, ms, A.error_flag);
+                res = !ms && v != 0ull;
+            }
+            const unsigned word = __ballot_sync(FULL, res);
+            if (lane_id() == 0) A.mask_out[widx] = word;
+        }
+    }
+}
+
+// ---- K4: range stages --------------------------------------------------------------------------------------
+__device__ __forceinline__ bool stage_member(const RangeArgs &a, int64_t rank1)
+{
+    if (a.kind == ST_RANGE) {
+        if (a.step > 0) return rank1 >= a.start && rank1 <= a.stop && (rank1 - a.start) % a.step == 0;
+        return rank1 <= a.start && rank1 >= a.stop && (a.start - rank1) % (-a.step) == 0;
+    }
+    int64_t lo = 0, hi = a.nidx - 1;
+    while (lo <= hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const int64_t v = a.idx[mid];
+        if (v == rank1) return true;
+        if (v < rank1) lo = mid + 1; else hi = mid - 1;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) fill_mask_kernel(const Geometry g, uint32_t *mask)
+{
+    const int64_t total = (int64_t)g.nblocks * g.wpb;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (int64_t)gridDim.x * blockDim.x) {
+        const int lb = (int)(w / g.wpb);
+        const int64_t r0 = (w - (int64_t)lb * g.wpb) * 32;
+        const int64_t rows_b = block_rows(g, lb);
+        uint32_t word = 0;
+        if (r0 + 32 <= rows_b) word = 0xffffffffu;
+        else if (r0 < rows_b) word = (1u << (rows_b - r0)) - 1u;
+        mask[w] = word;
+    }
+}
+
+// one warp per block: sums the popcounts of the block's mask words
+__global__ void __launch_bounds__(SCAN_THREADS) block_counts_kernel(const Geometry g, const uint32_t *mask, int64_t *counts)
+{
+    const int warps = gridDim.x * (SCAN_THREADS / 32);
+    for (int lb = blockIdx.x * (SCAN_THREADS / 32) + warp_id(); lb < g.nblocks; lb += warps) {
+        const uint32_t *m = mask + (int64_t)lb * g.wpb;
+        int c = 0;
+        for (int w = lane_id(); w < g.wpb; w += 32) c += __popc(m[w]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(FULL, c, d);
+        if (lane_id() == 0) counts[lb] = c;
+    }
+}
+
+// single CTA exclusive scan of n int64 (n up to a few hundred thousand); out[n] = total
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int64_t *in, int64_t *out, int n)
+{
+    __shared__ int64_t warp_tot[32];
+    __shared__ int64_t carry_s;
+    const int per = (n + 1023) / 1024;
+    const int lo = threadIdx.x * per;
+    int hi = lo + per;
+    if (hi > n) hi = n;
+    int64_t s = 0;
+    for (int i = lo; i < hi; i++) s += in[i];
+    // block exclusive scan of s
+    int64_t incl = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int64_t v = __shfl_up_sync(FULL, incl, d);
+        if (lane_id() >= d) incl += v;
+    }
+    if (lane_id() == 31) warp_tot[warp_id()] = incl;
+    __syncthreads();
+    if (warp_id() == 0) {
+        int64_t t = warp_tot[lane_id()];
+        int64_t ti = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t v = __shfl_up_sync(FULL, ti, d);
+            if (lane_id() >= d) ti += v;
+        }
+        warp_tot[lane_id()] = ti - t;
+        if (lane_id() == 31) carry_s = ti;
+    }
+    __syncthreads();
+    int64_t run = warp_tot[warp_id()] + incl - s;
+    for (int i = lo; i < hi; i++) { const int64_t v = in[i]; out[i] = run; run += v; }
+    if (threadIdx.x == 0) out[n] = carry_s;
+}
+
+// one warp per block walks the block's mask words in order with a running survivor rank
+__global__ void __launch_bounds__(SCAN_THREADS) range_stage_kernel(const RangeArgs A)
+{
+    const Geometry g = A.g;
+    const int warps = gridDim.x * (SCAN_THREADS / 32);
+    for (int lb = blockIdx.x * (SCAN_THREADS / 32) + warp_id(); lb < g.nblocks; lb += warps) {
+        uint32_t *m = A.mask + (int64_t)lb * g.wpb;
+        const int64_t rows_b = block_rows(g, lb);
+        int64_t base = A.dense ? (g.blk_lo + lb) * g.block_size : A.blk_base[lb] + A.rank_offset;
+        for (int w0 = 0; w0 < g.wpb; w0 += 32) {
+            const int w = w0 + lane_id();
+            uint32_t word = 0;
+            if (w < g.wpb) {
+                if (A.dense) {
+                    const int64_t r0 = (int64_t)w * 32;
+                    word = r0 + 32 <= rows_b ? 0xffffffffu : (r0 < rows_b ? (1u << (rows_b - r0)) - 1u : 0u);
+                } else word = m[w];
+            }
+            // exclusive prefix of popcounts over the 32 words held by the warp
+            const int c = __popc(word);
+            int incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, d);
+                if (lane_id() >= d) incl += v;
+            }
+            int64_t rank = base + (incl - c);
+            uint32_t keep = 0, rest = word;
+            while (rest) {
+                const int bit = __ffs(rest) - 1;
+                rest &= rest - 1;
+                rank++;
+                if (stage_member(A, rank)) keep |= 1u << bit;
+            }
+            if (w < g.wpb) m[w] = keep;
+            base += __shfl_sync(FULL, incl, 31);
+        }
+    }
+}
+
+// ---- K2: string offsets -------------------------------------------------------------------------------------
+// one warp per block: exclusive prefix sum of max(size, 0) in row order
+__global__ void __launch_bounds__(SCAN_THREADS) str_offsets_kernel(const Geometry g, const ColView col, int32_t *str_off, int32_t *status)
+{
+    const int warps = gridDim.x * (SCAN_THREADS / 32);
+    for (int lb = blockIdx.x * (SCAN_THREADS / 32) + warp_id(); lb < g.nblocks; lb += warps) {
+        const uint8_t *body = col_body(col, lb);
+        const int64_t rows_b = block_rows(g, lb);
+        const int32_t datasize = *reinterpret_cast<const int32_t *>(body);
+        const int32_t *sizes = reinterpret_cast<const int32_t *>(body + 4);
+        int32_t *out = str_off + (int64_t)lb * g.block_size;
+        long long run = 0;
+        // each lane takes 4 consecutive rows per step (one 16-byte load when aligned is not guaranteed: body+4)
+        for (int64_t r0 = 0; r0 < rows_b; r0 += 128) {
+            int s[4];
+            int local = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int64_t r = r0 + lane_id() * 4 + j;
+                s[j] = r < rows_b ? sizes[r] : 0;
+                if (s[j] < 0) s[j] = 0;
+                local += s[j];
+            }
+            int incl = local;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, d);
+                if (lane_id() >= d) incl += v;
+            }
+            long long o = run + (incl - local);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int64_t r = r0 + lane_id() * 4 + j;
+                if (r < rows_b) out[r] = (int32_t)o;
+                o += s[j];
+            }
+            run += __shfl_sync(FULL, incl, 31);
+        }
+        if (lane_id() == 0 && run != datasize) status[lb] = 5;   // sizes do not add up to datasize: corrupt body
+    }
+}
+
+// ---- K5/K6: warp-aggregated compaction --------------------------------------------------------------------
+// Work unit = (block, warp range of mask words).  Each CTA takes one block at a time; its 8 warps own
+// contiguous word ranges; a first pass counts, a second pass walks the words in order so every selected
+// row gets its output index = block base + prefix of earlier survivors (row order is preserved).
+template <typename F>
+__device__ __forceinline__ void compact_block(const Geometry &g, const uint32_t *mask, int lb, int64_t blk_base, int64_t *smem_base, F emit)
+{
+    const uint32_t *m = mask + (int64_t)lb * g.wpb;
+    const int nw = SCAN_THREADS / 32;
+    const int per = (g.wpb + nw - 1) / nw;
+    const int w_lo = warp_id() * per;
+    int w_hi = w_lo + per;
+    if (w_hi > g.wpb) w_hi = g.wpb;
+    int c = 0;
+    for (int w = w_lo + lane_id(); w < w_hi; w += 32) c += __popc(m[w]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(FULL, c, d);
+    __syncthreads();
+    if (lane_id() == 0) smem_base[warp_id()] = c;
+    __syncthreads();
+    int64_t base = blk_base;
+    for (int i = 0; i < warp_id(); i++) base += smem_base[i];
+    for (int w = w_lo; w < w_hi; w++) {
+        const uint32_t word = m[w];
+        if (word == 0) continue;
+        const bool sel = (word >> lane_id()) & 1u;
+        const int64_t idx = base + __popc(word & ((1u << lane_id()) - 1u));
+        if (sel) emit((int64_t)w * 32 + lane_id(), idx);
+        base += __popc(word);
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) gather_fixed_kernel(const GatherArgs A)
+{
+    __shared__ int64_t sbase[SCAN_THREADS / 32];
+    const Geometry g = A.g;
+    for (int lb = blockIdx.x; lb < g.nblocks; lb += gridDim.x) {
+        const int64_t rows_b = block_rows(g, lb);
+        const ColView &c = A.col;
+        const uint8_t *vals = col_values(c, lb, rows_b);
+        const int es = c.elsize;
+        compact_block(g, A.mask, lb, A.blk_base[lb], sbase, [&](int64_t r, int64_t idx) {
+            const bool ms = col_missing(c, lb, r);
+            if (A.out_missing) A.out_missing[idx] = ms ? 1 : 0;
+            uint8_t *o = A.out_values + idx * es;
+            const uint8_t *p = vals + r * es;
+            switch (es) {
+            case 8: *reinterpret_cast<unsigned long long *>(o) = ms ? 0ull : *reinterpret_cast<const unsigned long long *>(p); break;
+            case 4: *reinterpret_cast<uint32_t *>(o) = ms ? 0u : *reinterpret_cast<const uint32_t *>(p); break;
+            case 2: *reinterpret_cast<uint16_t *>(o) = ms ? (uint16_t)0 : *reinterpret_cast<const uint16_t *>(p); break;
+            case 1: *o = ms ? (uint8_t)0 : *p; break;
+            default:
+                for (int i = 0; i < es; i++) o[i] = ms ? (uint8_t)0 : p[i];
+                break;
+            }
+        });
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) gather_indices_kernel(const GatherArgs A)
+{
+    __shared__ int64_t sbase[SCAN_THREADS / 32];
+    const Geometry g = A.g;
+    for (int lb = blockIdx.x; lb < g.nblocks; lb += gridDim.x) {
+        const int64_t row_base = (g.blk_lo + lb) * g.block_size + 1;
+        compact_block(g, A.mask, lb, A.blk_base[lb], sbase, [&](int64_t r, int64_t idx) { A.out_indices[idx] = row_base + r; });
+    }
+}
+
+// selected string bytes per block (one warp per block)
+__global__ void __launch_bounds__(SCAN_THREADS) str_block_bytes_kernel(const GatherArgs A, int64_t *blk_bytes)
+{
+    const Geometry g = A.g;
+    const int warps = gridDim.x * (SCAN_THREADS / 32);
+    for (int lb = blockIdx.x * (SCAN_THREADS / 32) + warp_id(); lb < g.nblocks; lb += warps) {
+        const uint32_t *m = A.mask + (int64_t)lb * g.wpb;
+        const int32_t *sizes = reinterpret_cast<const int32_t *>(col_body(A.col, lb) + 4);
+        long long tot = 0;
+        for (int w = 0; w < g.wpb; w++) {
+            const uint32_t word = m[w];
+            if (word == 0) continue;
+            if ((word >> lane_id()) & 1u) {
+                const int s = sizes[(int64_t)w * 32 + lane_id()];
+                if (s > 0) tot += s;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(FULL, tot, d);
+        if (lane_id() == 0) blk_bytes[lb] = tot;
+    }
+}
+
+// sizes + chars of the selected rows: one warp per block walks the words in order, carrying the running
+// row and byte positions (FlatStringsVector gather, offset-aware)
+__global__ void __launch_bounds__(SCAN_THREADS) gather_strings_kernel(const GatherArgs A)
+{
+    const Geometry g = A.g;
+    const int warps = gridDim.x * (SCAN_THREADS / 32);
+    for (int lb = blockIdx.x * (SCAN_THREADS / 32) + warp_id(); lb < g.nblocks; lb += warps) {
+        const uint32_t *m = A.mask + (int64_t)lb * g.wpb;
+        const int64_t rows_b = block_rows(g, lb);
+        const uint8_t *body = col_body(A.col, lb);
+        const int32_t *sizes = reinterpret_cast<const int32_t *>(body + 4);
+        const uint8_t *chars = body + 4 + 4 * rows_b;
+        const int32_t *soff = A.col.str_off + (int64_t)lb * g.block_size;
+        int64_t row_pos = A.blk_base[lb];
+        int64_t byte_pos = A.blk_char_base[lb];
+        for (int w = 0; w < g.wpb; w++) {
+            const uint32_t word = m[w];
+            if (word == 0) continue;
+            const bool sel = (word >> lane_id()) & 1u;
+            const int64_t r = (int64_t)w * 32 + lane_id();
+            const int sz = sel ? sizes[r] : 0;
+            const int nb = sz > 0 ? sz : 0;
+            int incl = nb;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, d);
+                if (lane_id() >= d) incl += v;
+            }
+            if (sel) {
+                A.out_sizes[row_pos + __popc(word & ((1u << lane_id()) - 1u))] = sz;
+                const uint8_t *src = chars + soff[r];
+                uint8_t *dst = A.out_chars + byte_pos + (incl - nb);
+                for (int i = 0; i < nb; i++) dst[i] = src[i];
+            }
+            row_pos += __popc(word);
+            byte_pos += __shfl_sync(FULL, incl, 31);
+        }
+    }
+}
+
+// computed projection column: VM value of every selected row, in row order
+__global__ void __launch_bounds__(SCAN_THREADS) proj_vm_kernel(const ProjVmArgs A)
+{
+    __shared__ int64_t sbase[SCAN_THREADS / 32];
+    const Geometry g = A.g;
+    for (int lb = blockIdx.x; lb < g.nblocks; lb += gridDim.x) {
+        const int64_t rows_b = block_rows(g, lb);
+        compact_block(g, A.mask, lb, A.blk_base[lb], sbase, [&](int64_t r, int64_t idx) {
+            unsigned long long v;
+            bool ms;
+            vm_eval(A.prog, A.slot, g, lb, rows_b, r, v, ms, A.error_flag);
+            if (A.out_missing) A.out_missing[idx] = ms ? 1 : 0;
+            if (ms) v = 0ull;
+            uint8_t *o = A.out_values + idx * A.elsize;
+            const bool is_f32 = A.prog->result_class == VC_FLT && A.elsize == 4;
+            if (is_f32) { const float f = (float)__longlong_as_double((long long)v); *reinterpret_cast<float *>(o) = f; return; }
+            switch (A.elsize) {
+            case 8: *reinterpret_cast<unsigned long long *>(o) = v; break;
+            case 4: *reinterpret_cast<uint32_t *>(o) = (uint32_t)v; break;
+            case 2: *reinterpret_cast<uint16_t *>(o) = (uint16_t)v; break;
+            default: *o = (uint8_t)v; break;
+            }
+        });
+    }
+}
+
+int grid_for(int64_t work, int sm_count, int per_sm)
+{
+    int64_t g = (int64_t)sm_count * per_sm;
+    if (work < g) g = work;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+int g_sm_count = 148;
+
+}  // namespace
+
+#define CHECK_LAUNCH() (cudaGetLastError() == cudaSuccess ? 0 : 1)
+
+int launch_fused(const FusedArgs &a, int agg, bool emit_mask, bool wide, int sm_count, cudaStream_t stream)
+{
+    g_sm_count = sm_count;
+    const int nunits = a.g.nblocks * a.g.segs_per_block;
+    if (nunits <= 0) return 0;
+    const int grid = grid_for(nunits, sm_count, 8);
+    if (emit_mask) {
+        if (agg == 0) fused_scan_kernel<0, false, true><<<grid, SCAN_THREADS, 0, stream>>>(a);
+        else if (agg == 1) fused_scan_kernel<1, false, true><<<grid, SCAN_THREADS, 0, stream>>>(a);
+        else fused_scan_kernel<2, false, true><<<grid, SCAN_THREADS, 0, stream>>>(a);
+    } else if (wide) {
+        if (agg == 0) fused_scan_kernel<0, true, false><<<grid, SCAN_THREADS, 0, stream>>>(a);
+        else if (agg == 1) fused_scan_kernel<1, true, false><<<grid, SCAN_THREADS, 0, stream>>>(a);
+        else fused_scan_kernel<2, true, false><<<grid, SCAN_THREADS, 0, stream>>>(a);
+    } else {
+        if (agg == 0) fused_scan_kernel<0, false, false><<<grid, SCAN_THREADS, 0, stream>>>(a);
+        else if (agg == 1) fused_scan_kernel<1, false, false><<<grid, SCAN_THREADS, 0, stream>>>(a);
+        else fused_scan_kernel<2, false, false><<<grid, SCAN_THREADS, 0, stream>>>(a);
+    }
+    return CHECK_LAUNCH();
+}
+
+int launch_agg_finalize(const AggPartial *partials, int nunits, int cls, AggPartial *result, cudaStream_t stream)
+{
+    agg_finalize_kernel<<<1, SCAN_THREADS, 0, stream>>>(partials, nunits, cls, result);
+    return CHECK_LAUNCH();
+}
+
+int launch_vm_mask(const VmArgs &a, int sm_count, cudaStream_t stream)
+{
+    g_sm_count = sm_count;
+    const int tiles_per_block = (int)((a.g.block_size + TILE_ROWS - 1) / TILE_ROWS);
+    const int64_t ntiles = (int64_t)a.g.nblocks * tiles_per_block;
+    if (ntiles <= 0) return 0;
+    vm_mask_kernel<<<grid_for(ntiles, sm_count, 8), SCAN_THREADS, 0, stream>>>(a);
+    return CHECK_LAUNCH();
+}
+
+int launch_block_counts(const Geometry &g, const uint32_t *mask, int64_t *counts, cudaStream_t stream)
+{
+    if (g.nblocks <= 0) return 0;
+    block_counts_kernel<<<grid_for((g.nblocks + 7) / 8, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(g, mask, counts);
+    return CHECK_LAUNCH();
+}
+
+int launch_exclusive_scan(const int64_t *in, int64_t *out, int n, cudaStream_t stream)
+{
+    exclusive_scan_kernel<<<1, 1024, 0, stream>>>(in, out, n);
+    return CHECK_LAUNCH();
+}
+
+int launch_range_stage(const RangeArgs &a, cudaStream_t stream)
+{
+    if (a.g.nblocks <= 0) return 0;
+    range_stage_kernel<<<grid_for((a.g.nblocks + 7) / 8, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(a);
+    return CHECK_LAUNCH();
+}
+
+int launch_fill_mask(const Geometry &g, uint32_t *mask, cudaStream_t stream)
+{
+    const int64_t total = (int64_t)g.nblocks * g.wpb;
+    if (total <= 0) return 0;
+    fill_mask_kernel<<<grid_for((total + SCAN_THREADS - 1) / SCAN_THREADS, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(g, mask);
+    return CHECK_LAUNCH();
+}
+
+int launch_str_offsets(const Geometry &g, const ColView &col, int32_t *str_off, int32_t *status, cudaStream_t stream)
+{
+    if (g.nblocks <= 0) return 0;
+    str_offsets_kernel<<<grid_for((g.nblocks + 7) / 8, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(g, col, str_off, status);
+    return CHECK_LAUNCH();
+}
+
+int launch_gather_fixed(const GatherArgs &a, cudaStream_t stream)
+{
+    if (a.g.nblocks <= 0) return 0;
+    gather_fixed_kernel<<<grid_for(a.g.nblocks, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(a);
+    return CHECK_LAUNCH();
+}
+
+int launch_gather_indices(const GatherArgs &a, cudaStream_t stream)
+{
+    if (a.g.nblocks <= 0) return 0;
+    gather_indices_kernel<<<grid_for(a.g.nblocks, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(a);
+    return CHECK_LAUNCH();
+}
+
+int launch_str_block_bytes(const GatherArgs &a, int64_t *blk_bytes, cudaStream_t stream)
+{
+    if (a.g.nblocks <= 0) return 0;
+    str_block_bytes_kernel<<<grid_for((a.g.nblocks + 7) / 8, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(a, blk_bytes);
+    return CHECK_LAUNCH();
+}
+
+int launch_gather_strings(const GatherArgs &a, cudaStream_t stream)
+{
+    if (a.g.nblocks <= 0) return 0;
+    gather_strings_kernel<<<grid_for((a.g.nblocks + 7) / 8, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(a);
+    return CHECK_LAUNCH();
+}
+
+int launch_proj_vm(const ProjVmArgs &a, cudaStream_t stream)
+{
+    if (a.g.nblocks <= 0) return 0;
+    proj_vm_kernel<<<grid_for(a.g.nblocks, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(a);
+    return CHECK_LAUNCH();
+}
+
+}  // namespace dfdb

@@ -1,0 +1,149 @@
+/*
+ * dfdb_b200.h -- C ABI of libdfdb_b200.so: the B200-native column-scan path of DataFrameDBs.jl.
+ *
+ * The reference (pure Julia) has no FFI/plugin layer of its own; its only foreign call on this path is
+ * liblz4 (src/io/BlockStreams.jl:39,42,110).  The seams this library replaces are the Julia generic
+ * functions every consumer pulls from.  Each entry point cites the reference
+ * interface it stands in for (paths relative to /root/reference); INTEGRATION.md shows the `ccall`
+ * methods a maintainer adds on the Julia side, and dataframedbs.jl_b200/_capi.py is the ctypes
+ * binding used by the Python mirror of the same API.
+ *
+ * Conventions: every function returns an int32 status (0 = ok); the message of the last failure on
+ * the calling thread is available from dfdb_last_error().  Plain pointers and sizes only; the caller
+ * owns every output buffer; the library owns device memory and the opaque handles.  One in-flight
+ * call per handle.  All scans run on CUDA kernels for sm_100a -- there is no CPU fallback: without a
+ * usable device every compute entry point returns DFDB_ERR_CUDA.
+ */
+#ifndef DFDB_B200_H
+#define DFDB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFDB_API __attribute__((visibility("default")))
+
+/* status codes; the Julia shim maps them to the exception the reference throws */
+enum {
+    DFDB_OK = 0,
+    DFDB_ERR_IO = 1,          /* error("Table ... don't exists") creators.jl:8-9, filesystem.jl:58           */
+    DFDB_ERR_FORMAT = 2,      /* check_column_head mismatch filesystem.jl:47-54, unknown typestring          */
+    DFDB_ERR_CORRUPT = 3,     /* @assert size == sizes.origin "decompression error" BlockStreams.jl:112      */
+    DFDB_ERR_ARGUMENT = 4,    /* ArgumentError: selection.jl:54, empty range selection.jl:73                 */
+    DFDB_ERR_UNSUPPORTED = 5, /* expression outside the operator set -> shim raises ArgumentError            */
+    DFDB_ERR_KEY = 6,         /* KeyError(column) table.jl:54                                                */
+    DFDB_ERR_DIVIDE = 7,      /* DivideError from integer rem by zero inside a broadcast                     */
+    DFDB_ERR_CUDA = 8,        /* CUDA runtime failure / no device                                            */
+    DFDB_ERR_NOMEM = 9,
+    DFDB_ERR_STATE = 10       /* handle used in the wrong state (e.g. table not loaded)                      */
+};
+
+/* column element kinds (src/columntypes/base.jl:97-126,163-168 ; complex.jl) */
+enum {
+    DFDB_I8 = 1, DFDB_I16, DFDB_I32, DFDB_I64, DFDB_I128, DFDB_U8, DFDB_U16, DFDB_U32, DFDB_U64, DFDB_U128,
+    DFDB_F16, DFDB_F32, DFDB_F64, DFDB_BOOL, DFDB_CHAR, DFDB_STRING, DFDB_DATE, DFDB_DATETIME, DFDB_TIME, DFDB_TUPLE
+};
+
+/* residency modes for dfdb_table_load */
+enum {
+    DFDB_LOAD_HOST = 0,     /* compressed blocks in pinned host memory; every scan copies them H2D ("transfer-inclusive") */
+    DFDB_LOAD_HBM = 1,      /* compressed blocks resident in HBM; every scan decodes them ("HBM-resident")                */
+    DFDB_LOAD_DECODED = 2   /* HBM-resident + decoded bodies cached in HBM after the first scan                          */
+};
+
+typedef struct dfdb_table dfdb_table;
+typedef struct dfdb_scan dfdb_scan;
+
+/* result of sum/count/min/max over the selected rows of one projected column.
+ * Replaces the Base folds over Base.iterate(::DFColumn) (src/tables/column.jl:102-126). */
+typedef struct dfdb_agg {
+    int64_t count;       /* selected rows, missing included (length(col))                              */
+    int64_t nmissing;    /* selected rows that are missing (sum(col) is `missing` when > 0)             */
+    int64_t sum_i64;     /* wrapping two's-complement sum of integer / Bool values (Base.add_sum)       */
+    double sum_f64;      /* floating sum: fixed-order tree, compensated final fold; hi part             */
+    double sum_f64_lo;   /* low part of the compensated sum (hi + lo is the full-precision value)       */
+    int64_t min_i64, max_i64;
+    double min_f64, max_f64;   /* Julia semantics: NaN propagates, -0.0 < 0.0                           */
+    int32_t has_nan;
+    int32_t value_class; /* 1 signed int, 2 unsigned int, 3 float, 4 Bool, 0 = no non-missing values    */
+} dfdb_agg;
+
+/* caller-allocated output column for dfdb_scan_materialize (mirrors make_materialization +
+ * append! in src/tables/materialization.jl:27-40; strings use the FlatStringsVector layout of
+ * src/FlatStringsVectors.jl:5-9: Int32 sizes with -1 = missing, plus flat chars). */
+typedef struct dfdb_outcol {
+    void *values;        /* nrows * elsize bytes (fixed-width columns), else NULL                       */
+    uint8_t *missing;    /* nrows bytes, 1 = missing (Union{T,Missing} columns), may be NULL            */
+    int32_t *str_sizes;  /* nrows Int32 (String columns), else NULL                                     */
+    uint8_t *str_chars;  /* string bytes, size from dfdb_scan_materialize_sizes                         */
+} dfdb_outcol;
+
+/* ---- runtime ------------------------------------------------------------------------------ */
+DFDB_API int32_t dfdb_init(int32_t device);                 /* one process per GPU: selects the device, creates the stream */
+DFDB_API int32_t dfdb_shutdown(void);
+DFDB_API const char *dfdb_last_error(void);
+DFDB_API int32_t dfdb_set_stream(void *cuda_stream);        /* run on the caller's cudaStream_t (NULL = library stream)     */
+DFDB_API int32_t dfdb_synchronize(void);
+DFDB_API int64_t dfdb_kernel_launches(void);                /* number of kernels this library has launched so far           */
+DFDB_API int32_t dfdb_set_option(const char *name, int64_t value);
+/* per-phase device timing (CUDA events on the scan stream): phases "h2d","decode","unpack","select","consume","d2h" */
+DFDB_API int32_t dfdb_profile_enable(int32_t on);
+DFDB_API int32_t dfdb_profile_reset(void);
+DFDB_API int32_t dfdb_profile_get(const char *phase, double *total_ms, int64_t *launches, int64_t *bytes);
+
+/* ---- table: open_table (src/tables/creators.jl:7-16), read_table_meta (src/io/table_io.jl:21-33),
+ *      check_column_head (src/io/filesystem.jl:47-54); the block index replaces the header walk of
+ *      skip_block (src/io/BlockStreams.jl:74-78) ------------------------------------------------ */
+DFDB_API int32_t dfdb_table_open(const char *path, dfdb_table **out);
+DFDB_API int32_t dfdb_table_close(dfdb_table *t);
+DFDB_API int64_t dfdb_table_nrows(const dfdb_table *t);
+DFDB_API int64_t dfdb_table_ncols(const dfdb_table *t);
+DFDB_API int64_t dfdb_table_block_size(const dfdb_table *t);
+DFDB_API int64_t dfdb_table_nblocks(const dfdb_table *t);
+DFDB_API int32_t dfdb_table_column(const dfdb_table *t, int32_t index, int64_t *id, char *name, int32_t name_cap,
+                                   char *typestring, int32_t ts_cap, int32_t *kind, int32_t *nullable, int32_t *elsize);
+DFDB_API int32_t dfdb_table_column_stats(const dfdb_table *t, int64_t col_id, int64_t *compressed, int64_t *uncompressed);
+/* block-range shard of this process: blocks [nblocks*rank/world, nblocks*(rank+1)/world) of every column */
+DFDB_API int32_t dfdb_table_set_shard(dfdb_table *t, int32_t rank, int32_t world);
+DFDB_API int32_t dfdb_table_shard_range(const dfdb_table *t, int64_t *block_lo, int64_t *block_hi, int64_t *row_lo, int64_t *row_hi);
+/* read the shard's compressed blocks of the given columns (all columns when n == 0) */
+DFDB_API int32_t dfdb_table_load(dfdb_table *t, const int64_t *col_ids, int32_t n, int32_t mode);
+DFDB_API int32_t dfdb_table_drop_decoded(dfdb_table *t);    /* forget cached decoded bodies (mode DFDB_LOAD_DECODED) */
+
+/* ---- scan: BlocksIterator(v::DFView) (src/io/blocksiterator.jl:20-66) built from the view's
+ *      SelectionQueue (src/tables/selection.jl:4-10) and Projection (src/tables/projection.jl:1-9);
+ *      plan wire format in dataframedbs.jl_b200/plan.py ----------------------------------------- */
+DFDB_API int32_t dfdb_scan_prepare(dfdb_table *t, const uint8_t *plan, int64_t plan_len, dfdb_scan **out);
+DFDB_API int32_t dfdb_scan_free(dfdb_scan *s);
+DFDB_API int32_t dfdb_scan_nproj(const dfdb_scan *s);
+DFDB_API int32_t dfdb_scan_proj_type(const dfdb_scan *s, int32_t proj_idx, int32_t *kind, int32_t *nullable, int32_t *elsize);
+/* nrow(v): src/tables/view.jl:192-206 (BlockRowsIterator blocksiterator.jl:123-145) */
+DFDB_API int32_t dfdb_scan_count(dfdb_scan *s, int64_t *n);
+/* sum/minimum/maximum/mean/count over a DFColumn: src/tables/column.jl:102-126 */
+DFDB_API int32_t dfdb_scan_aggregate(dfdb_scan *s, int32_t proj_idx, dfdb_agg *out);
+/* parity hooks: apply(::SelectionExecutor, rows, block) src/tables/selection.jl:161-167 --
+ * global bitmask (bit r&63 of word r>>6 set <=> 0-based table row r selected) and 1-based row numbers */
+DFDB_API int32_t dfdb_scan_mask(dfdb_scan *s, uint64_t *words, int64_t nwords);
+DFDB_API int32_t dfdb_scan_indices(dfdb_scan *s, int64_t *idx, int64_t cap, int64_t *n);
+/* materialize(v::DFView) src/tables/materialization.jl:27-40: sizes first (pass 1 = nrow), then fill */
+DFDB_API int32_t dfdb_scan_materialize_sizes(dfdb_scan *s, int64_t *nrows, int64_t *str_bytes_per_col);
+DFDB_API int32_t dfdb_scan_materialize(dfdb_scan *s, dfdb_outcol *cols, int32_t ncols);
+
+/* ---- multi-GPU: one process per GPU; each rank scans its shard, the tiny partials are exchanged by
+ *      the host (NCCL all-gather) and folded in rank order on every rank ------------------------- */
+DFDB_API int32_t dfdb_agg_fold(const dfdb_agg *partials, int32_t n, dfdb_agg *out);
+/* device-resident copy of the last dfdb_scan_aggregate result (sizeof(dfdb_agg) bytes), for NCCL */
+DFDB_API int32_t dfdb_scan_aggregate_device(dfdb_scan *s, int32_t proj_idx, void *device_out);
+
+/* ---- codec hook: read_block (src/io/BlockStreams.jl:101-119) for n independent raw LZ4 blocks.
+ *      comp/out are HOST buffers; status[i] = 0 or DFDB_ERR_CORRUPT ------------------------------ */
+DFDB_API int32_t dfdb_lz4_decode_blocks(const uint8_t *comp, const int64_t *comp_off, const int64_t *comp_len,
+                                        uint8_t *out, const int64_t *out_off, const int64_t *origin, int32_t n,
+                                        int32_t *status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFDB_B200_H */
