@@ -1,0 +1,339 @@
+"""GPU parity tests: the CUDA library, called through its C ABI, against the CPU oracle and the reference's
+known-answer cases.  Bar: bit-exact masks, row indices, counts, integer aggregates, strings and missings;
+Float64 sums within 1e-12 relative of the oracle's compensated (Kahan/Neumaier) sum."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import dfdb_b200 as D
+import fixtures
+from dfdb_b200 import R, _capi
+from engines import GpuEngine, OracleEngine
+
+pytestmark = pytest.mark.gpu
+
+FSUM_RTOL = 1e-12
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    _capi.init(0)
+    yield
+
+
+# ---- K1 codec hook -------------------------------------------------------------------------------------
+
+def _bodies(oracle):
+    rng = np.random.default_rng(7)
+    N = 65536
+    brands = ["apple", "samsung", "huawai", "microsoft", "dell", "xbox", "sony", "intel"]
+    out = {
+        "rand100": rng.integers(1, 101, N).astype(np.int64).tobytes(),
+        "rand1000": rng.integers(1, 1001, N).astype(np.int64).tobytes(),
+        "iseq": np.arange(1, N + 1, dtype=np.int64).tobytes(),
+        "price": (1 + 0.1 * rng.integers(0, 19991, N)).astype(np.float64).tobytes(),
+        "f01": rng.random(N).tobytes(),
+        "zeros": bytes(100000),
+        "short3": b"abc",
+        "len13": b"0123456789abc",
+        "len1": b"x",
+        "rle_then_random": bytes(5000) + rng.integers(0, 256, 7001).astype(np.uint8).tobytes() + b"ab" * 3000,
+        "brands": oracle.block_body("String", [brands[i] for i in rng.integers(0, 8, N)], 0, N),
+        "missing_int": oracle.block_body("Missing(Int64)", (rng.integers(1, 101, N).astype(np.int64), rng.random(N) < 0.1), 0, N),
+        "small_ints": rng.integers(0, 4, 30011).astype(np.uint8).tobytes(),
+        "period3": (b"abc" * 20000)[:50001],
+        "odd_sizes": rng.integers(0, 2, 777).astype(np.uint8).tobytes(),
+    }
+    return out
+
+
+def _gpu_decode(blocks, origins):
+    L = _capi.lib()
+    n = len(blocks)
+    comp = b"".join(blocks)
+    coff = np.cumsum([0] + [len(b) for b in blocks[:-1]]).astype(np.int64)
+    clen = np.array([len(b) for b in blocks], dtype=np.int64)
+    ooff = np.cumsum([0] + list(origins[:-1])).astype(np.int64)
+    orig = np.array(origins, dtype=np.int64)
+    out = np.zeros(max(int(orig.sum()), 1), dtype=np.uint8)
+    status = np.zeros(n, dtype=np.int32)
+    cbuf = np.frombuffer(comp, dtype=np.uint8)
+    _capi.check(L.dfdb_lz4_decode_blocks(cbuf.ctypes.data, coff.ctypes.data, clen.ctypes.data, out.ctypes.data, ooff.ctypes.data,
+                                         orig.ctypes.data, n, status.ctypes.data))
+    return [bytes(out[o:o + s]) for o, s in zip(ooff, orig)], status
+
+
+@pytest.mark.parametrize("simple", [0, 1], ids=["batched", "sequential"])
+def test_lz4_decode_matches_reference_codec(oracle, simple):
+    """read_block BlockStreams.jl:101-119: decoded bytes are determined by the LZ4 block format."""
+    bodies = _bodies(oracle)
+    names = list(bodies)
+    blocks = [oracle.compress_block(bodies[k]) for k in names] + [oracle.lz4_compress(bodies[k], 1) for k in names]
+    origins = [len(bodies[k]) for k in names] * 2
+    _capi.check(_capi.lib().dfdb_set_option(b"lz4_simple", simple))
+    try:
+        got, status = _gpu_decode(blocks, origins)
+    finally:
+        _capi.lib().dfdb_set_option(b"lz4_simple", 0)
+    for i, k in enumerate(names + names):
+        assert status[i] == 0, (k, status[i])
+        assert got[i] == bodies[k], f"decoded bytes differ for {k} (first diff at {next(j for j in range(len(got[i])) if got[i][j] != bodies[k][j])})"
+
+
+def test_lz4_decode_rejects_corrupt_blocks(oracle):
+    """@assert size == sizes.origin "decompression error" (BlockStreams.jl:112)"""
+    body = np.random.default_rng(3).integers(1, 101, 4096).astype(np.int64).tobytes()
+    good = oracle.compress_block(body)
+    bad_trunc = good[: len(good) // 2]
+    bad_origin = good
+    bad_offset = bytes([0x00, 0xFF, 0xFF]) + good          # match with offset 65535 before any output
+    got, status = _gpu_decode([good, bad_trunc, bad_origin, bad_offset], [len(body), len(body), len(body) - 8, len(body)])
+    assert status[0] == 0 and got[0] == body
+    assert status[1] != 0 and status[2] != 0 and status[3] != 0
+    for blk, org in [(bad_trunc, len(body)), (bad_origin, len(body) - 8), (bad_offset, len(body))]:
+        with pytest.raises(oracle.OracleError):
+            oracle.lz4_decompress(blk, org)
+
+
+# ---- reference known-answer cases through the C ABI -----------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def ref_table(tmp_path_factory, oracle):
+    p = str(tmp_path_factory.mktemp("ref") / "test_data")
+    data = fixtures.make_reference_fixture(oracle, p)
+    t = D.open_table(p)
+    yield GpuEngine(), t, data
+    t.close()
+
+
+@pytest.mark.parametrize("case", [cases.case_view_full, cases.case_view_predicates, cases.case_view_projections,
+                                  cases.case_range_indexing, cases.case_range_composition, cases.case_column_broadcast,
+                                  cases.case_columns, cases.case_aggregates], ids=lambda f: f.__name__)
+def test_reference_fixture_cases(ref_table, case):
+    case(*ref_table)
+
+
+@pytest.mark.parametrize("block_size", [100, 50, 7])
+def test_selection_stages(tmp_path, oracle, block_size):
+    p = str(tmp_path / "sel")
+    data = fixtures.make_selection_fixture(oracle, p, block_size)
+    cases.case_selection_stages(GpuEngine(), D.open_table(p), data)
+
+
+def test_broadcast_eval(tmp_path, oracle):
+    p = str(tmp_path / "bc")
+    data = fixtures.make_broadcast_fixture(oracle, p)
+    cases.case_broadcast_eval(GpuEngine(), D.open_table(p), data)
+
+
+@pytest.mark.parametrize("block_size", [4, 64, 3])
+def test_missings(tmp_path, oracle, block_size):
+    p = str(tmp_path / "ms")
+    fixtures.make_missing_fixture(oracle, p, block_size)
+    cases.case_missings(GpuEngine(), D.open_table(p), None)
+
+
+@pytest.mark.parametrize("block_size", [4, 64])
+def test_flat_strings(tmp_path, oracle, block_size):
+    p = str(tmp_path / "st")
+    fixtures.make_strings_fixture(oracle, p, block_size)
+    cases.case_flat_strings(GpuEngine(), D.open_table(p), None)
+
+
+# ---- seeded synthetic tables: GPU vs oracle on the same files ---------------------------------------------------
+
+SPEC = ("a:Int64:iuniform:1:100;b:Float64:funiform;s:String:brands;"
+        "ma:Missing(Int64):iuniform:1:100:m=0.1;mb:Missing(Float64):funiform:m=0.1;ms:Missing(String):decimal:m=0.05;"
+        "p:Float64:fgrid:1:0.1:2000;q:Int64:iseq")
+
+
+@pytest.fixture(scope="module")
+def synth(tmp_path_factory, oracle):
+    p = str(tmp_path_factory.mktemp("synth") / "t")
+    nrows = 5 * 65536 + 12345
+    oracle.gen_table(p, SPEC, nrows, 65536, 0xDFDB0002, 4)
+    t = D.open_table(p)
+    ot = oracle.OracleTable(p)
+    yield t, ot, nrows
+    t.close()
+    ot.close()
+
+
+def _plans(t):
+    return {
+        "c1_gt50": t[t.a > 50, ["b"]],
+        "c2_range_pred": t[(t.a > 25) & (t.a <= 75), ["b", "a"]],
+        "float_const_on_int": t[(t.a > 25.5) & (t.a <= 75.0), ["a"]],
+        "float_pred": t[(t.b < 0.25) | (t.b >= 0.9), ["b"]],
+        "str_eq": t[t.s == "sony", ["s"]],
+        "str_prefix": t[D.startswith(t.s, "s"), ["s", "a"]],
+        "c4_missing_and": t[D.coalesce(t.ma > 50, False) & D.coalesce(t.mb < 0.5, False), ["ma", "mb", "a", "b"]],
+        "missing_str": t[D.coalesce(D.startswith(t.ms, "-1"), False), ["ms", "ma"]],
+        "ismissing": t[D.ismissing(t.ms) | D.ismissing(t.mb), ["ms", "mb"]],
+        "arith": t[(t.a * 2 + t.q) % 7 == 0, ["q"]],
+        "mixed_cmp": t[(t.p > t.a) & (t.q % 1000 < 10), ["p", "q"]],
+        "isin": t[D.isin(t.a, [3, 5, 99, 1000]), ["a"]],
+        "range_first": t[R(70000, 3, 250000), ["q", "s"]],
+        "range_pred_range": t[R(1000, 300000), :][t.a > 90, :][R(5, 7, 20000), ["q", "a"]],
+        "indexvec": t[[1, 65536, 65537, 131072, 340000, 17], ["q"]],
+        "pred_then_index": t[t.a == 7, :][[1, 2, 3, 500, 501, 3000], ["q", "a"]],
+        "computed_cols": t[t.a < 3, {"x": t.a * 2 + 1, "y": t.b / 2, "z": t.a > 1, "w": t.ma + 1}],
+        "empty": t[t.a > 1000, ["a", "s"]],
+    }
+
+
+def _same_cols(got, exp):
+    assert len(got) == len(exp)
+    for g, e in zip(got, exp):
+        if isinstance(g, D.FlatStringsVector):
+            assert np.array_equal(g.sizes, e.sizes) and g.data == e.chars
+        elif isinstance(g, np.ma.MaskedArray):
+            ev, em = e
+            assert np.array_equal(np.ma.getmaskarray(g), em)
+            assert np.array_equal(g.data[~em], ev[~em])
+        else:
+            assert g.dtype == e.dtype and np.array_equal(g, e), (g[:5], e[:5])
+
+
+def test_synthetic_plans_match_oracle(synth):
+    t, ot, nrows = synth
+    for name, v in _plans(t).items():
+        pb = D.plan_bytes(v)
+        exp_mask = ot.mask(pb)
+        assert np.array_equal(D.selection_mask(v), exp_mask), name
+        assert D.nrow(v) == ot.count(pb) == int(exp_mask.sum()), name
+        assert np.array_equal(D.selection_indices(v), np.nonzero(exp_mask)[0] + 1), name
+        _same_cols(D.materialize(v).columns, ot.materialize(pb))
+
+
+def _check_agg(got, ref, what):
+    assert got.count == ref.count and got.nmissing == ref.nmissing, what
+    if ref.count - ref.nmissing == 0:
+        return
+    if ref.kind in (12, 13):
+        gsum = got.sum_f64 + got.sum_f64_lo
+        assert abs(gsum - ref.sum_kahan) <= FSUM_RTOL * abs(ref.sum_kahan), (what, gsum, ref.sum_kahan)
+        assert got.min_f64 == ref.min_f64 and got.max_f64 == ref.max_f64, what
+    else:
+        assert got.sum_i64 == ref.sum_i64 and got.min_i64 == ref.min_i64 and got.max_i64 == ref.max_i64, what
+
+
+def test_synthetic_aggregates_match_oracle(synth):
+    t, ot, nrows = synth
+    views = {
+        "all_b": t[:, :], "c1": t[t.a > 50, :], "c2": t[(t.a > 25) & (t.a <= 75), :],
+        "missing": t[D.coalesce(t.ma > 50, False) & D.coalesce(t.mb < 0.5, False), :],
+        "str": t[t.s == "dell", :], "ranges": t[R(1000, 300000), :][t.a > 90, :][R(5, 7, 20000), :],
+        "none": t[t.a > 1000, :],
+    }
+    for name, v in views.items():
+        for col in ["a", "b", "ma", "mb", "p", "q"]:
+            c = getattr(v, col)
+            _check_agg(D.aggregate(c), ot.aggregate(D.plan_bytes(c), 0), (name, col))
+    v = views["c2"]
+    assert D.sum(v.a) == int(ot.aggregate(D.plan_bytes(v.a), 0).sum_i64)
+    assert D.minimum(v.b) == ot.aggregate(D.plan_bytes(v.b), 0).min_f64
+    assert D.sum(views["missing"].ma) is not None and D.sum(t[:, :].ma) is None      # missing + x == missing
+    with pytest.raises(D.ArgumentError):
+        D.minimum(views["none"].a)                                                    # empty collection
+    assert D.sum(views["none"].b) == 0.0
+    assert D.sum(D.ismissing(t.ms)) == int(ot.mask(D.plan_bytes(t[D.ismissing(t.ms), :])).sum())
+
+
+def test_residency_modes_and_kernel_variants_agree(synth, oracle):
+    t, ot, nrows = synth
+    v = t[(t.a > 25) & (t.a <= 75), ["b"]]
+    ref = ot.aggregate(D.plan_bytes(v.b), 0)
+    L = _capi.lib()
+    base = D.aggregate(v.b)
+    results = []
+    for mode in (D.LOAD_HOST, D.LOAD_DECODED, D.LOAD_HBM):
+        t2 = D.open_table(t.path, mode=mode)
+        v2 = t2[(t2.a > 25) & (t2.a <= 75), ["b"]]
+        for _ in range(2):
+            results.append(D.aggregate(v2.b))
+        t2.close()
+    for opt in (b"no_wide", b"no_fused", b"lz4_simple"):
+        L.dfdb_set_option(opt, 1)
+        try:
+            t2 = D.open_table(t.path)
+            v2 = t2[(t2.a > 25) & (t2.a <= 75), ["b"]]
+            results.append(D.aggregate(v2.b))
+            assert np.array_equal(D.selection_mask(v2), D.selection_mask(v))
+            t2.close()
+        finally:
+            L.dfdb_set_option(opt, 0)
+    for r in results:
+        _check_agg(r, ref, "variant")
+        # fixed combination order: identical bits run to run and across residency modes / load widths
+        assert (r.sum_f64, r.sum_f64_lo, r.count) == (base.sum_f64, base.sum_f64_lo, base.count)
+
+
+def test_sharded_scan_folds_to_the_unsharded_result(synth):
+    t, ot, nrows = synth
+    v = t[(t.a > 25) & (t.a <= 75), ["b", "s"]]
+    whole = D.aggregate(v.b)
+    exp_rows = D.materialize(v)
+    for world in (2, 3):
+        parts, counts, frames = [], [], []
+        for rank in range(world):
+            ts = D.open_table(t.path, rank=rank, world=world)
+            vs = ts[(ts.a > 25) & (ts.a <= 75), ["b", "s"]]
+            parts.append(D.aggregate(vs.b))
+            counts.append(D.nrow(vs))
+            frames.append(D.materialize(vs))
+            ts.close()
+        f = D.fold(parts)
+        assert f.count == whole.count == sum(counts)
+        assert abs((f.sum_f64 + f.sum_f64_lo) - (whole.sum_f64 + whole.sum_f64_lo)) <= 1e-13 * abs(whole.sum_f64)
+        assert f.min_f64 == whole.min_f64 and f.max_f64 == whole.max_f64
+        assert np.array_equal(np.concatenate([fr["b"] for fr in frames]), exp_rows["b"])
+        assert sum((fr["s"].tolist() for fr in frames), []) == exp_rows["s"].tolist()
+
+
+def test_corrupt_block_is_reported(tmp_path, oracle):
+    p = str(tmp_path / "c")
+    oracle.gen_table(p, "a:Int64:iuniform:1:100", 200000, 65536, 5, 2)
+    f = os.path.join(p, "1.bin")
+    raw = bytearray(open(f, "rb").read())
+    raw[len(raw) // 2] ^= 0xFF
+    raw[len(raw) // 2 + 1] ^= 0xFF
+    open(f, "wb").write(raw)
+    t = D.open_table(p)
+    ot = oracle.OracleTable(p)
+    v = t[t.a > 50, :]
+    try:
+        ref = ot.count(D.plan_bytes(v))
+    except oracle.OracleError:
+        ref = None
+    if ref is None:
+        with pytest.raises((AssertionError, D.DfdbError)):
+            D.nrow(v)
+    else:   # the flipped bytes happened to decode to a valid stream of the same size: results must still agree
+        assert D.nrow(v) == ref
+
+
+def test_size_independent_properties_at_scale(tmp_path, oracle):
+    """BASELINE config shapes at a size the test box generates in seconds: partition and complement laws."""
+    p = str(tmp_path / "big")
+    n = 20_000_000
+    oracle.gen_table(p, "a:Int64:iuniform:1:100;b:Float64:funiform", n, 65536, 0xDFDB0002, os.cpu_count() or 4)
+    t = D.open_table(p)
+    pred = (t.a > 25) & (t.a <= 75)
+    sel, rest = D.aggregate(t[pred, :].b), D.aggregate(t[~pred, :].b)
+    allb = D.aggregate(t.b)
+    assert sel.count + rest.count == allb.count == n
+    s1 = (sel.sum_f64 + sel.sum_f64_lo) + (rest.sum_f64 + rest.sum_f64_lo)
+    assert abs(s1 - (allb.sum_f64 + allb.sum_f64_lo)) <= 1e-12 * allb.sum_f64
+    assert min(sel.min_f64, rest.min_f64) == allb.min_f64 and max(sel.max_f64, rest.max_f64) == allb.max_f64
+    ia = D.aggregate(t.a)
+    assert 1 <= ia.min_i64 and ia.max_i64 <= 100 and abs(ia.sum_i64 / n - 50.5) < 0.05
+    # sampled oracle check on a prefix: range stage first, then the predicate
+    v = t[R(1, 1_000_000), :][pred, :]
+    ot = oracle.OracleTable(p)
+    ref = ot.aggregate(D.plan_bytes(v.b), 0)
+    _check_agg(D.aggregate(v.b), ref, "prefix")
+    t.close()

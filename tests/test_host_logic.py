@@ -1,0 +1,151 @@
+"""CPU: plan algebra (mirror of the reference's SelectionQueue / Projection / BlockBroadcasting), plan wire
+format, C-ABI surface, table indexing by the product's host code (no compute calls)."""
+import ctypes as C
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+import dfdb_b200 as D
+import fixtures
+from dfdb_b200 import R, _capi
+from dfdb_b200.plan import BlockBroadcasting as BB, ColRef, JType, Projection, SelectionQueue, add, encode_plan
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_selection_queue_algebra():
+    """test/selection.jl:5-37"""
+    sel = SelectionQueue()
+    assert sel.isempty()
+    a = ColRef("a", JType("Int64"), 1)
+    test_b = BB("==", (a, 1))
+    assert add(sel, slice(None)).isempty()
+    sel2 = add(sel, R(5, 20))
+    assert len(sel2) == 1
+    sel2 = add(sel2, R(1, 5))
+    assert len(sel2) == 1 and sel2.queue[0] == R(5, 9)
+    sel2 = add(sel2, test_b)
+    assert len(sel2) == 2
+    sel3 = add(add(sel, test_b), test_b)
+    assert len(sel3) == 1 and sel3.queue[0].f == "&"
+    assert len(add(sel3, R(1, 3))) == 2
+    with pytest.raises(D.ArgumentError):
+        add(sel3, BB("*", (a, 3)))
+    # reindexing of ranges and index vectors (selection.jl:40)
+    assert add(add(sel, R(1, 10, 1000)), R(1, 10)).queue[0] == R(1, 10, 91)
+    assert add(add(sel, [5, 9, 2]), R(2, 3)).queue[0] == [9, 2]
+    assert add(add(sel, R(10, 20)), [1, 3]).queue[0] == [10, 12]
+
+
+def test_projection_algebra():
+    """test/projection.jl:10-55"""
+    a = ColRef("a", JType("Int64"), 1)
+    p = Projection([("a", a), ("b", BB("*", (a, 2)))])
+    assert p.keys() == ("a", "b")
+    with pytest.raises(D.ArgumentError):
+        p.add([("a", a)])
+    p2 = Projection([("a", a)]).add([("c", ColRef("a", JType("Float64"), 1)), ("e", ColRef("e", JType("Float64"), 5))])
+    assert p2.keys() == ("a", "c", "e")
+    assert p2[2].keys() == ("c",) and p2[R(1, 2)].keys() == ("a", "c") and p2[[1, 3]].keys() == ("a", "e")
+    assert p2[["a", "e"]].keys() == ("a", "e")
+    assert p.required_columns() == ("a",)
+    assert Projection().isempty()
+
+
+def test_broadcast_typing():
+    """test/broadcast.jl:12-36 result types; arrays rejected :73-81"""
+    a, c, s = ColRef("a", JType("Int64"), 1), ColRef("c", JType("Float64"), 3), ColRef("s", JType("String"), 2)
+    m = ColRef("m", JType("Int64", True), 4)
+    assert BB("*", (a, 2)).eltype() == JType("Int64")
+    assert BB("+", (a, c)).eltype() == JType("Float64")
+    assert BB("+", (a, BB("+", (a, c)))).eltype() == JType("Float64")
+    assert BB("/", (a, 50)).eltype() == JType("Float64")
+    assert BB(">", (m, 5)).eltype() == JType("Bool", True)
+    assert BB("coalesce", (BB(">", (m, 5)), False)).eltype() == JType("Bool")
+    assert BB("startswith", (s, "x")).eltype() == JType("Bool")
+    assert BB("<", (s, 3)).eltype() is None
+    from dfdb_b200.plan import required_columns
+    assert required_columns(BB("+", (a, BB("+", (a, c))))) == ("a", "c")
+    with pytest.raises(D.ArgumentError):
+        BB("in", (a, [1, 11, 21]))
+
+
+def test_plan_wire_format():
+    a = ColRef("a", JType("Int64"), 7)
+    q = add(add(SelectionQueue(), R(5, 2, 20)), BB(">", (a, 50)))
+    plan = encode_plan(q, Projection([("a", a), ("x", BB("*", (a, 2.5)))]))
+    assert plan[:4] == b"DFP1" and struct.unpack_from("<I", plan, 4)[0] == 2
+    assert struct.unpack_from("<Bqqq", plan, 8) == (1, 5, 2, 19)
+    assert plan[33] == 3 and struct.unpack_from("<I", plan, 34)[0] == 3
+
+
+def test_header_declares_exactly_the_exported_symbols():
+    hdr = open(os.path.join(ROOT, "include", "dfdb_b200.h")).read()
+    declared = set(re.findall(r"DFDB_API\s+[\w\s\*]+?\b(dfdb_\w+)\s*\(", hdr))
+    assert declared == set(_capi.SYMBOLS), declared ^ set(_capi.SYMBOLS)
+    _capi.build()
+    lib = C.CDLL(_capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_product_fails_loudly_without_a_gpu(tmp_path, oracle):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    p = str(tmp_path / "t")
+    fixtures.make_selection_fixture(oracle, p, 50)
+    t = D.open_table(p)                     # host-only: parses headers, indexes blocks
+    assert t.total_rows() == 100 and t.nblocks() == 2 and t.names() == ["a", "b"]
+    with pytest.raises(D.DfdbError) as e:
+        D.nrow(t[t.a > 5, :])
+    assert e.value.code == _capi.ERR_CUDA
+
+
+def test_table_index_and_open_errors(tmp_path, oracle):
+    p = str(tmp_path / "t")
+    data = fixtures.make_reference_fixture(oracle, p, sz=1000, block_size=100)
+    t = D.open_table(p)
+    assert (t.total_rows(), t.nblocks(), t.block_size) == (1000, 10, 100)
+    assert [(m.id, m.name, m.typestring) for m in t.meta] == [(1, "a", "Int64"), (2, "b", "String"), (3, "c", "Int64")]
+    assert oracle.OracleTable(p).columns() == [(1, "a", "Int64"), (2, "b", "String"), (3, "c", "Int64")]
+    L = _capi.lib()
+    comp, unc = C.c_int64(), C.c_int64()
+    _capi.check(L.dfdb_table_column_stats(t._h, 1, C.byref(comp), C.byref(unc)))
+    assert unc.value == 8000
+    _capi.check(L.dfdb_table_set_shard(t._h, 1, 3))
+    lo, hi, rlo, rhi = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+    _capi.check(L.dfdb_table_shard_range(t._h, C.byref(lo), C.byref(hi), C.byref(rlo), C.byref(rhi)))
+    assert (lo.value, hi.value, rlo.value, rhi.value) == (3, 6, 300, 600)
+    with pytest.raises(KeyError):
+        t.getmeta("nope")
+    # header mismatch: block size in the column file differs from meta (filesystem.jl:47-54)
+    f = os.path.join(p, "1.bin")
+    raw = bytearray(open(f, "rb").read())
+    raw[0:8] = struct.pack("<q", 64)
+    open(f, "wb").write(raw)
+    with pytest.raises(RuntimeError):
+        D.open_table(p)
+    # plan validation happens on the host: unknown column, non-Bool predicate, empty range
+    p2 = str(tmp_path / "t2")
+    fixtures.make_selection_fixture(oracle, p2, 50)
+    t2 = D.open_table(p2)
+    h = C.c_void_p()
+    for plan, code in [(encode_plan(SelectionQueue((BB(">", (ColRef("zz", JType("Int64"), 99), 1)),)), Projection()), _capi.ERR_KEY),
+                       (encode_plan(SelectionQueue((R(1, 0),)), Projection()), _capi.ERR_ARGUMENT),
+                       (b"XXXX" + bytes(8), _capi.ERR_ARGUMENT)]:
+        assert L.dfdb_scan_prepare(t2._h, plan, len(plan), C.byref(h)) == code
+
+
+def test_agg_fold_is_a_fixed_order_host_fold():
+    parts = []
+    for cnt, s, mn, mx in [(3, 1.5, 0.25, 0.75), (0, 0.0, 0.0, 0.0), (2, 1e-17, -0.0, 0.5)]:
+        a = _capi.Agg()
+        a.count, a.sum_f64, a.min_f64, a.max_f64, a.value_class = cnt, s, mn, mx, (3 if cnt else 0)
+        parts.append(a)
+    f = D.fold(parts)
+    assert f.count == 5 and f.min_f64 == 0.0 and np.signbit(f.min_f64) and f.max_f64 == 0.75
+    assert f.sum_f64 + f.sum_f64_lo == 1.5 + 1e-17 or abs((f.sum_f64 + f.sum_f64_lo) - 1.5) < 1e-15
