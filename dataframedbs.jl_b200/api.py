@@ -348,8 +348,8 @@ def selection(v: DFView, el) -> DFView:
         if isinstance(el, ColRef):
             # a stored Bool column used as predicate: `col .== true`
             el = BlockBroadcasting("==", (el, True))
-    elif isinstance(el, (np.ndarray, tuple)):
-        el = [int(x) for x in el]
+    elif isinstance(el, (np.ndarray, tuple, list)):
+        el = tuple(int(x) for x in el)
     elif isinstance(el, np.integer):
         el = int(el)
     return DFView(v.table, v.projection, add(v.selection, el))

@@ -293,21 +293,22 @@ class SelectionQueue:
 
 
 def _is_rangeish(e) -> bool:
-    return isinstance(e, (JRange, int, list)) and not isinstance(e, bool)
+    return isinstance(e, (JRange, int, tuple)) and not isinstance(e, bool)
 
 
 def _reindex(old, elem):
     # old[1][elem]  (selection.jl:40)
     if isinstance(old, JRange):
-        return old[elem] if not isinstance(elem, int) else old[elem]
-    if isinstance(old, list):
+        r = old[elem]
+        return tuple(r) if isinstance(r, list) else r
+    if isinstance(old, tuple):
         if isinstance(elem, JRange):
-            return [old[k - 1] for k in (elem[i] for i in range(1, len(elem) + 1))]
-        if isinstance(elem, list):
-            return [old[k - 1] for k in elem]
+            return tuple(old[k - 1] for k in (elem[i] for i in range(1, len(elem) + 1)))
+        if isinstance(elem, tuple):
+            return tuple(old[k - 1] for k in elem)
         return old[elem - 1]
     # integer indexed by something: Julia numbers are iterable of length 1
-    if elem == 1 or elem == [1] or (isinstance(elem, JRange) and len(elem) == 1 and elem.start == 1):
+    if elem == 1 or elem == (1,) or (isinstance(elem, JRange) and len(elem) == 1 and elem.start == 1):
         return old
     raise IndexError("BoundsError")
 
@@ -318,8 +319,8 @@ def add(q, r):
         return q.add(r)
     if isinstance(r, slice) and r == slice(None):
         return q
-    if isinstance(r, tuple):
-        r = list(r)
+    if isinstance(r, (list, tuple)):
+        r = tuple(int(x) for x in r)      # index vectors are kept as tuples (hashable plan objects)
     if isinstance(r, BlockBroadcasting):
         # _check_element selection.jl:52-55
         if r.eltype() != BOOL:

@@ -36,8 +36,8 @@ def test_selection_queue_algebra():
         add(sel3, BB("*", (a, 3)))
     # reindexing of ranges and index vectors (selection.jl:40)
     assert add(add(sel, R(1, 10, 1000)), R(1, 10)).queue[0] == R(1, 10, 91)
-    assert add(add(sel, [5, 9, 2]), R(2, 3)).queue[0] == [9, 2]
-    assert add(add(sel, R(10, 20)), [1, 3]).queue[0] == [10, 12]
+    assert add(add(sel, [5, 9, 2]), R(2, 3)).queue[0] == (9, 2)
+    assert add(add(sel, R(10, 20)), [1, 3]).queue[0] == (10, 12)
 
 
 def test_projection_algebra():
