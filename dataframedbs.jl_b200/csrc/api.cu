@@ -37,6 +37,7 @@ struct Runtime {
     int64_t lz4_simple = 0;
     int64_t no_wide = 0;
     int64_t no_fused = 0;
+    int64_t no_tma = 0;
     // profiling
     bool profiling = false;
     std::vector<PhaseRec> recs;
@@ -408,6 +409,98 @@ int count_mask(dfdb_scan *s, int64_t *total)
     return DFDB_OK;
 }
 
+// Folds the conjunction of terms into one closed interval per column (+ up to two != constants) for the
+// TMA-staged kernel.  Returns false when the predicate / columns do not fit that kernel.
+bool build_tma_args(dfdb_scan *s, const Expr *e, Column *agg_col, TmaScanArgs *a, bool *const_false)
+{
+    dfdb_table *t = s->tbl;
+    a->ncols = 0;
+    a->ntests = 0;
+    a->agg_col = -1;
+    *const_false = false;
+    std::vector<Column *> staged;
+    auto stage_col = [&](Column *c) -> int {
+        for (size_t i = 0; i < staged.size(); i++) if (staged[i] == c) return (int)i;
+        if (staged.size() >= (size_t)TMA_MAX_COLS || !wide_ok(t, *c)) return -1;
+        staged.push_back(c);
+        a->col[staged.size() - 1] = make_view(*c);
+        return (int)staged.size() - 1;
+    };
+    const int nterms = e ? e->nterms : 0;
+    for (int i = 0; i < nterms; i++) {
+        const Term &tm = e->terms[i];
+        if (tm.constant_result == 0) { *const_false = true; continue; }
+        if (tm.constant_result == 1) continue;
+        Column *c = t->find(s->slots[(size_t)tm.slot]);
+        const int ci = stage_col(c);
+        if (ci < 0) return false;
+        ColTest *ct = nullptr;
+        for (int k = 0; k < a->ntests; k++) if (a->test[k].col == ci) ct = &a->test[k];
+        if (!ct) {
+            ct = &a->test[a->ntests++];
+            memset(ct, 0, sizeof *ct);
+            ct->col = ci;
+            ct->cls = tm.cls;
+            ct->nan_passes = tm.cls == VC_FLT;
+            if (tm.cls == VC_INT) { ct->lo_i = INT64_MIN; ct->hi_i = INT64_MAX; }
+            else if (tm.cls == VC_UINT) { ct->lo_i = 0; ct->hi_i = -1; }
+            else { ct->lo_f = -INFINITY; ct->hi_f = INFINITY; }
+        }
+        if (tm.cls == VC_FLT) {
+            const double c0 = tm.cf;
+            if (tm.code == 1) {
+                if (c0 != c0) continue;                        // x != NaN is always true
+                if (ct->n_ne >= 2) return false;
+                ct->ne_f[ct->n_ne++] = c0;
+                continue;
+            }
+            ct->nan_passes = 0;
+            if (c0 != c0) { *const_false = true; continue; }   // every ordered comparison with NaN is false
+            switch (tm.code) {
+            case 0: ct->lo_f = std::max(ct->lo_f, c0); ct->hi_f = std::min(ct->hi_f, c0); break;
+            case 2: ct->hi_f = std::min(ct->hi_f, std::nextafter(c0, -INFINITY)); if (c0 == -INFINITY) *const_false = true; break;
+            case 3: ct->hi_f = std::min(ct->hi_f, c0); break;
+            case 4: ct->lo_f = std::max(ct->lo_f, std::nextafter(c0, INFINITY)); if (c0 == INFINITY) *const_false = true; break;
+            default: ct->lo_f = std::max(ct->lo_f, c0); break;
+            }
+            if (ct->lo_f > ct->hi_f) *const_false = true;
+        } else if (tm.cls == VC_INT) {
+            const int64_t c0 = tm.ci;
+            switch (tm.code) {
+            case 0: ct->lo_i = std::max<int64_t>(ct->lo_i, c0); ct->hi_i = std::min<int64_t>(ct->hi_i, c0); break;
+            case 1: if (ct->n_ne >= 2) return false; ct->ne_i[ct->n_ne++] = c0; break;
+            case 2: if (c0 == INT64_MIN) *const_false = true; else ct->hi_i = std::min<int64_t>(ct->hi_i, c0 - 1); break;
+            case 3: ct->hi_i = std::min<int64_t>(ct->hi_i, c0); break;
+            case 4: if (c0 == INT64_MAX) *const_false = true; else ct->lo_i = std::max<int64_t>(ct->lo_i, c0 + 1); break;
+            default: ct->lo_i = std::max<int64_t>(ct->lo_i, c0); break;
+            }
+            if (ct->lo_i > ct->hi_i) *const_false = true;
+        } else {
+            const uint64_t c0 = (uint64_t)tm.ci;
+            uint64_t lo = (uint64_t)ct->lo_i, hi = (uint64_t)ct->hi_i;
+            switch (tm.code) {
+            case 0: lo = std::max(lo, c0); hi = std::min(hi, c0); break;
+            case 1: if (ct->n_ne >= 2) return false; ct->ne_i[ct->n_ne++] = (int64_t)c0; break;
+            case 2: if (c0 == 0) *const_false = true; else hi = std::min(hi, c0 - 1); break;
+            case 3: hi = std::min(hi, c0); break;
+            case 4: if (c0 == UINT64_MAX) *const_false = true; else lo = std::max(lo, c0 + 1); break;
+            default: lo = std::max(lo, c0); break;
+            }
+            if (lo > hi) *const_false = true;
+            ct->lo_i = (int64_t)lo;
+            ct->hi_i = (int64_t)hi;
+        }
+    }
+    if (agg_col) {
+        a->agg_col = stage_col(agg_col);
+        if (a->agg_col < 0) return false;
+    }
+    if (staged.empty()) return false;
+    a->ncols = (int)staged.size();
+    a->nstages = std::min(TMA_MAX_STAGES, (96 * 1024) / (a->ncols * TILE_ROWS * 8));   // two CTAs per SM
+    return true;
+}
+
 bool single_simple_pred(const dfdb_scan *s)
 {
     return !rt.no_fused && s->stages.size() == 1 && s->stages[0].kind == ST_PRED && s->stages[0].e.simple;
@@ -475,7 +568,19 @@ int run_aggregate(dfdb_scan *s, int32_t proj_idx, bool count_only, AggPartial *h
         int64_t bytes = 0;
         for (int64_t id : need) for (int64_t b = t->blk_lo; b < t->blk_hi; b++) bytes += t->find(id)->blocks[(size_t)b].origin;
         PhaseScope ps(PH_CONSUME, bytes);
-        if (nunits > 0) LAUNCH(launch_fused(a, agg, false, wide, rt.sm_count, rt.stream));
+        TmaScanArgs ta;
+        memset(&ta, 0, sizeof ta);
+        bool cfalse = false;
+        const bool use_tma = wide && !rt.no_tma && !a.mask_in &&
+                             build_tma_args(s, s->stages.empty() ? nullptr : &s->stages[0].e, ac, &ta, &cfalse) && !cfalse;
+        if (use_tma) {
+            ta.g = g;
+            ta.agg_cls = cls;
+            ta.partials = static_cast<AggPartial *>(s->d_partials);
+            // work units that hold no rows (segments past the end of a partial last block) are never visited
+            CUDA_TRY(cudaMemsetAsync(s->d_partials, 0, (size_t)std::max(nunits, 1) * sizeof(AggPartial), rt.stream));
+            if (nunits > 0) LAUNCH(launch_fused_tma(ta, agg, rt.sm_count, rt.stream));
+        } else if (nunits > 0) LAUNCH(launch_fused(a, agg, false, wide, rt.sm_count, rt.stream));
         LAUNCH(launch_agg_finalize(static_cast<AggPartial *>(s->d_partials), nunits, agg == 2 ? VC_FLT : cls, static_cast<AggPartial *>(s->d_result), rt.stream));
     }
     PhaseScope ps(PH_D2H, sizeof(AggPartial));
@@ -557,6 +662,7 @@ int32_t dfdb_set_option(const char *name, int64_t value)
     if (n == "lz4_simple") rt.lz4_simple = value;
     else if (n == "no_wide") rt.no_wide = value;
     else if (n == "no_fused") rt.no_fused = value;
+    else if (n == "no_tma") rt.no_tma = value;
     else return fail(DFDB_ERR_ARGUMENT, "unknown option %s", n.c_str());
     return DFDB_OK;
 }

@@ -70,6 +70,31 @@ struct FusedArgs {
 int launch_fused(const FusedArgs &a, int agg, bool emit_mask, bool wide, int sm_count, cudaStream_t stream);
 int launch_agg_finalize(const AggPartial *partials, int nunits, int cls, AggPartial *result, cudaStream_t stream);
 
+// ---- K3+K7 TMA-staged fast path (scan_tma.cu) -----------------------------------------------------------
+constexpr int TMA_MAX_STAGES = 12;
+constexpr int TMA_MAX_COLS = 4;
+// all terms on one column folded into a closed interval [lo, hi] plus up to two != constants
+struct ColTest {
+    int col;            // index into TmaScanArgs::col
+    int cls;            // VC_INT / VC_UINT / VC_FLT
+    int n_ne;
+    int nan_passes;     // Float64 column with only != terms: NaN rows pass
+    long long lo_i, hi_i;
+    double lo_f, hi_f;
+    long long ne_i[2];
+    double ne_f[2];
+};
+struct TmaScanArgs {
+    Geometry g;
+    ColView col[TMA_MAX_COLS];   // staged 8-byte columns
+    int ncols, nstages;
+    ColTest test[TMA_MAX_COLS];
+    int ntests;
+    int agg_col, agg_cls;
+    AggPartial *partials;
+};
+int launch_fused_tma(const TmaScanArgs &a, int agg, int sm_count, cudaStream_t stream);
+
 // ---- K3 generic: VM predicate -> mask ------------------------------------------------------------------
 struct VmArgs {
     Geometry g;

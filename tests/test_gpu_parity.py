@@ -249,27 +249,30 @@ def test_residency_modes_and_kernel_variants_agree(synth, oracle):
     ref = ot.aggregate(D.plan_bytes(v.b), 0)
     L = _capi.lib()
     base = D.aggregate(v.b)
-    results = []
     for mode in (D.LOAD_HOST, D.LOAD_DECODED, D.LOAD_HBM):
         t2 = D.open_table(t.path, mode=mode)
         v2 = t2[(t2.a > 25) & (t2.a <= 75), ["b"]]
         for _ in range(2):
-            results.append(D.aggregate(v2.b))
+            r = D.aggregate(v2.b)
+            _check_agg(r, ref, mode)
+            # fixed combination order: identical bits run to run and across residency modes
+            assert (r.sum_f64, r.sum_f64_lo, r.count) == (base.sum_f64, base.sum_f64_lo, base.count)
         t2.close()
-    for opt in (b"no_wide", b"no_fused", b"lz4_simple"):
+    for opt in (b"no_tma", b"no_wide", b"no_fused", b"lz4_simple"):
         L.dfdb_set_option(opt, 1)
         try:
             t2 = D.open_table(t.path)
             v2 = t2[(t2.a > 25) & (t2.a <= 75), ["b"]]
-            results.append(D.aggregate(v2.b))
+            r1, r2 = D.aggregate(v2.b), D.aggregate(v2.b)
+            _check_agg(r1, ref, opt)
+            assert (r1.sum_f64, r1.sum_f64_lo) == (r2.sum_f64, r2.sum_f64_lo)
+            for col in ("a", "ma", "mb", "q"):
+                c2 = getattr(t2[D.coalesce(t2.ma > 50, False) & (t2.b < 0.5), :], col)
+                _check_agg(D.aggregate(c2), ot.aggregate(D.plan_bytes(c2), 0), (opt, col))
             assert np.array_equal(D.selection_mask(v2), D.selection_mask(v))
             t2.close()
         finally:
             L.dfdb_set_option(opt, 0)
-    for r in results:
-        _check_agg(r, ref, "variant")
-        # fixed combination order: identical bits run to run and across residency modes / load widths
-        assert (r.sum_f64, r.sum_f64_lo, r.count) == (base.sum_f64, base.sum_f64_lo, base.count)
 
 
 def test_sharded_scan_folds_to_the_unsharded_result(synth):
