@@ -177,13 +177,17 @@ __device__ __forceinline__ uint8_t stg_or_global(const WarpSmem &sm, const uint8
 }
 
 // ---- batched decoder ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 __device__ int decode_batched(WarpSmem &sm, const uint8_t *__restrict__ src, int64_t comp_len, uint8_t *dst, int64_t origin)
 {
     const uint32_t lane = lane_id();
     const int64_t comp_pad = (comp_len + 15) & ~(int64_t)15;
+    const uint32_t win_sa = smem_addr(sm.win), pos_sa = smem_addr(sm.pos);
     int64_t ip = 0, op = 0;
     int64_t win_base = -(int64_t)WIN * 2;   // forces the first refill
     int64_t stg_base = 0;                   // 16-aligned; staging holds out bytes [stg_base, op)
+    bool stg_dirty = false;                 // staging holds bytes that are not in global memory yet
     bool done = false;
 
     while (!done) {
@@ -203,39 +207,113 @@ __device__ int decode_batched(WarpSmem &sm, const uint8_t *__restrict__ src, int
             }
             __syncwarp();
         }
-        // ---- A: token chain -----------------------------------------------------------------
-        uint32_t p = (uint32_t)(ip - win_base);
+        // ---- A: token chain: LDS token, STS position, shift, add (4 instructions per token) ----------
+        {
+            uint32_t a = win_sa + (uint32_t)(ip - win_base);
 #pragma unroll
-        for (int k = 0; k < 32; k++) {
-            uint32_t t = sm.win[p];
-            sm.pos[k] = (uint16_t)p;
-            p += 3 + (t >> 4);
+            for (int k = 0; k < 32; k++) {
+                uint32_t t;
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t) : "r"(a));
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(pos_sa + 2 * k), "h"((uint16_t)a));
+                a += 3 + (t >> 4);
+            }
         }
         __syncwarp();
         // ---- B: lane-parallel sequences -----------------------------------------------------
-        const uint32_t mypos = sm.pos[lane];
+        const uint32_t mypos = (uint32_t)sm.pos[lane] - (win_sa & 0xffffu);
         const uint32_t tok = sm.win[mypos];
-        const uint32_t L = tok >> 4, Mn = tok & 15;
+        const uint32_t L = tok >> 4, Mn = tok & 15, M = Mn + 4;
         const int64_t seq_end_in = win_base + mypos + 3 + L;
         const bool simple = (L < 15) && (Mn < 15) && (seq_end_in < comp_len);
+        const uint32_t off = simple ? ((uint32_t)sm.win[mypos + 1 + L] | ((uint32_t)sm.win[mypos + 2 + L] << 8)) : 1u;
+        // "regular" = one aligned 8-byte output word whose match source is an aligned word
+        const bool regular = simple && (L + M == 8) && ((off & 7u) == 0) && (off != 0);
         const uint32_t bs = __ballot_sync(0xffffffffu, simple);
+        const uint32_t rb = __ballot_sync(0xffffffffu, regular);
         const int nvalid = (bs == 0xffffffffu) ? 32 : (__ffs(~bs) - 1);
         if (nvalid == 0) {
             // make global memory complete up to op, run one cooperative sequence, re-seed the staging
-            const int carried = (int)(op - stg_base);
-            if ((int)lane < carried) dst[stg_base + lane] = sm.stg[lane];
-            __syncwarp();
+            if (stg_dirty) {
+                const int carried = (int)(op - stg_base);
+                if ((int)lane < carried) dst[stg_base + lane] = sm.stg[lane];
+                __syncwarp();
+            }
             int e = decode_one_sequence(src, comp_len, dst, origin, ip, op, done);
             if (e) return e;
             stg_base = op & ~(int64_t)15;
             const int tail = (int)(op - stg_base);
             if ((int)lane < tail) sm.stg[lane] = __ldcg(dst + stg_base + lane);
+            stg_dirty = false;
             __syncwarp();
             continue;
         }
-        const bool active = (int)lane < nvalid;
-        const uint32_t off = active ? ((uint32_t)sm.win[mypos + 1 + L] | ((uint32_t)sm.win[mypos + 2 + L] << 8)) : 1u;
-        const uint32_t M = Mn + 4;
+        int nreg = (rb == 0xffffffffu) ? 32 : (__ffs(~rb) - 1);
+        if (nreg > nvalid) nreg = nvalid;
+
+        if (nreg > 0 && (op & 7) == 0) {
+            // ---- B-fast: word forwarding ---------------------------------------------------------------
+            // Every lane < nreg produces exactly the aligned word dst[op + 8*lane]:
+            //   word = literal bytes (low L bytes) | source word (bytes >= L), source word = dst[o - off].
+            // Sources before `op` are read from global memory; sources inside the batch are another lane's
+            // word and are resolved by pointer jumping over warp shuffles (<= 5 rounds for any chain).
+            const int n = nreg;
+            if (stg_dirty) {
+                const int carried = (int)(op - stg_base);
+                if ((int)lane < carried) dst[stg_base + lane] = sm.stg[lane];
+                stg_dirty = false;
+                __syncwarp();
+            }
+            const bool active = (int)lane < n;
+            const int64_t o = op + 8 * (int64_t)lane;
+            if (__any_sync(0xffffffffu, active && (int64_t)off > o)) return E_OFFSET;
+            if (op + 8 * (int64_t)n > origin) return E_OVERFLOW;
+            unsigned long long lit = 0;
+            if (active) {
+#pragma unroll
+                for (uint32_t i = 0; i < 4; i++)
+                    if (i < L) lit |= (unsigned long long)sm.win[mypos + 1 + i] << (8 * i);
+            }
+            uint32_t Lc = active ? L : 0;                       // low Lc bytes of my word are already known
+            const uint32_t hop = off >> 3;
+            int dep = (active && hop <= lane) ? (int)(lane - hop) : -1;
+            unsigned long long val = lit;
+            bool fin = !active || dep < 0;
+            if (active && dep < 0) {
+                const unsigned long long W = __ldcg(reinterpret_cast<const unsigned long long *>(dst + (o - (int64_t)off)));
+                val = lit | (W & (~0ull << (8 * L)));
+            }
+            while (__any_sync(0xffffffffu, !fin)) {
+                const int j = dep < 0 ? (int)lane : dep;
+                const unsigned long long vj = __shfl_sync(0xffffffffu, val, j);
+                const unsigned long long lj = __shfl_sync(0xffffffffu, lit, j);
+                const uint32_t Lj = __shfl_sync(0xffffffffu, Lc, j);
+                const int dj = __shfl_sync(0xffffffffu, dep, j);
+                const bool fj = __shfl_sync(0xffffffffu, (int)fin, j) != 0;
+                if (!fin) {
+                    const unsigned long long keep = ~0ull << (8 * Lc);
+                    if (fj) { val = lit | (vj & keep); fin = true; dep = -1; }
+                    else { lit |= lj & keep; Lc = Lc > Lj ? Lc : Lj; dep = dj; }
+                }
+            }
+            if (active) *reinterpret_cast<unsigned long long *>(dst + o) = val;      // coalesced 64-bit stores
+            const int64_t new_op = op + 8 * (int64_t)n;
+            stg_base = new_op & ~(int64_t)15;
+            if ((new_op & 8) && (int)lane == n - 1) *reinterpret_cast<unsigned long long *>(sm.stg) = val;   // staging mirrors [stg_base, op)
+            op = new_op;
+            ip = __shfl_sync(0xffffffffu, seq_end_in, n - 1);
+            __syncwarp();
+            continue;
+        }
+
+        // ---- B-generic: byte-granular sequences through the staging area ---------------------------------
+        int ng = nvalid;
+        if ((op & 7) == 0) {
+            // stop in front of the next regular lane so the fast path takes over again
+            const uint32_t later = rb & ~1u;
+            const int g = later ? (__ffs(later) - 1) : 32;
+            if (g < ng) ng = g;
+        }
+        const bool active = (int)lane < ng;
         const uint32_t len = active ? L + M : 0u;
         uint32_t incl = len;
 #pragma unroll
@@ -266,15 +344,18 @@ __device__ int decode_batched(WarpSmem &sm, const uint8_t *__restrict__ src, int
                 const bool ready = mine && (src_end <= F || (int)lane == P);
                 if (ready) {
                     const int64_t sd = m_dst - stg_base;
-                    if (off >= 8 && ((m_dst | m_src) & 7) == 0 && M == 8) {
-                        unsigned long long v;
-                        if (m_src >= stg_base) v = *reinterpret_cast<const unsigned long long *>(sm.stg + (m_src - stg_base));
-                        else v = __ldcg(reinterpret_cast<const unsigned long long *>(dst + m_src));
-                        *reinterpret_cast<unsigned long long *>(sm.stg + sd) = v;
-                    } else {
-                        // byte-serial per lane: correct for self-overlapping matches (off < M) as well
-                        for (uint32_t i = 0; i < M; i++) sm.stg[sd + i] = stg_or_global(sm, dst, stg_base, m_src + i);
+                    uint32_t i = 0;
+                    if (off >= 8 && ((m_dst | m_src) & 7) == 0) {
+                        for (; i + 8 <= M; i += 8) {
+                            unsigned long long v;
+                            const int64_t x = m_src + i;
+                            if (x >= stg_base) v = *reinterpret_cast<const unsigned long long *>(sm.stg + (x - stg_base));
+                            else v = __ldcg(reinterpret_cast<const unsigned long long *>(dst + x));
+                            *reinterpret_cast<unsigned long long *>(sm.stg + sd + i) = v;
+                        }
                     }
+                    // byte-serial per lane: correct for self-overlapping matches (off < M) as well
+                    for (; i < M; i++) sm.stg[sd + i] = stg_or_global(sm, dst, stg_base, m_src + i);
                 }
                 __syncwarp();
                 pending &= ~__ballot_sync(0xffffffffu, ready);
@@ -298,8 +379,9 @@ __device__ int decode_batched(WarpSmem &sm, const uint8_t *__restrict__ src, int
         __syncwarp();
         if (nchunks > 0 && (int)lane < tail) sm.stg[lane] = tb;
         stg_base += (int64_t)nchunks * 16;
+        stg_dirty = tail > 0;
         op = new_op;
-        ip = __shfl_sync(0xffffffffu, seq_end_in, nvalid - 1);
+        ip = __shfl_sync(0xffffffffu, seq_end_in, ng - 1);
         __syncwarp();
     }
     // block finished inside decode_one_sequence (which leaves everything < op in global memory)
@@ -308,7 +390,7 @@ __device__ int decode_batched(WarpSmem &sm, const uint8_t *__restrict__ src, int
 
 }  // namespace
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) lz4_decode_kernel(DecodeArgs args, unsigned int *counter, int simple_mode)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) lz4_decode_kernel(DecodeArgs args, unsigned int *counter, int simple_mode)
 {
     __shared__ WarpSmem smem[WARPS_PER_CTA];
     const int warp = threadIdx.x >> 5;
