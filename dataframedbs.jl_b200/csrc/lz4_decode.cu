@@ -179,21 +179,33 @@ __device__ __forceinline__ uint8_t stg_or_global(const WarpSmem &sm, const uint8
 // ---- batched decoder ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ int decode_batched(WarpSmem &sm, const uint8_t *__restrict__ src, int64_t comp_len, uint8_t *dst, int64_t origin)
+template <int K>
+__device__ __forceinline__ void chain_steps(uint32_t &b, uint32_t pos_sa)
+{
+    uint32_t t;
+    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(t) : "r"(b), "n"(3 * K));
+    asm volatile("st.shared.u16 [%0+%1], %2;" ::"r"(pos_sa), "n"(2 * K), "h"((uint16_t)b));
+    b += t >> 4;
+    if constexpr (K + 1 < 32) chain_steps<K + 1>(b, pos_sa);
+}
+
+// Block sizes are < 2^31 (LZ4_MAX_INPUT_SIZE), so every stream / output offset is kept in 32 bits.
+__device__ int decode_batched(WarpSmem &sm, const uint8_t *__restrict__ src, int64_t comp_len64, uint8_t *dst, int64_t origin64)
 {
     const uint32_t lane = lane_id();
-    const int64_t comp_pad = (comp_len + 15) & ~(int64_t)15;
+    const int32_t comp_len = (int32_t)comp_len64, origin = (int32_t)origin64;
+    const int32_t comp_pad = (comp_len + 15) & ~15;
     const uint32_t win_sa = smem_addr(sm.win), pos_sa = smem_addr(sm.pos);
-    int64_t ip = 0, op = 0;
-    int64_t win_base = -(int64_t)WIN * 2;   // forces the first refill
-    int64_t stg_base = 0;                   // 16-aligned; staging holds out bytes [stg_base, op)
+    int32_t ip = 0, op = 0;
+    int32_t win_base = -2 * WIN;            // forces the first refill
+    int32_t stg_base = 0;                   // 16-aligned; staging holds out bytes [stg_base, op)
     bool stg_dirty = false;                 // staging holds bytes that are not in global memory yet
     bool done = false;
 
     while (!done) {
         // ---- input window -------------------------------------------------------------------
         if (ip < win_base || ip + BATCH_IN_MAX > win_base + WIN) {
-            win_base = ip & ~(int64_t)15;
+            win_base = ip & ~15;
             const uint4 *s16 = reinterpret_cast<const uint4 *>(src + win_base);
             uint4 *w16 = reinterpret_cast<uint4 *>(sm.win);
 #pragma unroll
@@ -201,29 +213,24 @@ __device__ int decode_batched(WarpSmem &sm, const uint8_t *__restrict__ src, int
                 int ch = c * 32 + lane;
                 if (ch < (WIN + WIN_PAD) / 16) {
                     uint4 v = make_uint4(0, 0, 0, 0);
-                    if (win_base + (int64_t)ch * 16 < comp_pad) v = __ldg(s16 + ch);
+                    if (win_base + ch * 16 < comp_pad) v = __ldg(s16 + ch);
                     w16[ch] = v;
                 }
             }
             __syncwarp();
         }
-        // ---- A: token chain: LDS token, STS position, shift, add (4 instructions per token) ----------
+        // ---- A: token chain, 3 instructions per token: LDS.U8 [b + 3k], STS.U16 [pos + 2k], b += token >> 4
+        // (b_k = window address of token k minus 3k, so the "+3" of every sequence rides in the immediates)
         {
-            uint32_t a = win_sa + (uint32_t)(ip - win_base);
-#pragma unroll
-            for (int k = 0; k < 32; k++) {
-                uint32_t t;
-                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t) : "r"(a));
-                asm volatile("st.shared.u16 [%0], %1;" ::"r"(pos_sa + 2 * k), "h"((uint16_t)a));
-                a += 3 + (t >> 4);
-            }
+            uint32_t b = win_sa + (uint32_t)(ip - win_base);
+            chain_steps<0>(b, pos_sa);
         }
         __syncwarp();
         // ---- B: lane-parallel sequences -----------------------------------------------------
-        const uint32_t mypos = (uint32_t)sm.pos[lane] - (win_sa & 0xffffu);
+        const uint32_t mypos = (uint32_t)sm.pos[lane] + 3u * lane - (win_sa & 0xffffu);
         const uint32_t tok = sm.win[mypos];
         const uint32_t L = tok >> 4, Mn = tok & 15, M = Mn + 4;
-        const int64_t seq_end_in = win_base + mypos + 3 + L;
+        const int32_t seq_end_in = win_base + (int32_t)(mypos + 3 + L);
         const bool simple = (L < 15) && (Mn < 15) && (seq_end_in < comp_len);
         const uint32_t off = simple ? ((uint32_t)sm.win[mypos + 1 + L] | ((uint32_t)sm.win[mypos + 2 + L] << 8)) : 1u;
         // "regular" = one aligned 8-byte output word whose match source is an aligned word
@@ -234,155 +241,168 @@ __device__ int decode_batched(WarpSmem &sm, const uint8_t *__restrict__ src, int
         if (nvalid == 0) {
             // make global memory complete up to op, run one cooperative sequence, re-seed the staging
             if (stg_dirty) {
-                const int carried = (int)(op - stg_base);
+                const int carried = op - stg_base;
                 if ((int)lane < carried) dst[stg_base + lane] = sm.stg[lane];
                 __syncwarp();
             }
-            int e = decode_one_sequence(src, comp_len, dst, origin, ip, op, done);
+            int64_t ip64 = ip, op64 = op;
+            int e = decode_one_sequence(src, comp_len64, dst, origin64, ip64, op64, done);
             if (e) return e;
-            stg_base = op & ~(int64_t)15;
-            const int tail = (int)(op - stg_base);
+            ip = (int32_t)ip64;
+            op = (int32_t)op64;
+            stg_base = op & ~15;
+            const int tail = op - stg_base;
             if ((int)lane < tail) sm.stg[lane] = __ldcg(dst + stg_base + lane);
             stg_dirty = false;
             __syncwarp();
             continue;
         }
-        int nreg = (rb == 0xffffffffu) ? 32 : (__ffs(~rb) - 1);
-        if (nreg > nvalid) nreg = nvalid;
-
-        if (nreg > 0 && (op & 7) == 0) {
-            // ---- B-fast: word forwarding ---------------------------------------------------------------
-            // Every lane < nreg produces exactly the aligned word dst[op + 8*lane]:
-            //   word = literal bytes (low L bytes) | source word (bytes >= L), source word = dst[o - off].
-            // Sources before `op` are read from global memory; sources inside the batch are another lane's
-            // word and are resolved by pointer jumping over warp shuffles (<= 5 rounds for any chain).
-            const int n = nreg;
-            if (stg_dirty) {
-                const int carried = (int)(op - stg_base);
-                if ((int)lane < carried) dst[stg_base + lane] = sm.stg[lane];
-                stg_dirty = false;
-                __syncwarp();
-            }
-            const bool active = (int)lane < n;
-            const int64_t o = op + 8 * (int64_t)lane;
-            if (__any_sync(0xffffffffu, active && (int64_t)off > o)) return E_OFFSET;
-            if (op + 8 * (int64_t)n > origin) return E_OVERFLOW;
-            unsigned long long lit = 0;
-            if (active) {
-#pragma unroll
-                for (uint32_t i = 0; i < 4; i++)
-                    if (i < L) lit |= (unsigned long long)sm.win[mypos + 1 + i] << (8 * i);
-            }
-            uint32_t Lc = active ? L : 0;                       // low Lc bytes of my word are already known
-            const uint32_t hop = off >> 3;
-            int dep = (active && hop <= lane) ? (int)(lane - hop) : -1;
-            unsigned long long val = lit;
-            bool fin = !active || dep < 0;
-            if (active && dep < 0) {
-                const unsigned long long W = __ldcg(reinterpret_cast<const unsigned long long *>(dst + (o - (int64_t)off)));
-                val = lit | (W & (~0ull << (8 * L)));
-            }
-            while (__any_sync(0xffffffffu, !fin)) {
-                const int j = dep < 0 ? (int)lane : dep;
-                const unsigned long long vj = __shfl_sync(0xffffffffu, val, j);
-                const unsigned long long lj = __shfl_sync(0xffffffffu, lit, j);
-                const uint32_t Lj = __shfl_sync(0xffffffffu, Lc, j);
-                const int dj = __shfl_sync(0xffffffffu, dep, j);
-                const bool fj = __shfl_sync(0xffffffffu, (int)fin, j) != 0;
-                if (!fin) {
-                    const unsigned long long keep = ~0ull << (8 * Lc);
-                    if (fj) { val = lit | (vj & keep); fin = true; dep = -1; }
-                    else { lit |= lj & keep; Lc = Lc > Lj ? Lc : Lj; dep = dj; }
+        // The nvalid sequences are consumed in runs: runs of regular lanes take the word-forwarding path,
+        // the lanes between them the byte-granular path; token positions are computed only once.
+        int s0 = 0;
+        while (s0 < nvalid) {
+            const uint32_t rrem = rb >> s0;                       // bit 0 = lane s0
+            if ((rrem & 1u) && (op & 7) == 0) {
+                // ---- B-fast: word forwarding ---------------------------------------------------------------
+                // Every lane of the run produces exactly the aligned word dst[op + 8*rel]:
+                //   word = literal bytes (low L bytes) | source word (bytes >= L), source word = dst[o - off].
+                // Sources before `op` are read from global memory; sources inside the run are another lane's
+                // word and are resolved by pointer jumping over warp shuffles (<= 5 rounds for any chain).
+                int n = (~rrem) ? (__ffs(~rrem) - 1) : 32;
+                if (n > nvalid - s0) n = nvalid - s0;
+                if (stg_dirty) {
+                    const int carried = op - stg_base;
+                    if ((int)lane < carried) dst[stg_base + lane] = sm.stg[lane];
+                    stg_dirty = false;
+                    __syncwarp();
                 }
-            }
-            if (active) *reinterpret_cast<unsigned long long *>(dst + o) = val;      // coalesced 64-bit stores
-            const int64_t new_op = op + 8 * (int64_t)n;
-            stg_base = new_op & ~(int64_t)15;
-            if ((new_op & 8) && (int)lane == n - 1) *reinterpret_cast<unsigned long long *>(sm.stg) = val;   // staging mirrors [stg_base, op)
-            op = new_op;
-            ip = __shfl_sync(0xffffffffu, seq_end_in, n - 1);
-            __syncwarp();
-            continue;
-        }
-
-        // ---- B-generic: byte-granular sequences through the staging area ---------------------------------
-        int ng = nvalid;
-        if ((op & 7) == 0) {
-            // stop in front of the next regular lane so the fast path takes over again
-            const uint32_t later = rb & ~1u;
-            const int g = later ? (__ffs(later) - 1) : 32;
-            if (g < ng) ng = g;
-        }
-        const bool active = (int)lane < ng;
-        const uint32_t len = active ? L + M : 0u;
-        uint32_t incl = len;
+                const int rel = (int)lane - s0;
+                const bool active = rel >= 0 && rel < n;
+                const int32_t o = op + 8 * rel;
+                if (__any_sync(0xffffffffu, active && (int32_t)off > o)) return E_OFFSET;
+                if (op + 8 * n > origin) return E_OVERFLOW;
+                unsigned long long lit = 0;
+                if (__any_sync(0xffffffffu, active && L > 0)) {
+                    if (active) {
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-            if ((int)lane >= d) incl += v;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        const int64_t o = op + (incl - len);          // my literals start here
-        const int64_t m_dst = o + L;                  // my match starts here
-        const int64_t m_src = m_dst - (int64_t)off;
-        const bool bad = active && (off == 0 || m_src < 0);
-        if (__any_sync(0xffffffffu, bad)) return E_OFFSET;
-        if (op + total > origin) return E_OVERFLOW;
-        // literals: compressed stream (smem window) -> staging
-        if (active) {
-            for (uint32_t i = 0; i < L; i++) sm.stg[o - stg_base + i] = sm.win[mypos + 1 + i];
-        }
-        __syncwarp();
-        // matches in dependency waves.  Frontier F: every output byte < F is final.
-        {
-            const int64_t src_end = (m_src + (int64_t)M < m_dst) ? m_src + M : m_dst;   // bytes needed from other producers end here
-            uint32_t pending = __ballot_sync(0xffffffffu, active);
-            int64_t F = op;
-            int P = 0;                                                                 // first lane whose match is not done
-            while (pending) {
-                const bool mine = (pending >> lane) & 1u;
-                const bool ready = mine && (src_end <= F || (int)lane == P);
-                if (ready) {
-                    const int64_t sd = m_dst - stg_base;
-                    uint32_t i = 0;
-                    if (off >= 8 && ((m_dst | m_src) & 7) == 0) {
-                        for (; i + 8 <= M; i += 8) {
-                            unsigned long long v;
-                            const int64_t x = m_src + i;
-                            if (x >= stg_base) v = *reinterpret_cast<const unsigned long long *>(sm.stg + (x - stg_base));
-                            else v = __ldcg(reinterpret_cast<const unsigned long long *>(dst + x));
-                            *reinterpret_cast<unsigned long long *>(sm.stg + sd + i) = v;
+                        for (uint32_t i = 0; i < 4; i++)
+                            if (i < L) lit |= (unsigned long long)sm.win[mypos + 1 + i] << (8 * i);
+                    }
+                }
+                uint32_t Lc = active ? L : 0;                       // low Lc bytes of my word are already known
+                const int hop = (int)(off >> 3);
+                int dep = (active && hop <= rel) ? (int)lane - hop : -1;
+                unsigned long long val = lit;
+                bool fin = !active || dep < 0;
+                if (active && dep < 0) {
+                    const unsigned long long W = __ldcg(reinterpret_cast<const unsigned long long *>(dst + (o - (int32_t)off)));
+                    val = lit | (W & (~0ull << (8 * L)));
+                }
+                while (__any_sync(0xffffffffu, !fin)) {
+                    const int j = dep < 0 ? (int)lane : dep;
+                    const unsigned long long vj = __shfl_sync(0xffffffffu, val, j);
+                    const unsigned long long lj = __shfl_sync(0xffffffffu, lit, j);
+                    const uint32_t Lj = __shfl_sync(0xffffffffu, Lc, j);
+                    const int dj = __shfl_sync(0xffffffffu, dep, j);
+                    const bool fj = __shfl_sync(0xffffffffu, (int)fin, j) != 0;
+                    if (!fin) {
+                        const unsigned long long keep = ~0ull << (8 * Lc);
+                        if (fj) { val = lit | (vj & keep); fin = true; dep = -1; }
+                        else { lit |= lj & keep; Lc = Lc > Lj ? Lc : Lj; dep = dj; }
+                    }
+                }
+                if (active) *reinterpret_cast<unsigned long long *>(dst + o) = val;      // coalesced 64-bit stores
+                const int32_t new_op = op + 8 * n;
+                stg_base = new_op & ~15;
+                if ((new_op & 8) && rel == n - 1) *reinterpret_cast<unsigned long long *>(sm.stg) = val;   // staging mirrors [stg_base, op)
+                op = new_op;
+                s0 += n;
+                __syncwarp();
+                continue;
+            }
+            // ---- B-generic: byte-granular sequences through the staging area ---------------------------------
+            int ng = nvalid - s0;
+            if ((op & 7) == 0) {
+                // stop in front of the next regular lane so the fast path takes over again
+                const uint32_t later = rrem & ~1u;
+                const int g = later ? (__ffs(later) - 1) : 32;
+                if (g < ng) ng = g;
+            }
+            const bool active = (int)lane >= s0 && (int)lane < s0 + ng;
+            const uint32_t len = active ? L + M : 0u;
+            uint32_t incl = len;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int)lane >= d) incl += v;
+            }
+            const int32_t total = (int32_t)__shfl_sync(0xffffffffu, incl, 31);
+            const int32_t o = op + (int32_t)(incl - len);   // my literals start here
+            const int32_t m_dst = o + (int32_t)L;           // my match starts here
+            const int32_t m_src = m_dst - (int32_t)off;
+            const bool bad = active && (off == 0 || m_src < 0);
+            if (__any_sync(0xffffffffu, bad)) return E_OFFSET;
+            if (op + total > origin) return E_OVERFLOW;
+            // literals: compressed stream (smem window) -> staging
+            if (active) {
+                for (uint32_t i = 0; i < L; i++) sm.stg[o - stg_base + i] = sm.win[mypos + 1 + i];
+            }
+            __syncwarp();
+            // matches in dependency waves.  Frontier F: every output byte < F is final.
+            {
+                const int32_t src_end = (m_src + (int32_t)M < m_dst) ? m_src + (int32_t)M : m_dst;   // bytes needed from other producers end here
+                uint32_t pending = __ballot_sync(0xffffffffu, active);
+                int32_t F = op;
+                int P = s0;                                                                 // first lane whose match is not done
+                while (pending) {
+                    const bool mine = (pending >> lane) & 1u;
+                    const bool ready = mine && (src_end <= F || (int)lane == P);
+                    if (ready) {
+                        const int32_t sd = m_dst - stg_base;
+                        uint32_t i = 0;
+                        if (off >= 8 && ((m_dst | m_src) & 7) == 0) {
+                            for (; i + 8 <= M; i += 8) {
+                                unsigned long long v;
+                                const int32_t x = m_src + (int32_t)i;
+                                if (x >= stg_base) v = *reinterpret_cast<const unsigned long long *>(sm.stg + (x - stg_base));
+                                else v = __ldcg(reinterpret_cast<const unsigned long long *>(dst + x));
+                                *reinterpret_cast<unsigned long long *>(sm.stg + sd + i) = v;
+                            }
+                        }
+                        // byte-serial per lane: correct for self-overlapping matches (off < M) as well
+                        for (; i < M; i++) {
+                            const int32_t x = m_src + (int32_t)i;
+                            sm.stg[sd + i] = x >= stg_base ? sm.stg[x - stg_base] : __ldcg(dst + x);
                         }
                     }
-                    // byte-serial per lane: correct for self-overlapping matches (off < M) as well
-                    for (; i < M; i++) sm.stg[sd + i] = stg_or_global(sm, dst, stg_base, m_src + i);
-                }
-                __syncwarp();
-                pending &= ~__ballot_sync(0xffffffffu, ready);
-                if (pending) {
-                    P = __ffs(pending) - 1;
-                    F = __shfl_sync(0xffffffffu, m_dst, P);
+                    __syncwarp();
+                    pending &= ~__ballot_sync(0xffffffffu, ready);
+                    if (pending) {
+                        P = __ffs(pending) - 1;
+                        F = __shfl_sync(0xffffffffu, m_dst, P);
+                    }
                 }
             }
+            // ---- C: flush whole 16-byte chunks, carry the partial tail ---------------------------
+            const int32_t new_op = op + total;
+            const int nchunks = (new_op >> 4) - (stg_base >> 4);
+            {
+                uint4 *d16 = reinterpret_cast<uint4 *>(dst + stg_base);
+                const uint4 *g16 = reinterpret_cast<const uint4 *>(sm.stg);
+                for (int c = lane; c < nchunks; c += 32) d16[c] = g16[c];
+            }
+            const int tail = new_op & 15;
+            uint8_t tb = 0;
+            if (nchunks > 0 && (int)lane < tail) tb = sm.stg[nchunks * 16 + lane];
+            __syncwarp();
+            if (nchunks > 0 && (int)lane < tail) sm.stg[lane] = tb;
+            stg_base += nchunks * 16;
+            stg_dirty = tail > 0;
+            op = new_op;
+            s0 += ng;
+            __syncwarp();
         }
-        // ---- C: flush whole 16-byte chunks, carry the partial tail ---------------------------
-        const int64_t new_op = op + total;
-        const int nchunks = (int)((new_op >> 4) - (stg_base >> 4));
-        {
-            uint4 *d16 = reinterpret_cast<uint4 *>(dst + stg_base);
-            const uint4 *g16 = reinterpret_cast<const uint4 *>(sm.stg);
-            for (int c = lane; c < nchunks; c += 32) d16[c] = g16[c];
-        }
-        const int tail = (int)(new_op & 15);
-        uint8_t tb = 0;
-        if (nchunks > 0 && (int)lane < tail) tb = sm.stg[nchunks * 16 + lane];
-        __syncwarp();
-        if (nchunks > 0 && (int)lane < tail) sm.stg[lane] = tb;
-        stg_base += (int64_t)nchunks * 16;
-        stg_dirty = tail > 0;
-        op = new_op;
-        ip = __shfl_sync(0xffffffffu, seq_end_in, ng - 1);
-        __syncwarp();
+        ip = __shfl_sync(0xffffffffu, seq_end_in, nvalid - 1);
     }
     // block finished inside decode_one_sequence (which leaves everything < op in global memory)
     return (op == origin && ip == comp_len) ? E_OK : E_SIZE;
