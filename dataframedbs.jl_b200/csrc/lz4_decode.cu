@@ -199,7 +199,6 @@ __device__ int decode_batched(WarpSmem &sm, const uint8_t *__restrict__ src, int
     int32_t ip = 0, op = 0;
     int32_t win_base = -2 * WIN;            // forces the first refill
     int32_t stg_base = 0;                   // 16-aligned; staging holds out bytes [stg_base, op)
-    bool stg_dirty = false;                 // staging holds bytes that are not in global memory yet
     bool done = false;
 
     while (!done) {
@@ -236,15 +235,9 @@ __device__ int decode_batched(WarpSmem &sm, const uint8_t *__restrict__ src, int
         // "regular" = one aligned 8-byte output word whose match source is an aligned word
         const bool regular = simple && (L + M == 8) && ((off & 7u) == 0) && (off != 0);
         const uint32_t bs = __ballot_sync(0xffffffffu, simple);
-        const uint32_t rb = __ballot_sync(0xffffffffu, regular);
         const int nvalid = (bs == 0xffffffffu) ? 32 : (__ffs(~bs) - 1);
         if (nvalid == 0) {
-            // make global memory complete up to op, run one cooperative sequence, re-seed the staging
-            if (stg_dirty) {
-                const int carried = op - stg_base;
-                if ((int)lane < carried) dst[stg_base + lane] = sm.stg[lane];
-                __syncwarp();
-            }
+            // global memory is complete below op: run one cooperative sequence, then re-seed the staging
             int64_t ip64 = ip, op64 = op;
             int e = decode_one_sequence(src, comp_len64, dst, origin64, ip64, op64, done);
             if (e) return e;
@@ -253,156 +246,145 @@ __device__ int decode_batched(WarpSmem &sm, const uint8_t *__restrict__ src, int
             stg_base = op & ~15;
             const int tail = op - stg_base;
             if ((int)lane < tail) sm.stg[lane] = __ldcg(dst + stg_base + lane);
-            stg_dirty = false;
             __syncwarp();
             continue;
         }
-        // The nvalid sequences are consumed in runs: runs of regular lanes take the word-forwarding path,
-        // the lanes between them the byte-granular path; token positions are computed only once.
-        int s0 = 0;
-        while (s0 < nvalid) {
-            const uint32_t rrem = rb >> s0;                       // bit 0 = lane s0
-            if ((rrem & 1u) && (op & 7) == 0) {
-                // ---- B-fast: word forwarding ---------------------------------------------------------------
-                // Every lane of the run produces exactly the aligned word dst[op + 8*rel]:
-                //   word = literal bytes (low L bytes) | source word (bytes >= L), source word = dst[o - off].
-                // Sources before `op` are read from global memory; sources inside the run are another lane's
-                // word and are resolved by pointer jumping over warp shuffles (<= 5 rounds for any chain).
-                int n = (~rrem) ? (__ffs(~rrem) - 1) : 32;
-                if (n > nvalid - s0) n = nvalid - s0;
-                if (stg_dirty) {
-                    const int carried = op - stg_base;
-                    if ((int)lane < carried) dst[stg_base + lane] = sm.stg[lane];
-                    stg_dirty = false;
-                    __syncwarp();
-                }
-                const int rel = (int)lane - s0;
-                const bool active = rel >= 0 && rel < n;
-                const int32_t o = op + 8 * rel;
-                if (__any_sync(0xffffffffu, active && (int32_t)off > o)) return E_OFFSET;
-                if (op + 8 * n > origin) return E_OVERFLOW;
-                unsigned long long lit = 0;
-                if (__any_sync(0xffffffffu, active && L > 0)) {
-                    if (active) {
+        // ---- one pass over the nvalid sequences of the batch ----------------------------------------------
+        // Output positions from one warp prefix sum; "regular" lanes (one aligned 8-byte word whose source is
+        // an aligned word: L + M == 8, off % 8 == 0, o % 8 == 0) are resolved by word forwarding, the few
+        // remaining lanes by byte-granular dependency waves; the batch leaves through the smem staging area.
+        const bool active = (int)lane < nvalid;
+        const uint32_t len = active ? L + M : 0u;
+        uint32_t incl = len;
 #pragma unroll
-                        for (uint32_t i = 0; i < 4; i++)
-                            if (i < L) lit |= (unsigned long long)sm.win[mypos + 1 + i] << (8 * i);
-                    }
-                }
-                uint32_t Lc = active ? L : 0;                       // low Lc bytes of my word are already known
-                const int hop = (int)(off >> 3);
-                int dep = (active && hop <= rel) ? (int)lane - hop : -1;
-                unsigned long long val = lit;
-                bool fin = !active || dep < 0;
-                if (active && dep < 0) {
-                    const unsigned long long W = __ldcg(reinterpret_cast<const unsigned long long *>(dst + (o - (int32_t)off)));
-                    val = lit | (W & (~0ull << (8 * L)));
-                }
-                while (__any_sync(0xffffffffu, !fin)) {
-                    const int j = dep < 0 ? (int)lane : dep;
-                    const unsigned long long vj = __shfl_sync(0xffffffffu, val, j);
-                    const unsigned long long lj = __shfl_sync(0xffffffffu, lit, j);
-                    const uint32_t Lj = __shfl_sync(0xffffffffu, Lc, j);
-                    const int dj = __shfl_sync(0xffffffffu, dep, j);
-                    const bool fj = __shfl_sync(0xffffffffu, (int)fin, j) != 0;
-                    if (!fin) {
-                        const unsigned long long keep = ~0ull << (8 * Lc);
-                        if (fj) { val = lit | (vj & keep); fin = true; dep = -1; }
-                        else { lit |= lj & keep; Lc = Lc > Lj ? Lc : Lj; dep = dj; }
-                    }
-                }
-                if (active) *reinterpret_cast<unsigned long long *>(dst + o) = val;      // coalesced 64-bit stores
-                const int32_t new_op = op + 8 * n;
-                stg_base = new_op & ~15;
-                if ((new_op & 8) && rel == n - 1) *reinterpret_cast<unsigned long long *>(sm.stg) = val;   // staging mirrors [stg_base, op)
-                op = new_op;
-                s0 += n;
-                __syncwarp();
-                continue;
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += v;
+        }
+        const int32_t total = (int32_t)__shfl_sync(0xffffffffu, incl, 31);
+        const int32_t o = op + (int32_t)(incl - len);   // my literals start here
+        const int32_t m_dst = o + (int32_t)L;           // my match starts here
+        const int32_t m_src = m_dst - (int32_t)off;
+        bool err = active && (off == 0 || m_src < 0);
+        if (op + total > origin) return E_OVERFLOW;      // uniform
+        const int32_t sw = o - (int32_t)off;             // source word of a regular lane
+        bool reg = active && regular && ((o & 7) == 0) && !err;
+        // in-batch source: the producer must be the regular lane that owns exactly that word
+        int dep = -1;
+        {
+            const int guess = (int)lane - (int)(off >> 3);
+            const int j = guess < 0 ? 0 : guess;
+            const int32_t oj = __shfl_sync(0xffffffffu, o, j);
+            const uint32_t regmask = __ballot_sync(0xffffffffu, reg);
+            if (reg && sw + 8 > op) {                    // source word not entirely below the batch start
+                if (guess >= 0 && oj == sw && ((regmask >> j) & 1u)) dep = j;
+                else reg = false;                        // source lies inside a non-regular sequence: byte path
             }
-            // ---- B-generic: byte-granular sequences through the staging area ---------------------------------
-            int ng = nvalid - s0;
-            if ((op & 7) == 0) {
-                // stop in front of the next regular lane so the fast path takes over again
-                const uint32_t later = rrem & ~1u;
-                const int g = later ? (__ffs(later) - 1) : 32;
-                if (g < ng) ng = g;
-            }
-            const bool active = (int)lane >= s0 && (int)lane < s0 + ng;
-            const uint32_t len = active ? L + M : 0u;
-            uint32_t incl = len;
+        }
+        // a regular lane whose producer was demoted must be demoted too (rare): iterate to a fixed point
+        for (;;) {
+            const uint32_t regmask = __ballot_sync(0xffffffffu, reg);
+            const bool drop = reg && dep >= 0 && !((regmask >> dep) & 1u);
+            if (!__any_sync(0xffffffffu, drop)) break;
+            if (drop) { reg = false; dep = -1; }
+        }
+        const uint32_t regmask = __ballot_sync(0xffffffffu, reg);
+        const uint32_t genmask = __ballot_sync(0xffffffffu, active && !reg && !err);
+
+        // ---- regular lanes: word forwarding ------------------------------------------------------------
+        if (regmask) {
+            unsigned long long lit = 0;
+            if (__any_sync(0xffffffffu, reg && L > 0)) {
+                if (reg) {
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                if ((int)lane >= d) incl += v;
+                    for (uint32_t i = 0; i < 4; i++)
+                        if (i < L) lit |= (unsigned long long)sm.win[mypos + 1 + i] << (8 * i);
+                }
             }
-            const int32_t total = (int32_t)__shfl_sync(0xffffffffu, incl, 31);
-            const int32_t o = op + (int32_t)(incl - len);   // my literals start here
-            const int32_t m_dst = o + (int32_t)L;           // my match starts here
-            const int32_t m_src = m_dst - (int32_t)off;
-            const bool bad = active && (off == 0 || m_src < 0);
-            if (__any_sync(0xffffffffu, bad)) return E_OFFSET;
-            if (op + total > origin) return E_OVERFLOW;
-            // literals: compressed stream (smem window) -> staging
-            if (active) {
+            uint32_t Lc = reg ? L : 0;                        // low Lc bytes of my word are already known
+            unsigned long long val = lit;
+            bool fin = !reg || dep < 0;
+            if (reg && dep < 0) {
+                const unsigned long long W = __ldcg(reinterpret_cast<const unsigned long long *>(dst + sw));
+                val = lit | (W & (~0ull << (8 * L)));
+            }
+            while (__any_sync(0xffffffffu, !fin)) {
+                const int j = dep < 0 ? (int)lane : dep;
+                const unsigned long long vj = __shfl_sync(0xffffffffu, val, j);
+                const unsigned long long lj = __shfl_sync(0xffffffffu, lit, j);
+                const uint32_t Lj = __shfl_sync(0xffffffffu, Lc, j);
+                const int dj = __shfl_sync(0xffffffffu, dep, j);
+                const uint32_t finmask = __ballot_sync(0xffffffffu, fin);
+                if (!fin) {
+                    const unsigned long long keep = ~0ull << (8 * Lc);
+                    if ((finmask >> j) & 1u) { val = lit | (vj & keep); fin = true; dep = -1; }
+                    else { lit |= lj & keep; Lc = Lc > Lj ? Lc : Lj; dep = dj; }
+                }
+            }
+            if (reg) *reinterpret_cast<unsigned long long *>(sm.stg + (o - stg_base)) = val;
+        }
+        // ---- remaining lanes: literals + matches in dependency waves ------------------------------------------
+        if (genmask) {
+            const bool gen = (genmask >> lane) & 1u;
+            if (gen) {
                 for (uint32_t i = 0; i < L; i++) sm.stg[o - stg_base + i] = sm.win[mypos + 1 + i];
             }
             __syncwarp();
-            // matches in dependency waves.  Frontier F: every output byte < F is final.
-            {
-                const int32_t src_end = (m_src + (int32_t)M < m_dst) ? m_src + (int32_t)M : m_dst;   // bytes needed from other producers end here
-                uint32_t pending = __ballot_sync(0xffffffffu, active);
-                int32_t F = op;
-                int P = s0;                                                                 // first lane whose match is not done
-                while (pending) {
-                    const bool mine = (pending >> lane) & 1u;
-                    const bool ready = mine && (src_end <= F || (int)lane == P);
-                    if (ready) {
-                        const int32_t sd = m_dst - stg_base;
-                        uint32_t i = 0;
-                        if (off >= 8 && ((m_dst | m_src) & 7) == 0) {
-                            for (; i + 8 <= M; i += 8) {
-                                unsigned long long v;
-                                const int32_t x = m_src + (int32_t)i;
-                                if (x >= stg_base) v = *reinterpret_cast<const unsigned long long *>(sm.stg + (x - stg_base));
-                                else v = __ldcg(reinterpret_cast<const unsigned long long *>(dst + x));
-                                *reinterpret_cast<unsigned long long *>(sm.stg + sd + i) = v;
-                            }
-                        }
-                        // byte-serial per lane: correct for self-overlapping matches (off < M) as well
-                        for (; i < M; i++) {
+            // Frontier F: every output byte < F is final (regular lanes are already done).
+            const int32_t src_end = (m_src + (int32_t)M < m_dst) ? m_src + (int32_t)M : m_dst;   // bytes needed from other producers end here
+            uint32_t pending = genmask;
+            int P = __ffs(pending) - 1;                                                     // first lane whose match is not done
+            int32_t F = __shfl_sync(0xffffffffu, m_dst, P);
+            while (pending) {
+                const bool mine = (pending >> lane) & 1u;
+                const bool ready = mine && (src_end <= F || (int)lane == P);
+                if (ready) {
+                    const int32_t sd = m_dst - stg_base;
+                    uint32_t i = 0;
+                    if (off >= 8 && ((m_dst | m_src) & 7) == 0) {
+                        for (; i + 8 <= M; i += 8) {
+                            unsigned long long v;
                             const int32_t x = m_src + (int32_t)i;
-                            sm.stg[sd + i] = x >= stg_base ? sm.stg[x - stg_base] : __ldcg(dst + x);
+                            if (x >= stg_base) v = *reinterpret_cast<const unsigned long long *>(sm.stg + (x - stg_base));
+                            else v = __ldcg(reinterpret_cast<const unsigned long long *>(dst + x));
+                            *reinterpret_cast<unsigned long long *>(sm.stg + sd + i) = v;
                         }
                     }
-                    __syncwarp();
-                    pending &= ~__ballot_sync(0xffffffffu, ready);
-                    if (pending) {
-                        P = __ffs(pending) - 1;
-                        F = __shfl_sync(0xffffffffu, m_dst, P);
+                    // byte-serial per lane: correct for self-overlapping matches (off < M) as well
+                    for (; i < M; i++) {
+                        const int32_t x = m_src + (int32_t)i;
+                        sm.stg[sd + i] = x >= stg_base ? sm.stg[x - stg_base] : __ldcg(dst + x);
                     }
                 }
+                __syncwarp();
+                pending &= ~__ballot_sync(0xffffffffu, ready);
+                if (pending) {
+                    P = __ffs(pending) - 1;
+                    F = __shfl_sync(0xffffffffu, m_dst, P);
+                }
             }
-            // ---- C: flush whole 16-byte chunks, carry the partial tail ---------------------------
-            const int32_t new_op = op + total;
-            const int nchunks = (new_op >> 4) - (stg_base >> 4);
-            {
-                uint4 *d16 = reinterpret_cast<uint4 *>(dst + stg_base);
-                const uint4 *g16 = reinterpret_cast<const uint4 *>(sm.stg);
-                for (int c = lane; c < nchunks; c += 32) d16[c] = g16[c];
-            }
-            const int tail = new_op & 15;
-            uint8_t tb = 0;
-            if (nchunks > 0 && (int)lane < tail) tb = sm.stg[nchunks * 16 + lane];
-            __syncwarp();
-            if (nchunks > 0 && (int)lane < tail) sm.stg[lane] = tb;
-            stg_base += nchunks * 16;
-            stg_dirty = tail > 0;
-            op = new_op;
-            s0 += ng;
-            __syncwarp();
         }
+        if (__any_sync(0xffffffffu, err)) return E_OFFSET;
+        __syncwarp();
+        // ---- C: flush every 16-byte chunk the batch touched (the partial last chunk too, so global memory is
+        //      always complete below op); the tail bytes stay in the staging area for the next batch ----------
+        const int32_t new_op = op + total;
+        const int nfull = (new_op >> 4) - (stg_base >> 4);
+        const int nchunks = nfull + ((new_op & 15) ? 1 : 0);
+        {
+            uint4 *d16 = reinterpret_cast<uint4 *>(dst + stg_base);
+            const uint4 *g16 = reinterpret_cast<const uint4 *>(sm.stg);
+            for (int c = lane; c < nchunks; c += 32) d16[c] = g16[c];
+        }
+        const int tail = new_op & 15;
+        uint8_t tb = 0;
+        if (nfull > 0 && (int)lane < tail) tb = sm.stg[nfull * 16 + lane];
+        __syncwarp();
+        if (nfull > 0 && (int)lane < tail) sm.stg[lane] = tb;
+        stg_base += nfull * 16;
+        op = new_op;
         ip = __shfl_sync(0xffffffffu, seq_end_in, nvalid - 1);
+        __syncwarp();
     }
     // block finished inside decode_one_sequence (which leaves everything < op in global memory)
     return (op == origin && ip == comp_len) ? E_OK : E_SIZE;
