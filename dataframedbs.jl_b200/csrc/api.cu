@@ -29,7 +29,7 @@ struct Runtime {
     bool inited = false;
     int device = 0;
     int sm_count = 148;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     unsigned int *d_counter = nullptr;
     int *d_error = nullptr;
     std::atomic<int64_t> launches{0};
@@ -66,13 +66,14 @@ int need_init()
 struct PhaseScope {
     int idx = -1;
     int64_t l0 = 0;
-    PhaseScope(int phase, int64_t bytes)
+    cudaStream_t st;
+    PhaseScope(int phase, int64_t bytes, cudaStream_t stream = nullptr) : st(stream ? stream : rt.stream)
     {
         if (!rt.profiling) return;
         PhaseRec r{phase, nullptr, nullptr, 0, bytes};
         cudaEventCreate(&r.a);
         cudaEventCreate(&r.b);
-        cudaEventRecord(r.a, rt.stream);
+        cudaEventRecord(r.a, st);
         rt.recs.push_back(r);
         idx = (int)rt.recs.size() - 1;
         l0 = rt.launches.load();
@@ -80,7 +81,7 @@ struct PhaseScope {
     ~PhaseScope()
     {
         if (idx < 0) return;
-        cudaEventRecord(rt.recs[(size_t)idx].b, rt.stream);
+        cudaEventRecord(rt.recs[(size_t)idx].b, st);
         rt.recs[(size_t)idx].launches = rt.launches.load() - l0;
     }
 };
@@ -174,29 +175,60 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids)
     }
     const int nblocks = (int)(t->blk_hi - t->blk_lo);
     if (todo.empty() || nblocks == 0) return DFDB_OK;
-    {
-        int64_t bytes = 0;
-        for (Column *c : todo) if (c->mode == DFDB_LOAD_HOST) bytes += (int64_t)c->comp_bytes;
-        if (bytes) {
-            PhaseScope ps(PH_H2D, bytes);
-            for (Column *c : todo)
-                if (c->mode == DFDB_LOAD_HOST) CUDA_TRY(cudaMemcpyAsync(c->d_comp, c->h_comp, c->comp_bytes, cudaMemcpyHostToDevice, rt.stream));
+    // Transfer-inclusive mode: the compressed blocks live in pinned host memory.  They are copied H2D in
+    // block-range chunks on a second stream while the previous chunk is being decoded on the scan stream.
+    int64_t host_bytes = 0;
+    for (Column *c : todo) if (c->mode == DFDB_LOAD_HOST) host_bytes += (int64_t)c->comp_bytes;
+    int nchunks = 1;
+    if (host_bytes > 0) {
+        nchunks = (int)std::min<int64_t>(16, std::max<int64_t>(1, host_bytes / (64ll << 20)));
+        if (nchunks > nblocks) nchunks = nblocks;
+    }
+    std::vector<cudaEvent_t> copied;
+    if (host_bytes > 0) {
+        cudaEvent_t start;
+        CUDA_TRY(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(start, rt.stream));
+        CUDA_TRY(cudaStreamWaitEvent(rt.copy_stream, start, 0));
+        cudaEventDestroy(start);
+        PhaseScope ps(PH_H2D, host_bytes, rt.copy_stream);
+        for (int k = 0; k < nchunks; k++) {
+            const int b0 = (int)((int64_t)nblocks * k / nchunks), b1 = (int)((int64_t)nblocks * (k + 1) / nchunks);
+            for (Column *c : todo) {
+                if (c->mode != DFDB_LOAD_HOST) continue;
+                const int64_t lo = c->h_comp_off[(size_t)b0];
+                const int64_t hi = b1 < nblocks ? c->h_comp_off[(size_t)b1] : (int64_t)c->comp_bytes;
+                CUDA_TRY(cudaMemcpyAsync(c->d_comp + lo, c->h_comp + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, rt.copy_stream));
+            }
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventRecord(e, rt.copy_stream));
+            copied.push_back(e);
         }
     }
-    for (size_t i = 0; i < todo.size(); i += DECODE_MAX_COLS) {
-        DecodeArgs a;
-        memset(&a, 0, sizeof a);
-        a.nblocks = nblocks;
-        int64_t bytes = 0;
-        for (size_t k = i; k < todo.size() && k < i + DECODE_MAX_COLS; k++) {
-            Column *c = todo[k];
-            DecodeCol &d = a.col[a.ncols++];
-            d.comp = c->d_comp; d.comp_off = c->d_comp_off; d.comp_len = c->d_comp_len; d.dec_off = c->d_dec_off;
-            d.origin = c->d_origin; d.out = c->d_decoded; d.status = c->d_status;
-            for (int64_t b = t->blk_lo; b < t->blk_hi; b++) bytes += c->blocks[(size_t)b].compressed + c->blocks[(size_t)b].origin;
+    for (int k = 0; k < nchunks; k++) {
+        const int b0 = (int)((int64_t)nblocks * k / nchunks), b1 = (int)((int64_t)nblocks * (k + 1) / nchunks);
+        if (!copied.empty()) {
+            CUDA_TRY(cudaStreamWaitEvent(rt.stream, copied[(size_t)k], 0));
+            cudaEventDestroy(copied[(size_t)k]);
         }
-        PhaseScope ps(PH_DECODE, bytes);
-        LAUNCH(launch_lz4_decode(a, rt.d_counter, rt.sm_count, (int)rt.lz4_simple, rt.stream));
+        if (b1 <= b0) continue;
+        for (size_t i = 0; i < todo.size(); i += DECODE_MAX_COLS) {
+            DecodeArgs a;
+            memset(&a, 0, sizeof a);
+            a.nblocks = b1 - b0;
+            a.blk0 = b0;
+            int64_t bytes = 0;
+            for (size_t q = i; q < todo.size() && q < i + DECODE_MAX_COLS; q++) {
+                Column *c = todo[q];
+                DecodeCol &d = a.col[a.ncols++];
+                d.comp = c->d_comp; d.comp_off = c->d_comp_off; d.comp_len = c->d_comp_len; d.dec_off = c->d_dec_off;
+                d.origin = c->d_origin; d.out = c->d_decoded; d.status = c->d_status;
+                for (int64_t b = t->blk_lo + b0; b < t->blk_lo + b1; b++) bytes += c->blocks[(size_t)b].compressed + c->blocks[(size_t)b].origin;
+            }
+            PhaseScope ps(PH_DECODE, bytes);
+            LAUNCH(launch_lz4_decode(a, rt.d_counter, rt.sm_count, (int)rt.lz4_simple, rt.stream));
+        }
     }
     const Geometry g = make_geometry(t);
     for (Column *c : todo)
@@ -618,6 +650,7 @@ int32_t dfdb_init(int32_t device)
     rt.sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&rt.own_stream, cudaStreamNonBlocking));
     rt.stream = rt.own_stream;
+    CUDA_TRY(cudaStreamCreateWithFlags(&rt.copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&rt.d_counter), 64));
     CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&rt.d_error), 64));
     CUDA_TRY(cudaMemset(rt.d_error, 0, 64));
@@ -633,6 +666,7 @@ int32_t dfdb_shutdown(void)
     cudaFree(rt.d_counter);
     cudaFree(rt.d_error);
     cudaStreamDestroy(rt.own_stream);
+    cudaStreamDestroy(rt.copy_stream);
     rt.inited = false;
     return DFDB_OK;
 }
@@ -793,6 +827,7 @@ int32_t dfdb_table_load(dfdb_table *t, const int64_t *col_ids, int32_t n, int32_
         c->comp_bytes = (size_t)cpos + 4096;       // slack for the decoder's aligned window over-read
         c->decoded_bytes = (size_t)dpos + 256;
         c->h_dec_off = dec_off;
+        c->h_comp_off = comp_off;
         CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&c->h_comp), c->comp_bytes));
         memset(c->h_comp + cpos, 0, 4096);
         {

@@ -63,7 +63,7 @@ struct Column {
     int32_t *d_status = nullptr;     // decode status per block
     int32_t *d_str_off = nullptr;    // String columns: per-row char offset inside the block's char area
     bool str_off_valid = false;
-    std::vector<int64_t> h_dec_off;
+    std::vector<int64_t> h_dec_off, h_comp_off;
 };
 
 }  // namespace dfdb

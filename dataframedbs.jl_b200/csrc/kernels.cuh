@@ -20,7 +20,8 @@ struct DecodeCol {
 struct DecodeArgs {
     DecodeCol col[DECODE_MAX_COLS];
     int ncols;
-    int nblocks;
+    int nblocks;   // blocks per column in this launch
+    int blk0;      // first local block of the launch (chunked, copy-overlapped decode)
 };
 int launch_lz4_decode(const DecodeArgs &args, unsigned int *d_counter, int sm_count, int simple_mode, cudaStream_t stream);
 

@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) lz4_decode_kernel(Decod
         job = __shfl_sync(0xffffffffu, job, 0);
         if (job >= njobs) break;
         const int c = (int)(job % (unsigned int)args.ncols);
-        const int b = (int)(job / (unsigned int)args.ncols);
+        const int b = args.blk0 + (int)(job / (unsigned int)args.ncols);
         const DecodeCol &col = args.col[c];
         const uint8_t *src = col.comp + col.comp_off[b];
         uint8_t *dst = col.out + col.dec_off[b];

@@ -1,0 +1,205 @@
+# DataFrameDBsB200.jl -- companion package that routes DataFrameDBs.jl's column-scan consumers to
+# libdfdb_b200.so (include/dfdb_b200.h) with `ccall`.  The reference's lazy API (open_table, DFTable,
+# DFView, DFColumn, t[pred, cols]) is untouched: this file only adds methods for the consumers that pull
+# from BlocksIterator (materialize, nrow, the aggregate reductions) and serialises the view's plan.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no julia binary (probed).  The same wire
+# format and call sequence are exercised by the Python twin (dataframedbs.jl_b200/_capi.py, api.py, plan.py),
+# which the parity tests drive.  Reference line numbers refer to waralex/DataFrameDBs.jl.
+module DataFrameDBsB200
+
+using DataFrameDBs
+using DataFrameDBs: DFTable, DFView, DFColumn, BlockBroadcasting, ColRef, SelectionQueue, Projection,
+                    FlatStringsVectors.FlatStringsVector
+import DataFrames
+
+const LIB = get(ENV, "DFDB_B200_LIB", "libdfdb_b200.so")
+
+# ---- status -> exception (same classes the reference throws) -----------------------------------------------
+last_error() = unsafe_string(ccall((:dfdb_last_error, LIB), Cstring, ()))
+function check(rc::Int32)
+    rc == 0 && return
+    msg = last_error()
+    rc == 4 && throw(ArgumentError(msg))            # selection.jl:54, selection.jl:73
+    rc == 5 && throw(ArgumentError("unsupported on the GPU path: " * msg))
+    rc == 6 && throw(KeyError(msg))                 # table.jl:54
+    rc == 7 && throw(DivideError())
+    rc == 3 && throw(AssertionError(msg))           # BlockStreams.jl:112 "decompression error"
+    error(msg)                                      # creators.jl:8-9, filesystem.jl:47-58
+end
+
+# ---- runtime / table handles ---------------------------------------------------------------------------------
+const TABLES = IdDict{DFTable,Ptr{Cvoid}}()
+const MODE = Ref{Int32}(1)                          # DFDB_LOAD_HBM
+
+function __init__()
+    check(ccall((:dfdb_init, LIB), Int32, (Int32,), parse(Int32, get(ENV, "LOCAL_RANK", "0"))))
+end
+
+function handle(t::DFTable)
+    get!(TABLES, t) do
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:dfdb_table_open, LIB), Int32, (Cstring, Ref{Ptr{Cvoid}}), t.path, h))
+        finalizer(_ -> ccall((:dfdb_table_close, LIB), Int32, (Ptr{Cvoid},), h[]), t)
+        check(ccall((:dfdb_table_load, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}, Int32, Int32), h[], C_NULL, 0, MODE[]))
+        h[]
+    end
+end
+
+# ---- plan serialisation (wire format: dataframedbs.jl_b200/plan.py) ----------------------------------------------
+const OPS = Dict{Any,UInt8}(
+    (==) => 0x10, (!=) => 0x11, (<) => 0x12, (<=) => 0x13, (>) => 0x14, (>=) => 0x15,
+    (&) => 0x20, (|) => 0x21, xor => 0x22, (!) => 0x23,
+    (+) => 0x30, (-) => 0x31, (*) => 0x32, (/) => 0x33, (%) => 0x34, rem => 0x34,
+    ismissing => 0x40, coalesce => 0x41, startswith => 0x50, endswith => 0x51)
+
+colid(t::DFTable, name::Symbol) = DataFrameDBs.getmeta(t, name).id
+
+function emit!(io::IO, t::DFTable, a)::Int
+    if a isa ColRef
+        write(io, 0x01, Int64(colid(t, a.name))); return 1
+    elseif a isa BlockBroadcasting
+        if a.f === in
+            n = emit!(io, t, a.args[1])
+            set = collect(Int64, a.args[2][])                 # Ref(collection)
+            write(io, 0x60, UInt32(length(set))); write(io, set)
+            return n + 1
+        end
+        op = get(OPS, a.f, nothing)
+        # closures of the Pair form (view.jl:64-70) are opaque: no CPU fallback, tell the user
+        op === nothing && throw(ArgumentError("function $(a.f) is not available on the GPU path"))
+        (a.f === (-) && length(a.args) == 1) && (op = 0x35)
+        n = sum(emit!(io, t, x) for x in a.args)
+        write(io, op); return n + 1
+    elseif a isa Base.RefValue{String}
+        s = a[]; write(io, 0x04, UInt32(sizeof(s))); write(io, s); return 1
+    elseif a isa Bool
+        write(io, 0x05, UInt8(a)); return 1
+    elseif a isa Integer
+        write(io, 0x02, Int64(a)); return 1
+    elseif a isa AbstractFloat
+        write(io, 0x03, Float64(a)); return 1
+    end
+    throw(ArgumentError("cannot serialise $(typeof(a))"))
+end
+
+function expr_bytes(t::DFTable, e)
+    body = IOBuffer(); n = emit!(body, t, e)
+    io = IOBuffer(); write(io, UInt32(n)); write(io, take!(body)); take!(io)
+end
+
+function plan_bytes(v::DFView)
+    io = IOBuffer()
+    write(io, 0x31504644 % UInt32, UInt32(length(v.selection.queue)))
+    for el in v.selection.queue
+        if el isa BlockBroadcasting
+            write(io, 0x03); write(io, expr_bytes(v.table, el))
+        elseif el isa AbstractRange
+            write(io, 0x01, Int64(first(el)), Int64(step(el)), Int64(last(el)))
+        elseif el isa Integer
+            write(io, 0x01, Int64(el), Int64(1), Int64(el))
+        else
+            idx = collect(Int64, el); write(io, 0x02, UInt32(length(idx))); write(io, idx)
+        end
+    end
+    write(io, UInt32(length(v.projection.cols)))
+    for c in values(v.projection.cols)
+        if c isa ColRef
+            write(io, 0x01, Int64(colid(v.table, c.name)))
+        else
+            write(io, 0x02); write(io, expr_bytes(v.table, c))
+        end
+    end
+    take!(io)
+end
+
+function with_scan(f, v::DFView)
+    plan = plan_bytes(v)
+    s = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:dfdb_scan_prepare, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int64, Ref{Ptr{Cvoid}}), handle(v.table), plan, length(plan), s))
+    try
+        f(s[])
+    finally
+        ccall((:dfdb_scan_free, LIB), Int32, (Ptr{Cvoid},), s[])
+    end
+end
+
+# ---- consumers --------------------------------------------------------------------------------------------------
+# nrow(v): view.jl:192-206
+function DataFrameDBs.nrow(v::DFView)
+    with_scan(v) do s
+        n = Ref{Int64}(0)
+        check(ccall((:dfdb_scan_count, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), s, n))
+        Int(n[])
+    end
+end
+
+struct OutCol
+    values::Ptr{Cvoid}; missing::Ptr{UInt8}; str_sizes::Ptr{Int32}; str_chars::Ptr{UInt8}
+end
+
+# materialize(v::DFView): materialization.jl:27-40 (sizes first = the reference's nrow pass, then fill)
+function DataFrameDBs.materialize(v::DFView)
+    names = keys(v.projection)
+    types = [DataFrameDBs.coltype(v.projection, i) for i in 1:length(names)]
+    with_scan(v) do s
+        n = Ref{Int64}(0); sb = zeros(Int64, length(names))
+        check(ccall((:dfdb_scan_materialize_sizes, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}, Ptr{Int64}), s, n, sb))
+        bufs = Any[]; outs = OutCol[]
+        for (i, T) in enumerate(types)
+            B = Base.nonmissingtype(T)
+            if B === String
+                sizes = Vector{Int32}(undef, n[]); chars = Base._string_n(sb[i])
+                push!(bufs, (sizes, chars)); push!(outs, OutCol(C_NULL, C_NULL, pointer(sizes), pointer(chars)))
+            else
+                vals = Vector{B}(undef, n[]); miss = T === B ? UInt8[] : Vector{UInt8}(undef, n[])
+                push!(bufs, (vals, miss)); push!(outs, OutCol(pointer(vals), T === B ? C_NULL : pointer(miss), C_NULL, C_NULL))
+            end
+        end
+        GC.@preserve bufs check(ccall((:dfdb_scan_materialize, LIB), Int32, (Ptr{Cvoid}, Ptr{OutCol}, Int32), s, outs, length(outs)))
+        cols = map(zip(types, bufs)) do (T, b)
+            B = Base.nonmissingtype(T)
+            if B === String
+                FlatStringsVector{T}(b[2]; sizes = b[1])          # FlatStringsVectors.jl:54-59: zero-copy wrap
+            elseif T === B
+                b[1]
+            else
+                r = Vector{T}(b[1]); r[b[2] .!= 0] .= missing; r
+            end
+        end
+        DataFrames.DataFrame(collect(cols), collect(names), copycols = false)
+    end
+end
+DataFrameDBs.materialize(c::DFColumn) = DataFrameDBs.materialize(c.view)[!, 1]     # materialization.jl:46-52
+
+struct Agg
+    count::Int64; nmissing::Int64; sum_i64::Int64; sum_f64::Float64; sum_f64_lo::Float64
+    min_i64::Int64; max_i64::Int64; min_f64::Float64; max_f64::Float64; has_nan::Int32; value_class::Int32
+end
+
+function aggregate(c::DFColumn)
+    with_scan(c.view) do s
+        a = Ref{Agg}()
+        check(ccall((:dfdb_scan_aggregate, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{Agg}), s, 0, a))
+        a[]
+    end
+end
+
+# Base folds over iterate(::DFColumn) (column.jl:102-126) replaced by one fused GPU pass
+Base.length(c::DFColumn) = DataFrameDBs.nrow(c.view)
+function Base.sum(c::DFColumn{T}) where {T}
+    a = aggregate(c)
+    a.nmissing > 0 && return missing
+    Base.nonmissingtype(T) <: AbstractFloat ? a.sum_f64 + a.sum_f64_lo : a.value_class == 2 ? reinterpret(UInt64, a.sum_i64) : a.sum_i64
+end
+function _extreme(c::DFColumn{T}, pick_i, pick_f) where {T}
+    a = aggregate(c)
+    a.count == 0 && throw(ArgumentError("reducing over an empty collection is not allowed"))
+    a.nmissing > 0 && return missing
+    Base.nonmissingtype(T) <: AbstractFloat ? pick_f(a) : convert(Base.nonmissingtype(T), pick_i(a))
+end
+Base.minimum(c::DFColumn) = _extreme(c, a -> a.min_i64, a -> a.min_f64)
+Base.maximum(c::DFColumn) = _extreme(c, a -> a.max_i64, a -> a.max_f64)
+Base.sum(c::DFColumn{Bool}) = DataFrameDBs.nrow(DataFrameDBs.selection(c.view, c))   # sum(ismissing.(t.x)) etc.
+
+end # module
