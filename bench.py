@@ -251,19 +251,14 @@ def main():
         t.load(["a", "b"])
         return t, v
 
-    gather_buf = torch.zeros(world * C.sizeof(_capi.Agg), dtype=torch.uint8, device="cuda") if world > 1 else None
-    mine = torch.zeros(C.sizeof(_capi.Agg), dtype=torch.uint8, device="cuda") if world > 1 else None
+    from dfdb_b200.dist import allgather_fold
 
     def step(v):
-        """one pass of the hot path over this rank's shard (+ the partial-aggregate exchange)"""
+        """one pass of the hot path over this rank's shard (+ the partial-aggregate exchange over NCCL)"""
         a = D.aggregate(v.b)
         if world == 1:
             return a
-        mine.copy_(torch.frombuffer(bytearray(bytes(a)), dtype=torch.uint8), non_blocking=False)
-        dist.all_gather_into_tensor(gather_buf, mine)
-        raw = gather_buf.cpu().numpy().tobytes()
-        parts = [_capi.Agg.from_buffer_copy(raw[i * C.sizeof(_capi.Agg):(i + 1) * C.sizeof(_capi.Agg)]) for i in range(world)]
-        return D.fold(parts)
+        return allgather_fold(a, device=torch.device("cuda", local))
 
     def timed(v, steps, warmup, profile=False):
         for _ in range(warmup):

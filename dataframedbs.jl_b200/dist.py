@@ -1,0 +1,40 @@
+"""Multi-GPU combine step (K8): one process per GPU, block-range shards, no data-path collective.
+
+Each rank produces a `dfdb_agg` partial for its shard; the 88-byte structs are all-gathered with
+torch.distributed (NCCL on GPUs, gloo in the CPU tests) and folded in rank order on every rank by
+`dfdb_agg_fold`, so every rank holds the same, deterministically combined result.  Row counts of sharded
+`nrow` / `materialize` calls combine the same way (sum / concatenation in rank order).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _capi
+
+
+def allgather_fold(agg: _capi.Agg, device=None) -> _capi.Agg:
+    """All-gather one dfdb_agg per rank and fold them in rank order.  `device`: torch device of the exchange buffers."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size()
+    n = C.sizeof(_capi.Agg)
+    mine = torch.frombuffer(bytearray(bytes(agg)), dtype=torch.uint8)
+    if device is not None:
+        mine = mine.to(device)
+    out = torch.empty(world * n, dtype=torch.uint8, device=mine.device)
+    dist.all_gather_into_tensor(out, mine)
+    raw = out.cpu().numpy().tobytes()
+    parts = (_capi.Agg * world)(*[_capi.Agg.from_buffer_copy(raw[i * n:(i + 1) * n]) for i in range(world)])
+    res = _capi.Agg()
+    _capi.check(_capi.lib().dfdb_agg_fold(parts, world, C.byref(res)))
+    return res
+
+
+def allreduce_count(n: int, device=None) -> int:
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([n], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return int(t.item())
