@@ -123,11 +123,13 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(kernel):
+def ncu_traffic(kernel, rows):
+    """dram bytes per launch from the committed `ncu --set full` capture, scaled linearly to `rows`."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(kernel)
+            t = json.load(open(p)).get(kernel)
+            return int(t["bytes"] * rows / t["rows"]) if t else None
         except Exception:
             return None
     return None
@@ -315,7 +317,7 @@ def main():
     dec_launch_ms = dec_ms / max(dec_n, 1)
     achieved = (dec_bytes / max(dec_n, 1)) / (dec_launch_ms / 1e3) / 1e9 if dec_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "lz4_decode_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic("lz4_decode_kernel"), "peak_source": peak_src, "algorithmic_bytes_per_launch": dec_bytes // max(dec_n, 1),
+                "traffic": ncu_traffic("lz4_decode_kernel", shard_rows), "peak_source": peak_src, "algorithmic_bytes_per_launch": dec_bytes // max(dec_n, 1),
                 "avg_launch_ms": dec_launch_ms, "share_of_step": dec_ms / ms if ms else None}
     scan_achieved = (con_bytes / max(args.steps, 1)) / ((con_ms / max(args.steps, 1)) / 1e3) / 1e9 if con_ms > 0 else 0.0
     hbm_result = res
