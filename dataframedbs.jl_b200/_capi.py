@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdfdb_b200.so")
+LIB_PATH = os.environ.get("DFDB_B200_LIB") or os.path.join(_HERE, "lib", "libdfdb_b200.so")   # override: diagnostics builds only
 CSRC = os.path.join(_HERE, "csrc")
 
 DFDB_OK = 0
@@ -58,6 +58,7 @@ SYMBOLS = {
     "dfdb_table_column": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.c_char_p, C.c_int32, C.c_char_p, C.c_int32,
                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "dfdb_table_column_stats": (C.c_int32, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "dfdb_table_column_stored": (C.c_int32, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dfdb_table_set_shard": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
     "dfdb_table_shard_range": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dfdb_table_load": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_int32]),

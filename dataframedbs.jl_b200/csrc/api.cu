@@ -34,10 +34,12 @@ struct Runtime {
     int *d_error = nullptr;
     std::atomic<int64_t> launches{0};
     // options
-    int64_t lz4_simple = 0;
+    int64_t lz4_simple = 0;   // one sequence at a time (baseline)
+    int64_t lz4_v1 = 0;       // first-generation warp-per-block decoder instead of the walker/consumer kernel
     int64_t no_wide = 0;
     int64_t no_fused = 0;
     int64_t no_tma = 0;
+    int64_t no_alias = 0;     // copy stored (incompressible) blocks like any other block instead of referencing them in place
     // profiling
     bool profiling = false;
     std::vector<PhaseRec> recs;
@@ -113,7 +115,8 @@ void column_release(Column &c)
 {
     if (c.h_comp) cudaFreeHost(c.h_comp);
     cudaFree(c.d_comp); cudaFree(c.d_decoded); cudaFree(c.d_comp_off); cudaFree(c.d_comp_len); cudaFree(c.d_dec_off);
-    cudaFree(c.d_origin); cudaFree(c.d_status); cudaFree(c.d_str_off);
+    cudaFree(c.d_origin); cudaFree(c.d_status); cudaFree(c.d_str_off); cudaFree(c.d_skip);
+    c.d_skip = nullptr; c.h_skip.clear(); c.stored_blocks = 0;
     c.h_comp = nullptr; c.d_comp = nullptr; c.d_decoded = nullptr; c.d_comp_off = nullptr; c.d_comp_len = nullptr;
     c.d_dec_off = nullptr; c.d_origin = nullptr; c.d_status = nullptr; c.d_str_off = nullptr;
     c.loaded = false; c.decoded_valid = false; c.str_off_valid = false;
@@ -164,6 +167,12 @@ bool wide_ok(const dfdb_table *t, const Column &c)
 }
 
 // ---- decode ---------------------------------------------------------------------------------------------
+int launch_decode(const DecodeArgs &a)
+{
+    if (rt.lz4_simple || rt.lz4_v1) return launch_lz4_decode(a, rt.d_counter, rt.sm_count, (int)rt.lz4_simple, rt.stream);
+    return launch_lz4_decode_v2(a, rt.d_counter, rt.sm_count, rt.stream);
+}
+
 int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids)
 {
     std::vector<Column *> todo;
@@ -223,11 +232,12 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids)
                 Column *c = todo[q];
                 DecodeCol &d = a.col[a.ncols++];
                 d.comp = c->d_comp; d.comp_off = c->d_comp_off; d.comp_len = c->d_comp_len; d.dec_off = c->d_dec_off;
-                d.origin = c->d_origin; d.out = c->d_decoded; d.status = c->d_status;
-                for (int64_t b = t->blk_lo + b0; b < t->blk_lo + b1; b++) bytes += c->blocks[(size_t)b].compressed + c->blocks[(size_t)b].origin;
+                d.origin = c->d_origin; d.out = c->d_decoded; d.status = c->d_status; d.skip = c->d_skip;
+                for (int64_t b = b0; b < b1; b++)
+                    if (!c->h_skip[(size_t)b]) bytes += c->blocks[(size_t)(t->blk_lo + b)].compressed + c->blocks[(size_t)(t->blk_lo + b)].origin;
             }
             PhaseScope ps(PH_DECODE, bytes);
-            LAUNCH(launch_lz4_decode(a, rt.d_counter, rt.sm_count, (int)rt.lz4_simple, rt.stream));
+            LAUNCH(launch_decode(a));
         }
     }
     const Geometry g = make_geometry(t);
@@ -694,9 +704,11 @@ int32_t dfdb_set_option(const char *name, int64_t value)
 {
     std::string n(name ? name : "");
     if (n == "lz4_simple") rt.lz4_simple = value;
+    else if (n == "lz4_v1") rt.lz4_v1 = value;
     else if (n == "no_wide") rt.no_wide = value;
     else if (n == "no_fused") rt.no_fused = value;
     else if (n == "no_tma") rt.no_tma = value;
+    else if (n == "no_alias") rt.no_alias = value;
     else return fail(DFDB_ERR_ARGUMENT, "unknown option %s", n.c_str());
     return DFDB_OK;
 }
@@ -767,6 +779,18 @@ int32_t dfdb_table_column_stats(const dfdb_table *t, int64_t col_id, int64_t *co
     return DFDB_OK;
 }
 
+int32_t dfdb_table_column_stored(const dfdb_table *t, int64_t col_id, int64_t *blocks, int64_t *bytes)
+{
+    const Column *c = const_cast<dfdb_table *>(t)->find(col_id);
+    if (!c) return fail(DFDB_ERR_KEY, "unknown column id %lld", (long long)col_id);
+    int64_t nb = 0, by = 0;
+    for (size_t b = 0; b < c->h_skip.size(); b++)
+        if (c->h_skip[b]) { nb++; by += c->blocks[(size_t)t->blk_lo + b].origin; }
+    if (blocks) *blocks = nb;
+    if (bytes) *bytes = by;
+    return DFDB_OK;
+}
+
 int32_t dfdb_table_set_shard(dfdb_table *t, int32_t rank, int32_t world)
 {
     if (world < 1 || rank < 0 || rank >= world) return fail(DFDB_ERR_ARGUMENT, "bad shard %d of %d", rank, world);
@@ -804,57 +828,88 @@ int32_t dfdb_table_load(dfdb_table *t, const int64_t *col_ids, int32_t n, int32_
     for (Column *c : cols) {
         if (c->loaded && c->mode == mode) continue;
         column_release(*c);
-        std::vector<int64_t> comp_off((size_t)nb), dec_off((size_t)nb);
+        std::vector<int64_t> comp_off((size_t)nb), dec_off((size_t)nb), lit_start((size_t)nb, 0);
         std::vector<int32_t> comp_len((size_t)nb), origin((size_t)nb);
+        std::vector<uint8_t> stored((size_t)nb, 0);
         int64_t cpos = 0, dpos = 0;
+        const std::string colfile = t->path + "/" + std::to_string(c->id) + ".bin";
+        int fd = open(colfile.c_str(), O_RDONLY);
+        if (fd < 0) return fail(DFDB_ERR_IO, "cannot open %s", colfile.c_str());
+        std::vector<uint8_t> head;
+        c->stored_blocks = 0;
         for (int64_t b = 0; b < nb; b++) {
             const BlockInfo &bi = c->blocks[(size_t)(t->blk_lo + b)];
-            if (c->type.kind == DFDB_STRING && bi.origin < 4 + 4 * (int64_t)bi.rows)
+            if (c->type.kind == DFDB_STRING && bi.origin < 4 + 4 * (int64_t)bi.rows) {
+                close(fd);
                 return fail(DFDB_ERR_CORRUPT, "column %s block %lld: string body smaller than its size table", c->name.c_str(), (long long)(t->blk_lo + b));
+            }
             if (c->type.kind != DFDB_STRING) {
                 int64_t expect = (int64_t)bi.rows * c->type.elsize + (c->type.nullable ? ((bi.rows + 63) / 64) * 8 : 0);
-                if (bi.origin != expect)
+                if (bi.origin != expect) {
+                    close(fd);
                     return fail(DFDB_ERR_CORRUPT, "column %s block %lld: body is %lld bytes, expected %lld", c->name.c_str(),
                                 (long long)(t->blk_lo + b), (long long)bi.origin, (long long)expect);
+                }
+            }
+            // A stored block -- what LZ4 emits for incompressible data -- is one literal run: token 0xF?, the length
+            // extension bytes, then the body itself.  Its body is referenced in place (no copy); the payload is
+            // placed so that the body starts on a 256-byte boundary like every decoded slot.
+            if (!rt.no_alias && bi.origin >= 15) {
+                const int64_t q = (bi.origin - 15) / 255, r = (bi.origin - 15) % 255, ls = 1 + q + 1;
+                if (bi.compressed == ls + bi.origin) {
+                    head.resize((size_t)ls);
+                    bool ok = pread(fd, head.data(), (size_t)ls, bi.file_off) == (ssize_t)ls && (head[0] >> 4) == 15 && head[(size_t)ls - 1] == (uint8_t)r;
+                    for (int64_t i = 1; ok && i <= q; i++) ok = head[(size_t)i] == 255;
+                    if (ok) { stored[(size_t)b] = 1; lit_start[(size_t)b] = ls; c->stored_blocks++; }
+                }
+            }
+            if (stored[(size_t)b]) {
+                // the payload of a stored block is never parsed on the device, so only its body needs alignment
+                const int64_t ls = lit_start[(size_t)b];
+                cpos = ((cpos + ls + 255) & ~(int64_t)255) - ls;
             }
             comp_off[(size_t)b] = cpos;
             comp_len[(size_t)b] = (int32_t)bi.compressed;
-            cpos += (bi.compressed + 15) & ~(int64_t)15;
-            dec_off[(size_t)b] = dpos;
+            cpos = (cpos + bi.compressed + 15) & ~(int64_t)15;
             origin[(size_t)b] = (int32_t)bi.origin;
-            dpos += (bi.origin + 255) & ~(int64_t)255;
+            if (!stored[(size_t)b]) {
+                dec_off[(size_t)b] = dpos;
+                dpos += (bi.origin + 255) & ~(int64_t)255;
+            }
         }
         c->comp_bytes = (size_t)cpos + 4096;       // slack for the decoder's aligned window over-read
         c->decoded_bytes = (size_t)dpos + 256;
-        c->h_dec_off = dec_off;
         c->h_comp_off = comp_off;
         CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&c->h_comp), c->comp_bytes));
         memset(c->h_comp + cpos, 0, 4096);
-        {
-            std::string p = t->path + "/" + std::to_string(c->id) + ".bin";
-            int fd = open(p.c_str(), O_RDONLY);
-            if (fd < 0) return fail(DFDB_ERR_IO, "cannot open %s", p.c_str());
-            for (int64_t b = 0; b < nb; b++) {
-                const BlockInfo &bi = c->blocks[(size_t)(t->blk_lo + b)];
-                int64_t got = 0;
-                while (got < bi.compressed) {
-                    ssize_t r = pread(fd, c->h_comp + comp_off[(size_t)b] + got, (size_t)(bi.compressed - got), bi.file_off + got);
-                    if (r <= 0) { close(fd); return fail(DFDB_ERR_IO, "short read in %s", p.c_str()); }
-                    got += r;
-                }
-                int64_t pad = ((bi.compressed + 15) & ~(int64_t)15) - bi.compressed;
-                if (pad) memset(c->h_comp + comp_off[(size_t)b] + bi.compressed, 0, (size_t)pad);
+        int64_t prev_end = 0;
+        for (int64_t b = 0; b < nb; b++) {
+            const BlockInfo &bi = c->blocks[(size_t)(t->blk_lo + b)];
+            if (comp_off[(size_t)b] > prev_end) memset(c->h_comp + prev_end, 0, (size_t)(comp_off[(size_t)b] - prev_end));   // alignment gap
+            prev_end = comp_off[(size_t)b] + bi.compressed;
+            int64_t got = 0;
+            while (got < bi.compressed) {
+                ssize_t r = pread(fd, c->h_comp + comp_off[(size_t)b] + got, (size_t)(bi.compressed - got), bi.file_off + got);
+                if (r <= 0) { close(fd); return fail(DFDB_ERR_IO, "short read in %s", colfile.c_str()); }
+                got += r;
             }
-            close(fd);
         }
+        close(fd);
+        if (cpos > prev_end) memset(c->h_comp + prev_end, 0, (size_t)(cpos - prev_end));
         CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&c->d_comp), c->comp_bytes));
         if ((rc = dev_upload(&c->d_comp_off, comp_off))) return rc;
         if ((rc = dev_upload(&c->d_comp_len, comp_len))) return rc;
-        if ((rc = dev_upload(&c->d_dec_off, dec_off))) return rc;
         if ((rc = dev_upload(&c->d_origin, origin))) return rc;
+        if ((rc = dev_upload(&c->d_skip, stored))) return rc;
+        c->h_skip = stored;
         CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&c->d_status), (size_t)std::max<int64_t>(nb, 1) * 4));
         CUDA_TRY(cudaMemset(c->d_status, 0, (size_t)std::max<int64_t>(nb, 1) * 4));
         CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&c->d_decoded), c->decoded_bytes));
+        // body offsets are relative to d_decoded; a stored block's body lives inside the compressed buffer
+        for (int64_t b = 0; b < nb; b++)
+            if (stored[(size_t)b]) dec_off[(size_t)b] = (int64_t)((c->d_comp + comp_off[(size_t)b] + lit_start[(size_t)b]) - c->d_decoded);
+        c->h_dec_off = dec_off;
+        if ((rc = dev_upload(&c->d_dec_off, dec_off))) return rc;
         if (c->type.kind == DFDB_STRING)
             CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&c->d_str_off), (size_t)std::max<int64_t>(nb, 1) * (size_t)t->block_size * 4));
         if (mode != DFDB_LOAD_HOST) {
@@ -1245,8 +1300,8 @@ int32_t dfdb_lz4_decode_blocks(const uint8_t *comp, const int64_t *comp_off, con
     memset(&a, 0, sizeof a);
     a.ncols = 1;
     a.nblocks = n;
-    a.col[0] = DecodeCol{d_comp, d_coff, d_clen, d_doff, d_orig, d_out, d_status};
-    if (launch_lz4_decode(a, rt.d_counter, rt.sm_count, (int)rt.lz4_simple, rt.stream) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "decode launch failed"); }
+    a.col[0] = DecodeCol{d_comp, d_coff, d_clen, d_doff, d_orig, d_out, d_status, nullptr};
+    if (launch_decode(a) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "decode launch failed"); }
     rt.launches++;
     std::vector<uint8_t> hout((size_t)dpos + 256);
     cudaMemcpyAsync(hout.data(), d_out, hout.size(), cudaMemcpyDeviceToHost, rt.stream);

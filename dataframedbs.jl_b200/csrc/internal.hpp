@@ -61,6 +61,9 @@ struct Column {
     int64_t *d_dec_off = nullptr;    // offset of body slot in d_decoded
     int32_t *d_origin = nullptr;
     int32_t *d_status = nullptr;     // decode status per block
+    uint8_t *d_skip = nullptr;       // 1 = stored block (one literal run): its body is referenced in place inside d_comp
+    std::vector<uint8_t> h_skip;
+    int64_t stored_blocks = 0;
     int32_t *d_str_off = nullptr;    // String columns: per-row char offset inside the block's char area
     bool str_off_valid = false;
     std::vector<int64_t> h_dec_off, h_comp_off;

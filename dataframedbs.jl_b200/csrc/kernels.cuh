@@ -16,14 +16,17 @@ struct DecodeCol {
     const int32_t *origin;
     uint8_t *out;
     int32_t *status;
+    const uint8_t *skip;        // per local block, may be null: 1 = stored block whose body is referenced in place
 };
 struct DecodeArgs {
     DecodeCol col[DECODE_MAX_COLS];
     int ncols;
     int nblocks;   // blocks per column in this launch
     int blk0;      // first local block of the launch (chunked, copy-overlapped decode)
+    unsigned long long *stats;   // optional diagnostics counters (null = off), see lz4_decode_v2.cu
 };
-int launch_lz4_decode(const DecodeArgs &args, unsigned int *d_counter, int sm_count, int simple_mode, cudaStream_t stream);
+int launch_lz4_decode(const DecodeArgs &args, unsigned int *d_counter, int sm_count, int simple_mode, cudaStream_t stream);      // v1: warp per block
+int launch_lz4_decode_v2(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream);                     // v2: walker / consumer warps
 
 // ---- scan geometry -------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 256;

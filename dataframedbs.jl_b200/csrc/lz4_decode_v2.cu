@@ -1,0 +1,802 @@
+// lz4_decode_v2.cu -- K1 (second generation): raw LZ4 block decode on sm_100a with the serial part of the
+// format split off into lane-per-block "walker" warps.
+//
+// Replaces read_block's LZ4_decompress_safe call (/root/reference/src/io/BlockStreams.jl:101-119, liblz4 via
+// CodecLz4) for whole batches of independent column blocks, with the same safety contract: never reads
+// outside the compressed payload, never writes outside `origin`, per-block status instead of the
+// reference's `@assert size == sizes.origin "decompression error"`.
+//
+// Why this shape.  The only inherently serial part of an LZ4 block is finding where each token starts
+// (token k+1 starts 3 + literal_length(k) bytes after token k).  The first-generation kernel let a whole
+// warp walk that chain (3 instructions, ~35 cycles of latency per token, 1 useful lane of 32).  Here one
+// persistent CTA per SM keeps NSLOT column blocks in flight at once:
+//   * NWALK walker warps: each LANE walks the token chain of one block through a shared-memory window of
+//     its compressed stream and emits one 8-byte ring entry per sequence {stream position, token, output
+//     position, generation tag}.  32 chains per warp advance in the latency of one, and the running
+//     output position replaces the per-batch prefix sum of the old kernel.
+//   * NCONS consumer warps, SPC block slots each: take up to 32 ring entries and materialise them
+//     lane-parallel.  "Word-regular" runs (8-byte aligned output, offset and length multiples of 8 --
+//     what LZ4 produces for Int64/Float64/Missing columns) are expanded to one output word per lane and
+//     resolved by word forwarding (far sources: one 8-byte load; in-batch sources: warp shuffles in
+//     dependency waves).  Everything else goes through byte-granular dependency waves in shared memory.
+//     Sequences with length extensions and the last sequence of a block ("special") are done one at a
+//     time by the whole warp (vectorised re-aligning memcpy for long literal runs).
+//   * Rings need no fences: an entry is valid when its generation tag matches the consumer's index
+//     (one atomic 8-byte shared store per entry); the window fill level and restart commands are
+//     published with release stores.
+//
+// Algorithmic bytes per block (roofline): compressed bytes read + origin bytes written.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+
+#include "kernels.cuh"
+#include "lz4_common.cuh"
+
+namespace dfdb {
+
+namespace {
+
+using namespace lz4;
+
+constexpr int NWALK = 2;                    // walker warps
+constexpr int NCONS = 30;                   // consumer warps
+constexpr int SPC = 2;                      // block slots per consumer warp
+constexpr int NSLOT = NCONS * SPC;          // 60 blocks in flight per SM
+constexpr int NSLOT_PAD = NWALK * 32;
+constexpr int V2_THREADS = (NWALK + NCONS) * 32;
+constexpr int W = 1024, WM = W - 1;         // compressed-stream window per slot (circular, by stream position)
+constexpr int R = 128, RM = R - 1;          // ring entries per slot
+constexpr int GEN_SHIFT = 17;               // generation tag = (index / R) & 0x7f, stored in bits 24..30
+constexpr int MAX_BURST = 8;                // batches a consumer takes from one slot before it looks at the other
+constexpr int STG = 1088;                   // staging per consumer warp: 15 carried + 32 * (14 + 18) bytes, padded
+constexpr uint32_t LIM_EXIT = 0xffffffffu;
+constexpr uint32_t POS_CAP = (1u << 24) - 512;   // stream / output positions travel in 24 bits
+constexpr int REG_MIN = 16;                 // shortest leading word-regular run worth its own batch
+static_assert(NSLOT <= NSLOT_PAD, "every slot needs a walker lane");
+static_assert(V2_THREADS <= 1024, "one CTA");
+
+enum { SLOT_EMPTY = 0, SLOT_ACTIVE = 1, SLOT_RETIRED = 2 };
+
+// diagnostics (DFDB_LZ4_STATS=1): per-launch totals
+enum { ST_W_ROUNDS = 0, ST_W_COMMITS, ST_W_RINGFULL, ST_W_WINEMPTY, ST_W_PARKED, ST_W_SLEEPS,
+       ST_C_POLLS, ST_C_SLEEPS, ST_C_PS_CALLS, ST_C_PS_FALSE, ST_C_REG, ST_C_REGSEQ, ST_C_GEN, ST_C_GENSEQ, ST_C_SPECIAL,
+       ST_C_PS_CYCLES, ST_C_LOOP_CYCLES, ST_C_REFILLS, ST_W_CYCLES, ST_C_START_CYCLES, ST_C_SLOW_CALLS, ST_C_SLOW_CYCLES,
+       ST_C_SPECIAL_CYCLES, ST_C_SLEEP_CYCLES, ST_COUNT };
+#ifdef DFDB_LZ4_STATS
+__device__ unsigned long long *g_stats;
+#define STAT_ADD(i, v) do { if (g_stats) atomicAdd(&g_stats[i], (unsigned long long)(v)); } while (0)
+#define STATS_ON (g_stats != nullptr)
+#else
+#define STAT_ADD(i, v) do { } while (0)
+#define STATS_ON false
+#endif
+
+struct SlotJob {                // consumer-private state of one block slot
+    const uint8_t *src;
+    uint8_t *dst;
+    int32_t *status;
+    uint32_t comp_len, origin;
+    uint32_t op;                // output bytes produced so far (global memory is complete below op)
+    uint32_t ip;                // stream position of the first unconsumed token
+    uint32_t tail;              // ring entries consumed
+    uint32_t whi;               // window holds stream bytes [whi - W, whi)
+    uint32_t state, err, seq;
+    uint32_t pend;              // window fill level once the refill in flight lands (0 = none in flight)
+    uint32_t rphase, pad[3];    // parity of the slot's refill mbarrier
+};
+
+struct V2Smem {
+    __align__(1024) uint8_t win[NSLOT][W];   // first, 1024-byte aligned: the walker forms addresses with one LOP3
+    uint32_t tail[NSLOT_PAD], whi[NSLOT_PAD], cmd_seq[NSLOT_PAD], cmd_p[NSLOT_PAD], cmd_o[NSLOT_PAD], cmd_lim[NSLOT_PAD];
+    unsigned long long dummy[NSLOT_PAD];     // sink for the ring stores of walker lanes that do not commit a step
+    uint32_t hint[NSLOT_PAD];                // walker -> consumer: entries emitted so far | parked << 31 (release store once per round)
+    SlotJob job[NSLOT];
+    unsigned long long rbar[NSLOT];          // mbarrier per slot: completion of the asynchronous window refill (32 arrivals)
+    uint2 ring[NSLOT][R + 1];                // +1: consecutive slots start 2 banks apart
+    __align__(16) uint8_t stg[NCONS][STG];
+};
+
+// ---- shared-memory accessors with explicit semantics (cross-warp traffic must not live in registers) ----
+__device__ __forceinline__ uint32_t ld_acq(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_addr(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_rlx(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_addr(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_rel(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_addr(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_rlx(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.relaxed.cta.shared.u32 [%0], %1;" ::"r"(smem_addr(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t sa)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(v) : "r"(sa) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t sa, uint32_t x, uint32_t y)
+{
+    asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint2 lds_v2(const uint2 *p)
+{
+    uint2 v;
+    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_addr(p)) : "memory");
+    return v;
+}
+
+// =====================================================================================================
+// walker: lane = block slot.  Emits {p | token << 24, o | gen << 24 | special << 31} per sequence.
+// =====================================================================================================
+__device__ void walker(V2Smem &S, int slot)
+{
+    constexpr int UNROLL = 4;
+    const bool has = slot < NSLOT;
+    const int sl = has ? slot : 0;
+    const uint32_t win_sa = smem_addr(S.win[sl]);     // 1024-byte aligned: window address = win_sa | (p & WM)
+    const uint32_t ring_sa = smem_addr(S.ring[sl]);
+    const uint32_t dummy_sa = smem_addr(&S.dummy[threadIdx.x & (NSLOT_PAD - 1)]);   // where non-committing lanes store
+    uint32_t p = 0, o = 0, lim = 0, head = 0, seen = 0, whi_c = 0, tail_c = 0;
+    bool running = false, finished = !has;
+    unsigned int st_rounds = 0, st_full = 0, st_empty = 0, st_parked = 0, st_sleeps = 0;
+    const long long st_t0 = clock64();
+    for (;;) {
+        // flow control and commands, once per UNROLL steps; all lanes issue the same three loads (no divergence)
+        const uint32_t whi_n = ld_acq(&S.whi[sl]), tail_n = ld_rlx(&S.tail[sl]), seq_n = ld_acq(&S.cmd_seq[sl]);
+        if (running) { whi_c = whi_n; tail_c = tail_n; }
+        if (!finished && seq_n != seen) {
+            seen = seq_n;
+            lim = ld_rlx(&S.cmd_lim[sl]);
+            if (lim == LIM_EXIT) { finished = true; running = false; }
+            else { p = ld_rlx(&S.cmd_p[sl]); o = ld_rlx(&S.cmd_o[sl]); running = true; whi_c = whi_n; tail_c = tail_n; }
+        }
+        // per round: ring space, output-position cap (POS_CAP leaves room for the UNROLL steps of one round)
+        const uint32_t room = running ? (uint32_t)R - (head - tail_c) : 0u;
+        const bool ocap = o >= POS_CAP;
+        const uint32_t head0 = head;
+        if (STATS_ON && has && !finished) {
+            st_rounds++;
+            if (!running) st_parked++;
+            else if (room == 0) st_full++;
+            else if (p >= whi_c) st_empty++;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            // Straight-line and branch-free: the token load is speculative (any window address is readable), a lane
+            // that does not commit stores its entry to a dummy word and keeps its state.  The dependent chain of a
+            // step is LDS -> SHF/IADD3 (next p) -> SEL -> LOP3 (next address); everything else fills the LDS shadow.
+            const uint32_t t = lds_u8(win_sa | (p & WM));
+            const bool commit = running & (p < whi_c) & (room > (uint32_t)u);
+            const uint32_t pn = p + 3 + (t >> 4);
+            const bool special = (t >= 0xf0u) | ((t & 15u) == 15u) | (pn > lim) | ocap;
+            const uint32_t x = __byte_perm(p, t, 0x4210);
+            const uint32_t y = o | ((head << GEN_SHIFT) & 0x7f000000u) | (special ? 0x80000000u : 0u);
+            const uint32_t ra = ring_sa + (head & RM) * 8;
+            sts_v2(commit ? ra : dummy_sa, x, y);
+            head += commit ? 1u : 0u;
+            o = commit ? o + (t >> 4) + (t & 15u) + 4 : o;
+            p = commit ? pn : p;                               // a parked lane gets a fresh position with its next command
+            running = running & !(commit & special);           // parked until the consumer posts the position behind this sequence
+        }
+        const bool any_commit = head != head0;
+        st_rel(&S.hint[sl], head | ((!running && !finished && has) ? 0x80000000u : 0u));   // entries below head are visible
+        if (__all_sync(FULL, finished)) break;
+        if (!__any_sync(FULL, any_commit)) { __nanosleep(60); st_sleeps++; }
+    }
+    if (STATS_ON && has) {
+        STAT_ADD(ST_W_ROUNDS, st_rounds); STAT_ADD(ST_W_COMMITS, head); STAT_ADD(ST_W_RINGFULL, st_full);
+        STAT_ADD(ST_W_WINEMPTY, st_empty); STAT_ADD(ST_W_PARKED, st_parked);
+        if ((threadIdx.x & 31) == 0) { STAT_ADD(ST_W_SLEEPS, st_sleeps); STAT_ADD(ST_W_CYCLES, clock64() - st_t0); }
+    }
+}
+
+// =====================================================================================================
+// consumer
+// =====================================================================================================
+
+// ---- asynchronous window refill: LDGSTS (cp.async) straight into the circular window, completion on the slot's
+//      mbarrier, fill level published to the walker when the data has landed -----------------------------------
+__device__ __forceinline__ bool refill_landed(V2Smem &S, int s, SlotJob &J, bool block)
+{
+    if (!J.pend) return false;
+    const uint32_t bar = smem_addr(&S.rbar[s]);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(J.rphase)
+            : "memory");
+        ok = __all_sync(FULL, ok != 0);
+    } while (block && !ok);
+    if (!ok) return false;
+    if (lane_id() == 0) {
+        J.whi = J.pend;
+        st_rel(&S.whi[s], J.pend);
+        J.pend = 0;
+        J.rphase ^= 1u;
+    }
+    __syncwarp();
+    return true;
+}
+
+// Start loading up to 512 more stream bytes (whole warp; at most one refill in flight per slot).  Returns bytes requested.
+__device__ __forceinline__ uint32_t refill_issue(V2Smem &S, int s, SlotJob &J, uint32_t min_n)
+{
+    const uint32_t lane = lane_id();
+    if (J.pend) return 0;
+    const uint32_t whi = J.whi;
+    const uint32_t whi_max = (J.comp_len + 16) & ~15u;          // strictly beyond the last stream byte
+    if (whi >= whi_max) return 0;
+    const uint32_t room = (J.ip & ~15u) + (uint32_t)W - whi;     // bytes below J.ip are consumed
+    uint32_t n = room < 512u ? room : 512u;
+    if (whi_max - whi < n) n = whi_max - whi;
+    if (n == 0 || (n < min_n && whi + n < whi_max)) return 0;
+    if (lane * 16 < n) {
+        const uint32_t pos = whi + lane * 16;
+        const bool in = pos < ((J.comp_len + 15) & ~15u);       // payload slots are padded to 16 bytes; beyond: zero fill
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr(&S.win[s][pos & WM])),
+                     "l"(J.src + (in ? pos : 0u)), "r"(in ? 16 : 0)
+                     : "memory");
+    }
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_addr(&S.rbar[s])) : "memory");
+    if (lane == 0) J.pend = whi + n;
+    __syncwarp();
+    return n;
+}
+
+// Synchronous flavour for the rare places that cannot proceed without the bytes.
+__device__ __forceinline__ uint32_t refill(V2Smem &S, int s, SlotJob &J, uint32_t min_n)
+{
+    refill_landed(S, s, J, true);
+    const uint32_t n = refill_issue(S, s, J, min_n);
+    if (n) refill_landed(S, s, J, true);
+    return n;
+}
+
+__device__ __forceinline__ void post_cmd(V2Smem &S, int s, SlotJob &J, uint32_t p, uint32_t o, uint32_t lim)
+{
+    if (lane_id() == 0) {
+        st_rlx(&S.cmd_p[s], p);
+        st_rlx(&S.cmd_o[s], o);
+        st_rlx(&S.cmd_lim[s], lim);
+        J.seq += 1;
+        st_rel(&S.cmd_seq[s], J.seq);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void finish_block(SlotJob &J, int e)
+{
+    if (lane_id() == 0) { *J.status = e; J.state = SLOT_EMPTY; }
+    __syncwarp();
+}
+
+// Generic batches assemble their output in the warp's staging area; flush every 16-byte chunk of
+// [stg_base, new_op) -- the partial last chunk too, so that global memory is always complete below op.
+__device__ __forceinline__ void flush(const SlotJob &J, const uint8_t *stg, uint32_t stg_base, uint32_t new_op)
+{
+    const uint32_t lane = lane_id();
+    const int nchunks = (int)((new_op + 15u) >> 4) - (int)(stg_base >> 4);
+    uint4 *d16 = reinterpret_cast<uint4 *>(J.dst + stg_base);
+    const uint4 *g16 = reinterpret_cast<const uint4 *>(stg);
+    for (int c = lane; c < nchunks; c += 32) d16[c] = g16[c];
+    __syncwarp();
+}
+
+// ---- word-regular batch: lanes [0, nreg) hold sequences with o % 8 == 0, off % 8 == 0, (L + M) % 8 == 0, L <= 2.
+//      One output word per lane, written straight to global memory (a coalesced 256-byte store per batch). ----
+__device__ __forceinline__ int regular_batch(const SlotJob &J, uint32_t o0, uint32_t o, uint32_t len, uint32_t L, uint32_t offv,
+                                             uint32_t lit, int nreg, uint32_t *new_op)
+{
+    const uint32_t lane = lane_id();
+    const uint32_t fw = (o - o0) >> 3;                        // first output word of my sequence
+    const uint32_t tw = __shfl_sync(FULL, fw + (len >> 3), nreg - 1);   // words in the batch (<= 32)
+    if (o0 + 8 * tw > J.origin) return E_OVERFLOW;
+    const bool wl = lane < tw;                                // from here on: lane = output word
+    uint32_t offw = offv, Lw = L, litw = lit;
+    if ((int)tw != nreg) {                                    // some sequence spans two words: expand sequences to words
+        const uint32_t startmask = __reduce_or_sync(FULL, (int)lane < nreg ? (1u << fw) : 0u);
+        int sq = __popc(startmask & (0xffffffffu >> (31 - lane))) - 1;
+        if (!wl) sq = 0;
+        const uint32_t pk = __shfl_sync(FULL, offv | (L << 16) | (fw << 24), sq);
+        const uint32_t lit_s = __shfl_sync(FULL, lit, sq);
+        const bool k0 = lane == (pk >> 24);                   // first word of its sequence carries the literals
+        offw = pk & 0xffffu;
+        Lw = k0 ? ((pk >> 16) & 0xffu) : 0u;
+        litw = k0 ? lit_s : 0u;
+    }
+    const uint32_t keep = 0xffffffffu << (8 * Lw);            // Lw <= 2
+    const int dep = (int)lane - (int)(offw >> 3);             // producer word inside the batch, or < 0: already in memory
+    const uint32_t ow = o0 + 8 * lane;
+    bool fin = !wl;
+    uint32_t vlo = 0, vhi = 0;
+    if (wl && dep < 0) {
+        const uint2 far = __ldcg(reinterpret_cast<const uint2 *>(J.dst + (ow - offw)));
+        vlo = litw | (far.x & keep);
+        vhi = far.y;
+        fin = true;
+    }
+    // in-batch sources: dependency waves over warp shuffles (the lowest unresolved word always has a resolved producer)
+    while (__any_sync(FULL, !fin)) {
+        const uint32_t finmask = __ballot_sync(FULL, fin);
+        const int j = fin ? (int)lane : dep;
+        const uint32_t a = __shfl_sync(FULL, vlo, j), b = __shfl_sync(FULL, vhi, j);
+        if (!fin && ((finmask >> j) & 1u)) { vlo = litw | (a & keep); vhi = b; fin = true; }
+    }
+    if (wl) *reinterpret_cast<uint2 *>(J.dst + ow) = make_uint2(vlo, vhi);
+    __syncwarp();
+    *new_op = o0 + 8 * tw;
+    return E_OK;
+}
+
+// ---- generic batch: lanes [0, g) hold simple sequences of any alignment; byte-granular dependency waves ----
+__device__ __forceinline__ int generic_batch(const uint8_t *win, uint8_t *stg, const SlotJob &J, uint32_t o0, uint32_t p, uint32_t o,
+                                             uint32_t L, uint32_t M, int g, uint32_t *new_op)
+{
+    const uint32_t lane = lane_id();
+    const bool active = (int)lane < g;
+    const int32_t stg_base = (int32_t)(o0 & ~15u);
+    const uint32_t off = active ? ((uint32_t)win[(p + 1 + L) & WM] | ((uint32_t)win[(p + 2 + L) & WM] << 8)) : 1u;
+    const uint32_t end = __shfl_sync(FULL, o + L + M, g - 1);
+    if (end > J.origin) return E_OVERFLOW;
+    const int32_t m_dst = (int32_t)(o + L), m_src = m_dst - (int32_t)off;
+    const bool bad = active && (off == 0 || m_src < 0);
+    if (__any_sync(FULL, bad)) return E_OFFSET;
+    if (active)
+        for (uint32_t i = 0; i < L; i++) stg[(int32_t)o - stg_base + (int32_t)i] = win[(p + 1 + i) & WM];
+    __syncwarp();
+    // Frontier F: every output byte < F is final.  A lane runs when all its source bytes are below F, or when it
+    // is the first pending lane (then every earlier sequence is complete).
+    const int32_t src_end = (m_src + (int32_t)M < m_dst) ? m_src + (int32_t)M : m_dst;
+    uint32_t pending = g >= 32 ? FULL : ((1u << g) - 1u);
+    int P = 0;
+    int32_t F = __shfl_sync(FULL, m_dst, 0);
+    while (pending) {
+        const bool mine = (pending >> lane) & 1u;
+        const bool ready = mine && (src_end <= F || (int)lane == P);
+        if (ready) {
+            const int32_t sd = m_dst - stg_base;
+            uint32_t i = 0;
+            if (off >= 8 && ((m_dst | m_src) & 7) == 0) {
+                for (; i + 8 <= M; i += 8) {
+                    unsigned long long v;
+                    const int32_t x = m_src + (int32_t)i;
+                    if (x >= stg_base) v = *reinterpret_cast<const unsigned long long *>(stg + (x - stg_base));
+                    else v = __ldcg(reinterpret_cast<const unsigned long long *>(J.dst + x));
+                    *reinterpret_cast<unsigned long long *>(stg + sd + i) = v;
+                }
+            }
+            // byte-serial per lane: correct for self-overlapping matches (off < M) as well
+            for (; i < M; i++) {
+                const int32_t x = m_src + (int32_t)i;
+                stg[sd + i] = x >= stg_base ? stg[x - stg_base] : __ldcg(J.dst + x);
+            }
+        }
+        __syncwarp();
+        pending &= ~__ballot_sync(FULL, ready);
+        if (pending) {
+            P = __ffs(pending) - 1;
+            F = __shfl_sync(FULL, m_dst, P);
+        }
+    }
+    *new_op = end;
+    return E_OK;
+}
+
+// A special entry (length extensions / last sequence / capped positions) heads the ring: the whole warp does that
+// one sequence against global memory, then restarts the walker lane behind it (or finishes the block).
+__device__ __noinline__ void special_step(V2Smem &S, int s, SlotJob &J, uint32_t p0)
+{
+    const uint32_t lane = lane_id();
+    int64_t ip = p0, op = J.op;
+    bool done = false;
+    int e = J.err ? (int)J.err : decode_one_sequence(J.src, J.comp_len, J.dst, J.origin, ip, op, done);
+    if (lane == 0) { J.tail += 1; st_rlx(&S.tail[s], J.tail); }
+    __syncwarp();
+    if (e) { finish_block(J, e); return; }
+    if (done) { finish_block(J, (op == (int64_t)J.origin && ip == (int64_t)J.comp_len) ? E_OK : E_SIZE); return; }
+    if (ip >= (int64_t)POS_CAP || op >= (int64_t)POS_CAP) {
+        // positions no longer fit the ring entries: finish this block one sequence at a time
+        while (!done) {
+            e = decode_one_sequence(J.src, J.comp_len, J.dst, J.origin, ip, op, done);
+            if (e) { finish_block(J, e); return; }
+        }
+        finish_block(J, (op == (int64_t)J.origin && ip == (int64_t)J.comp_len) ? E_OK : E_SIZE);
+        return;
+    }
+    refill_landed(S, s, J, true);
+    const uint32_t nop = (uint32_t)op;
+    if (lane == 0) {
+        J.op = nop;
+        J.ip = (uint32_t)ip;
+        if ((uint32_t)ip >= J.whi) { J.whi = (uint32_t)ip & ~15u; st_rlx(&S.whi[s], J.whi); }   // walker is parked: no race
+    }
+    __syncwarp();
+    while (refill(S, s, J, 16)) { }
+    post_cmd(S, s, J, (uint32_t)ip, nop, J.comp_len);
+}
+
+// Claim job `job` for slot s.  Trivial and oversized blocks are finished on the spot.
+__device__ __noinline__ void start_job(V2Smem &S, int s, SlotJob &J, const DecodeArgs &args, unsigned int job)
+{
+    const uint32_t lane = lane_id();
+    refill_landed(S, s, J, true);                              // a refill of the previous block may still be landing
+    const int c = (int)(job % (unsigned int)args.ncols);
+    const int b = args.blk0 + (int)(job / (unsigned int)args.ncols);
+    const DecodeCol &col = args.col[c];
+    if (col.skip && col.skip[b]) return;                       // body is referenced in place (stored block)
+    const uint8_t *src = col.comp + col.comp_off[b];
+    uint8_t *dst = col.out + col.dec_off[b];
+    const int64_t comp_len = col.comp_len[b], origin = col.origin[b];
+    if (comp_len <= 0) {
+        if (lane == 0) col.status[b] = E_TRUNCATED;
+        return;
+    }
+    if (comp_len >= (int64_t)POS_CAP || origin >= (int64_t)POS_CAP) {
+        const int e = decode_simple(src, comp_len, dst, origin);
+        if (lane == 0) col.status[b] = e;
+        return;
+    }
+    if (lane == 0) {
+        J.src = src; J.dst = dst; J.status = &col.status[b];
+        J.comp_len = (uint32_t)comp_len; J.origin = (uint32_t)origin;
+        J.op = 0; J.ip = 0; J.whi = 0; J.err = 0; J.pend = 0;
+        J.state = SLOT_ACTIVE;
+        st_rlx(&S.whi[s], 0u);
+    }
+    __syncwarp();
+    while (refill(S, s, J, 16)) { }
+    post_cmd(S, s, J, 0u, 0u, (uint32_t)comp_len);
+}
+
+// One batch of an active slot whose ring looks ready.  Returns true when it made progress.
+__device__ __noinline__ bool process_slot(V2Smem &S, int s, SlotJob &J, uint8_t *stg)
+{
+    const uint32_t lane = lane_id();
+    const uint32_t idx = J.tail + lane;
+    const uint2 e = lds_v2(&S.ring[s][idx & RM]);
+    const bool valid = ((e.y ^ (idx << GEN_SHIFT)) & 0x7f000000u) == 0;       // generation tag matches my index
+    const uint32_t vm = __ballot_sync(FULL, valid);
+    const int navail = (vm == FULL) ? 32 : (__ffs(~vm) - 1);
+    const uint32_t sm = __ballot_sync(FULL, (int)e.y < 0) & (navail >= 32 ? FULL : ((1u << navail) - 1u));
+    const int nv = sm ? (__ffs(sm) - 1) : navail;              // leading non-special entries
+    const uint32_t p = e.x & 0xffffffu, tok = e.x >> 24, o = e.y & 0xffffffu;
+    if (nv == 0) {
+        if (sm & 1u) {
+            const long long t0 = STATS_ON ? clock64() : 0;
+            special_step(S, s, J, __shfl_sync(FULL, p, 0));
+            if (STATS_ON && lane == 0) { STAT_ADD(ST_C_SPECIAL, 1); STAT_ADD(ST_C_SPECIAL_CYCLES, clock64() - t0); }
+            return true;
+        }
+        return false;
+    }
+    const uint32_t L = tok >> 4, M = (tok & 15u) + 4, len = L + M;
+    if (J.err) {   // a corrupt block drains its ring up to the closing special entry (the window keeps moving)
+        const uint32_t nip = __shfl_sync(FULL, p + 3 + L, nv - 1);
+        if (lane == 0) { J.ip = nip; J.tail += (uint32_t)nv; st_rlx(&S.tail[s], J.tail); }
+        __syncwarp();
+        refill_issue(S, s, J, 16);
+        return true;
+    }
+    if (nv < 32 && !((sm >> nv) & 1u)) return false;           // wait for a full batch unless the run ends in a special entry
+    const uint32_t o0 = __shfl_sync(FULL, o, 0);
+    int err = E_OK;
+    if (o0 != J.op) err = E_INTERNAL;
+    // the stream bytes of the whole batch must be in the window
+    const uint32_t need = __shfl_sync(FULL, p + 3 + L, nv - 1);
+    while (!err && J.whi < need)
+        if (!refill(S, s, J, 16)) err = E_INTERNAL;
+    int nproc = 0;
+    uint32_t new_op = o0;
+    if (!err) {
+        const uint8_t *win = S.win[s];
+        // 4 stream bytes behind the token: up to 2 literals and the offset of a word-regular sequence
+        const uint32_t a = p + 1, a4 = a & ~3u;
+        const uint32_t *w32 = reinterpret_cast<const uint32_t *>(win);
+        const uint32_t lo = __funnelshift_r(w32[(a4 & WM) >> 2], w32[((a4 + 4) & WM) >> 2], (a & 3u) * 8);
+        const uint32_t offv = (lo >> (8 * (L & 3u))) & 0xffffu;
+        const uint32_t lit = lo & ~(0xffffffffu << (8 * (L & 3u)));
+        const bool wr = (int)lane < nv && L <= 2 && ((len | offv | o) & 7u) == 0 && (offv - 1u) < o;
+        const uint32_t rm = __ballot_sync(FULL, wr && ((o - o0) >> 3) + (len >> 3) <= 32u);
+        const int nreg = rm == FULL ? 32 : (__ffs(~rm) - 1);
+        if (nreg >= REG_MIN || (nreg == nv)) {
+            nproc = nreg;
+            err = regular_batch(J, o0, o, len, L, offv, lit, nreg, &new_op);
+        } else {
+            // up to where a long word-regular run starts (those lanes are better served by the regular path)
+            const uint32_t rall = __ballot_sync(FULL, wr);
+            const uint32_t run = rall & (rall >> 1) & (rall >> 2) & (rall >> 3);
+            const uint32_t run16 = run & (run >> 4) & (run >> 8) & (run >> 12);      // bit i: lanes i..i+15 all regular
+            const uint32_t cand = run16 & ~1u & (nv >= 32 ? FULL : ((1u << nv) - 1u));
+            nproc = cand ? (__ffs(cand) - 1) : nv;
+            if (STATS_ON && lane == 0) { STAT_ADD(ST_C_GEN, 1); STAT_ADD(ST_C_GENSEQ, nproc); }
+            // the staging area starts at the 16-byte chunk that holds o0; its bytes below o0 come back from memory
+            if (lane == 0 && (o0 & 15u)) *reinterpret_cast<uint4 *>(stg) = __ldcg(reinterpret_cast<const uint4 *>(J.dst + (o0 & ~15u)));
+            __syncwarp();
+            err = generic_batch(win, stg, J, o0, p, o, L, M, nproc, &new_op);
+            if (!err) flush(J, stg, o0 & ~15u, new_op);
+        }
+    }
+    if (err) {
+        const uint32_t nip = __shfl_sync(FULL, p + 3 + L, nv - 1);
+        if (lane == 0) { J.err = (uint32_t)err; J.ip = nip; J.tail += (uint32_t)nv; st_rlx(&S.tail[s], J.tail); }
+        __syncwarp();
+        return true;
+    }
+    const uint32_t next_ip = __shfl_sync(FULL, p + 3 + L, nproc - 1);
+    if (lane == 0) { J.op = new_op; J.ip = next_ip; J.tail += (uint32_t)nproc; st_rlx(&S.tail[s], J.tail); }
+    __syncwarp();
+    refill_issue(S, s, J, 256);
+    return true;
+}
+
+// Cheap readiness poll of one slot (the ring entries themselves are only read once a batch looks complete).
+// ---- the hot path: a burst of full word-regular batches from one slot, slot state in registers -------------------
+// Anything else (partial batches, special entries, sequences that are not word-regular, window shortfalls, errors)
+// is handed to process_slot, which works on the slot state in shared memory.
+__device__ __noinline__ int burst(V2Smem &S, int s, SlotJob &J)
+{
+    const uint32_t lane = lane_id();
+    uint32_t tail = J.tail, op = J.op, ip = J.ip, whi = J.whi, pend = J.pend;
+    uint8_t *const dst = J.dst;
+    const uint32_t origin = J.origin;
+    const uint32_t whi_max = (J.comp_len + 16) & ~15u;
+    const uint2 *ring = S.ring[s];
+    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(S.win[s]);
+    bool progress = false, want_slow = false;
+    unsigned st_batches = 0, st_seqs = 0;
+    for (int it = 0; it < MAX_BURST; it++) {
+        if (pend) {                                           // a refill in flight: publish it once it has landed
+            if (refill_landed(S, s, J, false)) { whi = J.whi; pend = 0; progress = true; }
+        }
+        if (!pend && whi < whi_max && (ip & ~15u) + (uint32_t)W - whi >= 256u) {
+            if (lane == 0) { J.ip = ip; }
+            __syncwarp();
+            refill_issue(S, s, J, 256);
+            pend = J.pend;
+        }
+        const uint32_t h = ld_acq(&S.hint[s]);
+        const uint32_t avail = (h & 0x7fffffffu) - tail;
+        const bool parked = (h >> 31) != 0;
+        if (avail == 0) break;
+        bool slow = avail < 32u || (avail == 32u && parked);  // the last entry of a parked walker is special
+        if (slow && !parked) break;                           // partial batch: wait for the walker
+        uint32_t p = 0, L = 0, o = 0, len = 0, offv = 0, lit = 0;
+        int nreg = 0;
+        if (!slow) {
+            const uint2 e = lds_v2(&ring[(tail + lane) & RM]);
+            p = e.x & 0xffffffu;
+            o = e.y & 0xffffffu;
+            L = e.x >> 28;
+            len = L + ((e.x >> 24) & 15u) + 4;
+            const uint32_t need = __shfl_sync(FULL, p + 3 + L, 31);
+            // 4 stream bytes behind the token: up to 2 literals and the offset of a word-regular sequence
+            const uint32_t a = p + 1, a4 = a & ~3u;
+            const uint32_t lo = __funnelshift_r(w32[(a4 & WM) >> 2], w32[((a4 + 4) & WM) >> 2], (a & 3u) * 8);
+            offv = (lo >> (8 * (L & 3u))) & 0xffffu;
+            lit = lo & ~(0xffffffffu << (8 * (L & 3u)));
+            const bool wr = L <= 2 && ((len | offv | o) & 7u) == 0 && (offv - 1u) < o;
+            const uint32_t rm = __ballot_sync(FULL, wr && ((o - op) >> 3) + (len >> 3) <= 32u);
+            nreg = rm == FULL ? 32 : (__ffs(~rm) - 1);
+            slow = need > whi || nreg < REG_MIN || __shfl_sync(FULL, o, 0) != op;
+        }
+        if (slow) { want_slow = true; break; }
+        // ---- word-regular batch, one output word per lane, stored straight to global memory ----
+        const uint32_t fw = (o - op) >> 3;                        // first output word of my sequence
+        const uint32_t tw = __shfl_sync(FULL, fw + (len >> 3), nreg - 1);   // words in the batch (<= 32)
+        if (op + 8 * tw > origin) { want_slow = true; break; }    // overflow: the slow path records the error
+        const bool wl = lane < tw;                                // from here on: lane = output word
+        uint32_t offw = offv, Lw = L, litw = lit;
+        if ((int)tw != nreg) {                                    // some sequence spans two words: expand sequences to words
+            const uint32_t startmask = __reduce_or_sync(FULL, (int)lane < nreg ? (1u << fw) : 0u);
+            int sq = __popc(startmask & (0xffffffffu >> (31 - lane))) - 1;
+            if (!wl) sq = 0;
+            const uint32_t pk = __shfl_sync(FULL, offv | (L << 16) | (fw << 24), sq);
+            const uint32_t lit_s = __shfl_sync(FULL, lit, sq);
+            const bool k0 = lane == (pk >> 24);                   // first word of its sequence carries the literals
+            offw = pk & 0xffffu;
+            Lw = k0 ? ((pk >> 16) & 0xffu) : 0u;
+            litw = k0 ? lit_s : 0u;
+        }
+        const uint32_t keep = 0xffffffffu << (8 * Lw);            // Lw <= 2
+        const int dep = (int)lane - (int)(offw >> 3);             // producer word inside the batch, or < 0: already in memory
+        const uint32_t ow = op + 8 * lane;
+        bool fin = !wl;
+        uint32_t vlo = 0, vhi = 0;
+        if (wl && dep < 0) {
+            const uint2 far = __ldcg(reinterpret_cast<const uint2 *>(dst + (ow - offw)));
+            vlo = litw | (far.x & keep);
+            vhi = far.y;
+            fin = true;
+        }
+        // in-batch sources: dependency waves over warp shuffles (the lowest unresolved word always has a resolved producer)
+        while (__any_sync(FULL, !fin)) {
+            const uint32_t finmask = __ballot_sync(FULL, fin);
+            const int j = fin ? (int)lane : dep;
+            const uint32_t va = __shfl_sync(FULL, vlo, j), vb = __shfl_sync(FULL, vhi, j);
+            if (!fin && ((finmask >> j) & 1u)) { vlo = litw | (va & keep); vhi = vb; fin = true; }
+        }
+        if (wl) *reinterpret_cast<uint2 *>(dst + ow) = make_uint2(vlo, vhi);
+        ip = __shfl_sync(FULL, p + 3 + L, nreg - 1);
+        op += 8 * tw;
+        tail += (uint32_t)nreg;
+        if (lane == 0) st_rlx(&S.tail[s], tail);
+        __syncwarp();
+        progress = true;
+        st_batches++;
+        st_seqs += (unsigned)nreg;
+    }
+    if (STATS_ON && lane == 0) { STAT_ADD(ST_C_REG, st_batches); STAT_ADD(ST_C_REGSEQ, st_seqs); }
+    if (lane == 0) { J.tail = tail; J.op = op; J.ip = ip; }
+    __syncwarp();
+    return (progress ? 1 : 0) | (want_slow ? 2 : 0);
+}
+
+// One visit of a consumer warp to one of its slots.
+__device__ __forceinline__ bool slot_step(V2Smem &S, int s, uint8_t *stg, const DecodeArgs &args, unsigned int *counter,
+                                          unsigned int first_dynamic, unsigned int static_job, uint32_t &first, int k, int &live)
+{
+    const uint32_t lane = lane_id();
+    SlotJob &J = S.job[s];
+    const uint32_t st = J.state;
+    if (st == SLOT_RETIRED) return false;
+    if (st == SLOT_EMPTY) {
+        const unsigned int njobs = (unsigned int)args.ncols * (unsigned int)args.nblocks;
+        unsigned int job;
+        if ((first >> k) & 1u) {
+            first &= ~(1u << k);
+            job = static_job;
+        } else {
+            job = 0;
+            if (lane == 0) job = first_dynamic + atomicAdd(counter, 1u);
+            job = __shfl_sync(FULL, job, 0);
+        }
+        if (job >= njobs) {
+            if (lane == 0) J.state = SLOT_RETIRED;
+            __syncwarp();
+            post_cmd(S, s, J, 0u, 0u, LIM_EXIT);
+            live--;
+        } else {
+            const long long t0 = STATS_ON ? clock64() : 0;
+            start_job(S, s, J, args, job);
+            if (STATS_ON && lane == 0) STAT_ADD(ST_C_START_CYCLES, clock64() - t0);
+        }
+        return true;
+    }
+    const uint32_t h = ld_rlx(&S.hint[s]);
+    const uint32_t avail = (h & 0x7fffffffu) - J.tail;
+    if (avail >= 32u || ((h >> 31) && avail >= 1u) || J.pend) {
+        const long long t0 = STATS_ON ? clock64() : 0;
+        int code = burst(S, s, J);
+        bool r = (code & 1) != 0;
+        const long long t1 = STATS_ON ? clock64() : 0;
+        if (code & 2) r |= process_slot(S, s, J, stg);
+        if (STATS_ON && lane == 0 && (code & 2)) { STAT_ADD(ST_C_SLOW_CALLS, 1); STAT_ADD(ST_C_SLOW_CYCLES, clock64() - t1); }
+        if (STATS_ON && lane == 0) { STAT_ADD(ST_C_PS_CALLS, 1); STAT_ADD(ST_C_PS_CYCLES, clock64() - t0); if (!r) STAT_ADD(ST_C_PS_FALSE, 1); }
+        return r;
+    }
+    return false;
+}
+
+__device__ void consumer(V2Smem &S, const DecodeArgs &args, unsigned int *counter, unsigned int first_dynamic, int c)
+{
+    const uint32_t lane = lane_id();
+    uint8_t *stg = S.stg[c];
+    int live = SPC;
+    uint32_t first = (1u << SPC) - 1u;       // slots whose first job is the statically assigned one
+    long long last_progress = clock64();
+    const long long st_t0 = last_progress;
+    unsigned int st_polls = 0, st_sleeps = 0;
+    long long st_sleep_cycles = 0;
+    while (live > 0) {
+        bool progress = false;
+        st_polls++;
+        // first pass of jobs: spread over CTAs, then warps, then slot levels
+#pragma unroll 1
+        for (int k = 0; k < SPC; k++)
+            progress |= slot_step(S, c + k * NCONS, stg, args, counter, first_dynamic,
+                                  ((unsigned int)k * NCONS + (unsigned int)c) * gridDim.x + blockIdx.x, first, k, live);
+        if (progress) last_progress = clock64();
+        else {
+            const long long ts0 = STATS_ON ? clock64() : 0;
+            __nanosleep(200);
+            st_sleeps++;
+            if (STATS_ON) st_sleep_cycles += clock64() - ts0;
+            if (clock64() - last_progress > 4000000000ll) {
+                // watchdog (~2 s without progress): give up on the active slots instead of hanging the device
+                for (int k = 0; k < SPC; k++) {
+                    const int s = c + k * NCONS;
+                    SlotJob &J = S.job[s];
+                    if (J.state == SLOT_RETIRED) continue;
+                    if (J.state == SLOT_ACTIVE && lane == 0) *J.status = E_INTERNAL;
+                    if (lane == 0) J.state = SLOT_RETIRED;
+                    __syncwarp();
+                    post_cmd(S, s, J, 0u, 0u, LIM_EXIT);
+                }
+                live = 0;
+            }
+        }
+    }
+    if (STATS_ON && lane == 0) { STAT_ADD(ST_C_POLLS, st_polls); STAT_ADD(ST_C_SLEEPS, st_sleeps); STAT_ADD(ST_C_LOOP_CYCLES, clock64() - st_t0); STAT_ADD(ST_C_SLEEP_CYCLES, st_sleep_cycles); }
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(V2_THREADS, 1) lz4_decode_v2_kernel(const __grid_constant__ DecodeArgs args, unsigned int *counter,
+                                                                           unsigned int first_dynamic)
+{
+    extern __shared__ __align__(16) uint8_t v2_smem_raw[];
+    V2Smem &S = *reinterpret_cast<V2Smem *>(v2_smem_raw + ((1024u - (smem_addr(v2_smem_raw) & 1023u)) & 1023u));
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < NSLOT_PAD; i += blockDim.x) {
+        S.tail[i] = 0; S.whi[i] = 0; S.cmd_seq[i] = 0; S.cmd_p[i] = 0; S.cmd_o[i] = 0; S.cmd_lim[i] = 0; S.hint[i] = 0;
+    }
+    for (int i = threadIdx.x; i < NSLOT; i += blockDim.x) {
+        SlotJob &J = S.job[i];
+        J.src = nullptr; J.dst = nullptr; J.status = nullptr;
+        J.comp_len = 0; J.origin = 0; J.op = 0; J.ip = 0; J.tail = 0; J.whi = 0; J.state = SLOT_EMPTY; J.err = 0; J.seq = 0; J.pend = 0; J.rphase = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" ::"r"(smem_addr(&S.rbar[i])) : "memory");
+    }
+    // ring entries start with a generation tag no index in the first 127 laps can match
+    for (int i = threadIdx.x; i < NSLOT * (R + 1); i += blockDim.x) (&S.ring[0][0])[i] = make_uint2(0u, 0x7f000000u);
+    __syncthreads();
+    if (warp < NWALK) walker(S, warp * 32 + (int)(threadIdx.x & 31));
+    else consumer(S, args, counter, first_dynamic, warp - NWALK);
+}
+
+int launch_lz4_decode_v2(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream)
+{
+    static bool configured = false;
+    static unsigned long long *d_stats = nullptr;
+#ifdef DFDB_LZ4_STATS
+    static const bool want_stats = getenv("DFDB_LZ4_STATS") != nullptr;
+    if (want_stats && !d_stats) {
+        cudaMalloc(&d_stats, ST_COUNT * 8);
+        cudaMemcpyToSymbol(g_stats, &d_stats, sizeof d_stats);
+    }
+#endif
+    if (d_stats) cudaMemsetAsync(d_stats, 0, ST_COUNT * 8, stream);
+    if (!configured) {
+        if (cudaFuncSetAttribute(lz4_decode_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(V2Smem) + 1024)) != cudaSuccess) return 1;
+        configured = true;
+    }
+    const long long njobs = (long long)args.ncols * args.nblocks;
+    if (njobs <= 0) return 0;
+    // one persistent CTA per SM; with few jobs, one job per consumer warp before any warp takes a second
+    long long ctas = (njobs + NCONS - 1) / NCONS;
+    if (ctas > sm_count) ctas = sm_count;
+    if (ctas < 1) ctas = 1;
+    // dynamic job ids start after the statically assigned first pass
+    const unsigned int first_dynamic = (unsigned int)(ctas * NCONS * SPC);
+    cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream);
+    lz4_decode_v2_kernel<<<(unsigned int)ctas, V2_THREADS, sizeof(V2Smem) + 1024, stream>>>(args, d_counter, first_dynamic);
+    if (d_stats) {
+        unsigned long long h[ST_COUNT];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, d_stats, sizeof h, cudaMemcpyDeviceToHost);
+        static const char *names[ST_COUNT] = {"w_rounds", "w_commits", "w_ringfull", "w_winempty", "w_parked", "w_sleeps", "c_polls", "c_sleeps",
+                                              "c_ps_calls", "c_ps_false", "c_reg", "c_regseq", "c_gen", "c_genseq", "c_special", "c_ps_cycles",
+                                              "c_loop_cycles", "c_refills", "w_cycles", "c_start_cycles", "c_slow_calls", "c_slow_cycles",
+                                              "c_special_cycles", "c_sleep_cycles"};
+        fprintf(stderr, "[lz4 v2 stats] jobs=%lld ctas=%lld", njobs, ctas);
+        for (int i = 0; i < ST_COUNT; i++) fprintf(stderr, " %s=%llu", names[i], h[i]);
+        fprintf(stderr, "\n");
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace dfdb

@@ -105,6 +105,10 @@ DFDB_API int64_t dfdb_table_nblocks(const dfdb_table *t);
 DFDB_API int32_t dfdb_table_column(const dfdb_table *t, int32_t index, int64_t *id, char *name, int32_t name_cap,
                                    char *typestring, int32_t ts_cap, int32_t *kind, int32_t *nullable, int32_t *elsize);
 DFDB_API int32_t dfdb_table_column_stats(const dfdb_table *t, int64_t col_id, int64_t *compressed, int64_t *uncompressed);
+/* loaded column: how many of the shard's blocks are stored (incompressible: one LZ4 literal run, what
+ * LZ4_compress_fast emits when nothing matches, src/io/BlockStreams.jl:42-48) and are therefore referenced in
+ * place inside the compressed buffer instead of being copied by the decoder; bytes = their body bytes */
+DFDB_API int32_t dfdb_table_column_stored(const dfdb_table *t, int64_t col_id, int64_t *blocks, int64_t *bytes);
 /* block-range shard of this process: blocks [nblocks*rank/world, nblocks*(rank+1)/world) of every column */
 DFDB_API int32_t dfdb_table_set_shard(dfdb_table *t, int32_t rank, int32_t world);
 DFDB_API int32_t dfdb_table_shard_range(const dfdb_table *t, int64_t *block_lo, int64_t *block_hi, int64_t *row_lo, int64_t *row_hi);

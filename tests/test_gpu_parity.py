@@ -66,21 +66,44 @@ def _gpu_decode(blocks, origins):
     return [bytes(out[o:o + s]) for o, s in zip(ooff, orig)], status
 
 
-@pytest.mark.parametrize("simple", [0, 1], ids=["batched", "sequential"])
-def test_lz4_decode_matches_reference_codec(oracle, simple):
+@pytest.mark.parametrize("variant", ["v2", "lz4_v1", "lz4_simple"], ids=["walker", "warp_per_block", "sequential"])
+def test_lz4_decode_matches_reference_codec(oracle, variant):
     """read_block BlockStreams.jl:101-119: decoded bytes are determined by the LZ4 block format."""
     bodies = _bodies(oracle)
     names = list(bodies)
     blocks = [oracle.compress_block(bodies[k]) for k in names] + [oracle.lz4_compress(bodies[k], 1) for k in names]
     origins = [len(bodies[k]) for k in names] * 2
-    _capi.check(_capi.lib().dfdb_set_option(b"lz4_simple", simple))
+    if variant != "v2":
+        _capi.check(_capi.lib().dfdb_set_option(variant.encode(), 1))
     try:
         got, status = _gpu_decode(blocks, origins)
     finally:
         _capi.lib().dfdb_set_option(b"lz4_simple", 0)
+        _capi.lib().dfdb_set_option(b"lz4_v1", 0)
     for i, k in enumerate(names + names):
         assert status[i] == 0, (k, status[i])
         assert got[i] == bodies[k], f"decoded bytes differ for {k} (first diff at {next(j for j in range(len(got[i])) if got[i][j] != bodies[k][j])})"
+
+
+def test_lz4_decode_many_small_blocks(oracle):
+    """More blocks than the persistent decoder has slots (148 SMs x 87), ragged sizes, every body kind: slots are
+    reused, rings wrap, windows re-base after long literal / match runs."""
+    rng = np.random.default_rng(11)
+    kinds = list(_bodies(oracle).values())
+    pool = []
+    for body in kinds:
+        for _ in range(6):
+            n = int(rng.integers(1, min(len(body), 6000) + 1))
+            s0 = int(rng.integers(0, len(body) - n + 1))
+            pool.append(body[s0:s0 + n])
+    pool.append(b"")
+    comp = [oracle.compress_block(b) if b else b"\x00" for b in pool]
+    idx = rng.integers(0, len(pool), 14000)
+    blocks = [comp[i] for i in idx]
+    origins = [len(pool[i]) for i in idx]
+    got, status = _gpu_decode(blocks, origins)
+    bad = [k for k in range(len(idx)) if status[k] != 0 or got[k] != pool[idx[k]]]
+    assert not bad, f"{len(bad)} of {len(idx)} blocks differ, first: block {bad[0]} (pool {idx[bad[0]]}, origin {origins[bad[0]]}, status {status[bad[0]]})"
 
 
 def test_lz4_decode_rejects_corrupt_blocks(oracle):
@@ -258,12 +281,16 @@ def test_residency_modes_and_kernel_variants_agree(synth, oracle):
             # fixed combination order: identical bits run to run and across residency modes
             assert (r.sum_f64, r.sum_f64_lo, r.count) == (base.sum_f64, base.sum_f64_lo, base.count)
         t2.close()
-    for opt in (b"no_tma", b"no_wide", b"no_fused", b"lz4_simple"):
+    for opt in (b"no_tma", b"no_wide", b"no_fused", b"lz4_simple", b"lz4_v1", b"no_alias"):
         L.dfdb_set_option(opt, 1)
         try:
             t2 = D.open_table(t.path)
             v2 = t2[(t2.a > 25) & (t2.a <= 75), ["b"]]
             r1, r2 = D.aggregate(v2.b), D.aggregate(v2.b)
+            # uniform Float64 is incompressible: every block of b is a stored block, referenced in place unless no_alias
+            nst, byt = C.c_int64(), C.c_int64()
+            _capi.check(L.dfdb_table_column_stored(t2._h, t2.getmeta("b").id, C.byref(nst), C.byref(byt)))
+            assert nst.value == (0 if opt == b"no_alias" else t2.nblocks()), (opt, nst.value)
             _check_agg(r1, ref, opt)
             assert (r1.sum_f64, r1.sum_f64_lo) == (r2.sum_f64, r2.sum_f64_lo)
             for col in ("a", "ma", "mb", "q"):
