@@ -48,11 +48,12 @@ constexpr int NSLOT_PAD = NWALK * 32;
 constexpr int V2_THREADS = (NWALK + NCONS) * 32;
 constexpr int W = 1024, WM = W - 1;         // compressed-stream window per slot (circular, by stream position)
 constexpr int R = 128, RM = R - 1;          // ring entries per slot
-constexpr int GEN_SHIFT = 17;               // generation tag = (index / R) & 0x7f, stored in bits 24..30
-constexpr int MAX_BURST = 8;                // batches a consumer takes from one slot before it looks at the other
+constexpr int MAX_BURST = 16;
+constexpr int READY_MIN = 96;               // ring entries that wake a consumer up (R - READY_MIN is the walker's slack)
+constexpr unsigned IDLE_SLEEP_NS = 1000;     // consumer with nothing ready: about the time a walker needs for one batch               // batches a consumer takes from one slot before it looks at the other
 constexpr int STG = 1088;                   // staging per consumer warp: 15 carried + 32 * (14 + 18) bytes, padded
 constexpr uint32_t LIM_EXIT = 0xffffffffu;
-constexpr uint32_t POS_CAP = (1u << 24) - 512;   // stream / output positions travel in 24 bits
+constexpr uint32_t POS_CAP = 1u << 30;      // larger blocks take the one-sequence-at-a-time path
 constexpr int REG_MIN = 16;                 // shortest leading word-regular run worth its own batch
 static_assert(NSLOT <= NSLOT_PAD, "every slot needs a walker lane");
 static_assert(V2_THREADS <= 1024, "one CTA");
@@ -89,12 +90,12 @@ struct SlotJob {                // consumer-private state of one block slot
 
 struct V2Smem {
     __align__(1024) uint8_t win[NSLOT][W];   // first, 1024-byte aligned: the walker forms addresses with one LOP3
-    uint32_t tail[NSLOT_PAD], whi[NSLOT_PAD], cmd_seq[NSLOT_PAD], cmd_p[NSLOT_PAD], cmd_o[NSLOT_PAD], cmd_lim[NSLOT_PAD];
-    unsigned long long dummy[NSLOT_PAD];     // sink for the ring stores of walker lanes that do not commit a step
+    uint32_t tail[NSLOT_PAD], whi[NSLOT_PAD], cmd_seq[NSLOT_PAD], cmd_p[NSLOT_PAD], cmd_lim[NSLOT_PAD];
+    uint32_t dummy[NSLOT_PAD];               // sink for the ring stores of walker lanes that do not commit a step
     uint32_t hint[NSLOT_PAD];                // walker -> consumer: entries emitted so far | parked << 31 (release store once per round)
     SlotJob job[NSLOT];
     unsigned long long rbar[NSLOT];          // mbarrier per slot: completion of the asynchronous window refill (32 arrivals)
-    uint2 ring[NSLOT][R + 1];                // +1: consecutive slots start 2 banks apart
+    uint32_t ring[NSLOT][R + 1];             // token positions; +1: consecutive slots start one bank apart
     __align__(16) uint8_t stg[NCONS][STG];
 };
 
@@ -125,15 +126,9 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t sa)
     asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(v) : "r"(sa) : "memory");
     return v;
 }
-__device__ __forceinline__ void sts_v2(uint32_t sa, uint32_t x, uint32_t y)
+__device__ __forceinline__ void sts_u32(uint32_t sa, uint32_t x)
 {
-    asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa), "r"(x), "r"(y) : "memory");
-}
-__device__ __forceinline__ uint2 lds_v2(const uint2 *p)
-{
-    uint2 v;
-    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_addr(p)) : "memory");
-    return v;
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sa), "r"(x) : "memory");
 }
 
 // =====================================================================================================
@@ -147,58 +142,65 @@ __device__ void walker(V2Smem &S, int slot)
     const uint32_t win_sa = smem_addr(S.win[sl]);     // 1024-byte aligned: window address = win_sa | (p & WM)
     const uint32_t ring_sa = smem_addr(S.ring[sl]);
     const uint32_t dummy_sa = smem_addr(&S.dummy[threadIdx.x & (NSLOT_PAD - 1)]);   // where non-committing lanes store
-    uint32_t p = 0, o = 0, lim = 0, head = 0, seen = 0, whi_c = 0, tail_c = 0;
+    uint32_t p = 0, lim = 0, head = 0, seen = 0, whi_c = 0, tail_c = 0;
     bool running = false, finished = !has;
+#ifdef DFDB_LZ4_STATS
     unsigned int st_rounds = 0, st_full = 0, st_empty = 0, st_parked = 0, st_sleeps = 0;
     const long long st_t0 = clock64();
+#endif
     for (;;) {
         // flow control and commands, once per UNROLL steps; all lanes issue the same three loads (no divergence)
-        const uint32_t whi_n = ld_acq(&S.whi[sl]), tail_n = ld_rlx(&S.tail[sl]), seq_n = ld_acq(&S.cmd_seq[sl]);
+        // (the command sequence first: a new command's window level must not be older than the command)
+        const uint32_t seq_n = ld_acq(&S.cmd_seq[sl]), whi_n = ld_acq(&S.whi[sl]), tail_n = ld_rlx(&S.tail[sl]);
         if (running) { whi_c = whi_n; tail_c = tail_n; }
         if (!finished && seq_n != seen) {
             seen = seq_n;
             lim = ld_rlx(&S.cmd_lim[sl]);
             if (lim == LIM_EXIT) { finished = true; running = false; }
-            else { p = ld_rlx(&S.cmd_p[sl]); o = ld_rlx(&S.cmd_o[sl]); running = true; whi_c = whi_n; tail_c = tail_n; }
+            else { p = ld_rlx(&S.cmd_p[sl]); running = true; whi_c = whi_n; tail_c = tail_n; }
         }
-        // per round: ring space, output-position cap (POS_CAP leaves room for the UNROLL steps of one round)
         const uint32_t room = running ? (uint32_t)R - (head - tail_c) : 0u;
-        const bool ocap = o >= POS_CAP;
         const uint32_t head0 = head;
+#ifdef DFDB_LZ4_STATS
         if (STATS_ON && has && !finished) {
             st_rounds++;
             if (!running) st_parked++;
             else if (room == 0) st_full++;
             else if (p >= whi_c) st_empty++;
         }
+#endif
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
-            // Straight-line and branch-free: the token load is speculative (any window address is readable), a lane
-            // that does not commit stores its entry to a dummy word and keeps its state.  The dependent chain of a
-            // step is LDS -> SHF/IADD3 (next p) -> SEL -> LOP3 (next address); everything else fills the LDS shadow.
+            // The walker does nothing but the chain: one ring entry = the stream position of a token.  Straight-line
+            // and branch-free: the token load is speculative (any window address is readable), a lane that does not
+            // commit stores to a dummy word and keeps its state.  Dependent chain of a step: LDS -> LEA.HI/VIADD
+            // (next p) -> SEL -> LOP3 (next address).
             const uint32_t t = lds_u8(win_sa | (p & WM));
             const bool commit = running & (p < whi_c) & (room > (uint32_t)u);
             const uint32_t pn = p + 3 + (t >> 4);
-            const bool special = (t >= 0xf0u) | ((t & 15u) == 15u) | (pn > lim) | ocap;
-            const uint32_t x = __byte_perm(p, t, 0x4210);
-            const uint32_t y = o | ((head << GEN_SHIFT) & 0x7f000000u) | (special ? 0x80000000u : 0u);
-            const uint32_t ra = ring_sa + (head & RM) * 8;
-            sts_v2(commit ? ra : dummy_sa, x, y);
+            const bool special = (t >= 0xf0u) | ((t & 15u) == 15u) | (pn > lim);   // length extensions / last sequence
+            sts_u32(commit ? ring_sa + (head & RM) * 4 : dummy_sa, p);
             head += commit ? 1u : 0u;
-            o = commit ? o + (t >> 4) + (t & 15u) + 4 : o;
             p = commit ? pn : p;                               // a parked lane gets a fresh position with its next command
             running = running & !(commit & special);           // parked until the consumer posts the position behind this sequence
         }
         const bool any_commit = head != head0;
-        st_rel(&S.hint[sl], head | ((!running && !finished && has) ? 0x80000000u : 0u));   // entries below head are visible
+        if (has) st_rel(&S.hint[sl], head | ((!running && !finished) ? 0x80000000u : 0u));   // entries below head are visible
         if (__all_sync(FULL, finished)) break;
-        if (!__any_sync(FULL, any_commit)) { __nanosleep(60); st_sleeps++; }
+        if (!__any_sync(FULL, any_commit)) {
+            __nanosleep(60);
+#ifdef DFDB_LZ4_STATS
+            st_sleeps++;
+#endif
+        }
     }
+#ifdef DFDB_LZ4_STATS
     if (STATS_ON && has) {
         STAT_ADD(ST_W_ROUNDS, st_rounds); STAT_ADD(ST_W_COMMITS, head); STAT_ADD(ST_W_RINGFULL, st_full);
         STAT_ADD(ST_W_WINEMPTY, st_empty); STAT_ADD(ST_W_PARKED, st_parked);
         if ((threadIdx.x & 31) == 0) { STAT_ADD(ST_W_SLEEPS, st_sleeps); STAT_ADD(ST_W_CYCLES, clock64() - st_t0); }
     }
+#endif
 }
 
 // =====================================================================================================
@@ -267,11 +269,10 @@ __device__ __forceinline__ uint32_t refill(V2Smem &S, int s, SlotJob &J, uint32_
     return n;
 }
 
-__device__ __forceinline__ void post_cmd(V2Smem &S, int s, SlotJob &J, uint32_t p, uint32_t o, uint32_t lim)
+__device__ __forceinline__ void post_cmd(V2Smem &S, int s, SlotJob &J, uint32_t p, uint32_t lim)
 {
     if (lane_id() == 0) {
         st_rlx(&S.cmd_p[s], p);
-        st_rlx(&S.cmd_o[s], o);
         st_rlx(&S.cmd_lim[s], lim);
         J.seq += 1;
         st_rel(&S.cmd_seq[s], J.seq);
@@ -427,7 +428,7 @@ __device__ __noinline__ void special_step(V2Smem &S, int s, SlotJob &J, uint32_t
     }
     __syncwarp();
     while (refill(S, s, J, 16)) { }
-    post_cmd(S, s, J, (uint32_t)ip, nop, J.comp_len);
+    post_cmd(S, s, J, (uint32_t)ip, J.comp_len);
 }
 
 // Claim job `job` for slot s.  Trivial and oversized blocks are finished on the spot.
@@ -460,30 +461,38 @@ __device__ __noinline__ void start_job(V2Smem &S, int s, SlotJob &J, const Decod
     }
     __syncwarp();
     while (refill(S, s, J, 16)) { }
-    post_cmd(S, s, J, 0u, 0u, (uint32_t)comp_len);
+    post_cmd(S, s, J, 0u, (uint32_t)comp_len);
 }
 
-// One batch of an active slot whose ring looks ready.  Returns true when it made progress.
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v)
+{
+    const uint32_t lane = lane_id();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_up_sync(FULL, v, d);
+        if ((int)lane >= d) v += u;
+    }
+    return v;
+}
+
+// One batch of an active slot whose ring looks ready -- any kind of entries.  Returns true when it made progress.
 __device__ __noinline__ bool process_slot(V2Smem &S, int s, SlotJob &J, uint8_t *stg)
 {
     const uint32_t lane = lane_id();
-    const uint32_t idx = J.tail + lane;
-    const uint2 e = lds_v2(&S.ring[s][idx & RM]);
-    const bool valid = ((e.y ^ (idx << GEN_SHIFT)) & 0x7f000000u) == 0;       // generation tag matches my index
-    const uint32_t vm = __ballot_sync(FULL, valid);
-    const int navail = (vm == FULL) ? 32 : (__ffs(~vm) - 1);
-    const uint32_t sm = __ballot_sync(FULL, (int)e.y < 0) & (navail >= 32 ? FULL : ((1u << navail) - 1u));
-    const int nv = sm ? (__ffs(sm) - 1) : navail;              // leading non-special entries
-    const uint32_t p = e.x & 0xffffffu, tok = e.x >> 24, o = e.y & 0xffffffu;
+    const uint32_t h = ld_acq(&S.hint[s]);                     // ring entries below the count are visible
+    const uint32_t avail = (h & 0x7fffffffu) - J.tail;
+    const int navail = avail < 32u ? (int)avail : 32;
+    if (navail == 0) return false;
+    const bool ends_special = (h >> 31) && avail <= 32u;       // a parked walker's last entry is the special one
+    const int nv = navail - (ends_special ? 1 : 0);            // leading non-special entries
+    const uint32_t p = (int)lane < navail ? S.ring[s][(J.tail + lane) & RM] : 0u;
     if (nv == 0) {
-        if (sm & 1u) {
-            const long long t0 = STATS_ON ? clock64() : 0;
-            special_step(S, s, J, __shfl_sync(FULL, p, 0));
-            if (STATS_ON && lane == 0) { STAT_ADD(ST_C_SPECIAL, 1); STAT_ADD(ST_C_SPECIAL_CYCLES, clock64() - t0); }
-            return true;
-        }
-        return false;
+        const long long t0 = STATS_ON ? clock64() : 0;
+        special_step(S, s, J, __shfl_sync(FULL, p, 0));
+        if (STATS_ON && lane == 0) { STAT_ADD(ST_C_SPECIAL, 1); STAT_ADD(ST_C_SPECIAL_CYCLES, clock64() - t0); }
+        return true;
     }
+    const uint32_t tok = (int)lane < nv ? S.win[s][p & WM] : 0u;   // the walker only emits tokens that are in the window
     const uint32_t L = tok >> 4, M = (tok & 15u) + 4, len = L + M;
     if (J.err) {   // a corrupt block drains its ring up to the closing special entry (the window keeps moving)
         const uint32_t nip = __shfl_sync(FULL, p + 3 + L, nv - 1);
@@ -492,10 +501,10 @@ __device__ __noinline__ bool process_slot(V2Smem &S, int s, SlotJob &J, uint8_t 
         refill_issue(S, s, J, 16);
         return true;
     }
-    if (nv < 32 && !((sm >> nv) & 1u)) return false;           // wait for a full batch unless the run ends in a special entry
-    const uint32_t o0 = __shfl_sync(FULL, o, 0);
+    if (nv < 32 && !ends_special) return false;                // wait for a full batch unless the run ends in a special entry
+    const uint32_t o0 = J.op;
+    const uint32_t o = o0 + warp_incl_scan((int)lane < nv ? len : 0u) - ((int)lane < nv ? len : 0u);
     int err = E_OK;
-    if (o0 != J.op) err = E_INTERNAL;
     // the stream bytes of the whole batch must be in the window
     const uint32_t need = __shfl_sync(FULL, p + 3 + L, nv - 1);
     while (!err && J.whi < need)
@@ -548,6 +557,78 @@ __device__ __noinline__ bool process_slot(V2Smem &S, int s, SlotJob &J, uint8_t 
 // ---- the hot path: a burst of full word-regular batches from one slot, slot state in registers -------------------
 // Anything else (partial batches, special entries, sequences that are not word-regular, window shortfalls, errors)
 // is handed to process_slot, which works on the slot state in shared memory.
+//
+// The burst is software-pipelined over two batches.  Stage 1 of batch k+1 (ring entries -> stream bytes ->
+// one output word per lane -> classification of every word's source) runs before stage 2 of batch k (resolve
+// and store).  A source word is either inside the batch (warp shuffles, dependency waves), inside the previous
+// batch (one shuffle from the registers that still hold it), or older -- then it is already in global memory
+// and its load is issued in stage 1, a whole batch ahead of its use.
+struct Staged {
+    uint32_t meta;       // per word lane: offw | Lw << 16
+    uint32_t litw;
+    uint32_t far_lo, far_hi;
+    uint32_t tw;         // uniform: words in the batch, 0 = nothing staged
+};
+enum { STG_OK = 0, STG_WAIT = 1, STG_SLOW = 2 };   // stage1 verdicts: staged / ring not full yet / needs process_slot
+
+__device__ __forceinline__ int stage1(V2Smem &S, int s, const uint32_t *ring, const uint32_t *w32, const uint8_t *dst, uint32_t origin,
+                                      uint32_t &tail, uint32_t op, uint32_t pt, uint32_t whi, uint32_t &ip, Staged &r)
+{
+    const uint32_t lane = lane_id();
+    r.meta = 0; r.litw = 0; r.far_lo = 0; r.far_hi = 0; r.tw = 0;
+    const uint32_t h = ld_acq(&S.hint[s]);                              // ring entries below the count are visible
+    const uint32_t avail = (h & 0x7fffffffu) - tail;
+    if (avail < 32u) return (h >> 31) && avail ? STG_SLOW : STG_WAIT;   // partial batch: wait, unless it ends in a special entry
+    if (avail == 32u && (h >> 31)) return STG_SLOW;                     // the last entry of a parked walker is special
+    const uint32_t p = ring[(tail + lane) & RM];
+    // 8 stream bytes from the token on: token, up to 2 literals and the offset of a word-regular sequence
+    const uint32_t a4 = p & ~3u, sh = (p & 3u) * 8;
+    const uint32_t w0 = w32[(a4 & WM) >> 2], w1 = w32[((a4 + 4) & WM) >> 2];
+    const uint32_t b0 = __funnelshift_r(w0, w1, sh);                    // bytes p .. p+3
+    const uint32_t lo = __funnelshift_r(b0, w1 >> sh, 8);               // bytes p+1 .. p+4
+    const uint32_t L = (b0 >> 4) & 15u;
+    const uint32_t len = L + (b0 & 15u) + 4;
+    const uint32_t offv = (lo >> (8 * (L & 3u))) & 0xffffu;
+    const uint32_t lit = lo & ~(0xffffffffu << (8 * (L & 3u)));
+    // output position of my sequence: every length is 8 in most batches, else a warp scan
+    uint32_t o = op + 8 * lane;
+    if (!__all_sync(FULL, len == 8u)) o = op + warp_incl_scan(len) - len;
+    const bool wr = L <= 2 && ((len | offv | o) & 7u) == 0 && (offv - 1u) < o;
+    const uint32_t fw = (o - op) >> 3;                             // first output word of my sequence
+    const uint32_t rm = __ballot_sync(FULL, wr && fw + (len >> 3) <= 32u);
+    const int nreg = rm == FULL ? 32 : (__ffs(~rm) - 1);
+    if (nreg < REG_MIN) return STG_SLOW;
+    const uint32_t need = __shfl_sync(FULL, p + 3 + L, nreg - 1);  // stream bytes of the batch must be in the window
+    const uint32_t tw = __shfl_sync(FULL, fw + (len >> 3), nreg - 1);   // words in the batch (<= 32)
+    if (need > whi || op + 8 * tw > origin) return STG_SLOW;
+    uint32_t offw = offv, Lw = L, litw = lit;
+    if ((int)tw != nreg) {                                         // some sequence spans two words: expand sequences to words
+        const uint32_t startmask = __reduce_or_sync(FULL, (int)lane < nreg ? (1u << fw) : 0u);
+        int sq = __popc(startmask & (0xffffffffu >> (31 - lane))) - 1;
+        if (lane >= tw) sq = 0;
+        const uint32_t pk = __shfl_sync(FULL, offv | (L << 16) | (fw << 24), sq);
+        const uint32_t lit_s = __shfl_sync(FULL, lit, sq);
+        const bool k0 = lane == (pk >> 24);                        // first word of its sequence carries the literals
+        offw = pk & 0xffffu;
+        Lw = k0 ? ((pk >> 16) & 0xffu) : 0u;
+        litw = k0 ? lit_s : 0u;
+    }
+    r.meta = offw | (Lw << 16);
+    r.litw = litw;
+    // source older than the previous batch: already in global memory, load it now
+    if (lane < tw && (int)lane - (int)(offw >> 3) < -(int)pt) {
+        const uint2 far = __ldcg(reinterpret_cast<const uint2 *>(dst + (op + 8 * lane - offw)));
+        r.far_lo = far.x;
+        r.far_hi = far.y;
+    }
+    r.tw = tw;
+    // the entries and stream bytes of the batch are in registers now: release them to the walker / the refill
+    tail += (uint32_t)nreg;
+    ip = need;
+    if (lane == 0) st_rlx(&S.tail[s], tail);
+    return STG_OK;
+}
+
 __device__ __noinline__ int burst(V2Smem &S, int s, SlotJob &J)
 {
     const uint32_t lane = lane_id();
@@ -555,72 +636,42 @@ __device__ __noinline__ int burst(V2Smem &S, int s, SlotJob &J)
     uint8_t *const dst = J.dst;
     const uint32_t origin = J.origin;
     const uint32_t whi_max = (J.comp_len + 16) & ~15u;
-    const uint2 *ring = S.ring[s];
+    const uint32_t *ring = S.ring[s];
     const uint32_t *w32 = reinterpret_cast<const uint32_t *>(S.win[s]);
-    bool progress = false, want_slow = false;
-    unsigned st_batches = 0, st_seqs = 0;
-    for (int it = 0; it < MAX_BURST; it++) {
-        if (pend) {                                           // a refill in flight: publish it once it has landed
-            if (refill_landed(S, s, J, false)) { whi = J.whi; pend = 0; progress = true; }
-        }
+    bool progress = false;
+    unsigned st_batches = 0;
+    if (pend && refill_landed(S, s, J, false)) { whi = J.whi; pend = 0; progress = true; }
+    uint32_t pt = 0;                       // words of the previous batch still held in prev_lo / prev_hi
+    uint32_t prev_lo = 0, prev_hi = 0;
+    Staged cur;
+    int verdict = stage1(S, s, ring, w32, dst, origin, tail, op, 0u, whi, ip, cur);
+    for (int it = 0; cur.tw; it++) {
+        // window upkeep: publish a landed refill, start the next one when 256 bytes are free
+        if (pend && refill_landed(S, s, J, false)) { whi = J.whi; pend = 0; }
         if (!pend && whi < whi_max && (ip & ~15u) + (uint32_t)W - whi >= 256u) {
-            if (lane == 0) { J.ip = ip; }
+            if (lane == 0) J.ip = ip;
             __syncwarp();
             refill_issue(S, s, J, 256);
             pend = J.pend;
         }
-        const uint32_t h = ld_acq(&S.hint[s]);
-        const uint32_t avail = (h & 0x7fffffffu) - tail;
-        const bool parked = (h >> 31) != 0;
-        if (avail == 0) break;
-        bool slow = avail < 32u || (avail == 32u && parked);  // the last entry of a parked walker is special
-        if (slow && !parked) break;                           // partial batch: wait for the walker
-        uint32_t p = 0, L = 0, o = 0, len = 0, offv = 0, lit = 0;
-        int nreg = 0;
-        if (!slow) {
-            const uint2 e = lds_v2(&ring[(tail + lane) & RM]);
-            p = e.x & 0xffffffu;
-            o = e.y & 0xffffffu;
-            L = e.x >> 28;
-            len = L + ((e.x >> 24) & 15u) + 4;
-            const uint32_t need = __shfl_sync(FULL, p + 3 + L, 31);
-            // 4 stream bytes behind the token: up to 2 literals and the offset of a word-regular sequence
-            const uint32_t a = p + 1, a4 = a & ~3u;
-            const uint32_t lo = __funnelshift_r(w32[(a4 & WM) >> 2], w32[((a4 + 4) & WM) >> 2], (a & 3u) * 8);
-            offv = (lo >> (8 * (L & 3u))) & 0xffffu;
-            lit = lo & ~(0xffffffffu << (8 * (L & 3u)));
-            const bool wr = L <= 2 && ((len | offv | o) & 7u) == 0 && (offv - 1u) < o;
-            const uint32_t rm = __ballot_sync(FULL, wr && ((o - op) >> 3) + (len >> 3) <= 32u);
-            nreg = rm == FULL ? 32 : (__ffs(~rm) - 1);
-            slow = need > whi || nreg < REG_MIN || __shfl_sync(FULL, o, 0) != op;
-        }
-        if (slow) { want_slow = true; break; }
-        // ---- word-regular batch, one output word per lane, stored straight to global memory ----
-        const uint32_t fw = (o - op) >> 3;                        // first output word of my sequence
-        const uint32_t tw = __shfl_sync(FULL, fw + (len >> 3), nreg - 1);   // words in the batch (<= 32)
-        if (op + 8 * tw > origin) { want_slow = true; break; }    // overflow: the slow path records the error
-        const bool wl = lane < tw;                                // from here on: lane = output word
-        uint32_t offw = offv, Lw = L, litw = lit;
-        if ((int)tw != nreg) {                                    // some sequence spans two words: expand sequences to words
-            const uint32_t startmask = __reduce_or_sync(FULL, (int)lane < nreg ? (1u << fw) : 0u);
-            int sq = __popc(startmask & (0xffffffffu >> (31 - lane))) - 1;
-            if (!wl) sq = 0;
-            const uint32_t pk = __shfl_sync(FULL, offv | (L << 16) | (fw << 24), sq);
-            const uint32_t lit_s = __shfl_sync(FULL, lit, sq);
-            const bool k0 = lane == (pk >> 24);                   // first word of its sequence carries the literals
-            offw = pk & 0xffffu;
-            Lw = k0 ? ((pk >> 16) & 0xffu) : 0u;
-            litw = k0 ? lit_s : 0u;
-        }
+        // stage 1 of the next batch
+        Staged nxt;
+        nxt.tw = 0;
+        verdict = STG_WAIT;
+        if (it + 1 < MAX_BURST) verdict = stage1(S, s, ring, w32, dst, origin, tail, op + 8 * cur.tw, cur.tw, whi, ip, nxt);
+        // stage 2 of the current batch: resolve every word and store
+        const bool wl = lane < cur.tw;
+        const uint32_t offw = cur.meta & 0xffffu, Lw = cur.meta >> 16;
         const uint32_t keep = 0xffffffffu << (8 * Lw);            // Lw <= 2
-        const int dep = (int)lane - (int)(offw >> 3);             // producer word inside the batch, or < 0: already in memory
-        const uint32_t ow = op + 8 * lane;
+        const int dep = (int)lane - (int)(offw >> 3);             // >= 0: in this batch, >= -pt: previous batch, else memory
+        const int pidx = dep + (int)pt;
+        const uint32_t qlo = __shfl_sync(FULL, prev_lo, pidx & 31), qhi = __shfl_sync(FULL, prev_hi, pidx & 31);
         bool fin = !wl;
         uint32_t vlo = 0, vhi = 0;
         if (wl && dep < 0) {
-            const uint2 far = __ldcg(reinterpret_cast<const uint2 *>(dst + (ow - offw)));
-            vlo = litw | (far.x & keep);
-            vhi = far.y;
+            const bool inprev = pidx >= 0;
+            vlo = cur.litw | ((inprev ? qlo : cur.far_lo) & keep);
+            vhi = inprev ? qhi : cur.far_hi;
             fin = true;
         }
         // in-batch sources: dependency waves over warp shuffles (the lowest unresolved word always has a resolved producer)
@@ -628,70 +679,49 @@ __device__ __noinline__ int burst(V2Smem &S, int s, SlotJob &J)
             const uint32_t finmask = __ballot_sync(FULL, fin);
             const int j = fin ? (int)lane : dep;
             const uint32_t va = __shfl_sync(FULL, vlo, j), vb = __shfl_sync(FULL, vhi, j);
-            if (!fin && ((finmask >> j) & 1u)) { vlo = litw | (va & keep); vhi = vb; fin = true; }
+            if (!fin && ((finmask >> j) & 1u)) { vlo = cur.litw | (va & keep); vhi = vb; fin = true; }
         }
-        if (wl) *reinterpret_cast<uint2 *>(dst + ow) = make_uint2(vlo, vhi);
-        ip = __shfl_sync(FULL, p + 3 + L, nreg - 1);
-        op += 8 * tw;
-        tail += (uint32_t)nreg;
-        if (lane == 0) st_rlx(&S.tail[s], tail);
-        __syncwarp();
+        if (wl) *reinterpret_cast<uint2 *>(dst + op + 8 * lane) = make_uint2(vlo, vhi);
+        __syncwarp();                                             // the stores are ordered before the far loads of later batches
+        prev_lo = vlo; prev_hi = vhi; pt = cur.tw;
+        op += 8 * cur.tw;
         progress = true;
         st_batches++;
-        st_seqs += (unsigned)nreg;
+        cur = nxt;
     }
-    if (STATS_ON && lane == 0) { STAT_ADD(ST_C_REG, st_batches); STAT_ADD(ST_C_REGSEQ, st_seqs); }
+    if (STATS_ON && lane == 0) STAT_ADD(ST_C_REG, st_batches);
     if (lane == 0) { J.tail = tail; J.op = op; J.ip = ip; }
     __syncwarp();
-    return (progress ? 1 : 0) | (want_slow ? 2 : 0);
+    return (progress ? 1 : 0) | (verdict == STG_SLOW ? 2 : 0);
 }
 
-// One visit of a consumer warp to one of its slots.
-__device__ __forceinline__ bool slot_step(V2Smem &S, int s, uint8_t *stg, const DecodeArgs &args, unsigned int *counter,
-                                          unsigned int first_dynamic, unsigned int static_job, uint32_t &first, int k, int &live)
+// Slot upkeep that is not on the hot path: claim the next block for an empty slot, or retire the slot.
+__device__ __noinline__ void slot_refresh(V2Smem &S, int s, const DecodeArgs &args, unsigned int *counter, unsigned int first_dynamic,
+                                          unsigned int static_job, bool use_static, int &live)
 {
     const uint32_t lane = lane_id();
     SlotJob &J = S.job[s];
-    const uint32_t st = J.state;
-    if (st == SLOT_RETIRED) return false;
-    if (st == SLOT_EMPTY) {
-        const unsigned int njobs = (unsigned int)args.ncols * (unsigned int)args.nblocks;
-        unsigned int job;
-        if ((first >> k) & 1u) {
-            first &= ~(1u << k);
-            job = static_job;
-        } else {
-            job = 0;
-            if (lane == 0) job = first_dynamic + atomicAdd(counter, 1u);
-            job = __shfl_sync(FULL, job, 0);
-        }
-        if (job >= njobs) {
-            if (lane == 0) J.state = SLOT_RETIRED;
-            __syncwarp();
-            post_cmd(S, s, J, 0u, 0u, LIM_EXIT);
-            live--;
-        } else {
-            const long long t0 = STATS_ON ? clock64() : 0;
-            start_job(S, s, J, args, job);
-            if (STATS_ON && lane == 0) STAT_ADD(ST_C_START_CYCLES, clock64() - t0);
-        }
-        return true;
+    const unsigned int njobs = (unsigned int)args.ncols * (unsigned int)args.nblocks;
+    unsigned int job = static_job;
+    if (!use_static) {
+        job = 0;
+        if (lane == 0) job = first_dynamic + atomicAdd(counter, 1u);
+        job = __shfl_sync(FULL, job, 0);
     }
-    const uint32_t h = ld_rlx(&S.hint[s]);
-    const uint32_t avail = (h & 0x7fffffffu) - J.tail;
-    if (avail >= 32u || ((h >> 31) && avail >= 1u) || J.pend) {
+    if (job >= njobs) {
+        if (lane == 0) J.state = SLOT_RETIRED;
+        __syncwarp();
+        post_cmd(S, s, J, 0u, LIM_EXIT);
+        live--;
+    } else {
         const long long t0 = STATS_ON ? clock64() : 0;
-        int code = burst(S, s, J);
-        bool r = (code & 1) != 0;
-        const long long t1 = STATS_ON ? clock64() : 0;
-        if (code & 2) r |= process_slot(S, s, J, stg);
-        if (STATS_ON && lane == 0 && (code & 2)) { STAT_ADD(ST_C_SLOW_CALLS, 1); STAT_ADD(ST_C_SLOW_CYCLES, clock64() - t1); }
-        if (STATS_ON && lane == 0) { STAT_ADD(ST_C_PS_CALLS, 1); STAT_ADD(ST_C_PS_CYCLES, clock64() - t0); if (!r) STAT_ADD(ST_C_PS_FALSE, 1); }
-        return r;
+        start_job(S, s, J, args, job);
+        if (STATS_ON && lane == 0) STAT_ADD(ST_C_START_CYCLES, clock64() - t0);
     }
-    return false;
 }
 
+// Consumer warp: owns SPC slots.  The polling loop is kept to a handful of instructions and sleeps when nothing is
+// ready -- every issue slot a waiting consumer burns is taken from the walker warps, which pace the whole kernel.
 __device__ void consumer(V2Smem &S, const DecodeArgs &args, unsigned int *counter, unsigned int first_dynamic, int c)
 {
     const uint32_t lane = lane_id();
@@ -703,20 +733,71 @@ __device__ void consumer(V2Smem &S, const DecodeArgs &args, unsigned int *counte
     unsigned int st_polls = 0, st_sleeps = 0;
     long long st_sleep_cycles = 0;
     while (live > 0) {
-        bool progress = false;
+        bool progress = false, worked = false;   // worked: entries were consumed (anything less does not justify another poll right away)
         st_polls++;
-        // first pass of jobs: spread over CTAs, then warps, then slot levels
-#pragma unroll 1
-        for (int k = 0; k < SPC; k++)
-            progress |= slot_step(S, c + k * NCONS, stg, args, counter, first_dynamic,
-                                  ((unsigned int)k * NCONS + (unsigned int)c) * gridDim.x + blockIdx.x, first, k, live);
+#pragma unroll
+        for (int k = 0; k < SPC; k++) {
+            const int s = c + k * NCONS;
+            SlotJob &J = S.job[s];
+            const uint32_t st = J.state;
+            if (st == SLOT_ACTIVE) {
+                const uint32_t h = ld_rlx(&S.hint[s]);
+                const uint32_t avail = (h & 0x7fffffffu) - J.tail;
+                // Wake up for several batches at once (bursts amortise the slot's state and keep far loads a batch
+                // ahead) -- but do not wait for entries the walker cannot produce: when its last token sits near the
+                // end of the window it is about to stall until this warp has consumed a batch and refilled.
+                bool ready = avail >= (uint32_t)READY_MIN || ((h >> 31) && avail >= 1u);
+                if (!ready && avail >= 32u) ready = J.whi - S.ring[s][((h & 0x7fffffffu) - 1u) & RM] < 128u;
+                if (ready) {
+                    const long long t0 = STATS_ON ? clock64() : 0;
+                    const int code = burst(S, s, J);
+                    bool r = (code & 1) != 0;
+                    const long long t1 = STATS_ON ? clock64() : 0;
+                    if (code & 2) r |= process_slot(S, s, J, stg);
+                    if (STATS_ON && lane == 0) {
+                        STAT_ADD(ST_C_PS_CALLS, 1); STAT_ADD(ST_C_PS_CYCLES, t1 - t0);
+                        if (code & 2) { STAT_ADD(ST_C_SLOW_CALLS, 1); STAT_ADD(ST_C_SLOW_CYCLES, clock64() - t1); }
+                    }
+                    progress |= r;
+                    worked |= r;
+                } else if (J.pend) {
+                    // the window is topped up whenever 256 bytes are free: after every batch and whenever a refill lands
+                    if (refill_landed(S, s, J, false)) { refill_issue(S, s, J, 256); progress = true; }
+                }
+            } else if (st == SLOT_EMPTY) {
+                // first pass of jobs: spread over CTAs, then warps, then slot levels
+                slot_refresh(S, s, args, counter, first_dynamic, ((unsigned int)k * NCONS + (unsigned int)c) * gridDim.x + blockIdx.x,
+                             (first >> k) & 1u, live);
+                first &= ~(1u << k);
+                progress = true;
+                worked = true;
+            }
+        }
         if (progress) last_progress = clock64();
-        else {
+#ifdef DFDB_LZ4_STATS
+        if (STATS_ON && st_polls == 3000000u) {   // diagnostics build: a warp that polls this often is stuck -- dump its slots and give up
+            for (int k = 0; k < SPC; k++) {
+                const int s = c + k * NCONS;
+                SlotJob &J = S.job[s];
+                if (lane == 0)
+                    printf("[lz4 v2 stuck] cta %d cons %d slot %d state %u tail %u hint %08x op %u ip %u whi %u pend %u err %u origin %u comp %u ring[t] %u ring[t+1] %u\n",
+                           (int)blockIdx.x, c, s, J.state, J.tail, ld_rlx(&S.hint[s]), J.op, J.ip, J.whi, J.pend, J.err, J.origin, J.comp_len,
+                           S.ring[s][J.tail & RM], S.ring[s][(J.tail + 1) & RM]);
+                if (J.state == SLOT_RETIRED) continue;
+                if (J.state == SLOT_ACTIVE && lane == 0) *J.status = E_INTERNAL;
+                if (lane == 0) J.state = SLOT_RETIRED;
+                __syncwarp();
+                post_cmd(S, s, J, 0u, LIM_EXIT);
+            }
+            live = 0;
+        }
+#endif
+        if (!worked) {
             const long long ts0 = STATS_ON ? clock64() : 0;
-            __nanosleep(200);
+            __nanosleep(IDLE_SLEEP_NS);
             st_sleeps++;
             if (STATS_ON) st_sleep_cycles += clock64() - ts0;
-            if (clock64() - last_progress > 4000000000ll) {
+            if (!progress && clock64() - last_progress > 4000000000ll) {
                 // watchdog (~2 s without progress): give up on the active slots instead of hanging the device
                 for (int k = 0; k < SPC; k++) {
                     const int s = c + k * NCONS;
@@ -725,7 +806,7 @@ __device__ void consumer(V2Smem &S, const DecodeArgs &args, unsigned int *counte
                     if (J.state == SLOT_ACTIVE && lane == 0) *J.status = E_INTERNAL;
                     if (lane == 0) J.state = SLOT_RETIRED;
                     __syncwarp();
-                    post_cmd(S, s, J, 0u, 0u, LIM_EXIT);
+                    post_cmd(S, s, J, 0u, LIM_EXIT);
                 }
                 live = 0;
             }
@@ -743,7 +824,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) lz4_decode_v2_kernel(const __gr
     V2Smem &S = *reinterpret_cast<V2Smem *>(v2_smem_raw + ((1024u - (smem_addr(v2_smem_raw) & 1023u)) & 1023u));
     const int warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < NSLOT_PAD; i += blockDim.x) {
-        S.tail[i] = 0; S.whi[i] = 0; S.cmd_seq[i] = 0; S.cmd_p[i] = 0; S.cmd_o[i] = 0; S.cmd_lim[i] = 0; S.hint[i] = 0;
+        S.tail[i] = 0; S.whi[i] = 0; S.cmd_seq[i] = 0; S.cmd_p[i] = 0; S.cmd_lim[i] = 0; S.hint[i] = 0;
     }
     for (int i = threadIdx.x; i < NSLOT; i += blockDim.x) {
         SlotJob &J = S.job[i];
@@ -751,8 +832,6 @@ __global__ void __launch_bounds__(V2_THREADS, 1) lz4_decode_v2_kernel(const __gr
         J.comp_len = 0; J.origin = 0; J.op = 0; J.ip = 0; J.tail = 0; J.whi = 0; J.state = SLOT_EMPTY; J.err = 0; J.seq = 0; J.pend = 0; J.rphase = 0;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" ::"r"(smem_addr(&S.rbar[i])) : "memory");
     }
-    // ring entries start with a generation tag no index in the first 127 laps can match
-    for (int i = threadIdx.x; i < NSLOT * (R + 1); i += blockDim.x) (&S.ring[0][0])[i] = make_uint2(0u, 0x7f000000u);
     __syncthreads();
     if (warp < NWALK) walker(S, warp * 32 + (int)(threadIdx.x & 31));
     else consumer(S, args, counter, first_dynamic, warp - NWALK);

@@ -3,11 +3,11 @@
 TAG=${1:-s}; ROWS=${2:-1000000000}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-( timeout 120 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "lz4" ) > $OUT/pytest_lz4.log 2>&1
+( timeout 60 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "lz4" ) > $OUT/pytest_lz4.log 2>&1
 tail -3 $OUT/pytest_lz4.log
-( DFDB_B200_LIB=$PWD/dataframedbs.jl_b200/lib/libdfdb_b200_stats.so DFDB_LZ4_STATS=1 timeout 600 python bench.py --rows $ROWS --steps 2 --warmup 1 --no-e2e --no-verify ) > $OUT/bench_stats.json 2> $OUT/bench_stats.err
-grep "lz4 v2 stats" $OUT/bench_stats.err | tail -2
-( timeout 600 python bench.py --rows $ROWS --steps 5 --warmup 3 --no-e2e ) > $OUT/bench.json 2> $OUT/bench.err
+( DFDB_B200_LIB=$PWD/dataframedbs.jl_b200/lib/libdfdb_b200_stats.so DFDB_LZ4_STATS=1 timeout 150 python bench.py --rows $ROWS --steps 1 --warmup 0 --no-e2e --no-verify ) > $OUT/bench_stats.json 2> $OUT/bench_stats.err
+grep "lz4 v2" $OUT/bench_stats.err $OUT/bench_stats.json | head -12
+( timeout 150 python bench.py --rows $ROWS --steps 5 --warmup 3 --no-e2e ) > $OUT/bench.json 2> $OUT/bench.err
 python -c "
 import json
 d=json.load(open('$OUT/bench.json'))
