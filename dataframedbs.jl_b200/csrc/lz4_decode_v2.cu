@@ -136,7 +136,7 @@ __device__ __forceinline__ void sts_u32(uint32_t sa, uint32_t x)
 // =====================================================================================================
 __device__ void walker(V2Smem &S, int slot)
 {
-    constexpr int UNROLL = 4;
+    constexpr int UNROLL = 8;
     const bool has = slot < NSLOT;
     const int sl = has ? slot : 0;
     const uint32_t win_sa = smem_addr(S.win[sl]);     // 1024-byte aligned: window address = win_sa | (p & WM)
@@ -629,6 +629,15 @@ __device__ __forceinline__ int stage1(V2Smem &S, int s, const uint32_t *ring, co
     return STG_OK;
 }
 
+// Window upkeep of a burst, out of line: publish a landed refill, start the next one when 256 bytes are free.
+__device__ __noinline__ void window_upkeep(V2Smem &S, int s, SlotJob &J, uint32_t ip)
+{
+    if (lane_id() == 0) J.ip = ip;
+    __syncwarp();
+    if (J.pend && !refill_landed(S, s, J, false)) return;
+    refill_issue(S, s, J, 256);
+}
+
 __device__ __noinline__ int burst(V2Smem &S, int s, SlotJob &J)
 {
     const uint32_t lane = lane_id();
@@ -646,12 +655,10 @@ __device__ __noinline__ int burst(V2Smem &S, int s, SlotJob &J)
     Staged cur;
     int verdict = stage1(S, s, ring, w32, dst, origin, tail, op, 0u, whi, ip, cur);
     for (int it = 0; cur.tw; it++) {
-        // window upkeep: publish a landed refill, start the next one when 256 bytes are free
-        if (pend && refill_landed(S, s, J, false)) { whi = J.whi; pend = 0; }
-        if (!pend && whi < whi_max && (ip & ~15u) + (uint32_t)W - whi >= 256u) {
-            if (lane == 0) J.ip = ip;
-            __syncwarp();
-            refill_issue(S, s, J, 256);
+        // window upkeep (out of line): a refill is in flight, or 256 bytes of the window are free
+        if (pend || (whi < whi_max && (ip & ~15u) + (uint32_t)W - whi >= 256u)) {
+            window_upkeep(S, s, J, ip);
+            whi = J.whi;
             pend = J.pend;
         }
         // stage 1 of the next batch
