@@ -15,6 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 DFDB_OK = 0
 ERR_IO, ERR_FORMAT, ERR_CORRUPT, ERR_ARGUMENT, ERR_UNSUPPORTED, ERR_KEY, ERR_DIVIDE, ERR_CUDA, ERR_NOMEM, ERR_STATE = range(1, 11)
+NEED_EXCHANGE = 11
 LOAD_HOST, LOAD_HBM, LOAD_DECODED = 0, 1, 2
 
 KIND_NAMES = {1: "Int8", 2: "Int16", 3: "Int32", 4: "Int64", 5: "Int128", 6: "UInt8", 7: "UInt16", 8: "UInt32", 9: "UInt64",
@@ -74,6 +75,8 @@ SYMBOLS = {
     "dfdb_scan_materialize_sizes": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dfdb_scan_materialize": (C.c_int32, [C.c_void_p, C.POINTER(OutCol), C.c_int32]),
     "dfdb_agg_fold": (C.c_int32, [C.POINTER(Agg), C.c_int32, C.POINTER(Agg)]),
+    "dfdb_scan_exchange_count": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "dfdb_scan_exchange_offset": (C.c_int32, [C.c_void_p, C.c_int64]),
     "dfdb_scan_aggregate_device": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
     "dfdb_lz4_decode_blocks": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
 }

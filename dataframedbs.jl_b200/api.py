@@ -166,6 +166,7 @@ class DFTable:
             cols.append(_ColumnMeta(cid.value, name.value.decode(), ts.value.decode()))
         d["meta"] = cols
         d["block_size"] = L.dfdb_table_block_size(h)
+        d["rank"], d["world"] = 0, 1
         if world > 1:
             self.set_shard(rank, world)
 
@@ -174,6 +175,7 @@ class DFTable:
         self._drop_scans()
         _capi.check(_capi.lib().dfdb_table_set_shard(self._h, rank, world))
         self._loaded.clear()
+        self.__dict__["rank"], self.__dict__["world"] = rank, world
 
     def load(self, columns=None, mode: int | None = None):
         """Read the shard's compressed blocks of `columns` (default: all) into pinned host / HBM."""
@@ -438,6 +440,37 @@ def nrow(v) -> int:
     except DfdbError as e:
         _raise(e)
     return n.value
+
+
+def resolve_sharded_selection(views, allgather=None):
+    """Range / index-vector stages behind a predicate rank rows among ALL survivors (selection.jl:94-111); on a
+    sharded table every shard therefore needs the survivor counts of the lower-ranked shards before such a stage.
+    `views`: the same view on every shard held by this process (one per rank in the multi-process case, all of
+    them in a single-process test); `allgather(count) -> [count of every rank]` for the multi-process case."""
+    views = [DFView(v) if isinstance(v, DFTable) else (v.view if isinstance(v, DFColumn) else v) for v in views]
+    handles = [_scan_handle(v) for v in views]
+    L = _capi.lib()
+    while True:
+        counts, pending = [], []
+        for h in handles:
+            n, p = C.c_int64(), C.c_int32()
+            try:
+                _capi.check(L.dfdb_scan_exchange_count(h, C.byref(n), C.byref(p)))
+            except DfdbError as e:
+                _raise(e)
+            counts.append(n.value)
+            pending.append(p.value)
+        if not any(pending):
+            return
+        if allgather is not None:           # one view per process: `counts` of all ranks come from the collective
+            allc = allgather(counts[0])
+            _capi.check(L.dfdb_scan_exchange_offset(handles[0], sum(allc[:views[0].table.rank])))
+        else:                               # every shard lives in this process, in rank order
+            by_rank = sorted(range(len(views)), key=lambda i: views[i].table.rank)
+            run = 0
+            for i in by_rank:
+                _capi.check(L.dfdb_scan_exchange_offset(handles[i], run))
+                run += counts[i]
 
 
 def ncol(v) -> int:

@@ -361,6 +361,8 @@ int run_selection(dfdb_scan *s)
     const Geometry g = make_geometry(t);
     bool dense = true;   // every row of the shard survives so far and the mask is not materialised
     bool used_vm = false;
+    int nondense = 0;    // range stages met so far that rank among survivors
+    s->exchange_count = -1;
     for (auto &st : s->stages) {
         if (st.kind != ST_PRED) {
             RangeArgs a;
@@ -378,12 +380,23 @@ int run_selection(dfdb_scan *s)
             if (dense) {
                 a.dense = 1;
             } else {
-                if (t->world > 1)
-                    return fail(DFDB_ERR_UNSUPPORTED, "a range stage after a predicate needs global survivor ranks; not available on a sharded table yet");
                 LAUNCH(launch_block_counts(g, s->d_mask, s->d_blk_counts, rt.stream));
                 LAUNCH(launch_exclusive_scan(s->d_blk_counts, s->d_blk_base, g.nblocks, rt.stream));
                 a.dense = 0;
                 a.blk_base = s->d_blk_base;
+                if (t->world > 1) {
+                    // the rank of a survivor counts the survivors of the lower-ranked shards too (selection.jl:94-111)
+                    if ((size_t)nondense >= s->rank_offsets.size()) {
+                        CUDA_TRY(cudaMemcpyAsync(s->h_result, s->d_blk_base + g.nblocks, 8, cudaMemcpyDeviceToHost, rt.stream));
+                        CUDA_TRY(cudaStreamSynchronize(rt.stream));
+                        s->exchange_count = *static_cast<int64_t *>(s->h_result);
+                        s->mask_valid = false;
+                        return fail(DFDB_NEED_EXCHANGE, "sharded scan: stage %d selects on the global survivor rank; exchange the shard counts first "
+                                                        "(dfdb_scan_exchange_count / dfdb_scan_exchange_offset)", nondense);
+                    }
+                    a.rank_offset = s->rank_offsets[(size_t)nondense];
+                }
+                nondense++;
             }
             LAUNCH(launch_range_stage(a, rt.stream));
             dense = false;
@@ -1054,6 +1067,34 @@ int32_t dfdb_agg_fold(const dfdb_agg *partials, int32_t n, dfdb_agg *out)
     r.sum_f64_lo = (r.sum_f64 - s) + r.sum_f64_lo;
     r.sum_f64 = s;
     *out = r;
+    return DFDB_OK;
+}
+
+int32_t dfdb_scan_exchange_count(dfdb_scan *s, int64_t *local_survivors, int32_t *pending)
+{
+    int rc = need_init();
+    if (rc) return rc;
+    if (!s || !local_survivors || !pending) return fail(DFDB_ERR_ARGUMENT, "null argument");
+    invalidate_decoded(s->tbl);
+    rc = run_selection(s);
+    if (rc == DFDB_NEED_EXCHANGE) {
+        *local_survivors = s->exchange_count;
+        *pending = 1;
+        return DFDB_OK;
+    }
+    *local_survivors = 0;
+    *pending = 0;
+    return rc;
+}
+
+int32_t dfdb_scan_exchange_offset(dfdb_scan *s, int64_t survivors_in_lower_ranks)
+{
+    if (!s) return fail(DFDB_ERR_ARGUMENT, "null argument");
+    if (s->exchange_count < 0) return fail(DFDB_ERR_STATE, "no exchange is pending on this scan (call dfdb_scan_exchange_count first)");
+    if (survivors_in_lower_ranks < 0) return fail(DFDB_ERR_ARGUMENT, "negative survivor count");
+    s->rank_offsets.push_back(survivors_in_lower_ranks);
+    s->exchange_count = -1;
+    s->mask_valid = false;
     return DFDB_OK;
 }
 

@@ -206,6 +206,9 @@ struct dfdb_scan {
     bool mask_valid = false;
     int64_t selected = -1;
     std::vector<int64_t> str_bytes;    // per projection
+    // sharded tables: survivors of lower-ranked shards entering each range stage that follows a predicate
+    std::vector<int64_t> rank_offsets;
+    int64_t exchange_count = -1;       // this shard's count at the first stage whose offset is missing
 };
 
 namespace dfdb {

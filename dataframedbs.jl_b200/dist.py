@@ -38,3 +38,22 @@ def allreduce_count(n: int, device=None) -> int:
     t = torch.tensor([n], dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return int(t.item())
+
+
+def allgather_counts(n: int, device=None):
+    """Every rank's integer, in rank order (the survivor counts of a sharded selection stage)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size()
+    mine = torch.tensor([n], dtype=torch.int64, device=device)
+    out = torch.empty(world, dtype=torch.int64, device=mine.device)
+    dist.all_gather_into_tensor(out, mine)
+    return [int(x) for x in out.cpu().tolist()]
+
+
+def resolve_selection(view, device=None):
+    """Multi-process flavour of api.resolve_sharded_selection: the survivor counts travel by all_gather."""
+    from . import api
+
+    api.resolve_sharded_selection([view], lambda n: allgather_counts(n, device))

@@ -37,7 +37,8 @@ enum {
     DFDB_ERR_DIVIDE = 7,      /* DivideError from integer rem by zero inside a broadcast                     */
     DFDB_ERR_CUDA = 8,        /* CUDA runtime failure / no device                                            */
     DFDB_ERR_NOMEM = 9,
-    DFDB_ERR_STATE = 10       /* handle used in the wrong state (e.g. table not loaded)                      */
+    DFDB_ERR_STATE = 10,      /* handle used in the wrong state (e.g. table not loaded)                      */
+    DFDB_NEED_EXCHANGE = 11   /* not an error: a sharded scan needs survivor counts of the other shards first */
 };
 
 /* column element kinds (src/columntypes/base.jl:97-126,163-168 ; complex.jl) */
@@ -138,6 +139,16 @@ DFDB_API int32_t dfdb_scan_materialize(dfdb_scan *s, dfdb_outcol *cols, int32_t 
 /* ---- multi-GPU: one process per GPU; each rank scans its shard, the tiny partials are exchanged by
  *      the host (NCCL all-gather) and folded in rank order on every rank ------------------------- */
 DFDB_API int32_t dfdb_agg_fold(const dfdb_agg *partials, int32_t n, dfdb_agg *out);
+/* Range / index-vector stages that follow a predicate select on the rank among ALL survivors
+ * (RangeToProcess.offset runs across blocks, src/tables/selection.jl:94-111), so a shard has to know how many
+ * rows of the preceding shards survived up to that stage.  Protocol on a sharded table, for every such stage in
+ * turn: every rank calls dfdb_scan_exchange_count -- it runs the selection up to the first stage whose offset is
+ * still unknown and returns this shard's survivor count there (*pending = 1), or *pending = 0 when nothing is
+ * missing; the host all-gathers the counts (NCCL / gloo) and hands each rank the sum over lower ranks with
+ * dfdb_scan_exchange_offset.  Any scan entry point called before the offsets are complete returns
+ * DFDB_NEED_EXCHANGE. */
+DFDB_API int32_t dfdb_scan_exchange_count(dfdb_scan *s, int64_t *local_survivors, int32_t *pending);
+DFDB_API int32_t dfdb_scan_exchange_offset(dfdb_scan *s, int64_t survivors_in_lower_ranks);
 /* device-resident copy of the last dfdb_scan_aggregate result (sizeof(dfdb_agg) bytes), for NCCL */
 DFDB_API int32_t dfdb_scan_aggregate_device(dfdb_scan *s, int32_t proj_idx, void *device_out);
 

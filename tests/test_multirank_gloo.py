@@ -26,7 +26,7 @@ def _worker(rank, world, port, path, q):
     import torch.distributed as dist
     import dfdb_b200 as D
     from dfdb_b200 import _capi
-    from dfdb_b200.dist import allgather_fold, allreduce_count
+    from dfdb_b200.dist import allgather_counts, allgather_fold, allreduce_count
     from oracle import oracle as O
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -48,6 +48,9 @@ def _worker(rank, world, port, path, q):
         mine.value_class = 3 if ref.count else 0
         folded = allgather_fold(mine)
         total = allreduce_count(ref.count)
+        # survivor counts of a sharded range stage travel the same way (dfdb_scan_exchange_count / _offset)
+        counts = allgather_counts(ref.count)
+        assert len(counts) == world and counts[rank] == ref.count and sum(counts) == total
         whole = ot.aggregate(pb, 0)
         q.put((rank, lo.value, hi.value, folded.count, total, folded.sum_f64 + folded.sum_f64_lo, folded.min_f64, folded.max_f64,
                whole.count, whole.sum_kahan, whole.min_f64, whole.max_f64))
