@@ -111,6 +111,43 @@ int dev_upload(T **dptr, const std::vector<T> &h)
     return DFDB_OK;
 }
 
+// Device -> caller memory.  The caller's buffers are ordinary (pageable) host memory, which the driver copies at a
+// few GB/s; large results go through two pinned bounce buffers instead, the copy of chunk k+1 overlapping the
+// host memcpy of chunk k.  Returns after the data is in `dst`.
+cudaError_t copy_out(void *dst, const void *d_src, size_t n)
+{
+    constexpr size_t CHUNK = 32u << 20;
+    if (n < (8u << 20)) {
+        cudaError_t e = cudaMemcpyAsync(dst, d_src, n, cudaMemcpyDeviceToHost, rt.stream);
+        return e != cudaSuccess ? e : cudaStreamSynchronize(rt.stream);
+    }
+    static uint8_t *bounce[2] = {nullptr, nullptr};
+    static cudaEvent_t done[2];
+    if (!bounce[0]) {
+        for (int i = 0; i < 2; i++) {
+            cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&bounce[i]), CHUNK);
+            if (e != cudaSuccess) { bounce[0] = nullptr; return e; }
+            cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
+        }
+    }
+    const size_t nchunks = (n + CHUNK - 1) / CHUNK;
+    for (size_t k = 0; k <= nchunks; k++) {
+        if (k < nchunks) {
+            const size_t off = k * CHUNK, len = std::min(CHUNK, n - off);
+            cudaError_t e = cudaMemcpyAsync(bounce[k & 1], static_cast<const uint8_t *>(d_src) + off, len, cudaMemcpyDeviceToHost, rt.stream);
+            if (e != cudaSuccess) return e;
+            cudaEventRecord(done[k & 1], rt.stream);
+        }
+        if (k > 0) {
+            const size_t off = (k - 1) * CHUNK, len = std::min(CHUNK, n - off);
+            cudaError_t e = cudaEventSynchronize(done[(k - 1) & 1]);
+            if (e != cudaSuccess) return e;
+            memcpy(static_cast<uint8_t *>(dst) + off, bounce[(k - 1) & 1], len);
+        }
+    }
+    return cudaSuccess;
+}
+
 void column_release(Column &c)
 {
     if (c.h_comp) cudaFreeHost(c.h_comp);
@@ -1242,8 +1279,9 @@ int32_t dfdb_scan_materialize(dfdb_scan *s, dfdb_outcol *cols, int32_t ncols)
                 a.out_chars = d_chars;
                 if (launch_gather_strings(a, rt.stream) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "gather_strings launch failed"); }
                 rt.launches++;
-                cudaMemcpyAsync(oc.str_sizes, d_sizes, (size_t)total * 4, cudaMemcpyDeviceToHost, rt.stream);
-                if (nbytes > 0 && oc.str_chars) cudaMemcpyAsync(oc.str_chars, d_chars, (size_t)nbytes, cudaMemcpyDeviceToHost, rt.stream);
+                PhaseScope ps2(PH_D2H, total * 4 + nbytes);
+                copy_out(oc.str_sizes, d_sizes, (size_t)total * 4);
+                if (nbytes > 0 && oc.str_chars) copy_out(oc.str_chars, d_chars, (size_t)nbytes);
             } else {
                 if (!oc.values) return fail(DFDB_ERR_ARGUMENT, "output column %zu needs a values buffer", i);
                 const int es = c->type.elsize;
@@ -1260,8 +1298,8 @@ int32_t dfdb_scan_materialize(dfdb_scan *s, dfdb_outcol *cols, int32_t ncols)
                     rt.launches++;
                 }
                 PhaseScope ps(PH_D2H, total * es);
-                cudaMemcpyAsync(oc.values, d_vals, (size_t)total * es, cudaMemcpyDeviceToHost, rt.stream);
-                if (c->type.nullable && oc.missing) cudaMemcpyAsync(oc.missing, d_miss, (size_t)total, cudaMemcpyDeviceToHost, rt.stream);
+                copy_out(oc.values, d_vals, (size_t)total * es);
+                if (c->type.nullable && oc.missing) copy_out(oc.missing, d_miss, (size_t)total);
             }
         } else {
             rc = ensure_decoded(t, p.e.col_ids);
@@ -1290,8 +1328,8 @@ int32_t dfdb_scan_materialize(dfdb_scan *s, dfdb_outcol *cols, int32_t ncols)
             a.error_flag = rt.d_error;
             if (launch_proj_vm(a, rt.stream) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "proj_vm launch failed"); }
             rt.launches++;
-            cudaMemcpyAsync(oc.values, d_vals, (size_t)total * es, cudaMemcpyDeviceToHost, rt.stream);
-            if (p.type.nullable && oc.missing) cudaMemcpyAsync(oc.missing, d_miss, (size_t)total, cudaMemcpyDeviceToHost, rt.stream);
+            copy_out(oc.values, d_vals, (size_t)total * es);
+            if (p.type.nullable && oc.missing) copy_out(oc.missing, d_miss, (size_t)total);
             cudaStreamSynchronize(rt.stream);
             rc = check_device_error();
             if (rc) { cleanup(); return rc; }
