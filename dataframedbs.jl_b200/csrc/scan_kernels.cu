@@ -844,65 +844,107 @@ __global__ void __launch_bounds__(SCAN_THREADS) gather_indices_kernel(const Gath
 }
 
 // selected string bytes per block (one warp per block)
-__global__ void __launch_bounds__(SCAN_THREADS) str_block_bytes_kernel(const GatherArgs A, int64_t *blk_bytes)
+// One CTA per block; warp k owns the contiguous chunk of mask words [k*C, (k+1)*C).  Mask words are fetched 32 at a
+// time (one coalesced load per lane) and handed round by shuffle, so the per-word loop carries no dependent mask load.
+__device__ __forceinline__ void str_chunk_totals(const GatherArgs &A, int lb, int w0, int w1, long long &rows, long long &bytes)
 {
-    const Geometry g = A.g;
-    const int warps = gridDim.x * (SCAN_THREADS / 32);
-    for (int lb = blockIdx.x * (SCAN_THREADS / 32) + warp_id(); lb < g.nblocks; lb += warps) {
-        const uint32_t *m = A.mask + (int64_t)lb * g.wpb;
-        const int32_t *sizes = reinterpret_cast<const int32_t *>(col_body(A.col, lb) + 4);
-        long long tot = 0;
-        for (int w = 0; w < g.wpb; w++) {
-            const uint32_t word = m[w];
-            if (word == 0) continue;
+    const Geometry &g = A.g;
+    const uint32_t *m = A.mask + (int64_t)lb * g.wpb;
+    const int32_t *sizes = reinterpret_cast<const int32_t *>(col_body(A.col, lb) + 4);
+    rows = 0;
+    bytes = 0;
+    for (int wb = w0; wb < w1; wb += 32) {
+        const uint32_t mine = wb + lane_id() < w1 ? m[wb + lane_id()] : 0u;
+        uint32_t nz = __ballot_sync(FULL, mine != 0);
+        while (nz) {
+            const int j = __ffs(nz) - 1;
+            nz &= nz - 1;
+            const uint32_t word = __shfl_sync(FULL, mine, j);
             if ((word >> lane_id()) & 1u) {
-                const int s = sizes[(int64_t)w * 32 + lane_id()];
-                if (s > 0) tot += s;
+                const int s = sizes[(int64_t)(wb + j) * 32 + lane_id()];
+                rows++;
+                if (s > 0) bytes += s;
             }
         }
+    }
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(FULL, tot, d);
-        if (lane_id() == 0) blk_bytes[lb] = tot;
+    for (int d = 16; d > 0; d >>= 1) {
+        rows += __shfl_xor_sync(FULL, rows, d);
+        bytes += __shfl_xor_sync(FULL, bytes, d);
     }
 }
 
-// sizes + chars of the selected rows: one warp per block walks the words in order, carrying the running
-// row and byte positions (FlatStringsVector gather, offset-aware)
+__global__ void __launch_bounds__(SCAN_THREADS) str_block_bytes_kernel(const GatherArgs A, int64_t *blk_bytes)
+{
+    __shared__ long long s_bytes[SCAN_THREADS / 32];
+    const Geometry g = A.g;
+    const int C = (g.wpb + SCAN_THREADS / 32 - 1) / (SCAN_THREADS / 32);
+    for (int lb = blockIdx.x; lb < g.nblocks; lb += gridDim.x) {
+        const int w0 = warp_id() * C, w1 = w0 + C < g.wpb ? w0 + C : g.wpb;
+        long long rows, bytes;
+        str_chunk_totals(A, lb, w0, w1, rows, bytes);
+        if (lane_id() == 0) s_bytes[warp_id()] = bytes;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long tot = 0;
+            for (int k = 0; k < SCAN_THREADS / 32; k++) tot += s_bytes[k];
+            blk_bytes[lb] = tot;
+        }
+        __syncthreads();
+    }
+}
+
+// sizes + chars of the selected rows (FlatStringsVector gather, offset-aware, /root/reference/src/FlatStringsVectors.jl:136-157):
+// every warp first totals its chunk (rows, bytes), an exclusive scan over the CTA's warps gives its output positions,
+// then it walks its chunk carrying the running row and byte positions.
 __global__ void __launch_bounds__(SCAN_THREADS) gather_strings_kernel(const GatherArgs A)
 {
+    __shared__ long long s_rows[SCAN_THREADS / 32], s_bytes[SCAN_THREADS / 32];
     const Geometry g = A.g;
-    const int warps = gridDim.x * (SCAN_THREADS / 32);
-    for (int lb = blockIdx.x * (SCAN_THREADS / 32) + warp_id(); lb < g.nblocks; lb += warps) {
+    const int C = (g.wpb + SCAN_THREADS / 32 - 1) / (SCAN_THREADS / 32);
+    for (int lb = blockIdx.x; lb < g.nblocks; lb += gridDim.x) {
         const uint32_t *m = A.mask + (int64_t)lb * g.wpb;
         const int64_t rows_b = block_rows(g, lb);
         const uint8_t *body = col_body(A.col, lb);
         const int32_t *sizes = reinterpret_cast<const int32_t *>(body + 4);
         const uint8_t *chars = body + 4 + 4 * rows_b;
         const int32_t *soff = A.col.str_off + (int64_t)lb * g.block_size;
+        const int w0 = warp_id() * C, w1 = w0 + C < g.wpb ? w0 + C : g.wpb;
+        long long rows, bytes;
+        str_chunk_totals(A, lb, w0, w1, rows, bytes);
+        if (lane_id() == 0) { s_rows[warp_id()] = rows; s_bytes[warp_id()] = bytes; }
+        __syncthreads();
         int64_t row_pos = A.blk_base[lb];
         int64_t byte_pos = A.blk_char_base[lb];
-        for (int w = 0; w < g.wpb; w++) {
-            const uint32_t word = m[w];
-            if (word == 0) continue;
-            const bool sel = (word >> lane_id()) & 1u;
-            const int64_t r = (int64_t)w * 32 + lane_id();
-            const int sz = sel ? sizes[r] : 0;
-            const int nb = sz > 0 ? sz : 0;
-            int incl = nb;
+        for (int k = 0; k < warp_id(); k++) { row_pos += s_rows[k]; byte_pos += s_bytes[k]; }
+        for (int wb = w0; wb < w1; wb += 32) {
+            const uint32_t mine = wb + lane_id() < w1 ? m[wb + lane_id()] : 0u;
+            uint32_t nz = __ballot_sync(FULL, mine != 0);
+            while (nz) {
+                const int j = __ffs(nz) - 1;
+                nz &= nz - 1;
+                const uint32_t word = __shfl_sync(FULL, mine, j);
+                const bool sel = (word >> lane_id()) & 1u;
+                const int64_t r = (int64_t)(wb + j) * 32 + lane_id();
+                const int sz = sel ? sizes[r] : 0;
+                const int nb = sz > 0 ? sz : 0;
+                int incl = nb;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int v = __shfl_up_sync(FULL, incl, d);
-                if (lane_id() >= d) incl += v;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, d);
+                    if (lane_id() >= d) incl += v;
+                }
+                if (sel) {
+                    A.out_sizes[row_pos + __popc(word & ((1u << lane_id()) - 1u))] = sz;
+                    const uint8_t *src = chars + soff[r];
+                    uint8_t *dst = A.out_chars + byte_pos + (incl - nb);
+                    for (int i = 0; i < nb; i++) dst[i] = src[i];
+                }
+                row_pos += __popc(word);
+                byte_pos += __shfl_sync(FULL, incl, 31);
             }
-            if (sel) {
-                A.out_sizes[row_pos + __popc(word & ((1u << lane_id()) - 1u))] = sz;
-                const uint8_t *src = chars + soff[r];
-                uint8_t *dst = A.out_chars + byte_pos + (incl - nb);
-                for (int i = 0; i < nb; i++) dst[i] = src[i];
-            }
-            row_pos += __popc(word);
-            byte_pos += __shfl_sync(FULL, incl, 31);
         }
+        __syncthreads();
     }
 }
 
@@ -1035,14 +1077,14 @@ int launch_gather_indices(const GatherArgs &a, cudaStream_t stream)
 int launch_str_block_bytes(const GatherArgs &a, int64_t *blk_bytes, cudaStream_t stream)
 {
     if (a.g.nblocks <= 0) return 0;
-    str_block_bytes_kernel<<<grid_for((a.g.nblocks + 7) / 8, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(a, blk_bytes);
+    str_block_bytes_kernel<<<grid_for(a.g.nblocks, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(a, blk_bytes);
     return CHECK_LAUNCH();
 }
 
 int launch_gather_strings(const GatherArgs &a, cudaStream_t stream)
 {
     if (a.g.nblocks <= 0) return 0;
-    gather_strings_kernel<<<grid_for((a.g.nblocks + 7) / 8, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(a);
+    gather_strings_kernel<<<grid_for(a.g.nblocks, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(a);
     return CHECK_LAUNCH();
 }
 
