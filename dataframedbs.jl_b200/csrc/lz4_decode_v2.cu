@@ -53,6 +53,11 @@ constexpr int READY_MIN = 96;               // ring entries that wake a consumer
 constexpr unsigned IDLE_SLEEP_NS = 1000;     // consumer with nothing ready: about the time a walker needs for one batch               // batches a consumer takes from one slot before it looks at the other
 constexpr int STG = 1088;                   // staging per consumer warp: 15 carried + 32 * (14 + 18) bytes, padded
 constexpr uint32_t LIM_EXIT = 0xffffffffu;
+// hint word (walker -> consumer): entries emitted so far | flags
+constexpr uint32_t H_PARKED = 0x80000000u;  // the last entry is a special token the walker could not get past: it waits for a command
+constexpr uint32_t H_STARVED = 0x40000000u; // the walker's next token lies beyond the window
+constexpr uint32_t H_CNT = 0x3fffffffu;
+constexpr int HYST = 8;                     // plain tokens in a row that end a consumer-side run of special sequences
 constexpr uint32_t POS_CAP = 1u << 30;      // larger blocks take the one-sequence-at-a-time path
 constexpr int REG_MIN = 16;                 // shortest leading word-regular run worth its own batch
 static_assert(NSLOT <= NSLOT_PAD, "every slot needs a walker lane");
@@ -91,6 +96,7 @@ struct SlotJob {                // consumer-private state of one block slot
 struct V2Smem {
     __align__(1024) uint8_t win[NSLOT][W];   // first, 1024-byte aligned: the walker forms addresses with one LOP3
     uint32_t tail[NSLOT_PAD], whi[NSLOT_PAD], cmd_seq[NSLOT_PAD], cmd_p[NSLOT_PAD], cmd_lim[NSLOT_PAD];
+    uint32_t cmd_ack[NSLOT_PAD], cmd_head[NSLOT_PAD];   // walker -> consumer: last command taken, and the ring position its entries start at
     uint32_t dummy[NSLOT_PAD];               // sink for the ring stores of walker lanes that do not commit a step
     uint32_t hint[NSLOT_PAD];                // walker -> consumer: entries emitted so far | parked << 31 (release store once per round)
     SlotJob job[NSLOT];
@@ -158,7 +164,10 @@ __device__ void walker(V2Smem &S, int slot)
             lim = ld_rlx(&S.cmd_lim[sl]);
             if (lim == LIM_EXIT) { finished = true; running = false; }
             else { p = ld_rlx(&S.cmd_p[sl]); running = true; whi_c = whi_n; tail_c = tail_n; }
+            // a command flushes the ring: whatever this lane emitted so far belongs to an abandoned block
+            if (has) { st_rlx(&S.hint[sl], head); st_rlx(&S.cmd_head[sl], head); st_rel(&S.cmd_ack[sl], seq_n); }
         }
+        const bool run0 = running;
         const uint32_t room = running ? (uint32_t)R - (head - tail_c) : 0u;
         const uint32_t head0 = head;
 #ifdef DFDB_LZ4_STATS
@@ -185,7 +194,44 @@ __device__ void walker(V2Smem &S, int slot)
             running = running & !(commit & special);           // parked until the consumer posts the position behind this sequence
         }
         const bool any_commit = head != head0;
-        if (has) st_rel(&S.hint[sl], head | ((!running && !finished) ? 0x80000000u : 0u));   // entries below head are visible
+        // Resolve step (rare, divergent): a lane that stopped on a token with length extensions in this round reads the
+        // extension bytes itself when they are in the window, and walks on behind the sequence.  The entry stays in the
+        // ring; the consumer recognises it by its nibbles and does that sequence on its own.  Not resolvable (extension
+        // bytes beyond the window, last sequence): the lane stays parked and the consumer restarts it with a command.
+        const bool newly = run0 && !running && !finished;
+        if (__any_sync(FULL, newly)) {
+            if (newly) {
+                uint32_t ps;
+                asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(ps) : "r"(ring_sa + ((head - 1u) & RM) * 4) : "memory");
+                const uint32_t t = lds_u8(win_sa | (ps & WM));
+                uint32_t q = ps + 1, L = t >> 4;
+                bool ok = true;
+                if (L == 15u) {
+                    for (;;) {
+                        if (q >= whi_c) { ok = false; break; }
+                        const uint32_t e = lds_u8(win_sa | (q & WM));
+                        q++;
+                        L += e;
+                        if (e != 255u) break;
+                        if (L > 65536u) { ok = false; break; }
+                    }
+                }
+                q += L + 2;                                   // behind the offset
+                if (q > lim) ok = false;                      // last sequence (or a truncated stream): the consumer closes the block
+                if (ok && (t & 15u) == 15u) {
+                    for (;;) {
+                        if (q >= whi_c || q >= lim) { ok = false; break; }
+                        const uint32_t e = lds_u8(win_sa | (q & WM));
+                        q++;
+                        if (e != 255u) break;
+                    }
+                }
+                if (ok) { p = q; running = true; }
+            }
+            __syncwarp();
+        }
+        if (has)   // entries below head are visible
+            st_rel(&S.hint[sl], head | ((!running && !finished) ? H_PARKED : 0u) | ((running && p >= whi_c) ? H_STARVED : 0u));
         if (__all_sync(FULL, finished)) break;
         if (!__any_sync(FULL, any_commit)) {
             __nanosleep(60);
@@ -398,37 +444,167 @@ __device__ __forceinline__ int generic_batch(const uint8_t *win, uint8_t *stg, c
     return E_OK;
 }
 
-// A special entry (length extensions / last sequence / capped positions) heads the ring: the whole warp does that
-// one sequence against global memory, then restarts the walker lane behind it (or finishes the block).
-__device__ __noinline__ void special_step(V2Smem &S, int s, SlotJob &J, uint32_t p0)
+// ---- one sequence at a time, whole warp: the path of "special" tokens (length extensions, last sequence) ------------
+// The stream is read through a 256-byte register chunk (one aligned 8-byte word per lane, bytes fetched with warp
+// shuffles), so a sequence costs no dependent global loads for its token / extension bytes / literals / offset; the
+// match bytes of a short match stay pending in registers across the parse of the next sequence (their load latency
+// hides behind it).  Same checks, in the same order, as decode_one_sequence.
+__device__ __forceinline__ uint2 chunk_load(const uint8_t *src, uint32_t lim16, uint32_t base)
+{
+    const uint32_t a = base + 8 * lane_id();                  // base is a multiple of 8, payload slots are 16-byte aligned and padded
+    uint2 w = make_uint2(0u, 0u);
+    if (a < lim16) w = __ldg(reinterpret_cast<const uint2 *>(src + a));
+    const uint32_t nx = base + 256 + 128 * lane_id();         // the next chunk's two lines: into L2 while this one is parsed
+    if (lane_id() < 2 && nx < lim16) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + nx));
+    return w;
+}
+__device__ __forceinline__ uint32_t chunk_byte_u(const uint2 w, uint32_t k)     // k < 256, uniform over the warp
+{
+    return (__shfl_sync(FULL, (k & 4u) ? w.y : w.x, k >> 3) >> ((k & 3u) * 8)) & 0xffu;
+}
+__device__ __forceinline__ uint32_t chunk_byte_v(const uint2 w, uint32_t k)     // k < 256, any value per lane
+{
+    const uint32_t lo = __shfl_sync(FULL, w.x, k >> 3), hi = __shfl_sync(FULL, w.y, k >> 3);
+    return (((k & 4u) ? hi : lo) >> ((k & 3u) * 8)) & 0xffu;
+}
+
+// Decodes the sequence at ip.  single: just that one (the walker got past it on its own and has gone on emitting
+// entries).  Otherwise the walker is parked behind it, and the run goes on until HYST plain tokens in a row have been
+// seen (a walker restart costs far more than a sequence done here).
+// Returns E_*; on E_OK either done (last sequence consumed) or ip is the position of the next token.
+__device__ __noinline__ int special_run(const SlotJob &J, uint32_t &ip_io, uint32_t &op_io, bool &done, bool single)
 {
     const uint32_t lane = lane_id();
-    int64_t ip = p0, op = J.op;
-    bool done = false;
-    int e = J.err ? (int)J.err : decode_one_sequence(J.src, J.comp_len, J.dst, J.origin, ip, op, done);
-    if (lane == 0) { J.tail += 1; st_rlx(&S.tail[s], J.tail); }
-    __syncwarp();
-    if (e) { finish_block(J, e); return; }
-    if (done) { finish_block(J, (op == (int64_t)J.origin && ip == (int64_t)J.comp_len) ? E_OK : E_SIZE); return; }
-    if (ip >= (int64_t)POS_CAP || op >= (int64_t)POS_CAP) {
-        // positions no longer fit the ring entries: finish this block one sequence at a time
-        while (!done) {
-            e = decode_one_sequence(J.src, J.comp_len, J.dst, J.origin, ip, op, done);
-            if (e) { finish_block(J, e); return; }
+    const uint8_t *const src = J.src;
+    uint8_t *const dst = J.dst;
+    const uint32_t comp_len = J.comp_len, origin = J.origin, lim16 = (comp_len + 15u) & ~15u;
+    uint32_t ip = ip_io, op = op_io;
+    uint32_t base = ip & ~7u, k = ip - base;
+    uint2 w = chunk_load(src, lim16, base);
+    uint32_t pend_b = 0;
+    uint8_t *pend_a = nullptr;                                // this lane's pending match byte (nullptr: none)
+    int err = E_OK;
+    bool first = true;
+    int nplain = 0;
+#define DFDB_ENSURE(n)                                                                                   \
+    if (k + (n) > 256u) {                                                                                \
+        const uint32_t pos_ = base + k;                                                                  \
+        base = pos_ & ~7u; k = pos_ - base;                                                              \
+        w = chunk_load(src, lim16, base);                                                                \
+    }
+    for (;;) {
+        ip = base + k;
+        if (ip >= comp_len) { err = E_TRUNCATED; break; }
+        DFDB_ENSURE(1u)
+        const uint32_t t = chunk_byte_u(w, k);
+        uint32_t L = t >> 4;
+        if (!first) {
+            if (single) break;
+            if (t < 0xf0u && (t & 15u) != 15u && ip + 3u + L <= comp_len) {
+                if (++nplain > HYST) break;                                               // plain tokens: back to the walker
+            } else nplain = 0;
         }
-        finish_block(J, (op == (int64_t)J.origin && ip == (int64_t)J.comp_len) ? E_OK : E_SIZE);
-        return;
+        first = false;
+        k++;
+        if (L == 15u) {
+            for (;;) {
+                if (base + k >= comp_len) { err = E_TRUNCATED; break; }
+                DFDB_ENSURE(1u)
+                const uint32_t e = chunk_byte_u(w, k);
+                k++;
+                L += e;
+                if (e != 255u) break;
+                if (L > origin) break;                                                    // caught as overflow below
+            }
+            if (err) break;
+        }
+        if (base + k + L > comp_len || base + k + L < L) { err = E_TRUNCATED; break; }
+        if (op + L > origin) { err = E_OVERFLOW; break; }
+        if (L <= 240u) {
+            DFDB_ENSURE(L)
+            for (uint32_t j0 = 0; j0 < L; j0 += 32) {
+                const uint32_t j = j0 + lane, kk = k + j < 255u ? k + j : 255u;
+                const uint32_t b = chunk_byte_v(w, kk);
+                if (j < L) dst[op + j] = (uint8_t)b;
+            }
+        } else {
+            warp_copy(dst + op, src + base + k, (int64_t)L);
+        }
+        k += L;
+        op += L;
+        ip = base + k;
+        if (ip == comp_len) { done = true; break; }                                       // last sequence: literals only
+        if (ip + 2u > comp_len) { err = E_TRUNCATED; break; }
+        DFDB_ENSURE(2u)
+        const uint32_t off = chunk_byte_u(w, k) | (chunk_byte_u(w, k + 1) << 8);
+        k += 2;
+        uint32_t M = t & 15u;
+        if (M == 15u) {
+            for (;;) {
+                if (base + k >= comp_len) { err = E_TRUNCATED; break; }
+                DFDB_ENSURE(1u)
+                const uint32_t e = chunk_byte_u(w, k);
+                k++;
+                M += e;
+                if (e != 255u) break;
+                if (M > origin) break;
+            }
+            if (err) break;
+        }
+        M += 4;
+        if (off == 0 || off > op) { err = E_OFFSET; break; }
+        if (op + M > origin) { err = E_OVERFLOW; break; }
+        if (pend_a) { *pend_a = (uint8_t)pend_b; pend_a = nullptr; }
+        __syncwarp();                                          // literals and the previous match are visible to the whole warp
+        // every source byte is < op, i.e. final: the copy is fully parallel even when it overlaps itself
+        uint8_t *m_dst = dst + op;
+        const uint8_t *m_src = m_dst - off;
+        if (M <= 32u) {
+            if (lane < M) { pend_b = __ldcg(m_src + (off >= M ? lane : lane % off)); pend_a = m_dst + lane; }
+        } else if (off >= M) {
+            for (uint32_t i = lane; i < M; i += 32) m_dst[i] = __ldcg(m_src + i);
+        } else {
+            for (uint32_t i = lane; i < M; i += 32) m_dst[i] = __ldcg(m_src + (i % off));
+        }
+        op += M;
     }
+#undef DFDB_ENSURE
+    if (pend_a) *pend_a = (uint8_t)pend_b;
+    __syncwarp();
+    ip_io = base + k;
+    op_io = op;
+    return err;
+}
+
+// A special entry (length extensions / last sequence) heads the ring: the whole warp does that sequence against global
+// memory.  parked: the walker waits behind it, so the warp may carry on over the following sequences before it restarts
+// the walker lane (or finishes the block).  Not parked: the walker has already gone on; just that one sequence.
+__device__ __noinline__ void special_step(V2Smem &S, int s, SlotJob &J, uint32_t p0, bool parked)
+{
+    const uint32_t lane = lane_id();
+    uint32_t ip = p0, op = J.op;
+    bool done = false;
+    const int e = special_run(J, ip, op, done, !parked);
+    // a finished block -- good or bad -- leaves its ring as it is: the next block's first command flushes it
+    if (e) { finish_block(J, e); return; }
+    if (done) { finish_block(J, (op == J.origin && ip == J.comp_len) ? E_OK : E_SIZE); return; }
     refill_landed(S, s, J, true);
-    const uint32_t nop = (uint32_t)op;
     if (lane == 0) {
-        J.op = nop;
-        J.ip = (uint32_t)ip;
-        if ((uint32_t)ip >= J.whi) { J.whi = (uint32_t)ip & ~15u; st_rlx(&S.whi[s], J.whi); }   // walker is parked: no race
+        J.op = op;
+        J.ip = ip;
+        J.tail += 1;
+        st_rlx(&S.tail[s], J.tail);
+        // the next token lies beyond the window (long literal run): re-base the window.  The walker cannot be reading
+        // there: parked, or waiting for exactly this position to come into the window.
+        if (ip >= J.whi) { J.whi = ip & ~15u; st_rlx(&S.whi[s], J.whi); }
     }
     __syncwarp();
-    while (refill(S, s, J, 16)) { }
-    post_cmd(S, s, J, (uint32_t)ip, J.comp_len);
+    if (parked) {
+        while (refill(S, s, J, 16)) { }
+        post_cmd(S, s, J, ip, J.comp_len);
+    } else {
+        refill_issue(S, s, J, 16);
+    }
 }
 
 // Claim job `job` for slot s.  Trivial and oversized blocks are finished on the spot.
@@ -462,6 +638,12 @@ __device__ __noinline__ void start_job(V2Smem &S, int s, SlotJob &J, const Decod
     __syncwarp();
     while (refill(S, s, J, 16)) { }
     post_cmd(S, s, J, 0u, (uint32_t)comp_len);
+    // the command flushes the ring (a block that ended in an error is dropped where it stood, its entries with it):
+    // the walker answers with the ring position the new block's entries start at
+    while (ld_acq(&S.cmd_ack[s]) != J.seq) __nanosleep(100);
+    const uint32_t hd = ld_rlx(&S.cmd_head[s]);
+    if (lane == 0) { J.tail = hd; st_rlx(&S.tail[s], hd); }
+    __syncwarp();
 }
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v)
@@ -476,32 +658,30 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v)
 }
 
 // One batch of an active slot whose ring looks ready -- any kind of entries.  Returns true when it made progress.
-__device__ __noinline__ bool process_slot(V2Smem &S, int s, SlotJob &J, uint8_t *stg)
+__device__ __noinline__ bool process_slot(V2Smem &S, int s, SlotJob &J, uint8_t *stg, bool force)
 {
     const uint32_t lane = lane_id();
     const uint32_t h = ld_acq(&S.hint[s]);                     // ring entries below the count are visible
-    const uint32_t avail = (h & 0x7fffffffu) - J.tail;
+    const uint32_t avail = (h - J.tail) & H_CNT;
     const int navail = avail < 32u ? (int)avail : 32;
     if (navail == 0) return false;
-    const bool ends_special = (h >> 31) && avail <= 32u;       // a parked walker's last entry is the special one
-    const int nv = navail - (ends_special ? 1 : 0);            // leading non-special entries
     const uint32_t p = (int)lane < navail ? S.ring[s][(J.tail + lane) & RM] : 0u;
+    const uint32_t tok = (int)lane < navail ? S.win[s][p & WM] : 0u;   // the walker only emits tokens that are in the window
+    // special entries: tokens with length extensions, and the last entry of a parked walker whatever its nibbles say
+    const bool parked_last = (h & H_PARKED) && avail <= 32u;
+    uint32_t sm = __ballot_sync(FULL, (int)lane < navail && (tok >= 0xf0u || (tok & 15u) == 15u));
+    if (parked_last) sm |= 1u << (navail - 1);
+    const int nv = sm ? __ffs(sm) - 1 : navail;                // leading plain entries
     if (nv == 0) {
         const long long t0 = STATS_ON ? clock64() : 0;
-        special_step(S, s, J, __shfl_sync(FULL, p, 0));
+        special_step(S, s, J, __shfl_sync(FULL, p, 0), parked_last && navail == 1);
         if (STATS_ON && lane == 0) { STAT_ADD(ST_C_SPECIAL, 1); STAT_ADD(ST_C_SPECIAL_CYCLES, clock64() - t0); }
         return true;
     }
-    const uint32_t tok = (int)lane < nv ? S.win[s][p & WM] : 0u;   // the walker only emits tokens that are in the window
     const uint32_t L = tok >> 4, M = (tok & 15u) + 4, len = L + M;
-    if (J.err) {   // a corrupt block drains its ring up to the closing special entry (the window keeps moving)
-        const uint32_t nip = __shfl_sync(FULL, p + 3 + L, nv - 1);
-        if (lane == 0) { J.ip = nip; J.tail += (uint32_t)nv; st_rlx(&S.tail[s], J.tail); }
-        __syncwarp();
-        refill_issue(S, s, J, 16);
-        return true;
-    }
-    if (nv < 32 && !ends_special) return false;                // wait for a full batch unless the run ends in a special entry
+    // wait for a full batch unless the run ends in a special entry, or the walker cannot go on before this warp has
+    // made room in the window
+    if (nv < 32 && sm == 0 && !force) return false;
     const uint32_t o0 = J.op;
     const uint32_t o = o0 + warp_incl_scan((int)lane < nv ? len : 0u) - ((int)lane < nv ? len : 0u);
     int err = E_OK;
@@ -540,12 +720,7 @@ __device__ __noinline__ bool process_slot(V2Smem &S, int s, SlotJob &J, uint8_t 
             if (!err) flush(J, stg, o0 & ~15u, new_op);
         }
     }
-    if (err) {
-        const uint32_t nip = __shfl_sync(FULL, p + 3 + L, nv - 1);
-        if (lane == 0) { J.err = (uint32_t)err; J.ip = nip; J.tail += (uint32_t)nv; st_rlx(&S.tail[s], J.tail); }
-        __syncwarp();
-        return true;
-    }
+    if (err) { finish_block(J, err); return true; }   // dropped where it stands; the next block's command flushes the ring
     const uint32_t next_ip = __shfl_sync(FULL, p + 3 + L, nproc - 1);
     if (lane == 0) { J.op = new_op; J.ip = next_ip; J.tail += (uint32_t)nproc; st_rlx(&S.tail[s], J.tail); }
     __syncwarp();
@@ -577,7 +752,7 @@ __device__ __forceinline__ int stage1(V2Smem &S, int s, const uint32_t *ring, co
     const uint32_t lane = lane_id();
     r.meta = 0; r.litw = 0; r.far_lo = 0; r.far_hi = 0; r.tw = 0;
     const uint32_t h = ld_acq(&S.hint[s]);                              // ring entries below the count are visible
-    const uint32_t avail = (h & 0x7fffffffu) - tail;
+    const uint32_t avail = (h - tail) & H_CNT;
     if (avail < 32u) return (h >> 31) && avail ? STG_SLOW : STG_WAIT;   // partial batch: wait, unless it ends in a special entry
     if (avail == 32u && (h >> 31)) return STG_SLOW;                     // the last entry of a parked walker is special
     const uint32_t p = ring[(tail + lane) & RM];
@@ -749,18 +924,20 @@ __device__ void consumer(V2Smem &S, const DecodeArgs &args, unsigned int *counte
             const uint32_t st = J.state;
             if (st == SLOT_ACTIVE) {
                 const uint32_t h = ld_rlx(&S.hint[s]);
-                const uint32_t avail = (h & 0x7fffffffu) - J.tail;
+                const uint32_t avail = (h - J.tail) & H_CNT;
                 // Wake up for several batches at once (bursts amortise the slot's state and keep far loads a batch
                 // ahead) -- but do not wait for entries the walker cannot produce: when its last token sits near the
                 // end of the window it is about to stall until this warp has consumed a batch and refilled.
                 bool ready = avail >= (uint32_t)READY_MIN || ((h >> 31) && avail >= 1u);
-                if (!ready && avail >= 32u) ready = J.whi - S.ring[s][((h & 0x7fffffffu) - 1u) & RM] < 128u;
-                if (ready) {
+                if (!ready && avail >= 32u) ready = J.whi - S.ring[s][((h & H_CNT) - 1u) & RM] < 128u;
+                // the walker needs stream bytes that only fit into the window once entries have been consumed
+                const bool force = (h & H_STARVED) && avail >= 1u && J.pend == 0 && J.whi - (J.ip & ~15u) > (uint32_t)(W - 256);
+                if (ready || force) {
                     const long long t0 = STATS_ON ? clock64() : 0;
-                    const int code = burst(S, s, J);
+                    const int code = avail >= 32u ? burst(S, s, J) : 2;
                     bool r = (code & 1) != 0;
                     const long long t1 = STATS_ON ? clock64() : 0;
-                    if (code & 2) r |= process_slot(S, s, J, stg);
+                    if (code & 2) r |= process_slot(S, s, J, stg, force);
                     if (STATS_ON && lane == 0) {
                         STAT_ADD(ST_C_PS_CALLS, 1); STAT_ADD(ST_C_PS_CYCLES, t1 - t0);
                         if (code & 2) { STAT_ADD(ST_C_SLOW_CALLS, 1); STAT_ADD(ST_C_SLOW_CYCLES, clock64() - t1); }
@@ -831,7 +1008,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) lz4_decode_v2_kernel(const __gr
     V2Smem &S = *reinterpret_cast<V2Smem *>(v2_smem_raw + ((1024u - (smem_addr(v2_smem_raw) & 1023u)) & 1023u));
     const int warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < NSLOT_PAD; i += blockDim.x) {
-        S.tail[i] = 0; S.whi[i] = 0; S.cmd_seq[i] = 0; S.cmd_p[i] = 0; S.cmd_lim[i] = 0; S.hint[i] = 0;
+        S.tail[i] = 0; S.whi[i] = 0; S.cmd_seq[i] = 0; S.cmd_p[i] = 0; S.cmd_lim[i] = 0; S.hint[i] = 0; S.cmd_ack[i] = 0; S.cmd_head[i] = 0;
     }
     for (int i = threadIdx.x; i < NSLOT; i += blockDim.x) {
         SlotJob &J = S.job[i];
