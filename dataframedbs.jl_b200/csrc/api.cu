@@ -39,6 +39,7 @@ struct Runtime {
     int64_t no_wide = 0;
     int64_t no_fused = 0;
     int64_t no_tma = 0;
+    int64_t lz4_flavour = 0;  // K1 flavour: 0 = per column from a token sample at load, 1 = word-regular decoder (v2), 2 = general decoder (v3)
     int64_t no_alias = 0;     // copy stored (incompressible) blocks like any other block instead of referencing them in place
     // profiling
     bool profiling = false;
@@ -204,10 +205,50 @@ bool wide_ok(const dfdb_table *t, const Column &c)
 }
 
 // ---- decode ---------------------------------------------------------------------------------------------
-int launch_decode(const DecodeArgs &a)
+int launch_decode(const DecodeArgs &a, bool general)
 {
     if (rt.lz4_simple || rt.lz4_v1) return launch_lz4_decode(a, rt.d_counter, rt.sm_count, (int)rt.lz4_simple, rt.stream);
-    return launch_lz4_decode_v2(a, rt.d_counter, rt.sm_count, rt.stream);
+    if (rt.lz4_flavour == 1) general = false;
+    if (rt.lz4_flavour == 2) general = true;
+    return general ? launch_lz4_decode_v3(a, rt.d_counter, rt.sm_count, rt.stream) : launch_lz4_decode_v2(a, rt.d_counter, rt.sm_count, rt.stream);
+}
+
+// Which K1 flavour suits a column: walk the token stream of one compressed block on the host (done once, at load).
+// The word-regular decoder (v2) is the faster one when nearly every sequence is plain (no length extensions) and
+// word-regular (8-byte aligned output, offset and length multiples of 8, at most 2 literals) and its source is not
+// the few words right before it (chains serialise v2's dependency waves).  Returns -1 when the block gives no verdict.
+int sample_flavour(const uint8_t *src, int64_t n, int64_t origin)
+{
+    int64_t ip = 0, op = 0, nseq = 0, regular = 0, chained = 0;
+    while (ip < n && nseq < 20000) {
+        const uint32_t t = src[ip++];
+        int64_t L = t >> 4;
+        bool plain = true;
+        if (L == 15) {
+            plain = false;
+            for (;;) { if (ip >= n) return -1; const uint32_t e = src[ip++]; L += e; if (e != 255) break; }
+        }
+        ip += L;
+        op += L;
+        if (ip + 2 > n) break;                                   // last sequence
+        const uint32_t off = (uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8);
+        ip += 2;
+        int64_t M = t & 15;
+        if (M == 15) {
+            plain = false;
+            for (;;) { if (ip >= n) return -1; const uint32_t e = src[ip++]; M += e; if (e != 255) break; }
+        }
+        M += 4;
+        nseq++;
+        if (plain && L <= 2 && (((L + M) | off | (op - L)) & 7) == 0) {
+            regular++;
+            if (off <= 64) chained++;
+        }
+        op += M;
+        if (op > origin) return -1;
+    }
+    if (nseq < 64) return -1;
+    return (regular * 100 >= nseq * 98 && chained * 2 <= nseq) ? 0 : 1;
 }
 
 int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids)
@@ -259,14 +300,18 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids)
             cudaEventDestroy(copied[(size_t)k]);
         }
         if (b1 <= b0) continue;
-        for (size_t i = 0; i < todo.size(); i += DECODE_MAX_COLS) {
+        // columns of one flavour share a launch
+        for (int general = 0; general < 2; general++) {
+          std::vector<Column *> grp;
+          for (Column *c : todo) if ((int)c->lz4_general == general) grp.push_back(c);
+          for (size_t i = 0; i < grp.size(); i += DECODE_MAX_COLS) {
             DecodeArgs a;
             memset(&a, 0, sizeof a);
             a.nblocks = b1 - b0;
             a.blk0 = b0;
             int64_t bytes = 0;
-            for (size_t q = i; q < todo.size() && q < i + DECODE_MAX_COLS; q++) {
-                Column *c = todo[q];
+            for (size_t q = i; q < grp.size() && q < i + DECODE_MAX_COLS; q++) {
+                Column *c = grp[q];
                 DecodeCol &d = a.col[a.ncols++];
                 d.comp = c->d_comp; d.comp_off = c->d_comp_off; d.comp_len = c->d_comp_len; d.dec_off = c->d_dec_off;
                 d.origin = c->d_origin; d.out = c->d_decoded; d.status = c->d_status; d.skip = c->d_skip;
@@ -274,7 +319,8 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids)
                     if (!c->h_skip[(size_t)b]) bytes += c->blocks[(size_t)(t->blk_lo + b)].compressed + c->blocks[(size_t)(t->blk_lo + b)].origin;
             }
             PhaseScope ps(PH_DECODE, bytes);
-            LAUNCH(launch_decode(a));
+            LAUNCH(launch_decode(a, general != 0));
+          }
         }
     }
     const Geometry g = make_geometry(t);
@@ -758,6 +804,7 @@ int32_t dfdb_set_option(const char *name, int64_t value)
     else if (n == "no_wide") rt.no_wide = value;
     else if (n == "no_fused") rt.no_fused = value;
     else if (n == "no_tma") rt.no_tma = value;
+    else if (n == "lz4_flavour") rt.lz4_flavour = value;
     else if (n == "no_alias") rt.no_alias = value;
     else return fail(DFDB_ERR_ARGUMENT, "unknown option %s", n.c_str());
     return DFDB_OK;
@@ -946,6 +993,18 @@ int32_t dfdb_table_load(dfdb_table *t, const int64_t *col_ids, int32_t n, int32_
         }
         close(fd);
         if (cpos > prev_end) memset(c->h_comp + prev_end, 0, (size_t)(cpos - prev_end));
+        // K1 flavour of the column: first, middle and last block vote (stored blocks are never decoded and abstain)
+        {
+            int votes[2] = {0, 0};
+            const int64_t cand[3] = {0, nb / 2, nb - 1};
+            for (int k = 0; k < 3 && nb > 0; k++) {
+                const int64_t b = cand[k];
+                if (stored[(size_t)b]) continue;
+                const int v = sample_flavour(c->h_comp + comp_off[(size_t)b], comp_len[(size_t)b], origin[(size_t)b]);
+                if (v >= 0) votes[v]++;
+            }
+            c->lz4_general = votes[1] > votes[0];
+        }
         CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&c->d_comp), c->comp_bytes));
         if ((rc = dev_upload(&c->d_comp_off, comp_off))) return rc;
         if ((rc = dev_upload(&c->d_comp_len, comp_len))) return rc;
@@ -1380,7 +1439,7 @@ int32_t dfdb_lz4_decode_blocks(const uint8_t *comp, const int64_t *comp_off, con
     a.ncols = 1;
     a.nblocks = n;
     a.col[0] = DecodeCol{d_comp, d_coff, d_clen, d_doff, d_orig, d_out, d_status, nullptr};
-    if (launch_decode(a) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "decode launch failed"); }
+    if (launch_decode(a, true) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "decode launch failed"); }
     rt.launches++;
     std::vector<uint8_t> hout((size_t)dpos + 256);
     cudaMemcpyAsync(hout.data(), d_out, hout.size(), cudaMemcpyDeviceToHost, rt.stream);

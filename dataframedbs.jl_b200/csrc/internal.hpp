@@ -64,6 +64,7 @@ struct Column {
     uint8_t *d_skip = nullptr;       // 1 = stored block (one literal run): its body is referenced in place inside d_comp
     std::vector<uint8_t> h_skip;
     int64_t stored_blocks = 0;
+    bool lz4_general = false;        // K1 flavour: general decoder (v3) instead of the word-regular one (v2), decided at load
     int32_t *d_str_off = nullptr;    // String columns: per-row char offset inside the block's char area
     bool str_off_valid = false;
     std::vector<int64_t> h_dec_off, h_comp_off;

@@ -26,7 +26,8 @@ struct DecodeArgs {
     unsigned long long *stats;   // optional diagnostics counters (null = off), see lz4_decode_v2.cu
 };
 int launch_lz4_decode(const DecodeArgs &args, unsigned int *d_counter, int sm_count, int simple_mode, cudaStream_t stream);      // v1: warp per block
-int launch_lz4_decode_v2(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream);                     // v2: walker / consumer warps
+int launch_lz4_decode_v2(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream);                     // v2: walker / consumer warps, word-regular columns
+int launch_lz4_decode_v3(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream);                     // v3: same organisation, general columns (strings, literal-heavy, chains)
 
 // ---- scan geometry -------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 256;

@@ -53,6 +53,11 @@ constexpr int READY_MIN = 96;               // ring entries that wake a consumer
 constexpr unsigned IDLE_SLEEP_NS = 1000;     // consumer with nothing ready: about the time a walker needs for one batch               // batches a consumer takes from one slot before it looks at the other
 constexpr int STG = 1088;                   // staging per consumer warp: 15 carried + 32 * (14 + 18) bytes, padded
 constexpr uint32_t LIM_EXIT = 0xffffffffu;
+// hint word (walker -> consumer): entries emitted so far | flags
+constexpr uint32_t H_PARKED = 0x80000000u;  // the last entry is a special token the walker could not get past: it waits for a command
+constexpr uint32_t H_STARVED = 0x40000000u; // the walker's next token lies beyond the window
+constexpr uint32_t H_CNT = 0x3fffffffu;
+constexpr int HYST = 8;                     // plain tokens in a row that end a consumer-side run of special sequences
 constexpr uint32_t POS_CAP = 1u << 30;      // larger blocks take the one-sequence-at-a-time path
 constexpr int REG_MIN = 16;                 // shortest leading word-regular run worth its own batch
 static_assert(NSLOT <= NSLOT_PAD, "every slot needs a walker lane");
@@ -64,7 +69,7 @@ enum { SLOT_EMPTY = 0, SLOT_ACTIVE = 1, SLOT_RETIRED = 2 };
 enum { ST_W_ROUNDS = 0, ST_W_COMMITS, ST_W_RINGFULL, ST_W_WINEMPTY, ST_W_PARKED, ST_W_SLEEPS,
        ST_C_POLLS, ST_C_SLEEPS, ST_C_PS_CALLS, ST_C_PS_FALSE, ST_C_REG, ST_C_REGSEQ, ST_C_GEN, ST_C_GENSEQ, ST_C_SPECIAL,
        ST_C_PS_CYCLES, ST_C_LOOP_CYCLES, ST_C_REFILLS, ST_W_CYCLES, ST_C_START_CYCLES, ST_C_SLOW_CALLS, ST_C_SLOW_CYCLES,
-       ST_C_SPECIAL_CYCLES, ST_C_SLEEP_CYCLES, ST_COUNT };
+       ST_C_SPECIAL_CYCLES, ST_C_SLEEP_CYCLES, ST_G_PRO, ST_G_HEAD, ST_G_BATCH, ST_G_FLUSH, ST_G_EPI, ST_G_WAVES, ST_COUNT };
 #ifdef DFDB_LZ4_STATS
 __device__ unsigned long long *g_stats;
 #define STAT_ADD(i, v) do { if (g_stats) atomicAdd(&g_stats[i], (unsigned long long)(v)); } while (0)
@@ -85,17 +90,20 @@ struct SlotJob {                // consumer-private state of one block slot
     uint32_t whi;               // window holds stream bytes [whi - W, whi)
     uint32_t state, err, seq;
     uint32_t pend;              // window fill level once the refill in flight lands (0 = none in flight)
-    uint32_t rphase, pad[3];    // parity of the slot's refill mbarrier
+    uint32_t rphase;            // parity of the slot's refill mbarrier
+    uint32_t chainy, pad[2];    // burst flavour: batches are chains of in-batch copies
 };
 
 struct V2Smem {
     __align__(1024) uint8_t win[NSLOT][W];   // first, 1024-byte aligned: the walker forms addresses with one LOP3
     uint32_t tail[NSLOT_PAD], whi[NSLOT_PAD], cmd_seq[NSLOT_PAD], cmd_p[NSLOT_PAD], cmd_lim[NSLOT_PAD];
+    uint32_t cmd_ack[NSLOT_PAD], cmd_head[NSLOT_PAD];   // walker -> consumer: last command taken, and the ring position its entries start at
     uint32_t dummy[NSLOT_PAD];               // sink for the ring stores of walker lanes that do not commit a step
     uint32_t hint[NSLOT_PAD];                // walker -> consumer: entries emitted so far | parked << 31 (release store once per round)
     SlotJob job[NSLOT];
     unsigned long long rbar[NSLOT];          // mbarrier per slot: completion of the asynchronous window refill (32 arrivals)
     uint32_t ring[NSLOT][R + 1];             // token positions; +1: consecutive slots start one bank apart
+    uint32_t stg_slot[NCONS], stg_op[NCONS];  // whose output chunk sits in stg[c][0..16): slot and output position (generic batches)
     __align__(16) uint8_t stg[NCONS][STG];
 };
 
@@ -131,6 +139,38 @@ __device__ __forceinline__ void sts_u32(uint32_t sa, uint32_t x)
     asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sa), "r"(x) : "memory");
 }
 
+// Out of line (the walker's loop should stay small): the lane stopped on the token of ring entry head - 1.  Reads its
+// length extension bytes when they are in the window and returns true with p behind the sequence; false = stay parked.
+__device__ __noinline__ bool walker_resolve(uint32_t win_sa, uint32_t ring_sa, uint32_t head, uint32_t whi_c, uint32_t lim, uint32_t &p)
+{
+    uint32_t ps;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(ps) : "r"(ring_sa + ((head - 1u) & RM) * 4) : "memory");
+    const uint32_t t = lds_u8(win_sa | (ps & WM));
+    uint32_t q = ps + 1, L = t >> 4;
+    if (L == 15u) {
+        for (;;) {
+            if (q >= whi_c) return false;
+            const uint32_t e = lds_u8(win_sa | (q & WM));
+            q++;
+            L += e;
+            if (e != 255u) break;
+            if (L > 65536u) return false;
+        }
+    }
+    q += L + 2;                                   // behind the offset
+    if (q > lim) return false;                    // last sequence (or a truncated stream): the consumer closes the block
+    if ((t & 15u) == 15u) {
+        for (;;) {
+            if (q >= whi_c || q >= lim) return false;
+            const uint32_t e = lds_u8(win_sa | (q & WM));
+            q++;
+            if (e != 255u) break;
+        }
+    }
+    p = q;
+    return true;
+}
+
 // =====================================================================================================
 // walker: lane = block slot.  Emits {p | token << 24, o | gen << 24 | special << 31} per sequence.
 // =====================================================================================================
@@ -158,7 +198,11 @@ __device__ void walker(V2Smem &S, int slot)
             lim = ld_rlx(&S.cmd_lim[sl]);
             if (lim == LIM_EXIT) { finished = true; running = false; }
             else { p = ld_rlx(&S.cmd_p[sl]); running = true; whi_c = whi_n; tail_c = tail_n; }
+            // a command flushes the ring: whatever this lane emitted so far belongs to an abandoned block
+            if (has) { st_rlx(&S.hint[sl], head); st_rlx(&S.cmd_head[sl], head); st_rel(&S.cmd_ack[sl], seq_n); }
         }
+        const bool run0 = running;
+        bool starved = false;
         const uint32_t room = running ? (uint32_t)R - (head - tail_c) : 0u;
         const uint32_t head0 = head;
 #ifdef DFDB_LZ4_STATS
@@ -176,7 +220,9 @@ __device__ void walker(V2Smem &S, int slot)
             // commit stores to a dummy word and keeps its state.  Dependent chain of a step: LDS -> LEA.HI/VIADD
             // (next p) -> SEL -> LOP3 (next address).
             const uint32_t t = lds_u8(win_sa | (p & WM));
-            const bool commit = running & (p < whi_c) & (room > (uint32_t)u);
+            const bool inwin = p < whi_c;
+            if (u == UNROLL - 1) starved = running & !inwin;   // (as of the last step: a lane that ran dry later shows up a round late)
+            const bool commit = running & inwin & (room > (uint32_t)u);
             const uint32_t pn = p + 3 + (t >> 4);
             const bool special = (t >= 0xf0u) | ((t & 15u) == 15u) | (pn > lim);   // length extensions / last sequence
             sts_u32(commit ? ring_sa + (head & RM) * 4 : dummy_sa, p);
@@ -185,7 +231,13 @@ __device__ void walker(V2Smem &S, int slot)
             running = running & !(commit & special);           // parked until the consumer posts the position behind this sequence
         }
         const bool any_commit = head != head0;
-        if (has) st_rel(&S.hint[sl], head | ((!running && !finished) ? 0x80000000u : 0u));   // entries below head are visible
+        // Resolve step (rare, divergent): a lane that stopped on a token with length extensions in this round reads the
+        // extension bytes itself when they are in the window, and walks on behind the sequence.  The entry stays in the
+        // ring; the consumer recognises it by its nibbles and does that sequence on its own.  Not resolvable (extension
+        // bytes beyond the window, last sequence): the lane stays parked and the consumer restarts it with a command.
+        if (run0 & !running) running = walker_resolve(win_sa, ring_sa, head, whi_c, lim, p);
+        if (has)   // entries below head are visible
+            st_rel(&S.hint[sl], head | ((!running && !finished) ? H_PARKED : 0u) | (starved ? H_STARVED : 0u));
         if (__all_sync(FULL, finished)) break;
         if (!__any_sync(FULL, any_commit)) {
             __nanosleep(60);
@@ -298,6 +350,42 @@ __device__ __forceinline__ void flush(const SlotJob &J, const uint8_t *stg, uint
     __syncwarp();
 }
 
+// In-batch sources of a word-regular batch.  Word i is  lit_i | (word[dep_i] & keep_i)  (low half; the high half is a plain
+// copy).  Dependency waves over warp shuffles settle the usual case (a producer a few words back that came from
+// memory) in one or two rounds; when many words are still open after the first wave they form chains (sorted /
+// sequential columns: every word copies its predecessor), and those are collapsed by pointer jumping -- the maps compose, (lit, keep) o (lit', keep') = (lit | lit' & keep, keep & keep')
+// -- in at most five more rounds instead of one round per word.
+__device__ __noinline__ void resolve_chains(bool &fin, int dep, uint32_t litw, uint32_t keep, uint32_t &vlo, uint32_t &vhi)
+{
+    const uint32_t lane = lane_id();
+    while (__any_sync(FULL, !fin)) {
+        const uint32_t finmask = __ballot_sync(FULL, fin);
+        const int j = fin ? (int)lane : dep;
+        const uint32_t a = __shfl_sync(FULL, vlo, j), b = __shfl_sync(FULL, vhi, j);
+        const uint32_t pl = __shfl_sync(FULL, litw, j), pk = __shfl_sync(FULL, keep, j);
+        const int pd = __shfl_sync(FULL, dep, j);
+        if (!fin) {
+            if ((finmask >> j) & 1u) { vlo = litw | (a & keep); vhi = b; fin = true; }
+            else { litw |= pl & keep; keep &= pk; dep = pd; }
+        }
+    }
+}
+__device__ __forceinline__ void resolve_in_batch(bool &fin, int dep, uint32_t litw, uint32_t keep, uint32_t &vlo, uint32_t &vhi)
+{
+    const uint32_t lane = lane_id();
+    bool first = true;
+    for (;;) {
+        const uint32_t finmask = __ballot_sync(FULL, fin);
+        if (finmask == FULL) return;
+        // many words still open after the first wave: chains, not the odd producer a few words back
+        if (!first && __popc(~finmask) > 12) { resolve_chains(fin, dep, litw, keep, vlo, vhi); return; }
+        first = false;
+        const int j = fin ? (int)lane : dep;
+        const uint32_t a = __shfl_sync(FULL, vlo, j), b = __shfl_sync(FULL, vhi, j);
+        if (!fin && ((finmask >> j) & 1u)) { vlo = litw | (a & keep); vhi = b; fin = true; }
+    }
+}
+
 // ---- word-regular batch: lanes [0, nreg) hold sequences with o % 8 == 0, off % 8 == 0, (L + M) % 8 == 0, L <= 2.
 //      One output word per lane, written straight to global memory (a coalesced 256-byte store per batch). ----
 __device__ __forceinline__ int regular_batch(const SlotJob &J, uint32_t o0, uint32_t o, uint32_t len, uint32_t L, uint32_t offv,
@@ -331,13 +419,7 @@ __device__ __forceinline__ int regular_batch(const SlotJob &J, uint32_t o0, uint
         vhi = far.y;
         fin = true;
     }
-    // in-batch sources: dependency waves over warp shuffles (the lowest unresolved word always has a resolved producer)
-    while (__any_sync(FULL, !fin)) {
-        const uint32_t finmask = __ballot_sync(FULL, fin);
-        const int j = fin ? (int)lane : dep;
-        const uint32_t a = __shfl_sync(FULL, vlo, j), b = __shfl_sync(FULL, vhi, j);
-        if (!fin && ((finmask >> j) & 1u)) { vlo = litw | (a & keep); vhi = b; fin = true; }
-    }
+    resolve_in_batch(fin, dep, litw, keep, vlo, vhi);
     if (wl) *reinterpret_cast<uint2 *>(J.dst + ow) = make_uint2(vlo, vhi);
     __syncwarp();
     *new_op = o0 + 8 * tw;
@@ -369,7 +451,39 @@ __device__ __forceinline__ int generic_batch(const uint8_t *win, uint8_t *stg, c
     while (pending) {
         const bool mine = (pending >> lane) & 1u;
         const bool ready = mine && (src_end <= F || (int)lane == P);
-        if (ready) {
+        const bool far = m_src + (int32_t)M <= stg_base;            // whole source below the staging area: in global memory
+        const bool near = m_src >= stg_base && off >= M;            // whole source in the staging area, not overlapping the destination
+        if (ready && (far || near)) {
+            // aligned 8-byte loads, all in flight at once (only the words that hold source bytes, so nothing beyond
+            // the bytes already written is touched), then the bytes are stored from registers
+            const int32_t sd = m_dst - stg_base;
+            const uint32_t sh = (uint32_t)m_src & 7u, span = sh + M;                      // M <= 18: span <= 25
+            unsigned long long w0, w1 = 0, w2 = 0, w3 = 0;
+            if (far) {
+                const unsigned long long *g8 = reinterpret_cast<const unsigned long long *>(J.dst + (m_src - (int32_t)sh));
+                w0 = __ldcg(g8);
+                if (span > 8u) w1 = __ldcg(g8 + 1);
+                if (span > 16u) w2 = __ldcg(g8 + 2);
+                if (span > 24u) w3 = __ldcg(g8 + 3);
+            } else {
+                const unsigned long long *s8 = reinterpret_cast<const unsigned long long *>(stg + (m_src - stg_base - (int32_t)sh));
+                w0 = s8[0];
+                if (span > 8u) w1 = s8[1];
+                if (span > 16u) w2 = s8[2];
+                if (span > 24u) w3 = s8[3];
+            }
+            const uint32_t s8b = sh * 8;
+            if (s8b) {
+                w0 = (w0 >> s8b) | (w1 << (64 - s8b));
+                w1 = (w1 >> s8b) | (w2 << (64 - s8b));
+                w2 = (w2 >> s8b) | (w3 << (64 - s8b));
+            }
+#pragma unroll
+            for (int i = 0; i < 18; i++) {
+                const unsigned long long w = i < 8 ? w0 : (i < 16 ? w1 : w2);
+                if ((uint32_t)i < M) stg[sd + i] = (uint8_t)(w >> (8 * (i & 7)));
+            }
+        } else if (ready) {
             const int32_t sd = m_dst - stg_base;
             uint32_t i = 0;
             if (off >= 8 && ((m_dst | m_src) & 7) == 0) {
@@ -388,6 +502,7 @@ __device__ __forceinline__ int generic_batch(const uint8_t *win, uint8_t *stg, c
             }
         }
         __syncwarp();
+        if (STATS_ON && lane == 0) STAT_ADD(ST_G_WAVES, 1);
         pending &= ~__ballot_sync(FULL, ready);
         if (pending) {
             P = __ffs(pending) - 1;
@@ -398,37 +513,167 @@ __device__ __forceinline__ int generic_batch(const uint8_t *win, uint8_t *stg, c
     return E_OK;
 }
 
-// A special entry (length extensions / last sequence / capped positions) heads the ring: the whole warp does that
-// one sequence against global memory, then restarts the walker lane behind it (or finishes the block).
-__device__ __noinline__ void special_step(V2Smem &S, int s, SlotJob &J, uint32_t p0)
+// ---- one sequence at a time, whole warp: the path of "special" tokens (length extensions, last sequence) ------------
+// The stream is read through a 256-byte register chunk (one aligned 8-byte word per lane, bytes fetched with warp
+// shuffles), so a sequence costs no dependent global loads for its token / extension bytes / literals / offset; the
+// match bytes of a short match stay pending in registers across the parse of the next sequence (their load latency
+// hides behind it).  Same checks, in the same order, as decode_one_sequence.
+__device__ __forceinline__ uint2 chunk_load(const uint8_t *src, uint32_t lim16, uint32_t base)
+{
+    const uint32_t a = base + 8 * lane_id();                  // base is a multiple of 8, payload slots are 16-byte aligned and padded
+    uint2 w = make_uint2(0u, 0u);
+    if (a < lim16) w = __ldg(reinterpret_cast<const uint2 *>(src + a));
+    const uint32_t nx = base + 256 + 128 * lane_id();         // the next chunk's two lines: into L2 while this one is parsed
+    if (lane_id() < 2 && nx < lim16) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + nx));
+    return w;
+}
+__device__ __forceinline__ uint32_t chunk_byte_u(const uint2 w, uint32_t k)     // k < 256, uniform over the warp
+{
+    return (__shfl_sync(FULL, (k & 4u) ? w.y : w.x, k >> 3) >> ((k & 3u) * 8)) & 0xffu;
+}
+__device__ __forceinline__ uint32_t chunk_byte_v(const uint2 w, uint32_t k)     // k < 256, any value per lane
+{
+    const uint32_t lo = __shfl_sync(FULL, w.x, k >> 3), hi = __shfl_sync(FULL, w.y, k >> 3);
+    return (((k & 4u) ? hi : lo) >> ((k & 3u) * 8)) & 0xffu;
+}
+
+// Decodes the sequence at ip.  single: just that one (the walker got past it on its own and has gone on emitting
+// entries).  Otherwise the walker is parked behind it, and the run goes on until HYST plain tokens in a row have been
+// seen (a walker restart costs far more than a sequence done here).
+// Returns E_*; on E_OK either done (last sequence consumed) or ip is the position of the next token.
+__device__ __noinline__ int special_run(const SlotJob &J, uint32_t &ip_io, uint32_t &op_io, bool &done, bool single)
 {
     const uint32_t lane = lane_id();
-    int64_t ip = p0, op = J.op;
-    bool done = false;
-    int e = J.err ? (int)J.err : decode_one_sequence(J.src, J.comp_len, J.dst, J.origin, ip, op, done);
-    if (lane == 0) { J.tail += 1; st_rlx(&S.tail[s], J.tail); }
-    __syncwarp();
-    if (e) { finish_block(J, e); return; }
-    if (done) { finish_block(J, (op == (int64_t)J.origin && ip == (int64_t)J.comp_len) ? E_OK : E_SIZE); return; }
-    if (ip >= (int64_t)POS_CAP || op >= (int64_t)POS_CAP) {
-        // positions no longer fit the ring entries: finish this block one sequence at a time
-        while (!done) {
-            e = decode_one_sequence(J.src, J.comp_len, J.dst, J.origin, ip, op, done);
-            if (e) { finish_block(J, e); return; }
+    const uint8_t *const src = J.src;
+    uint8_t *const dst = J.dst;
+    const uint32_t comp_len = J.comp_len, origin = J.origin, lim16 = (comp_len + 15u) & ~15u;
+    uint32_t ip = ip_io, op = op_io;
+    uint32_t base = ip & ~7u, k = ip - base;
+    uint2 w = chunk_load(src, lim16, base);
+    uint32_t pend_b = 0;
+    uint8_t *pend_a = nullptr;                                // this lane's pending match byte (nullptr: none)
+    int err = E_OK;
+    bool first = true;
+    int nplain = 0;
+#define DFDB_ENSURE(n)                                                                                   \
+    if (k + (n) > 256u) {                                                                                \
+        const uint32_t pos_ = base + k;                                                                  \
+        base = pos_ & ~7u; k = pos_ - base;                                                              \
+        w = chunk_load(src, lim16, base);                                                                \
+    }
+    for (;;) {
+        ip = base + k;
+        if (ip >= comp_len) { err = E_TRUNCATED; break; }
+        DFDB_ENSURE(1u)
+        const uint32_t t = chunk_byte_u(w, k);
+        uint32_t L = t >> 4;
+        if (!first) {
+            if (single) break;
+            if (t < 0xf0u && (t & 15u) != 15u && ip + 3u + L <= comp_len) {
+                if (++nplain > HYST) break;                                               // plain tokens: back to the walker
+            } else nplain = 0;
         }
-        finish_block(J, (op == (int64_t)J.origin && ip == (int64_t)J.comp_len) ? E_OK : E_SIZE);
-        return;
+        first = false;
+        k++;
+        if (L == 15u) {
+            for (;;) {
+                if (base + k >= comp_len) { err = E_TRUNCATED; break; }
+                DFDB_ENSURE(1u)
+                const uint32_t e = chunk_byte_u(w, k);
+                k++;
+                L += e;
+                if (e != 255u) break;
+                if (L > origin) break;                                                    // caught as overflow below
+            }
+            if (err) break;
+        }
+        if (base + k + L > comp_len || base + k + L < L) { err = E_TRUNCATED; break; }
+        if (op + L > origin) { err = E_OVERFLOW; break; }
+        if (L <= 240u) {
+            DFDB_ENSURE(L)
+            for (uint32_t j0 = 0; j0 < L; j0 += 32) {
+                const uint32_t j = j0 + lane, kk = k + j < 255u ? k + j : 255u;
+                const uint32_t b = chunk_byte_v(w, kk);
+                if (j < L) dst[op + j] = (uint8_t)b;
+            }
+        } else {
+            warp_copy(dst + op, src + base + k, (int64_t)L);
+        }
+        k += L;
+        op += L;
+        ip = base + k;
+        if (ip == comp_len) { done = true; break; }                                       // last sequence: literals only
+        if (ip + 2u > comp_len) { err = E_TRUNCATED; break; }
+        DFDB_ENSURE(2u)
+        const uint32_t off = chunk_byte_u(w, k) | (chunk_byte_u(w, k + 1) << 8);
+        k += 2;
+        uint32_t M = t & 15u;
+        if (M == 15u) {
+            for (;;) {
+                if (base + k >= comp_len) { err = E_TRUNCATED; break; }
+                DFDB_ENSURE(1u)
+                const uint32_t e = chunk_byte_u(w, k);
+                k++;
+                M += e;
+                if (e != 255u) break;
+                if (M > origin) break;
+            }
+            if (err) break;
+        }
+        M += 4;
+        if (off == 0 || off > op) { err = E_OFFSET; break; }
+        if (op + M > origin) { err = E_OVERFLOW; break; }
+        if (pend_a) { *pend_a = (uint8_t)pend_b; pend_a = nullptr; }
+        __syncwarp();                                          // literals and the previous match are visible to the whole warp
+        // every source byte is < op, i.e. final: the copy is fully parallel even when it overlaps itself
+        uint8_t *m_dst = dst + op;
+        const uint8_t *m_src = m_dst - off;
+        if (M <= 32u) {
+            if (lane < M) { pend_b = __ldcg(m_src + (off >= M ? lane : lane % off)); pend_a = m_dst + lane; }
+        } else if (off >= M) {
+            for (uint32_t i = lane; i < M; i += 32) m_dst[i] = __ldcg(m_src + i);
+        } else {
+            for (uint32_t i = lane; i < M; i += 32) m_dst[i] = __ldcg(m_src + (i % off));
+        }
+        op += M;
     }
-    refill_landed(S, s, J, true);
-    const uint32_t nop = (uint32_t)op;
+#undef DFDB_ENSURE
+    if (pend_a) *pend_a = (uint8_t)pend_b;
+    __syncwarp();
+    ip_io = base + k;
+    op_io = op;
+    return err;
+}
+
+// A special entry (length extensions / last sequence) heads the ring: the whole warp does that sequence against global
+// memory.  parked: the walker waits behind it, so the warp may carry on over the following sequences before it restarts
+// the walker lane (or finishes the block).  Not parked: the walker has already gone on; just that one sequence.
+__device__ __noinline__ void special_step(V2Smem &S, int s, SlotJob &J, uint32_t p0, bool parked)
+{
+    const uint32_t lane = lane_id();
+    uint32_t ip = p0, op = J.op;
+    bool done = false;
+    const int e = special_run(J, ip, op, done, !parked);
+    // a finished block -- good or bad -- leaves its ring as it is: the next block's first command flushes it
+    if (e) { finish_block(J, e); return; }
+    if (done) { finish_block(J, (op == J.origin && ip == J.comp_len) ? E_OK : E_SIZE); return; }
+    if (parked || ip >= J.whi) refill_landed(S, s, J, true);
     if (lane == 0) {
-        J.op = nop;
-        J.ip = (uint32_t)ip;
-        if ((uint32_t)ip >= J.whi) { J.whi = (uint32_t)ip & ~15u; st_rlx(&S.whi[s], J.whi); }   // walker is parked: no race
+        J.op = op;
+        J.ip = ip;
+        J.tail += 1;
+        st_rlx(&S.tail[s], J.tail);
+        // the next token lies beyond the window (long literal run): re-base the window.  The walker cannot be reading
+        // there: parked, or waiting for exactly this position to come into the window.
+        if (ip >= J.whi) { J.whi = ip & ~15u; st_rlx(&S.whi[s], J.whi); }
     }
     __syncwarp();
-    while (refill(S, s, J, 16)) { }
-    post_cmd(S, s, J, (uint32_t)ip, J.comp_len);
+    if (parked) {
+        while (refill(S, s, J, 16)) { }
+        post_cmd(S, s, J, ip, J.comp_len);
+    } else {
+        refill_issue(S, s, J, 16);
+    }
 }
 
 // Claim job `job` for slot s.  Trivial and oversized blocks are finished on the spot.
@@ -455,13 +700,19 @@ __device__ __noinline__ void start_job(V2Smem &S, int s, SlotJob &J, const Decod
     if (lane == 0) {
         J.src = src; J.dst = dst; J.status = &col.status[b];
         J.comp_len = (uint32_t)comp_len; J.origin = (uint32_t)origin;
-        J.op = 0; J.ip = 0; J.whi = 0; J.err = 0; J.pend = 0;
+        J.op = 0; J.ip = 0; J.whi = 0; J.err = 0; J.pend = 0; J.chainy = 0;
         J.state = SLOT_ACTIVE;
         st_rlx(&S.whi[s], 0u);
     }
     __syncwarp();
     while (refill(S, s, J, 16)) { }
     post_cmd(S, s, J, 0u, (uint32_t)comp_len);
+    // the command flushes the ring (a block that ended in an error is dropped where it stood, its entries with it):
+    // the walker answers with the ring position the new block's entries start at
+    while (ld_acq(&S.cmd_ack[s]) != J.seq) __nanosleep(100);
+    const uint32_t hd = ld_rlx(&S.cmd_head[s]);
+    if (lane == 0) { J.tail = hd; st_rlx(&S.tail[s], hd); }
+    __syncwarp();
 }
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v)
@@ -475,33 +726,33 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v)
     return v;
 }
 
-// One batch of an active slot whose ring looks ready -- any kind of entries.  Returns true when it made progress.
-__device__ __noinline__ bool process_slot(V2Smem &S, int s, SlotJob &J, uint8_t *stg)
+// One batch of an active slot whose ring looks ready -- any kind of entries.  Returns 0: nothing to do yet, 1: progress,
+// 3: progress, and the batch was a generic one (more of the same is likely to follow).
+__device__ __noinline__ int process_slot(V2Smem &S, int s, SlotJob &J, uint8_t *stg, bool force)
 {
     const uint32_t lane = lane_id();
+    const long long tp0 = STATS_ON ? clock64() : 0;
     const uint32_t h = ld_acq(&S.hint[s]);                     // ring entries below the count are visible
-    const uint32_t avail = (h & 0x7fffffffu) - J.tail;
+    const uint32_t avail = (h - J.tail) & H_CNT;
     const int navail = avail < 32u ? (int)avail : 32;
-    if (navail == 0) return false;
-    const bool ends_special = (h >> 31) && avail <= 32u;       // a parked walker's last entry is the special one
-    const int nv = navail - (ends_special ? 1 : 0);            // leading non-special entries
+    if (navail == 0) return 0;
     const uint32_t p = (int)lane < navail ? S.ring[s][(J.tail + lane) & RM] : 0u;
+    const uint32_t tok = (int)lane < navail ? S.win[s][p & WM] : 0u;   // the walker only emits tokens that are in the window
+    // special entries: tokens with length extensions, and the last entry of a parked walker whatever its nibbles say
+    const bool parked_last = (h & H_PARKED) && avail <= 32u;
+    uint32_t sm = __ballot_sync(FULL, (int)lane < navail && (tok >= 0xf0u || (tok & 15u) == 15u));
+    if (parked_last) sm |= 1u << (navail - 1);
+    const int nv = sm ? __ffs(sm) - 1 : navail;                // leading plain entries
     if (nv == 0) {
         const long long t0 = STATS_ON ? clock64() : 0;
-        special_step(S, s, J, __shfl_sync(FULL, p, 0));
+        special_step(S, s, J, __shfl_sync(FULL, p, 0), parked_last && navail == 1);
         if (STATS_ON && lane == 0) { STAT_ADD(ST_C_SPECIAL, 1); STAT_ADD(ST_C_SPECIAL_CYCLES, clock64() - t0); }
-        return true;
+        return 3;
     }
-    const uint32_t tok = (int)lane < nv ? S.win[s][p & WM] : 0u;   // the walker only emits tokens that are in the window
     const uint32_t L = tok >> 4, M = (tok & 15u) + 4, len = L + M;
-    if (J.err) {   // a corrupt block drains its ring up to the closing special entry (the window keeps moving)
-        const uint32_t nip = __shfl_sync(FULL, p + 3 + L, nv - 1);
-        if (lane == 0) { J.ip = nip; J.tail += (uint32_t)nv; st_rlx(&S.tail[s], J.tail); }
-        __syncwarp();
-        refill_issue(S, s, J, 16);
-        return true;
-    }
-    if (nv < 32 && !ends_special) return false;                // wait for a full batch unless the run ends in a special entry
+    // wait for a full batch unless the run ends in a special entry, or the walker cannot go on before this warp has
+    // made room in the window
+    if (nv < 32 && sm == 0 && !force) return 0;
     const uint32_t o0 = J.op;
     const uint32_t o = o0 + warp_incl_scan((int)lane < nv ? len : 0u) - ((int)lane < nv ? len : 0u);
     int err = E_OK;
@@ -510,7 +761,9 @@ __device__ __noinline__ bool process_slot(V2Smem &S, int s, SlotJob &J, uint8_t 
     while (!err && J.whi < need)
         if (!refill(S, s, J, 16)) err = E_INTERNAL;
     int nproc = 0;
+    bool generic = false;
     uint32_t new_op = o0;
+    long long tp4 = 0;
     if (!err) {
         const uint8_t *win = S.win[s];
         // 4 stream bytes behind the token: up to 2 literals and the offset of a word-regular sequence
@@ -532,28 +785,56 @@ __device__ __noinline__ bool process_slot(V2Smem &S, int s, SlotJob &J, uint8_t 
             const uint32_t run16 = run & (run >> 4) & (run >> 8) & (run >> 12);      // bit i: lanes i..i+15 all regular
             const uint32_t cand = run16 & ~1u & (nv >= 32 ? FULL : ((1u << nv) - 1u));
             nproc = cand ? (__ffs(cand) - 1) : nv;
+            generic = true;
             if (STATS_ON && lane == 0) { STAT_ADD(ST_C_GEN, 1); STAT_ADD(ST_C_GENSEQ, nproc); }
-            // the staging area starts at the 16-byte chunk that holds o0; its bytes below o0 come back from memory
-            if (lane == 0 && (o0 & 15u)) *reinterpret_cast<uint4 *>(stg) = __ldcg(reinterpret_cast<const uint4 *>(J.dst + (o0 & ~15u)));
+            const long long tp1 = STATS_ON ? clock64() : 0;
+            // the staging area starts at the 16-byte chunk that holds o0; its bytes below o0 are still there when the
+            // warp's last generic batch was this slot's previous one, else they come back from memory
+            const int cw = (int)(threadIdx.x >> 5) - NWALK;
+            if (lane == 0 && (o0 & 15u) && !(S.stg_slot[cw] == (uint32_t)s && S.stg_op[cw] == o0))
+                *reinterpret_cast<uint4 *>(stg) = __ldcg(reinterpret_cast<const uint4 *>(J.dst + (o0 & ~15u)));
             __syncwarp();
+            const long long tp2 = STATS_ON ? clock64() : 0;
             err = generic_batch(win, stg, J, o0, p, o, L, M, nproc, &new_op);
-            if (!err) flush(J, stg, o0 & ~15u, new_op);
+            const long long tp3 = STATS_ON ? clock64() : 0;
+            if (!err) {
+                flush(J, stg, o0 & ~15u, new_op);
+                // keep the chunk the next batch starts in
+                uint4 keepv = make_uint4(0u, 0u, 0u, 0u);
+                if (lane == 0) keepv = *reinterpret_cast<const uint4 *>(stg + ((new_op & ~15u) - (o0 & ~15u)));
+                __syncwarp();
+                if (lane == 0) { *reinterpret_cast<uint4 *>(stg) = keepv; S.stg_slot[cw] = (uint32_t)s; S.stg_op[cw] = new_op; }
+                __syncwarp();
+            }
+            if (STATS_ON) {
+                tp4 = clock64();
+                if (lane == 0) { STAT_ADD(ST_G_PRO, tp1 - tp0); STAT_ADD(ST_G_HEAD, tp2 - tp1); STAT_ADD(ST_G_BATCH, tp3 - tp2); STAT_ADD(ST_G_FLUSH, tp4 - tp3); }
+            }
         }
     }
-    if (err) {
-        const uint32_t nip = __shfl_sync(FULL, p + 3 + L, nv - 1);
-        if (lane == 0) { J.err = (uint32_t)err; J.ip = nip; J.tail += (uint32_t)nv; st_rlx(&S.tail[s], J.tail); }
-        __syncwarp();
-        return true;
-    }
+    if (err) { finish_block(J, err); return 1; }   // dropped where it stands; the next block's command flushes the ring
     const uint32_t next_ip = __shfl_sync(FULL, p + 3 + L, nproc - 1);
     if (lane == 0) { J.op = new_op; J.ip = next_ip; J.tail += (uint32_t)nproc; st_rlx(&S.tail[s], J.tail); }
     __syncwarp();
     refill_issue(S, s, J, 256);
-    return true;
+    if (STATS_ON && tp4 && lane == 0) STAT_ADD(ST_G_EPI, clock64() - tp4);
+    return generic ? 3 : 1;
 }
 
-// Cheap readiness poll of one slot (the ring entries themselves are only read once a batch looks complete).
+// The slow path takes one batch per call.  After a generic batch or a special sequence, keep going while full batches
+// are waiting: more of the same is likely to follow, and a wake-up otherwise costs a sleep period per batch.  (After a
+// word-regular batch the burst path takes over again.)
+__device__ __noinline__ bool slow_path(V2Smem &S, int s, SlotJob &J, uint8_t *stg, bool force)
+{
+    bool r = false;
+    for (int n = 0; n < 4; n++) {
+        const int rr = process_slot(S, s, J, stg, force);
+        r |= rr != 0;
+        if (rr != 3 || J.state != SLOT_ACTIVE || ((ld_rlx(&S.hint[s]) - J.tail) & H_CNT) < 32u) break;
+    }
+    return r;
+}
+
 // ---- the hot path: a burst of full word-regular batches from one slot, slot state in registers -------------------
 // Anything else (partial batches, special entries, sequences that are not word-regular, window shortfalls, errors)
 // is handed to process_slot, which works on the slot state in shared memory.
@@ -577,7 +858,7 @@ __device__ __forceinline__ int stage1(V2Smem &S, int s, const uint32_t *ring, co
     const uint32_t lane = lane_id();
     r.meta = 0; r.litw = 0; r.far_lo = 0; r.far_hi = 0; r.tw = 0;
     const uint32_t h = ld_acq(&S.hint[s]);                              // ring entries below the count are visible
-    const uint32_t avail = (h & 0x7fffffffu) - tail;
+    const uint32_t avail = (h - tail) & H_CNT;
     if (avail < 32u) return (h >> 31) && avail ? STG_SLOW : STG_WAIT;   // partial batch: wait, unless it ends in a special entry
     if (avail == 32u && (h >> 31)) return STG_SLOW;                     // the last entry of a parked walker is special
     const uint32_t p = ring[(tail + lane) & RM];
@@ -638,6 +919,10 @@ __device__ __noinline__ void window_upkeep(V2Smem &S, int s, SlotJob &J, uint32_
     refill_issue(S, s, J, 256);
 }
 
+// CHAINS: the slot's batches are dominated by in-batch chains (sorted / sequential columns: every word copies its
+// predecessor); they are collapsed by pointer jumping instead of one dependency wave per word.  The plain flavour
+// notices such batches and sets J.chainy, the other one clears it again; the consumer picks the flavour per call.
+template <bool CHAINS>
 __device__ __noinline__ int burst(V2Smem &S, int s, SlotJob &J)
 {
     const uint32_t lane = lane_id();
@@ -653,19 +938,25 @@ __device__ __noinline__ int burst(V2Smem &S, int s, SlotJob &J)
     uint32_t pt = 0;                       // words of the previous batch still held in prev_lo / prev_hi
     uint32_t prev_lo = 0, prev_hi = 0;
     Staged cur;
-    int verdict = stage1(S, s, ring, w32, dst, origin, tail, op, 0u, whi, ip, cur);
-    for (int it = 0; cur.tw; it++) {
+    cur.meta = 0; cur.litw = 0; cur.far_lo = 0; cur.far_hi = 0; cur.tw = 0;
+    int verdict = STG_WAIT;
+    for (int it = 0;; it++) {
         // window upkeep (out of line): a refill is in flight, or 256 bytes of the window are free
-        if (pend || (whi < whi_max && (ip & ~15u) + (uint32_t)W - whi >= 256u)) {
+        if (it && (pend || (whi < whi_max && (ip & ~15u) + (uint32_t)W - whi >= 256u))) {
             window_upkeep(S, s, J, ip);
             whi = J.whi;
             pend = J.pend;
         }
-        // stage 1 of the next batch
+        // stage 1 of the next batch (the only call site: the loop's first pass has no current batch yet)
         Staged nxt;
         nxt.tw = 0;
         verdict = STG_WAIT;
-        if (it + 1 < MAX_BURST) verdict = stage1(S, s, ring, w32, dst, origin, tail, op + 8 * cur.tw, cur.tw, whi, ip, nxt);
+        if (it < MAX_BURST) verdict = stage1(S, s, ring, w32, dst, origin, tail, op + 8 * cur.tw, cur.tw, whi, ip, nxt);
+        if (!cur.tw) {
+            cur = nxt;
+            if (!cur.tw) break;
+            continue;
+        }
         // stage 2 of the current batch: resolve every word and store
         const bool wl = lane < cur.tw;
         const uint32_t offw = cur.meta & 0xffffu, Lw = cur.meta >> 16;
@@ -681,12 +972,34 @@ __device__ __noinline__ int burst(V2Smem &S, int s, SlotJob &J)
             vhi = inprev ? qhi : cur.far_hi;
             fin = true;
         }
-        // in-batch sources: dependency waves over warp shuffles (the lowest unresolved word always has a resolved producer)
-        while (__any_sync(FULL, !fin)) {
-            const uint32_t finmask = __ballot_sync(FULL, fin);
-            const int j = fin ? (int)lane : dep;
-            const uint32_t va = __shfl_sync(FULL, vlo, j), vb = __shfl_sync(FULL, vhi, j);
-            if (!fin && ((finmask >> j) & 1u)) { vlo = cur.litw | (va & keep); vhi = vb; fin = true; }
+        // in-batch sources
+        const uint32_t open = __ballot_sync(FULL, !fin);
+        if (open) {
+            if (CHAINS) {
+                int d = dep;
+                uint32_t lt = cur.litw, kp = keep;
+                do {   // pointer jumping: (lit, keep) o (lit', keep') = (lit | lit' & keep, keep & keep')
+                    const uint32_t finmask = __ballot_sync(FULL, fin);
+                    const int j = fin ? (int)lane : d;
+                    const uint32_t va = __shfl_sync(FULL, vlo, j), vb = __shfl_sync(FULL, vhi, j);
+                    const uint32_t pl = __shfl_sync(FULL, lt, j), pk = __shfl_sync(FULL, kp, j);
+                    const int pd = __shfl_sync(FULL, d, j);
+                    if (!fin) {
+                        if ((finmask >> j) & 1u) { vlo = lt | (va & kp); vhi = vb; fin = true; }
+                        else { lt |= pl & kp; kp &= pk; d = pd; }
+                    }
+                } while (__any_sync(FULL, !fin));
+                if (__popc(open) < 8 && lane == 0) J.chainy = 0;
+            } else {
+                // dependency waves over warp shuffles (the lowest unresolved word always has a resolved producer)
+                do {
+                    const uint32_t finmask = __ballot_sync(FULL, fin);
+                    const int j = fin ? (int)lane : dep;
+                    const uint32_t va = __shfl_sync(FULL, vlo, j), vb = __shfl_sync(FULL, vhi, j);
+                    if (!fin && ((finmask >> j) & 1u)) { vlo = cur.litw | (va & keep); vhi = vb; fin = true; }
+                } while (__any_sync(FULL, !fin));
+                if (__popc(open) > 20 && lane == 0) J.chainy = 1;
+            }
         }
         if (wl) *reinterpret_cast<uint2 *>(dst + op + 8 * lane) = make_uint2(vlo, vhi);
         __syncwarp();                                             // the stores are ordered before the far loads of later batches
@@ -695,6 +1008,7 @@ __device__ __noinline__ int burst(V2Smem &S, int s, SlotJob &J)
         progress = true;
         st_batches++;
         cur = nxt;
+        if (!cur.tw) break;
     }
     if (STATS_ON && lane == 0) STAT_ADD(ST_C_REG, st_batches);
     if (lane == 0) { J.tail = tail; J.op = op; J.ip = ip; }
@@ -727,6 +1041,19 @@ __device__ __noinline__ void slot_refresh(V2Smem &S, int s, const DecodeArgs &ar
     }
 }
 
+__device__ __noinline__ void give_up(V2Smem &S, int c)
+{
+    for (int k = 0; k < SPC; k++) {
+        const int s = c + k * NCONS;
+        SlotJob &J = S.job[s];
+        if (J.state == SLOT_RETIRED) continue;
+        if (J.state == SLOT_ACTIVE && lane_id() == 0) *J.status = E_INTERNAL;
+        if (lane_id() == 0) J.state = SLOT_RETIRED;
+        __syncwarp();
+        post_cmd(S, s, J, 0u, LIM_EXIT);
+    }
+}
+
 // Consumer warp: owns SPC slots.  The polling loop is kept to a handful of instructions and sleeps when nothing is
 // ready -- every issue slot a waiting consumer burns is taken from the walker warps, which pace the whole kernel.
 __device__ void consumer(V2Smem &S, const DecodeArgs &args, unsigned int *counter, unsigned int first_dynamic, int c)
@@ -742,25 +1069,27 @@ __device__ void consumer(V2Smem &S, const DecodeArgs &args, unsigned int *counte
     while (live > 0) {
         bool progress = false, worked = false;   // worked: entries were consumed (anything less does not justify another poll right away)
         st_polls++;
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < SPC; k++) {
             const int s = c + k * NCONS;
             SlotJob &J = S.job[s];
             const uint32_t st = J.state;
             if (st == SLOT_ACTIVE) {
                 const uint32_t h = ld_rlx(&S.hint[s]);
-                const uint32_t avail = (h & 0x7fffffffu) - J.tail;
+                const uint32_t avail = (h - J.tail) & H_CNT;
                 // Wake up for several batches at once (bursts amortise the slot's state and keep far loads a batch
                 // ahead) -- but do not wait for entries the walker cannot produce: when its last token sits near the
                 // end of the window it is about to stall until this warp has consumed a batch and refilled.
                 bool ready = avail >= (uint32_t)READY_MIN || ((h >> 31) && avail >= 1u);
-                if (!ready && avail >= 32u) ready = J.whi - S.ring[s][((h & 0x7fffffffu) - 1u) & RM] < 128u;
-                if (ready) {
+                if (!ready && avail >= 32u) ready = J.whi - S.ring[s][((h & H_CNT) - 1u) & RM] < 128u;
+                // the walker needs stream bytes that only fit into the window once entries have been consumed
+                const bool force = (h & H_STARVED) && avail >= 1u && J.pend == 0 && J.whi - (J.ip & ~15u) > (uint32_t)(W - 256);
+                if (ready || force) {
                     const long long t0 = STATS_ON ? clock64() : 0;
-                    const int code = burst(S, s, J);
+                    const int code = avail < 32u ? 2 : (J.chainy ? burst<true>(S, s, J) : burst<false>(S, s, J));
                     bool r = (code & 1) != 0;
                     const long long t1 = STATS_ON ? clock64() : 0;
-                    if (code & 2) r |= process_slot(S, s, J, stg);
+                    if (code & 2) r |= slow_path(S, s, J, stg, force);
                     if (STATS_ON && lane == 0) {
                         STAT_ADD(ST_C_PS_CALLS, 1); STAT_ADD(ST_C_PS_CYCLES, t1 - t0);
                         if (code & 2) { STAT_ADD(ST_C_SLOW_CALLS, 1); STAT_ADD(ST_C_SLOW_CYCLES, clock64() - t1); }
@@ -787,7 +1116,7 @@ __device__ void consumer(V2Smem &S, const DecodeArgs &args, unsigned int *counte
                 const int s = c + k * NCONS;
                 SlotJob &J = S.job[s];
                 if (lane == 0)
-                    printf("[lz4 v2 stuck] cta %d cons %d slot %d state %u tail %u hint %08x op %u ip %u whi %u pend %u err %u origin %u comp %u ring[t] %u ring[t+1] %u\n",
+                    printf("[lz4 v3 stuck] cta %d cons %d slot %d state %u tail %u hint %08x op %u ip %u whi %u pend %u err %u origin %u comp %u ring[t] %u ring[t+1] %u\n",
                            (int)blockIdx.x, c, s, J.state, J.tail, ld_rlx(&S.hint[s]), J.op, J.ip, J.whi, J.pend, J.err, J.origin, J.comp_len,
                            S.ring[s][J.tail & RM], S.ring[s][(J.tail + 1) & RM]);
                 if (J.state == SLOT_RETIRED) continue;
@@ -806,15 +1135,7 @@ __device__ void consumer(V2Smem &S, const DecodeArgs &args, unsigned int *counte
             if (STATS_ON) st_sleep_cycles += clock64() - ts0;
             if (!progress && clock64() - last_progress > 4000000000ll) {
                 // watchdog (~2 s without progress): give up on the active slots instead of hanging the device
-                for (int k = 0; k < SPC; k++) {
-                    const int s = c + k * NCONS;
-                    SlotJob &J = S.job[s];
-                    if (J.state == SLOT_RETIRED) continue;
-                    if (J.state == SLOT_ACTIVE && lane == 0) *J.status = E_INTERNAL;
-                    if (lane == 0) J.state = SLOT_RETIRED;
-                    __syncwarp();
-                    post_cmd(S, s, J, 0u, LIM_EXIT);
-                }
+                give_up(S, c);
                 live = 0;
             }
         }
@@ -824,19 +1145,20 @@ __device__ void consumer(V2Smem &S, const DecodeArgs &args, unsigned int *counte
 
 }  // namespace
 
-__global__ void __launch_bounds__(V2_THREADS, 1) lz4_decode_v2_kernel(const __grid_constant__ DecodeArgs args, unsigned int *counter,
+__global__ void __launch_bounds__(V2_THREADS, 1) lz4_decode_v3_kernel(const __grid_constant__ DecodeArgs args, unsigned int *counter,
                                                                            unsigned int first_dynamic)
 {
-    extern __shared__ __align__(16) uint8_t v2_smem_raw[];
-    V2Smem &S = *reinterpret_cast<V2Smem *>(v2_smem_raw + ((1024u - (smem_addr(v2_smem_raw) & 1023u)) & 1023u));
+    extern __shared__ __align__(16) uint8_t v3_smem_raw[];
+    V2Smem &S = *reinterpret_cast<V2Smem *>(v3_smem_raw + ((1024u - (smem_addr(v3_smem_raw) & 1023u)) & 1023u));
     const int warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < NSLOT_PAD; i += blockDim.x) {
-        S.tail[i] = 0; S.whi[i] = 0; S.cmd_seq[i] = 0; S.cmd_p[i] = 0; S.cmd_lim[i] = 0; S.hint[i] = 0;
+        if (i < NCONS) { S.stg_slot[i] = 0xffffffffu; S.stg_op[i] = 0; }
+        S.tail[i] = 0; S.whi[i] = 0; S.cmd_seq[i] = 0; S.cmd_p[i] = 0; S.cmd_lim[i] = 0; S.hint[i] = 0; S.cmd_ack[i] = 0; S.cmd_head[i] = 0;
     }
     for (int i = threadIdx.x; i < NSLOT; i += blockDim.x) {
         SlotJob &J = S.job[i];
         J.src = nullptr; J.dst = nullptr; J.status = nullptr;
-        J.comp_len = 0; J.origin = 0; J.op = 0; J.ip = 0; J.tail = 0; J.whi = 0; J.state = SLOT_EMPTY; J.err = 0; J.seq = 0; J.pend = 0; J.rphase = 0;
+        J.comp_len = 0; J.origin = 0; J.op = 0; J.ip = 0; J.tail = 0; J.whi = 0; J.state = SLOT_EMPTY; J.err = 0; J.seq = 0; J.pend = 0; J.rphase = 0; J.chainy = 0;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" ::"r"(smem_addr(&S.rbar[i])) : "memory");
     }
     __syncthreads();
@@ -844,7 +1166,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) lz4_decode_v2_kernel(const __gr
     else consumer(S, args, counter, first_dynamic, warp - NWALK);
 }
 
-int launch_lz4_decode_v2(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream)
+int launch_lz4_decode_v3(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream)
 {
     static bool configured = false;
     static unsigned long long *d_stats = nullptr;
@@ -857,19 +1179,19 @@ int launch_lz4_decode_v2(const DecodeArgs &args, unsigned int *d_counter, int sm
 #endif
     if (d_stats) cudaMemsetAsync(d_stats, 0, ST_COUNT * 8, stream);
     if (!configured) {
-        if (cudaFuncSetAttribute(lz4_decode_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(V2Smem) + 1024)) != cudaSuccess) return 1;
+        if (cudaFuncSetAttribute(lz4_decode_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(V2Smem) + 1024)) != cudaSuccess) return 1;
         configured = true;
     }
     const long long njobs = (long long)args.ncols * args.nblocks;
     if (njobs <= 0) return 0;
     // one persistent CTA per SM; with few jobs, one job per consumer warp before any warp takes a second
-    long long ctas = (njobs + NCONS - 1) / NCONS;
+    long long ctas = njobs;
     if (ctas > sm_count) ctas = sm_count;
     if (ctas < 1) ctas = 1;
     // dynamic job ids start after the statically assigned first pass
     const unsigned int first_dynamic = (unsigned int)(ctas * NCONS * SPC);
     cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream);
-    lz4_decode_v2_kernel<<<(unsigned int)ctas, V2_THREADS, sizeof(V2Smem) + 1024, stream>>>(args, d_counter, first_dynamic);
+    lz4_decode_v3_kernel<<<(unsigned int)ctas, V2_THREADS, sizeof(V2Smem) + 1024, stream>>>(args, d_counter, first_dynamic);
     if (d_stats) {
         unsigned long long h[ST_COUNT];
         cudaStreamSynchronize(stream);
@@ -877,8 +1199,8 @@ int launch_lz4_decode_v2(const DecodeArgs &args, unsigned int *d_counter, int sm
         static const char *names[ST_COUNT] = {"w_rounds", "w_commits", "w_ringfull", "w_winempty", "w_parked", "w_sleeps", "c_polls", "c_sleeps",
                                               "c_ps_calls", "c_ps_false", "c_reg", "c_regseq", "c_gen", "c_genseq", "c_special", "c_ps_cycles",
                                               "c_loop_cycles", "c_refills", "w_cycles", "c_start_cycles", "c_slow_calls", "c_slow_cycles",
-                                              "c_special_cycles", "c_sleep_cycles"};
-        fprintf(stderr, "[lz4 v2 stats] jobs=%lld ctas=%lld", njobs, ctas);
+                                              "c_special_cycles", "c_sleep_cycles", "g_pro", "g_head", "g_batch", "g_flush", "g_epi", "g_waves"};
+        fprintf(stderr, "[lz4 v3 stats] jobs=%lld ctas=%lld", njobs, ctas);
         for (int i = 0; i < ST_COUNT; i++) fprintf(stderr, " %s=%llu", names[i], h[i]);
         fprintf(stderr, "\n");
     }

@@ -43,6 +43,11 @@ def _bodies(oracle):
         "rle_then_random": bytes(5000) + rng.integers(0, 256, 7001).astype(np.uint8).tobytes() + b"ab" * 3000,
         "brands": oracle.block_body("String", [brands[i] for i in rng.integers(0, 8, N)], 0, N),
         "missing_int": oracle.block_body("Missing(Int64)", (rng.integers(1, 101, N).astype(np.int64), rng.random(N) < 0.1), 0, N),
+        # literal-heavy: nearly every token carries a literal-length extension
+        "missing_float": oracle.block_body("Missing(Float64)", (rng.random(N), rng.random(N) < 0.1), 0, N),
+        "decimals": oracle.block_body("String", [str(int(v)) for v in rng.integers(-2**31, 2**31, N)], 0, N),
+        # long matches (match-length extensions) between long literal runs
+        "repeats": b"".join(rng.integers(0, 256, 700).astype(np.uint8).tobytes() * 3 for _ in range(40)),
         "small_ints": rng.integers(0, 4, 30011).astype(np.uint8).tobytes(),
         "period3": (b"abc" * 20000)[:50001],
         "odd_sizes": rng.integers(0, 2, 777).astype(np.uint8).tobytes(),
@@ -66,26 +71,39 @@ def _gpu_decode(blocks, origins):
     return [bytes(out[o:o + s]) for o, s in zip(ooff, orig)], status
 
 
-@pytest.mark.parametrize("variant", ["v2", "lz4_v1", "lz4_simple"], ids=["walker", "warp_per_block", "sequential"])
+def _set_variant(variant):
+    """K1 variants: the two walker/consumer flavours (v2 word-regular, v3 general), the warp-per-block and the sequential decoder."""
+    L = _capi.lib()
+    L.dfdb_set_option(b"lz4_simple", 0)
+    L.dfdb_set_option(b"lz4_v1", 0)
+    L.dfdb_set_option(b"lz4_flavour", 0)
+    if variant == "v2":
+        _capi.check(L.dfdb_set_option(b"lz4_flavour", 1))
+    elif variant == "v3":
+        _capi.check(L.dfdb_set_option(b"lz4_flavour", 2))
+    elif variant is not None:
+        _capi.check(L.dfdb_set_option(variant.encode(), 1))
+
+
+@pytest.mark.parametrize("variant", ["v2", "v3", "lz4_v1", "lz4_simple"], ids=["walker_regular", "walker_general", "warp_per_block", "sequential"])
 def test_lz4_decode_matches_reference_codec(oracle, variant):
     """read_block BlockStreams.jl:101-119: decoded bytes are determined by the LZ4 block format."""
     bodies = _bodies(oracle)
     names = list(bodies)
     blocks = [oracle.compress_block(bodies[k]) for k in names] + [oracle.lz4_compress(bodies[k], 1) for k in names]
     origins = [len(bodies[k]) for k in names] * 2
-    if variant != "v2":
-        _capi.check(_capi.lib().dfdb_set_option(variant.encode(), 1))
+    _set_variant(variant)
     try:
         got, status = _gpu_decode(blocks, origins)
     finally:
-        _capi.lib().dfdb_set_option(b"lz4_simple", 0)
-        _capi.lib().dfdb_set_option(b"lz4_v1", 0)
+        _set_variant(None)
     for i, k in enumerate(names + names):
         assert status[i] == 0, (k, status[i])
         assert got[i] == bodies[k], f"decoded bytes differ for {k} (first diff at {next(j for j in range(len(got[i])) if got[i][j] != bodies[k][j])})"
 
 
-def test_lz4_decode_many_small_blocks(oracle):
+@pytest.mark.parametrize("variant", ["v2", "v3"], ids=["walker_regular", "walker_general"])
+def test_lz4_decode_many_small_blocks(oracle, variant):
     """More blocks than the persistent decoder has slots (148 SMs x 87), ragged sizes, every body kind: slots are
     reused, rings wrap, windows re-base after long literal / match runs."""
     rng = np.random.default_rng(11)
@@ -101,24 +119,70 @@ def test_lz4_decode_many_small_blocks(oracle):
     idx = rng.integers(0, len(pool), 14000)
     blocks = [comp[i] for i in idx]
     origins = [len(pool[i]) for i in idx]
-    got, status = _gpu_decode(blocks, origins)
+    _set_variant(variant)
+    try:
+        got, status = _gpu_decode(blocks, origins)
+    finally:
+        _set_variant(None)
     bad = [k for k in range(len(idx)) if status[k] != 0 or got[k] != pool[idx[k]]]
     assert not bad, f"{len(bad)} of {len(idx)} blocks differ, first: block {bad[0]} (pool {idx[bad[0]]}, origin {origins[bad[0]]}, status {status[bad[0]]})"
 
 
-def test_lz4_decode_rejects_corrupt_blocks(oracle):
+@pytest.mark.parametrize("variant", ["v2", "v3"], ids=["walker_regular", "walker_general"])
+def test_lz4_decode_rejects_corrupt_blocks(oracle, variant):
     """@assert size == sizes.origin "decompression error" (BlockStreams.jl:112)"""
     body = np.random.default_rng(3).integers(1, 101, 4096).astype(np.int64).tobytes()
     good = oracle.compress_block(body)
     bad_trunc = good[: len(good) // 2]
     bad_origin = good
     bad_offset = bytes([0x00, 0xFF, 0xFF]) + good          # match with offset 65535 before any output
-    got, status = _gpu_decode([good, bad_trunc, bad_origin, bad_offset], [len(body), len(body), len(body) - 8, len(body)])
+    _set_variant(variant)
+    try:
+        got, status = _gpu_decode([good, bad_trunc, bad_origin, bad_offset], [len(body), len(body), len(body) - 8, len(body)])
+    finally:
+        _set_variant(None)
     assert status[0] == 0 and got[0] == body
     assert status[1] != 0 and status[2] != 0 and status[3] != 0
     for blk, org in [(bad_trunc, len(body)), (bad_origin, len(body) - 8), (bad_offset, len(body))]:
         with pytest.raises(oracle.OracleError):
             oracle.lz4_decompress(blk, org)
+
+
+@pytest.mark.parametrize("variant", ["v2", "v3"], ids=["walker_regular", "walker_general"])
+def test_lz4_decode_fuzzed_streams(oracle, variant):
+    """LZ4_decompress_safe contract on damaged streams: no crash, no out-of-bounds write, and whatever the CPU codec
+    accepts decodes to the same bytes.  (The GPU decoders do not enforce liblz4's end-of-block rules, so they may accept
+    a damaged stream the CPU codec refuses; they must never disagree on an accepted one.)"""
+    rng = np.random.default_rng(23)
+    brands = ["apple", "samsung", "huawai", "microsoft", "dell", "xbox", "sony", "intel"]
+    bodies = [rng.integers(1, 101, 4096).astype(np.int64).tobytes(),
+              oracle.block_body("String", [brands[i] for i in rng.integers(0, 8, 4096)], 0, 4096),
+              oracle.block_body("Missing(Float64)", (rng.random(4096), rng.random(4096) < 0.1), 0, 4096)]
+    blocks, origins, expect = [], [], []
+    for body in bodies:
+        good = oracle.compress_block(body)
+        for _ in range(100):
+            bad = bytearray(good)
+            for _ in range(int(rng.integers(1, 4))):
+                bad[int(rng.integers(0, len(bad)))] = int(rng.integers(0, 256))
+            if rng.random() < 0.2:
+                bad = bad[: int(rng.integers(1, len(bad)))]
+            bad = bytes(bad)
+            try:
+                ref = oracle.lz4_decompress(bad, len(body))
+            except oracle.OracleError:
+                ref = None
+            blocks.append(bad)
+            origins.append(len(body))
+            expect.append(ref)
+    _set_variant(variant)
+    try:
+        got, status = _gpu_decode(blocks, origins)
+    finally:
+        _set_variant(None)
+    for k, ref in enumerate(expect):
+        if ref is not None:
+            assert status[k] == 0 and got[k] == ref, f"stream {k}: the CPU codec accepts it, GPU status {status[k]}"
 
 
 # ---- reference known-answer cases through the C ABI -----------------------------------------------------------
