@@ -64,6 +64,8 @@ SYMBOLS = {
     "dfdb_table_shard_range": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dfdb_table_load": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_int32]),
     "dfdb_table_drop_decoded": (C.c_int32, [C.c_void_p]),
+    "dfdb_host_alloc": (C.c_int32, [C.c_int64, C.POINTER(C.c_void_p)]),
+    "dfdb_host_free": (C.c_int32, [C.c_void_p]),
     "dfdb_scan_prepare": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int64, C.POINTER(C.c_void_p)]),
     "dfdb_scan_free": (C.c_int32, [C.c_void_p]),
     "dfdb_scan_nproj": (C.c_int32, [C.c_void_p]),
@@ -125,3 +127,35 @@ def init(device: int | None = None):
     elif _inited_device != device:
         raise DfdbError(ERR_STATE, f"already initialised on device {_inited_device}")
     return _inited_device
+
+
+class _PinnedBuffer:
+    """A buffer of the library's result arena (dfdb_host_alloc): page-locked host memory that dfdb_scan_materialize
+    fills with a direct device-to-host copy.  Goes back to the arena when the last numpy view of it dies."""
+
+    def __init__(self, nbytes: int):
+        p = C.c_void_p()
+        check(lib().dfdb_host_alloc(nbytes, C.byref(p)))
+        self.ptr, self.nbytes = p.value, nbytes
+        self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            if self.ptr and _lib is not None:
+                _lib.dfdb_host_free(C.c_void_p(self.ptr))
+        except Exception:
+            pass
+        self.ptr = None
+
+
+PINNED_MIN_BYTES = 1 << 20
+
+
+def result_array(n: int, dtype) -> "np.ndarray":
+    """Output vector for materialize: from the pinned result arena when it is large enough to matter."""
+    import numpy as np
+    dtype = np.dtype(dtype)
+    nbytes = max(n, 1) * dtype.itemsize
+    if nbytes < PINNED_MIN_BYTES:
+        return np.zeros(max(n, 1), dtype=dtype)
+    return np.asarray(_PinnedBuffer(nbytes)).view(dtype)

@@ -58,12 +58,20 @@ class FlatStringsVector:
     """FlatStringsVector layout (src/FlatStringsVectors.jl:5-9): Int32 sizes (-1 = missing), Int64 offsets
     (exclusive scan of max(size, 0)) and the flat char buffer."""
 
-    def __init__(self, sizes: np.ndarray, data: bytes):
+    def __init__(self, sizes: np.ndarray, data):
         self.sizes = np.asarray(sizes, dtype=np.int32)
-        self.data = data
-        self.offsets = np.zeros(len(self.sizes), dtype=np.int64)
-        if len(self.sizes) > 1:
-            np.cumsum(np.maximum(self.sizes[:-1], 0), out=self.offsets[1:])
+        self.data = data if isinstance(data, bytes) else memoryview(data).cast("B")   # bytes, or a zero-copy view of the result buffer
+        self._offsets = None
+
+    @property
+    def offsets(self):
+        """exclusive scan of max(size, 0) (unsafe_remake_offsets!, FlatStringsVectors.jl:61-70); built on first use"""
+        if self._offsets is None:
+            off = np.zeros(len(self.sizes), dtype=np.int64)
+            if len(self.sizes) > 1:
+                np.cumsum(np.maximum(self.sizes[:-1], 0), out=off[1:])
+            self._offsets = off
+        return self._offsets
 
     def __len__(self):
         return len(self.sizes)
@@ -74,7 +82,7 @@ class FlatStringsVector:
             if s < 0:
                 return None
             o = int(self.offsets[i])
-            return self.data[o:o + s].decode("utf-8")
+            return bytes(self.data[o:o + s]).decode("utf-8")
         return [self[int(k)] for k in np.arange(len(self))[i]]
 
     def tolist(self):
@@ -516,17 +524,17 @@ def materialize(v):
         _capi.check(L.dfdb_scan_proj_type(h, i, C.byref(kind), C.byref(nullable), C.byref(elsize)))
         kname = _capi.KIND_NAMES[kind.value]
         if kname == "String":
-            sizes = np.zeros(max(nrows, 1), dtype=np.int32)
-            chars = np.zeros(max(sb[i], 1), dtype=np.uint8)
+            sizes = _capi.result_array(nrows, np.int32)
+            chars = _capi.result_array(sb[i], np.uint8)
             outs[i].str_sizes = sizes.ctypes.data
             outs[i].str_chars = chars.ctypes.data
             keep.append(("str", sizes, chars, sb[i]))
         else:
-            vals = np.zeros(max(nrows, 1), dtype=_np_dtype(kname, elsize.value))
+            vals = _capi.result_array(nrows, _np_dtype(kname, elsize.value))
             outs[i].values = vals.ctypes.data
             miss = None
             if nullable.value:
-                miss = np.zeros(max(nrows, 1), dtype=np.uint8)
+                miss = _capi.result_array(nrows, np.uint8)
                 outs[i].missing = miss.ctypes.data
             keep.append(("fix", vals, miss, 0))
     try:
@@ -536,9 +544,9 @@ def materialize(v):
     cols = []
     for tag, a, b, nb in keep:
         if tag == "str":
-            cols.append(FlatStringsVector(a[:nrows], bytes(b[:nb].tobytes())))
+            cols.append(FlatStringsVector(a[:nrows], b[:nb]))
         elif b is not None:
-            cols.append(np.ma.MaskedArray(a[:nrows], mask=b[:nrows].astype(bool)))
+            cols.append(np.ma.MaskedArray(a[:nrows], mask=b[:nrows].view(np.bool_)))
         else:
             cols.append(a[:nrows])
     return Frame(v.projection.keys(), cols)

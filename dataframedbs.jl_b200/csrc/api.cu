@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cmath>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -112,13 +113,58 @@ int dev_upload(T **dptr, const std::vector<T> &h)
     return DFDB_OK;
 }
 
-// Device -> caller memory.  The caller's buffers are ordinary (pageable) host memory, which the driver copies at a
-// few GB/s; large results go through two pinned bounce buffers instead, the copy of chunk k+1 overlapping the
-// host memcpy of chunk k.  Returns after the data is in `dst`.
+// ---- result arena: page-locked host memory handed to the caller for materialized columns (dfdb_host_alloc) ------
+// cudaHostAlloc is slow (it pins page by page), so freed buffers are kept and reused: a scan that runs again finds
+// its result buffers ready.  `live` lets copy_out recognise a pinned destination and copy straight into it.
+struct HostArena {
+    std::mutex mu;
+    std::map<uintptr_t, size_t> live;                  // base -> capacity of buffers handed out
+    std::multimap<size_t, void *> spare;               // capacity -> cached buffer
+    size_t spare_bytes = 0;
+    size_t cap_bytes = (size_t)24 << 30;               // cache at most this much (option "host_arena_cap_mb")
+    bool pinned(const void *p, size_t n)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = live.upper_bound(reinterpret_cast<uintptr_t>(p));
+        if (it == live.begin()) return false;
+        --it;
+        return reinterpret_cast<uintptr_t>(p) + n <= it->first + it->second;
+    }
+    void trim(size_t keep)
+    {
+        while (spare_bytes > keep && !spare.empty()) {
+            auto it = std::prev(spare.end());
+            cudaFreeHost(it->second);
+            spare_bytes -= it->first;
+            spare.erase(it);
+        }
+    }
+} arena;
+
+// Stream-ordered device scratch (gather outputs): the pool keeps its memory between scans.
+cudaError_t scratch_alloc(void **p, size_t n)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, rt.device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        configured = true;
+    }
+    return cudaMallocAsync(p, std::max<size_t>(n, 1), rt.stream);
+}
+void scratch_free(void *p) { if (p) cudaFreeAsync(p, rt.stream); }
+
+// Device -> caller memory.  A destination inside the result arena is page-locked: one asynchronous copy at full PCIe
+// rate.  Anything else is ordinary (pageable) host memory, which the driver copies at a few GB/s; large results go
+// through two pinned bounce buffers instead, the copy of chunk k+1 overlapping the host memcpy of chunk k.  Returns
+// after the data is in `dst`.
 cudaError_t copy_out(void *dst, const void *d_src, size_t n)
 {
     constexpr size_t CHUNK = 32u << 20;
-    if (n < (8u << 20)) {
+    if (n < (8u << 20) || arena.pinned(dst, n)) {
         cudaError_t e = cudaMemcpyAsync(dst, d_src, n, cudaMemcpyDeviceToHost, rt.stream);
         return e != cudaSuccess ? e : cudaStreamSynchronize(rt.stream);
     }
@@ -771,6 +817,7 @@ int32_t dfdb_shutdown(void)
     profile_collect();
     cudaFree(rt.d_counter);
     cudaFree(rt.d_error);
+    { std::lock_guard<std::mutex> lk(arena.mu); arena.trim(0); }
     cudaStreamDestroy(rt.own_stream);
     cudaStreamDestroy(rt.copy_stream);
     rt.inited = false;
@@ -806,6 +853,7 @@ int32_t dfdb_set_option(const char *name, int64_t value)
     else if (n == "no_tma") rt.no_tma = value;
     else if (n == "lz4_flavour") rt.lz4_flavour = value;
     else if (n == "no_alias") rt.no_alias = value;
+    else if (n == "host_arena_cap_mb") { std::lock_guard<std::mutex> lk(arena.mu); arena.cap_bytes = (size_t)std::max<int64_t>(value, 0) << 20; arena.trim(arena.cap_bytes); }
     else return fail(DFDB_ERR_ARGUMENT, "unknown option %s", n.c_str());
     return DFDB_OK;
 }
@@ -1310,7 +1358,7 @@ int32_t dfdb_scan_materialize(dfdb_scan *s, dfdb_outcol *cols, int32_t ncols)
         dfdb_outcol &oc = cols[i];
         uint8_t *d_vals = nullptr, *d_miss = nullptr, *d_chars = nullptr;
         int32_t *d_sizes = nullptr;
-        auto cleanup = [&]() { cudaFree(d_vals); cudaFree(d_miss); cudaFree(d_chars); cudaFree(d_sizes); };
+        auto cleanup = [&]() { scratch_free(d_vals); scratch_free(d_miss); scratch_free(d_chars); scratch_free(d_sizes); };
         if (p.kind == PJ_COL) {
             rc = ensure_decoded(t, {p.col});
             if (rc) return rc;
@@ -1323,29 +1371,31 @@ int32_t dfdb_scan_materialize(dfdb_scan *s, dfdb_outcol *cols, int32_t ncols)
             a.col = make_view(*c);
             if (c->type.kind == DFDB_STRING) {
                 if (!oc.str_sizes) return fail(DFDB_ERR_ARGUMENT, "output column %zu needs str_sizes", i);
-                // per-block char bases for this column
-                PhaseScope ps(PH_CONSUME, c->total_origin);
-                LAUNCH(launch_str_block_bytes(a, s->d_blk_bytes, rt.stream));
-                LAUNCH(launch_exclusive_scan(s->d_blk_bytes, s->d_blk_bytes + g.nblocks + 1, g.nblocks, rt.stream));
-                a.blk_char_base = s->d_blk_bytes + g.nblocks + 1;
                 const int64_t nbytes = s->str_bytes[i];
-                if (cudaMalloc(reinterpret_cast<void **>(&d_sizes), (size_t)total * 4) != cudaSuccess ||
-                    cudaMalloc(reinterpret_cast<void **>(&d_chars), (size_t)std::max<int64_t>(nbytes, 1)) != cudaSuccess) {
+                if (scratch_alloc(reinterpret_cast<void **>(&d_sizes), (size_t)total * 4) != cudaSuccess ||
+                    scratch_alloc(reinterpret_cast<void **>(&d_chars), (size_t)std::max<int64_t>(nbytes, 1)) != cudaSuccess) {
                     cleanup();
                     return fail(DFDB_ERR_NOMEM, "out of device memory for string gather");
                 }
-                a.out_sizes = d_sizes;
-                a.out_chars = d_chars;
-                if (launch_gather_strings(a, rt.stream) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "gather_strings launch failed"); }
-                rt.launches++;
+                {
+                    // per-block char bases for this column, then the gather
+                    PhaseScope ps(PH_CONSUME, c->total_origin);
+                    LAUNCH(launch_str_block_bytes(a, s->d_blk_bytes, rt.stream));
+                    LAUNCH(launch_exclusive_scan(s->d_blk_bytes, s->d_blk_bytes + g.nblocks + 1, g.nblocks, rt.stream));
+                    a.blk_char_base = s->d_blk_bytes + g.nblocks + 1;
+                    a.out_sizes = d_sizes;
+                    a.out_chars = d_chars;
+                    if (launch_gather_strings(a, rt.stream) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "gather_strings launch failed"); }
+                    rt.launches++;
+                }
                 PhaseScope ps2(PH_D2H, total * 4 + nbytes);
                 copy_out(oc.str_sizes, d_sizes, (size_t)total * 4);
                 if (nbytes > 0 && oc.str_chars) copy_out(oc.str_chars, d_chars, (size_t)nbytes);
             } else {
                 if (!oc.values) return fail(DFDB_ERR_ARGUMENT, "output column %zu needs a values buffer", i);
                 const int es = c->type.elsize;
-                if (cudaMalloc(reinterpret_cast<void **>(&d_vals), (size_t)total * es) != cudaSuccess ||
-                    (c->type.nullable && cudaMalloc(reinterpret_cast<void **>(&d_miss), (size_t)total) != cudaSuccess)) {
+                if (scratch_alloc(reinterpret_cast<void **>(&d_vals), (size_t)total * es) != cudaSuccess ||
+                    (c->type.nullable && scratch_alloc(reinterpret_cast<void **>(&d_miss), (size_t)total) != cudaSuccess)) {
                     cleanup();
                     return fail(DFDB_ERR_NOMEM, "out of device memory for gather");
                 }
@@ -1373,8 +1423,8 @@ int32_t dfdb_scan_materialize(dfdb_scan *s, dfdb_outcol *cols, int32_t ncols)
             rc = prog.upload(p.e.prog);
             if (rc) return rc;
             const int es = p.type.elsize;
-            if (cudaMalloc(reinterpret_cast<void **>(&d_vals), (size_t)total * es) != cudaSuccess ||
-                (p.type.nullable && cudaMalloc(reinterpret_cast<void **>(&d_miss), (size_t)total) != cudaSuccess)) {
+            if (scratch_alloc(reinterpret_cast<void **>(&d_vals), (size_t)total * es) != cudaSuccess ||
+                (p.type.nullable && scratch_alloc(reinterpret_cast<void **>(&d_miss), (size_t)total) != cudaSuccess)) {
                 cleanup();
                 return fail(DFDB_ERR_NOMEM, "out of device memory for computed column");
             }
@@ -1396,6 +1446,57 @@ int32_t dfdb_scan_materialize(dfdb_scan *s, dfdb_outcol *cols, int32_t ncols)
         cudaError_t e = cudaStreamSynchronize(rt.stream);
         cleanup();
         if (e != cudaSuccess) return fail(DFDB_ERR_CUDA, "materialize failed: %s", cudaGetErrorString(e));
+    }
+    return DFDB_OK;
+}
+
+// ---- result arena ------------------------------------------------------------------------------------
+int32_t dfdb_host_alloc(int64_t bytes, void **ptr)
+{
+    int rc = need_init();
+    if (rc) return rc;
+    if (!ptr || bytes < 0) return fail(DFDB_ERR_ARGUMENT, "bad host allocation request");
+    const size_t want = ((size_t)std::max<int64_t>(bytes, 1) + ((1u << 21) - 1)) & ~(size_t)((1u << 21) - 1);   // whole 2 MB pages
+    void *p = nullptr;
+    size_t cap = 0;
+    {
+        std::lock_guard<std::mutex> lk(arena.mu);
+        auto it = arena.spare.lower_bound(want);
+        if (it != arena.spare.end() && it->first <= want + want / 2) {                     // a close enough fit
+            p = it->second;
+            cap = it->first;
+            arena.spare_bytes -= cap;
+            arena.spare.erase(it);
+        }
+    }
+    if (!p) {
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            { std::lock_guard<std::mutex> lk(arena.mu); arena.trim(0); }
+            e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        }
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(DFDB_ERR_NOMEM, "cannot pin %zu bytes of host memory: %s", want, cudaGetErrorString(e)); }
+        cap = want;
+    }
+    std::lock_guard<std::mutex> lk(arena.mu);
+    arena.live[reinterpret_cast<uintptr_t>(p)] = cap;
+    *ptr = p;
+    return DFDB_OK;
+}
+
+int32_t dfdb_host_free(void *ptr)
+{
+    if (!ptr) return DFDB_OK;
+    std::lock_guard<std::mutex> lk(arena.mu);
+    auto it = arena.live.find(reinterpret_cast<uintptr_t>(ptr));
+    if (it == arena.live.end()) return fail(DFDB_ERR_ARGUMENT, "not a dfdb_host_alloc buffer");
+    const size_t cap = it->second;
+    arena.live.erase(it);
+    if (rt.inited && arena.spare_bytes + cap <= arena.cap_bytes) {
+        arena.spare.emplace(cap, ptr);
+        arena.spare_bytes += cap;
+    } else {
+        cudaFreeHost(ptr);
     }
     return DFDB_OK;
 }

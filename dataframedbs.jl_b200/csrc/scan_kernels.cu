@@ -894,57 +894,115 @@ __global__ void __launch_bounds__(SCAN_THREADS) str_block_bytes_kernel(const Gat
     }
 }
 
-// sizes + chars of the selected rows (FlatStringsVector gather, offset-aware, /root/reference/src/FlatStringsVectors.jl:136-157):
-// every warp first totals its chunk (rows, bytes), an exclusive scan over the CTA's warps gives its output positions,
-// then it walks its chunk carrying the running row and byte positions.
+// sizes + chars of the selected rows (FlatStringsVector gather, offset-aware, /root/reference/src/FlatStringsVectors.jl:136-157).
+// One CTA per block, tiles of 1024 rows (4 consecutive rows per thread).  A CTA-wide scan over (selected rows, selected
+// bytes, all bytes) gives every row its output row, its output byte position and -- since a block's chars are the
+// concatenation of its rows -- its source position too, so the per-row offsets of K2 are not read here.  The tile's chars
+// come in with aligned 16-byte loads, are compacted in shared memory and leave as one contiguous run; only tiles whose
+// chars do not fit the staging buffers (very long strings) copy row by row through global memory.
+constexpr int STR_TILE = SCAN_THREADS * 4;
+constexpr int STR_STAGE = 20480;
+
 __global__ void __launch_bounds__(SCAN_THREADS) gather_strings_kernel(const GatherArgs A)
 {
-    __shared__ long long s_rows[SCAN_THREADS / 32], s_bytes[SCAN_THREADS / 32];
+    __shared__ __align__(16) uint8_t s_in[STR_STAGE + 32];
+    __shared__ __align__(16) uint8_t s_out[STR_STAGE];
+    __shared__ long long s_tot[3][SCAN_THREADS / 32];
     const Geometry g = A.g;
-    const int C = (g.wpb + SCAN_THREADS / 32 - 1) / (SCAN_THREADS / 32);
+    const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
     for (int lb = blockIdx.x; lb < g.nblocks; lb += gridDim.x) {
         const uint32_t *m = A.mask + (int64_t)lb * g.wpb;
         const int64_t rows_b = block_rows(g, lb);
         const uint8_t *body = col_body(A.col, lb);
         const int32_t *sizes = reinterpret_cast<const int32_t *>(body + 4);
         const uint8_t *chars = body + 4 + 4 * rows_b;
-        const int32_t *soff = A.col.str_off + (int64_t)lb * g.block_size;
-        const int w0 = warp_id() * C, w1 = w0 + C < g.wpb ? w0 + C : g.wpb;
-        long long rows, bytes;
-        str_chunk_totals(A, lb, w0, w1, rows, bytes);
-        if (lane_id() == 0) { s_rows[warp_id()] = rows; s_bytes[warp_id()] = bytes; }
-        __syncthreads();
-        int64_t row_pos = A.blk_base[lb];
+        int64_t row_pos = A.blk_base[lb];          // output row / output byte / source byte position of the tile (uniform)
         int64_t byte_pos = A.blk_char_base[lb];
-        for (int k = 0; k < warp_id(); k++) { row_pos += s_rows[k]; byte_pos += s_bytes[k]; }
-        for (int wb = w0; wb < w1; wb += 32) {
-            const uint32_t mine = wb + lane_id() < w1 ? m[wb + lane_id()] : 0u;
-            uint32_t nz = __ballot_sync(FULL, mine != 0);
-            while (nz) {
-                const int j = __ffs(nz) - 1;
-                nz &= nz - 1;
-                const uint32_t word = __shfl_sync(FULL, mine, j);
-                const bool sel = (word >> lane_id()) & 1u;
-                const int64_t r = (int64_t)(wb + j) * 32 + lane_id();
-                const int sz = sel ? sizes[r] : 0;
-                const int nb = sz > 0 ? sz : 0;
-                int incl = nb;
+        int64_t char_pos = 0;
+        for (int64_t tile0 = 0; tile0 < rows_b; tile0 += STR_TILE) {
+            const int64_t r0 = tile0 + 4 * tid;
+            const uint32_t bits = r0 < rows_b ? (m[r0 >> 5] >> (r0 & 31)) & 15u : 0u;
+            int sz[4];
+            long long nsel = 0, bsel = 0, ball = 0;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int v = __shfl_up_sync(FULL, incl, d);
-                    if (lane_id() >= d) incl += v;
-                }
-                if (sel) {
-                    A.out_sizes[row_pos + __popc(word & ((1u << lane_id()) - 1u))] = sz;
-                    const uint8_t *src = chars + soff[r];
-                    uint8_t *dst = A.out_chars + byte_pos + (incl - nb);
-                    for (int i = 0; i < nb; i++) dst[i] = src[i];
-                }
-                row_pos += __popc(word);
-                byte_pos += __shfl_sync(FULL, incl, 31);
+            for (int k = 0; k < 4; k++) {
+                sz[k] = r0 + k < rows_b ? sizes[r0 + k] : 0;
+                const long long nb = sz[k] > 0 ? sz[k] : 0;
+                ball += nb;
+                if ((bits >> k) & 1u) { nsel++; bsel += nb; }
             }
+            // exclusive CTA scan of the three sums
+            long long xs = nsel, xb = bsel, xa = ball;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const long long a = __shfl_up_sync(FULL, xs, d), b = __shfl_up_sync(FULL, xb, d), c = __shfl_up_sync(FULL, xa, d);
+                if (lane >= d) { xs += a; xb += b; xa += c; }
+            }
+            if (lane == 31) { s_tot[0][wid] = xs; s_tot[1][wid] = xb; s_tot[2][wid] = xa; }
+            __syncthreads();
+            long long ps = xs - nsel, pb = xb - bsel, pa = xa - ball, ts = 0, tb = 0, ta = 0;
+#pragma unroll
+            for (int k = 0; k < SCAN_THREADS / 32; k++) {
+                const long long a = s_tot[0][k], b = s_tot[1][k], c = s_tot[2][k];
+                if (k < wid) { ps += a; pb += b; pa += c; }
+                ts += a; tb += b; ta += c;
+            }
+            if (ts > 0) {
+                // sizes of the selected rows
+                int q = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if ((bits >> k) & 1u) { A.out_sizes[row_pos + ps + q] = sz[k]; q++; }
+                const uint8_t *src0 = chars + char_pos;
+                uint8_t *dst0 = A.out_chars + byte_pos;
+                if (ta <= STR_STAGE && tb > 0) {
+                    // stage the tile's chars (aligned 16-byte loads; the over-read stays inside the block's slot)
+                    const int mis = (int)(reinterpret_cast<uintptr_t>(src0) & 15);
+                    const uint4 *src16 = reinterpret_cast<const uint4 *>(src0 - mis);
+                    const int nch = (int)((ta + mis + 15) >> 4);
+                    for (int c = tid; c < nch; c += SCAN_THREADS) reinterpret_cast<uint4 *>(s_in)[c] = src16[c];
+                    __syncthreads();
+                    int so = (int)pa + mis, dpos = (int)pb;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int nb = sz[k] > 0 ? sz[k] : 0;
+                        if ((bits >> k) & 1u)
+                            for (int i = 0; i < nb; i++) s_out[dpos + i] = s_in[so + i];
+                        if ((bits >> k) & 1u) dpos += nb;
+                        so += nb;
+                    }
+                    __syncthreads();
+                    // one contiguous run: bytes up to the first 4-byte boundary of the destination, then words
+                    const int head = (int)((4 - (reinterpret_cast<uintptr_t>(dst0) & 3)) & 3);
+                    const int nhead = head < (int)tb ? head : (int)tb;
+                    if (tid < nhead) dst0[tid] = s_out[tid];
+                    const int nwords = ((int)tb - nhead) >> 2;
+                    uint32_t *dw = reinterpret_cast<uint32_t *>(dst0 + nhead);
+                    for (int w = tid; w < nwords; w += SCAN_THREADS) {
+                        const uint8_t *b4 = s_out + nhead + 4 * w;
+                        dw[w] = (uint32_t)b4[0] | ((uint32_t)b4[1] << 8) | ((uint32_t)b4[2] << 16) | ((uint32_t)b4[3] << 24);
+                    }
+                    const int done = nhead + 4 * nwords;
+                    if (tid < (int)tb - done) dst0[done + tid] = s_out[done + tid];
+                } else if (tb > 0) {
+                    // long strings: row by row through global memory
+                    long long so = pa, dpos = pb;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int nb = sz[k] > 0 ? sz[k] : 0;
+                        if ((bits >> k) & 1u) {
+                            for (int i = 0; i < nb; i++) dst0[dpos + i] = src0[so + i];
+                            dpos += nb;
+                        }
+                        so += nb;
+                    }
+                }
+            }
+            row_pos += ts;
+            byte_pos += tb;
+            char_pos += ta;
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 

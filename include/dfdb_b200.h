@@ -152,6 +152,15 @@ DFDB_API int32_t dfdb_scan_exchange_offset(dfdb_scan *s, int64_t survivors_in_lo
 /* device-resident copy of the last dfdb_scan_aggregate result (sizeof(dfdb_agg) bytes), for NCCL */
 DFDB_API int32_t dfdb_scan_aggregate_device(dfdb_scan *s, int32_t proj_idx, void *device_out);
 
+/* ---- result buffers.  materialize(::DFView) allocates its result vectors (`sizehint!` + `append!`,
+ *      src/tables/materialization.jl:1-25,29-37); a caller that takes them from here gets page-locked memory, which
+ *      dfdb_scan_materialize recognises and fills with one device-to-host copy at full PCIe rate (ordinary pageable
+ *      buffers work too, through pinned bounce buffers, at a fraction of that).  Freed buffers are kept for reuse
+ *      (option "host_arena_cap_mb", default 24576).  The Julia shim wraps the pointer with unsafe_wrap(Array, ...; own =
+ *      false) and a finalizer that calls dfdb_host_free. --------------------------------------------------------- */
+DFDB_API int32_t dfdb_host_alloc(int64_t bytes, void **ptr);
+DFDB_API int32_t dfdb_host_free(void *ptr);
+
 /* ---- codec hook: read_block (src/io/BlockStreams.jl:101-119) for n independent raw LZ4 blocks.
  *      comp/out are HOST buffers; status[i] = 0 or DFDB_ERR_CORRUPT ------------------------------ */
 DFDB_API int32_t dfdb_lz4_decode_blocks(const uint8_t *comp, const int64_t *comp_off, const int64_t *comp_len,
