@@ -806,6 +806,7 @@ int32_t dfdb_init(int32_t device)
     CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&rt.d_counter), 64));
     CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&rt.d_error), 64));
     CUDA_TRY(cudaMemset(rt.d_error, 0, 64));
+    if (const char *fl = getenv("DFDB_LZ4_FLAVOUR")) rt.lz4_flavour = atoll(fl);   // A/B: force one K1 flavour (see dfdb_set_option "lz4_flavour")
     rt.inited = true;
     return DFDB_OK;
 }

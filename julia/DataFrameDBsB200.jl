@@ -138,6 +138,16 @@ struct OutCol
     values::Ptr{Cvoid}; missing::Ptr{UInt8}; str_sizes::Ptr{Int32}; str_chars::Ptr{UInt8}
 end
 
+# Result vectors come from the library's page-locked result arena (dfdb_host_alloc): dfdb_scan_materialize then fills them
+# with one device-to-host copy at full PCIe rate.  The Array does not own the memory; a finalizer hands it back.
+function pinned_vector(::Type{T}, n::Integer) where {T}
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:dfdb_host_alloc, LIB), Int32, (Int64, Ref{Ptr{Cvoid}}), max(n, 1) * sizeof(T), p))
+    a = unsafe_wrap(Array, Ptr{T}(p[]), n; own = false)
+    finalizer(_ -> ccall((:dfdb_host_free, LIB), Int32, (Ptr{Cvoid},), p[]), a)
+    a
+end
+
 # materialize(v::DFView): materialization.jl:27-40 (sizes first = the reference's nrow pass, then fill)
 function DataFrameDBs.materialize(v::DFView)
     names = keys(v.projection)
@@ -149,10 +159,10 @@ function DataFrameDBs.materialize(v::DFView)
         for (i, T) in enumerate(types)
             B = Base.nonmissingtype(T)
             if B === String
-                sizes = Vector{Int32}(undef, n[]); chars = Base._string_n(sb[i])
+                sizes = pinned_vector(Int32, n[]); chars = pinned_vector(UInt8, sb[i])
                 push!(bufs, (sizes, chars)); push!(outs, OutCol(C_NULL, C_NULL, pointer(sizes), pointer(chars)))
             else
-                vals = Vector{B}(undef, n[]); miss = T === B ? UInt8[] : Vector{UInt8}(undef, n[])
+                vals = pinned_vector(B, n[]); miss = T === B ? UInt8[] : pinned_vector(UInt8, n[])
                 push!(bufs, (vals, miss)); push!(outs, OutCol(pointer(vals), T === B ? C_NULL : pointer(miss), C_NULL, C_NULL))
             end
         end
@@ -160,7 +170,7 @@ function DataFrameDBs.materialize(v::DFView)
         cols = map(zip(types, bufs)) do (T, b)
             B = Base.nonmissingtype(T)
             if B === String
-                FlatStringsVector{T}(b[2]; sizes = b[1])          # FlatStringsVectors.jl:54-59: zero-copy wrap
+                FlatStringsVector{T}(b[2]; sizes = b[1])          # FlatStringsVectors.jl:54-59: zero-copy wrap (data::AbstractVector{UInt8})
             elseif T === B
                 b[1]
             else

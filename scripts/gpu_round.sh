@@ -1,5 +1,5 @@
 #!/bin/bash
-# One gpurun call: GPU parity tests, bench (both arms), ncu launch list, ncu --set full of the two hot kernels.
+# One gpurun call: GPU parity tests, bench (both arms), ncu launch list, ncu --set full of the hot kernels.
 # usage: gpurun --timeout 1800 -- 'bash scripts/gpu_round.sh <tag>'
 TAG=${1:-r1}
 OUT=gpurun_out/$TAG
@@ -14,9 +14,15 @@ cat $OUT/bench_ref.json
 # launch list (cold-cache, serialised: shares only)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-verify > $OUT/launches_bench.log 2>&1
-# full capture of the two hot kernels on a 200M-row table (>> L2), 2 launches each
+# full capture of the two hot kernels of the headline bench at 1B rows
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:lz4_decode_v2 -s 1 -c 1 -o $OUT/prof_lz4 -f \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-verify > $OUT/prof_lz4.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fused_scan -s 1 -c 1 -o $OUT/prof_scan -f \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-verify > $OUT/prof_scan.log 2>&1
+# the general decoder and the string gather on configs[2] (200M-row string table)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:lz4_decode_v3 -s 1 -c 1 -o $OUT/prof_lz4_v3 -f \
+    python bench_configs.py --config 3 --reps 1 > $OUT/prof_lz4_v3.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gather_strings -s 1 -c 1 -o $OUT/prof_gather_str -f \
+    python bench_configs.py --config 3 --reps 1 > $OUT/prof_gather_str.log 2>&1
+timeout 600 python scripts/decode_kinds.py --rows 200000000 > $OUT/kinds.json 2> $OUT/kinds.err
 ls -la $OUT
