@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <functional>
 #include <cmath>
 #include <map>
 #include <mutex>
@@ -31,6 +32,8 @@ struct Runtime {
     int device = 0;
     int sm_count = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaStream_t decode_stream = nullptr, decode_stream2 = nullptr;   // above the scan stream's priority: the full rounds and the last round of a
+                                                                      // decode that the scan of the earlier rounds runs beside (ensure_decoded)
     unsigned int *d_counter = nullptr;
     int *d_error = nullptr;
     std::atomic<int64_t> launches{0};
@@ -41,6 +44,7 @@ struct Runtime {
     int64_t no_fused = 0;
     int64_t no_tma = 0;
     int64_t lz4_flavour = 0;  // K1 flavour: 0 = per column from a token sample at load, 1 = word-regular decoder (v2), 2 = general decoder (v3)
+    int64_t no_overlap = 0;   // do not run the scan of the decoded part of a shard beside the decode of its last part
     int64_t no_alias = 0;     // copy stored (incompressible) blocks like any other block instead of referencing them in place
     // profiling
     bool profiling = false;
@@ -251,12 +255,14 @@ bool wide_ok(const dfdb_table *t, const Column &c)
 }
 
 // ---- decode ---------------------------------------------------------------------------------------------
-int launch_decode(const DecodeArgs &a, bool general)
+int launch_decode(const DecodeArgs &a, bool general, cudaStream_t stream = nullptr, int cta_limit = 0, int counter_slot = 0)
 {
-    if (rt.lz4_simple || rt.lz4_v1) return launch_lz4_decode(a, rt.d_counter, rt.sm_count, (int)rt.lz4_simple, rt.stream);
+    if (!stream) stream = rt.stream;
+    unsigned int *counter = rt.d_counter + 4 * counter_slot;   // launches that may run at the same time need their own job counter
+    if (rt.lz4_simple || rt.lz4_v1) return launch_lz4_decode(a, counter, rt.sm_count, (int)rt.lz4_simple, stream);
     if (rt.lz4_flavour == 1) general = false;
     if (rt.lz4_flavour == 2) general = true;
-    return general ? launch_lz4_decode_v3(a, rt.d_counter, rt.sm_count, rt.stream) : launch_lz4_decode_v2(a, rt.d_counter, rt.sm_count, rt.stream);
+    return general ? launch_lz4_decode_v3(a, counter, rt.sm_count, stream, cta_limit) : launch_lz4_decode_v2(a, counter, rt.sm_count, stream, cta_limit);
 }
 
 // Which K1 flavour suits a column: walk the token stream of one compressed block on the host (done once, at load).
@@ -297,7 +303,15 @@ int sample_flavour(const uint8_t *src, int64_t n, int64_t origin)
     return (regular * 100 >= nseq * 98 && chained * 2 <= nseq) ? 0 : 1;
 }
 
-int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids)
+// on_part(b0, b1, sms): optional.  Called (once or twice) with consecutive local block ranges that cover the shard, each
+// time after work that makes rt.stream wait for the decode of [b0, b1) has been enqueued; `sms` is the number of SMs a
+// kernel launched now on rt.stream can expect to find free.  A shard with more blocks to decode than the decoder keeps in
+// flight (sm_count x LZ4_SLOTS_PER_SM) decodes in rounds, and its last round is rarely full: the decode of that round is
+// given only the SMs it can fill, on a higher-priority stream, and the caller's scan of everything before it runs beside it
+// on the others.  Never called when nothing had to be decoded.
+using PartFn = std::function<int(int, int, int)>;
+
+int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const PartFn *on_part = nullptr)
 {
     std::vector<Column *> todo;
     for (int64_t id : col_ids) {
@@ -339,7 +353,73 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids)
             copied.push_back(e);
         }
     }
-    for (int k = 0; k < nchunks; k++) {
+    // ---- decode / scan overlap (compressed blocks resident, one flavour, more than one round of blocks) ----
+    bool parted = false;
+    if (on_part && host_bytes == 0 && !rt.no_overlap && !rt.lz4_simple && !rt.lz4_v1 && todo.size() <= (size_t)DECODE_MAX_COLS) {
+        bool one_flavour = true;
+        for (Column *c : todo) one_flavour = one_flavour && c->lz4_general == todo[0]->lz4_general;
+        const int64_t wave = (int64_t)rt.sm_count * LZ4_SLOTS_PER_SM;
+        int64_t real = 0;
+        for (Column *c : todo) for (int b = 0; b < nblocks; b++) real += c->h_skip[(size_t)b] ? 0 : 1;
+        // the last round: what is left after the full rounds
+        int split = 0;
+        int64_t last_real = real % wave, acc = 0;
+        if (one_flavour && real > wave && last_real > 0) {
+            for (int b = 0; b < nblocks && acc < real - last_real; b++) {
+                for (Column *c : todo) acc += c->h_skip[(size_t)b] ? 0 : 1;
+                split = b + 1;
+            }
+        }
+        const int last_ctas = (int)((last_real + LZ4_SLOTS_PER_SM - 1) / LZ4_SLOTS_PER_SM);
+        if (split > 0 && split < nblocks && rt.sm_count - last_ctas >= 8) {
+            // The full rounds go to one launch (its slots pick up blocks as they finish: no barrier between rounds); the last
+            // round is a launch of its own on a second stream, so that its CTAs move in as the first launch's CTAs run out
+            // of blocks -- again no barrier -- and it is limited to the SMs it can fill.
+            int64_t bytes = 0;
+            auto decode_range = [&](int b0, int b1, int cta_limit, cudaStream_t stream, int counter_slot) -> int {
+                DecodeArgs a;
+                memset(&a, 0, sizeof a);
+                a.nblocks = b1 - b0;
+                a.blk0 = b0;
+                for (Column *c : todo) {
+                    DecodeCol &d = a.col[a.ncols++];
+                    d.comp = c->d_comp; d.comp_off = c->d_comp_off; d.comp_len = c->d_comp_len; d.dec_off = c->d_dec_off;
+                    d.origin = c->d_origin; d.out = c->d_decoded; d.status = c->d_status; d.skip = c->d_skip;
+                    for (int64_t b = b0; b < b1; b++)
+                        if (!c->h_skip[(size_t)b]) bytes += c->blocks[(size_t)(t->blk_lo + b)].compressed + c->blocks[(size_t)(t->blk_lo + b)].origin;
+                }
+                LAUNCH(launch_decode(a, todo[0]->lz4_general, stream, cta_limit, counter_slot));
+                return DFDB_OK;
+            };
+            // one decode phase record for both launches: from the start of the first to the end of the second
+            PhaseRec pr{PH_DECODE, nullptr, nullptr, 2, 0};
+            if (rt.profiling) { cudaEventCreate(&pr.a); cudaEventCreate(&pr.b); }
+            cudaEvent_t e0, e1, e2;
+            CUDA_TRY(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventRecord(e0, rt.stream));
+            CUDA_TRY(cudaStreamWaitEvent(rt.decode_stream, e0, 0));
+            CUDA_TRY(cudaStreamWaitEvent(rt.decode_stream2, e0, 0));
+            if (pr.a) cudaEventRecord(pr.a, rt.decode_stream);
+            int rc = decode_range(0, split, 0, rt.decode_stream, 0);
+            if (!rc) { CUDA_TRY(cudaEventRecord(e1, rt.decode_stream)); rc = decode_range(split, nblocks, last_ctas, rt.decode_stream2, 1); }
+            if (pr.a) { cudaEventRecord(pr.b, rt.decode_stream2); pr.bytes = bytes; rt.recs.push_back(pr); }
+            if (!rc) {
+                CUDA_TRY(cudaEventRecord(e2, rt.decode_stream2));
+                CUDA_TRY(cudaStreamWaitEvent(rt.stream, e1, 0));
+                rc = (*on_part)(0, split, rt.sm_count - last_ctas);
+            }
+            if (!rc) {
+                CUDA_TRY(cudaStreamWaitEvent(rt.stream, e2, 0));
+                rc = (*on_part)(split, nblocks, rt.sm_count);
+            }
+            cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+            if (rc) return rc;
+            parted = true;
+        }
+    }
+    for (int k = 0; k < nchunks && !parted; k++) {
         const int b0 = (int)((int64_t)nblocks * k / nchunks), b1 = (int)((int64_t)nblocks * (k + 1) / nchunks);
         if (!copied.empty()) {
             CUDA_TRY(cudaStreamWaitEvent(rt.stream, copied[(size_t)k], 0));
@@ -368,6 +448,10 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids)
             LAUNCH(launch_decode(a, general != 0));
           }
         }
+    }
+    if (on_part && !parted) {
+        const int rc = (*on_part)(0, nblocks, rt.sm_count);
+        if (rc) return rc;
     }
     const Geometry g = make_geometry(t);
     for (Column *c : todo)
@@ -731,40 +815,69 @@ int run_aggregate(dfdb_scan *s, int32_t proj_idx, bool count_only, AggPartial *h
         wide = wide && wide_ok(t, *ac);
     }
     const int nunits = g.nblocks * g.segs_per_block;
+    int64_t scan_bytes = 0;
+    TmaScanArgs ta;
+    memset(&ta, 0, sizeof ta);
+    bool use_tma = false, scanned = false;
+    // the TMA scan of local blocks [b0, b1) on `sms` SMs (partials are per work unit, so parts compose)
+    auto scan_part = [&](int b0, int b1, int sms) -> int {
+        if (!use_tma || b1 <= b0) return DFDB_OK;
+        if (!scanned) {
+            // work units that hold no rows (segments past the end of a partial last block) are never visited
+            CUDA_TRY(cudaMemsetAsync(s->d_partials, 0, (size_t)std::max(nunits, 1) * sizeof(AggPartial), rt.stream));
+            scanned = true;
+        }
+        TmaScanArgs part = ta;
+        part.g.blk_lo = g.blk_lo + b0;
+        part.g.nblocks = b1 - b0;
+        for (int c = 0; c < part.ncols; c++) part.col[c].blk_off += b0;
+        part.partials = static_cast<AggPartial *>(s->d_partials) + (int64_t)b0 * g.segs_per_block;
+        PhaseScope ps(PH_CONSUME, scan_bytes * (b1 - b0) / std::max(g.nblocks, 1));
+        LAUNCH(launch_fused_tma(part, agg, sms, rt.stream));
+        return DFDB_OK;
+    };
+    const PartFn part_fn = scan_part;
     if (s->stages.empty() || single_simple_pred(s)) {
         if (!s->stages.empty()) for (int64_t id : s->stages[0].e.col_ids) need.push_back(id);
-        rc = ensure_decoded(t, need);
-        if (rc) return rc;
+        for (int64_t id : need) {
+            Column *c = t->find(id);
+            if (!c) return fail(DFDB_ERR_KEY, "unknown column id %lld", (long long)id);
+            for (int64_t b = t->blk_lo; b < t->blk_hi; b++) scan_bytes += c->blocks[(size_t)b].origin;
+        }
         if (!s->stages.empty()) {
             fill_terms(s, s->stages[0].e, &a);
             wide = wide && fused_terms_wide(s, s->stages[0].e);
         }
+        // the fast path is set up before the decode so that it can start on the part of the shard that is decoded
+        bool cfalse = false;
+        bool loaded = true;
+        for (int64_t id : need) loaded = loaded && t->find(id)->loaded;
+        use_tma = loaded && wide && !rt.no_tma && nunits > 0 &&
+                  build_tma_args(s, s->stages.empty() ? nullptr : &s->stages[0].e, ac, &ta, &cfalse) && !cfalse;
+        if (use_tma) {
+            ta.g = g;
+            ta.agg_cls = cls;
+        }
+        rc = ensure_decoded(t, need, use_tma ? &part_fn : nullptr);
+        if (rc) return rc;
     } else {
         rc = run_selection(s);
         if (rc) return rc;
         rc = ensure_decoded(t, need);
         if (rc) return rc;
+        for (int64_t id : need) for (int64_t b = t->blk_lo; b < t->blk_hi; b++) scan_bytes += t->find(id)->blocks[(size_t)b].origin;
         a.mask_in = s->d_mask;
         wide = false;
     }
     if (ac) { a.agg_col = make_view(*ac); a.agg_cls = cls; }
     {
-        int64_t bytes = 0;
-        for (int64_t id : need) for (int64_t b = t->blk_lo; b < t->blk_hi; b++) bytes += t->find(id)->blocks[(size_t)b].origin;
-        PhaseScope ps(PH_CONSUME, bytes);
-        TmaScanArgs ta;
-        memset(&ta, 0, sizeof ta);
-        bool cfalse = false;
-        const bool use_tma = wide && !rt.no_tma && !a.mask_in &&
-                             build_tma_args(s, s->stages.empty() ? nullptr : &s->stages[0].e, ac, &ta, &cfalse) && !cfalse;
         if (use_tma) {
-            ta.g = g;
-            ta.agg_cls = cls;
-            ta.partials = static_cast<AggPartial *>(s->d_partials);
-            // work units that hold no rows (segments past the end of a partial last block) are never visited
-            CUDA_TRY(cudaMemsetAsync(s->d_partials, 0, (size_t)std::max(nunits, 1) * sizeof(AggPartial), rt.stream));
-            if (nunits > 0) LAUNCH(launch_fused_tma(ta, agg, rt.sm_count, rt.stream));
-        } else if (nunits > 0) LAUNCH(launch_fused(a, agg, false, wide, rt.sm_count, rt.stream));
+            if (!scanned) { rc = scan_part(0, g.nblocks, rt.sm_count); if (rc) return rc; }   // everything was decoded already
+        } else if (nunits > 0) {
+            PhaseScope ps(PH_CONSUME, scan_bytes);
+            LAUNCH(launch_fused(a, agg, false, wide, rt.sm_count, rt.stream));
+        }
+        PhaseScope ps(PH_CONSUME, 0);
         LAUNCH(launch_agg_finalize(static_cast<AggPartial *>(s->d_partials), nunits, agg == 2 ? VC_FLT : cls, static_cast<AggPartial *>(s->d_result), rt.stream));
     }
     PhaseScope ps(PH_D2H, sizeof(AggPartial));
@@ -803,10 +916,17 @@ int32_t dfdb_init(int32_t device)
     CUDA_TRY(cudaStreamCreateWithFlags(&rt.own_stream, cudaStreamNonBlocking));
     rt.stream = rt.own_stream;
     CUDA_TRY(cudaStreamCreateWithFlags(&rt.copy_stream, cudaStreamNonBlocking));
+    {
+        int least = 0, greatest = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CUDA_TRY(cudaStreamCreateWithPriority(&rt.decode_stream, cudaStreamNonBlocking, greatest));
+        CUDA_TRY(cudaStreamCreateWithPriority(&rt.decode_stream2, cudaStreamNonBlocking, greatest < least - 1 ? greatest + 1 : greatest));
+    }
     CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&rt.d_counter), 64));
     CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&rt.d_error), 64));
     CUDA_TRY(cudaMemset(rt.d_error, 0, 64));
-    if (const char *fl = getenv("DFDB_LZ4_FLAVOUR")) rt.lz4_flavour = atoll(fl);   // A/B: force one K1 flavour (see dfdb_set_option "lz4_flavour")
+    if (const char *fl = getenv("DFDB_LZ4_FLAVOUR")) rt.lz4_flavour = atoll(fl);
+    if (const char *ov = getenv("DFDB_NO_OVERLAP")) rt.no_overlap = atoll(ov);       // A/B: decode / scan overlap off   // A/B: force one K1 flavour (see dfdb_set_option "lz4_flavour")
     rt.inited = true;
     return DFDB_OK;
 }
@@ -821,6 +941,8 @@ int32_t dfdb_shutdown(void)
     { std::lock_guard<std::mutex> lk(arena.mu); arena.trim(0); }
     cudaStreamDestroy(rt.own_stream);
     cudaStreamDestroy(rt.copy_stream);
+    cudaStreamDestroy(rt.decode_stream);
+    cudaStreamDestroy(rt.decode_stream2);
     rt.inited = false;
     return DFDB_OK;
 }
@@ -853,6 +975,7 @@ int32_t dfdb_set_option(const char *name, int64_t value)
     else if (n == "no_fused") rt.no_fused = value;
     else if (n == "no_tma") rt.no_tma = value;
     else if (n == "lz4_flavour") rt.lz4_flavour = value;
+    else if (n == "no_overlap") rt.no_overlap = value;
     else if (n == "no_alias") rt.no_alias = value;
     else if (n == "host_arena_cap_mb") { std::lock_guard<std::mutex> lk(arena.mu); arena.cap_bytes = (size_t)std::max<int64_t>(value, 0) << 20; arena.trim(arena.cap_bytes); }
     else return fail(DFDB_ERR_ARGUMENT, "unknown option %s", n.c_str());

@@ -26,8 +26,9 @@ struct DecodeArgs {
     unsigned long long *stats;   // optional diagnostics counters (null = off), see lz4_decode_v2.cu
 };
 int launch_lz4_decode(const DecodeArgs &args, unsigned int *d_counter, int sm_count, int simple_mode, cudaStream_t stream);      // v1: warp per block
-int launch_lz4_decode_v2(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream);                     // v2: walker / consumer warps, word-regular columns
-int launch_lz4_decode_v3(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream);                     // v3: same organisation, general columns (strings, literal-heavy, chains)
+constexpr int LZ4_SLOTS_PER_SM = 60;   // column blocks one decoder CTA keeps in flight (NSLOT of both walker/consumer flavours)
+int launch_lz4_decode_v2(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit = 0);                     // v2: walker / consumer warps, word-regular columns
+int launch_lz4_decode_v3(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit = 0);                     // v3: same organisation, general columns (strings, literal-heavy, chains)
 
 // ---- scan geometry -------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 256;

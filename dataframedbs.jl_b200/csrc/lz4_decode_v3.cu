@@ -1166,7 +1166,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) lz4_decode_v3_kernel(const __gr
     else consumer(S, args, counter, first_dynamic, warp - NWALK);
 }
 
-int launch_lz4_decode_v3(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream)
+int launch_lz4_decode_v3(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit)
 {
     static bool configured = false;
     static unsigned long long *d_stats = nullptr;
@@ -1187,6 +1187,7 @@ int launch_lz4_decode_v3(const DecodeArgs &args, unsigned int *d_counter, int sm
     // one persistent CTA per SM; with few jobs, one job per consumer warp before any warp takes a second
     long long ctas = njobs;
     if (ctas > sm_count) ctas = sm_count;
+    if (cta_limit > 0 && ctas > cta_limit) ctas = cta_limit;   // leave the other SMs to a concurrent kernel (api.cu: decode / scan overlap)
     if (ctas < 1) ctas = 1;
     // dynamic job ids start after the statically assigned first pass
     const unsigned int first_dynamic = (unsigned int)(ctas * NCONS * SPC);

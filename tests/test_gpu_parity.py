@@ -366,6 +366,35 @@ def test_residency_modes_and_kernel_variants_agree(synth, oracle):
             L.dfdb_set_option(opt, 0)
 
 
+def test_decode_scan_overlap_matches_the_plain_path(tmp_path, oracle):
+    """A shard with more blocks than the decoder keeps in flight (148 SMs x 60) decodes in rounds, and the scan of the
+    earlier rounds runs beside the decode of the last one (api.cu ensure_decoded / run_aggregate).  Same partials, same
+    fixed combination order: the result must be bit-identical to the one-kernel-after-the-other path."""
+    p = str(tmp_path / "many_blocks")
+    nrows, bs = 1_400_000, 128                                   # 10 938 blocks per column
+    oracle.gen_table(p, "a:Int64:iuniform:1:100;b:Float64:funiform;c:Int64:iseq", nrows, bs, 0xDFDB0099, 4)
+    ot = oracle.OracleTable(p)
+    L = _capi.lib()
+    results = {}
+    for no_overlap in (0, 1):
+        _capi.check(L.dfdb_set_option(b"no_overlap", no_overlap))
+        try:
+            t = D.open_table(p)
+            for name, mk in {"b": lambda t: t[(t.a > 25) & (t.a <= 75), ["b"]].b, "c": lambda t: t[t.a > 50, ["c"]].c,
+                             "count": lambda t: t[t.c > 700_000, ["a"]].a}.items():
+                col = mk(t)
+                r1, r2 = D.aggregate(col), D.aggregate(col)
+                _check_agg(r1, ot.aggregate(D.plan_bytes(col), 0), (no_overlap, name))
+                assert (r1.sum_f64, r1.sum_f64_lo, r1.sum_i64, r1.count) == (r2.sum_f64, r2.sum_f64_lo, r2.sum_i64, r2.count)
+                results[(no_overlap, name)] = (r1.sum_f64, r1.sum_f64_lo, r1.sum_i64, r1.count, r1.min_f64, r1.max_f64, r1.min_i64, r1.max_i64)
+            t.close()
+        finally:
+            L.dfdb_set_option(b"no_overlap", 0)
+    for name in ("b", "c", "count"):
+        assert results[(0, name)] == results[(1, name)], name
+    ot.close()
+
+
 def test_sharded_scan_folds_to_the_unsharded_result(synth):
     t, ot, nrows = synth
     v = t[(t.a > 25) & (t.a <= 75), ["b", "s"]]
