@@ -159,7 +159,27 @@ cudaError_t scratch_alloc(void **p, size_t n)
     }
     return cudaMallocAsync(p, std::max<size_t>(n, 1), rt.stream);
 }
-void scratch_free(void *p) { if (p) cudaFreeAsync(p, rt.stream); }
+void scratch_free(void *p, cudaStream_t stream = nullptr) { if (p) cudaFreeAsync(p, stream ? stream : rt.stream); }
+
+cudaError_t copy_out(void *dst, const void *d_src, size_t n);
+
+// Result column -> caller memory without stalling the scan stream: a destination in the result arena is copied on the
+// copy stream (behind an event on the scan stream), so that the gather -- or the decode -- of the next projected column
+// runs during the transfer.  Returns true when the copy was queued that way (the caller then frees the scratch on the copy
+// stream and synchronises it before returning); anything else is copied synchronously by copy_out.
+bool copy_out_queued(void *dst, const void *d_src, size_t n, cudaError_t *err)
+{
+    *err = cudaSuccess;
+    if (n == 0) return false;
+    if (!arena.pinned(dst, n)) { *err = copy_out(dst, d_src, n); return false; }
+    cudaEvent_t ready;
+    if ((*err = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming)) != cudaSuccess) return false;
+    cudaEventRecord(ready, rt.stream);
+    cudaStreamWaitEvent(rt.copy_stream, ready, 0);
+    cudaEventDestroy(ready);
+    *err = cudaMemcpyAsync(dst, d_src, n, cudaMemcpyDeviceToHost, rt.copy_stream);
+    return *err == cudaSuccess;
+}
 
 // Device -> caller memory.  A destination inside the result arena is page-locked: one asynchronous copy at full PCIe
 // rate.  Anything else is ordinary (pageable) host memory, which the driver copies at a few GB/s; large results go
@@ -1477,12 +1497,18 @@ int32_t dfdb_scan_materialize(dfdb_scan *s, dfdb_outcol *cols, int32_t ncols)
     const int64_t total = s->selected;
     const Geometry g = make_geometry(t);
     if (total == 0) return DFDB_OK;
+    struct CopyDrain { ~CopyDrain() { cudaStreamSynchronize(rt.copy_stream); } } drain;   // no queued copy outlives this call, on any path
     for (size_t i = 0; i < s->projs.size(); i++) {
         const Proj &p = s->projs[i];
         dfdb_outcol &oc = cols[i];
         uint8_t *d_vals = nullptr, *d_miss = nullptr, *d_chars = nullptr;
         int32_t *d_sizes = nullptr;
-        auto cleanup = [&]() { scratch_free(d_vals); scratch_free(d_miss); scratch_free(d_chars); scratch_free(d_sizes); };
+        bool queued = false;      // this column's copies went to the copy stream: its scratch is freed there
+        cudaError_t ce = cudaSuccess;
+        auto cleanup = [&]() {
+            cudaStream_t fs = queued ? rt.copy_stream : rt.stream;
+            scratch_free(d_vals, fs); scratch_free(d_miss, fs); scratch_free(d_chars, fs); scratch_free(d_sizes, fs);
+        };
         if (p.kind == PJ_COL) {
             rc = ensure_decoded(t, {p.col});
             if (rc) return rc;
@@ -1512,9 +1538,15 @@ int32_t dfdb_scan_materialize(dfdb_scan *s, dfdb_outcol *cols, int32_t ncols)
                     if (launch_gather_strings(a, rt.stream) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "gather_strings launch failed"); }
                     rt.launches++;
                 }
-                PhaseScope ps2(PH_D2H, total * 4 + nbytes);
-                copy_out(oc.str_sizes, d_sizes, (size_t)total * 4);
-                if (nbytes > 0 && oc.str_chars) copy_out(oc.str_chars, d_chars, (size_t)nbytes);
+                const bool pin = arena.pinned(oc.str_sizes, (size_t)total * 4) && (nbytes == 0 || !oc.str_chars || arena.pinned(oc.str_chars, (size_t)nbytes));
+                PhaseScope ps2(PH_D2H, total * 4 + nbytes, pin ? rt.copy_stream : rt.stream);
+                if (pin) {
+                    queued = copy_out_queued(oc.str_sizes, d_sizes, (size_t)total * 4, &ce);
+                    if (ce == cudaSuccess && nbytes > 0 && oc.str_chars) copy_out_queued(oc.str_chars, d_chars, (size_t)nbytes, &ce);
+                } else {
+                    ce = copy_out(oc.str_sizes, d_sizes, (size_t)total * 4);
+                    if (ce == cudaSuccess && nbytes > 0 && oc.str_chars) ce = copy_out(oc.str_chars, d_chars, (size_t)nbytes);
+                }
             } else {
                 if (!oc.values) return fail(DFDB_ERR_ARGUMENT, "output column %zu needs a values buffer", i);
                 const int es = c->type.elsize;
@@ -1530,9 +1562,15 @@ int32_t dfdb_scan_materialize(dfdb_scan *s, dfdb_outcol *cols, int32_t ncols)
                     if (launch_gather_fixed(a, rt.stream) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "gather launch failed"); }
                     rt.launches++;
                 }
-                PhaseScope ps(PH_D2H, total * es);
-                copy_out(oc.values, d_vals, (size_t)total * es);
-                if (c->type.nullable && oc.missing) copy_out(oc.missing, d_miss, (size_t)total);
+                const bool pin = arena.pinned(oc.values, (size_t)total * es) && (!c->type.nullable || !oc.missing || arena.pinned(oc.missing, (size_t)total));
+                PhaseScope ps(PH_D2H, total * es, pin ? rt.copy_stream : rt.stream);
+                if (pin) {
+                    queued = copy_out_queued(oc.values, d_vals, (size_t)total * es, &ce);
+                    if (ce == cudaSuccess && c->type.nullable && oc.missing) copy_out_queued(oc.missing, d_miss, (size_t)total, &ce);
+                } else {
+                    ce = copy_out(oc.values, d_vals, (size_t)total * es);
+                    if (ce == cudaSuccess && c->type.nullable && oc.missing) ce = copy_out(oc.missing, d_miss, (size_t)total);
+                }
             }
         } else {
             rc = ensure_decoded(t, p.e.col_ids);
@@ -1567,10 +1605,15 @@ int32_t dfdb_scan_materialize(dfdb_scan *s, dfdb_outcol *cols, int32_t ncols)
             rc = check_device_error();
             if (rc) { cleanup(); return rc; }
         }
-        cudaError_t e = cudaStreamSynchronize(rt.stream);
+        cudaError_t e = queued ? cudaSuccess : cudaStreamSynchronize(rt.stream);
         cleanup();
-        if (e != cudaSuccess) return fail(DFDB_ERR_CUDA, "materialize failed: %s", cudaGetErrorString(e));
+        if (e == cudaSuccess) e = ce;
+        if (e != cudaSuccess) { cudaStreamSynchronize(rt.copy_stream); return fail(DFDB_ERR_CUDA, "materialize failed: %s", cudaGetErrorString(e)); }
     }
+    // queued copies: the results are complete when the copy stream has drained
+    cudaError_t e = cudaStreamSynchronize(rt.copy_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(rt.stream);
+    if (e != cudaSuccess) return fail(DFDB_ERR_CUDA, "materialize failed: %s", cudaGetErrorString(e));
     return DFDB_OK;
 }
 
