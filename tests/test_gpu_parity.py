@@ -395,6 +395,37 @@ def test_decode_scan_overlap_matches_the_plain_path(tmp_path, oracle):
     ot.close()
 
 
+def test_result_arena(synth):
+    """dfdb_host_alloc / dfdb_host_free: page-locked result buffers, reused after they are freed; materialize fills both
+    arena buffers (direct copy) and ordinary memory (bounce buffers) with the same bytes."""
+    t, ot, nrows = synth
+    L = _capi.lib()
+    p1, p2 = C.c_void_p(), C.c_void_p()
+    _capi.check(L.dfdb_host_alloc(3 << 20, C.byref(p1)))
+    assert p1.value and p1.value % 4096 == 0
+    (C.c_uint8 * (3 << 20)).from_address(p1.value)[(3 << 20) - 1] = 7          # writable to the last byte
+    _capi.check(L.dfdb_host_free(p1))
+    seen = set()
+    for _ in range(4):                                                           # freed buffers are handed out again
+        _capi.check(L.dfdb_host_alloc(3 << 20, C.byref(p2)))
+        seen.add(p2.value)
+        _capi.check(L.dfdb_host_free(p2))
+    assert len(seen) == 1
+    assert L.dfdb_host_free(C.c_void_p(12345)) != 0                              # not an arena buffer
+    v = t[t.a > 50, ["a", "b", "s", "ma"]]
+    old = _capi.PINNED_MIN_BYTES
+    try:
+        _capi.PINNED_MIN_BYTES = 1                                               # every result vector from the arena
+        pinned = D.materialize(v).to_dict()
+        _capi.PINNED_MIN_BYTES = 1 << 62                                         # none
+        pageable = D.materialize(v).to_dict()
+    finally:
+        _capi.PINNED_MIN_BYTES = old
+    assert pinned == pageable
+    exp = ot.materialize(D.plan_bytes(v))
+    assert pinned["a"] == exp[0].tolist() and pinned["s"] == exp[2].tolist()
+
+
 def test_sharded_scan_folds_to_the_unsharded_result(synth):
     t, ot, nrows = synth
     v = t[(t.a > 25) & (t.a <= 75), ["b", "s"]]
