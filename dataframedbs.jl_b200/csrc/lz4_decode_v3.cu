@@ -1,29 +1,32 @@
-// lz4_decode_v2.cu -- K1 (second generation): raw LZ4 block decode on sm_100a with the serial part of the
-// format split off into lane-per-block "walker" warps.
+// lz4_decode_v3.cu -- K1, general flavour: raw LZ4 block decode on sm_100a for columns whose token stream is not
+// word-regular (strings, literal-heavy bodies such as Union{Float64,Missing}, sorted integers, shifted Float64 grids).
 //
 // Replaces read_block's LZ4_decompress_safe call (/root/reference/src/io/BlockStreams.jl:101-119, liblz4 via
 // CodecLz4) for whole batches of independent column blocks, with the same safety contract: never reads
 // outside the compressed payload, never writes outside `origin`, per-block status instead of the
 // reference's `@assert size == sizes.origin "decompression error"`.
 //
-// Why this shape.  The only inherently serial part of an LZ4 block is finding where each token starts
-// (token k+1 starts 3 + literal_length(k) bytes after token k).  The first-generation kernel let a whole
-// warp walk that chain (3 instructions, ~35 cycles of latency per token, 1 useful lane of 32).  Here one
-// persistent CTA per SM keeps NSLOT column blocks in flight at once:
-//   * NWALK walker warps: each LANE walks the token chain of one block through a shared-memory window of
-//     its compressed stream and emits one 8-byte ring entry per sequence {stream position, token, output
-//     position, generation tag}.  32 chains per warp advance in the latency of one, and the running
-//     output position replaces the per-batch prefix sum of the old kernel.
-//   * NCONS consumer warps, SPC block slots each: take up to 32 ring entries and materialise them
-//     lane-parallel.  "Word-regular" runs (8-byte aligned output, offset and length multiples of 8 --
-//     what LZ4 produces for Int64/Float64/Missing columns) are expanded to one output word per lane and
-//     resolved by word forwarding (far sources: one 8-byte load; in-batch sources: warp shuffles in
-//     dependency waves).  Everything else goes through byte-granular dependency waves in shared memory.
-//     Sequences with length extensions and the last sequence of a block ("special") are done one at a
-//     time by the whole warp (vectorised re-aligning memcpy for long literal runs).
-//   * Rings need no fences: an entry is valid when its generation tag matches the consumer's index
-//     (one atomic 8-byte shared store per entry); the window fill level and restart commands are
-//     published with release stores.
+// Same organisation as lz4_decode_v2.cu (read that header first): one persistent CTA per SM, NWALK walker warps whose
+// LANES walk the token chains of NSLOT blocks through shared-memory windows of their compressed streams and emit one
+// 4-byte ring entry (the token's stream position) per sequence, NCONS consumer warps with SPC block slots each that
+// take 32 entries at a time.  What is different here:
+//   * the walker gets past tokens with length extensions on its own when the extension bytes are in the window
+//     (walker_resolve); the entry stays in the ring, the consumer recognises it by its nibbles.  Only the last
+//     sequence of a block and extensions that reach beyond the window still park the lane until the consumer posts a
+//     restart command.  The hint word carries two flags: PARKED and STARVED (next token beyond the window: the
+//     consumer then takes a partial batch, because the window only moves when entries are consumed);
+//   * a sequence that is done one at a time (special_run) reads the stream through a 256-byte register chunk -- no
+//     dependent global loads for token / extension bytes / literals / offset -- and keeps a short match pending in
+//     registers across the parse of the next sequence; while the walker is parked the warp carries on over the
+//     following sequences;
+//   * generic batches (generic_batch) fetch a match source with aligned 8-byte loads issued together -- from global
+//     memory or from the staging area -- and store from registers; byte-serial copies remain only for overlapping
+//     matches.  The partial 16-byte output chunk a batch ends in stays in the staging area for the next batch;
+//   * in-batch chains of word-regular batches (sorted / sequential columns: every word copies its predecessor) are
+//     collapsed by pointer jumping (resolve_chains, burst<true>) instead of one dependency wave per word;
+//   * every block start flushes the ring (command -> acknowledgement with the ring position the new block's entries
+//     start at), so a block that ends in an error is dropped where it stands.
+// Which flavour a column gets is decided at load from a token sample (api.cu: sample_flavour).
 //
 // Algorithmic bytes per block (roofline): compressed bytes read + origin bytes written.
 #include <cuda_runtime.h>
