@@ -28,7 +28,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=200_000_000)
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--cols", default="")
+    ap.add_argument("--cols", default="", help="columns to measure AND to generate (default: all eight)")
     ap.add_argument("--check-rows", type=int, default=1_000_000)
     args = ap.parse_args()
     import torch
@@ -37,11 +37,13 @@ def main():
     from oracle import oracle as O
 
     base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
-    path = os.path.join(base, f"dfdb_b200_kinds_{args.rows}")
+    want_cols = [c for c in args.cols.split(",") if c]
+    spec = ";".join(p for p in SPEC.split(";") if not want_cols or p.split(":")[0] in want_cols)
+    path = os.path.join(base, f"dfdb_b200_kinds_{args.rows}" + ("_" + "_".join(want_cols) if want_cols else ""))
     if not os.path.exists(os.path.join(path, ".complete")):
         shutil.rmtree(path, ignore_errors=True)
         t0 = time.time()
-        unc, comp = O.gen_table(path, SPEC, args.rows, 65536, 0xDFDB0007, os.cpu_count() or 1)
+        unc, comp = O.gen_table(path, spec, args.rows, 65536, 0xDFDB0007, os.cpu_count() or 1)
         open(os.path.join(path, ".complete"), "w").write("ok")
         print(f"[kinds] generated {args.rows} rows in {time.time() - t0:.1f} s: {unc / 1e9:.2f} GB -> {comp / 1e9:.2f} GB", file=sys.stderr, flush=True)
     torch.cuda.set_device(0)
