@@ -826,7 +826,44 @@ int run_aggregate(dfdb_scan *s, int32_t proj_idx, bool count_only, AggPartial *h
     if (!count_only) {
         if (proj_idx < 0 || (size_t)proj_idx >= s->projs.size()) return fail(DFDB_ERR_ARGUMENT, "projection index out of range");
         const Proj &p = s->projs[(size_t)proj_idx];
-        if (p.kind != PJ_COL) return fail(DFDB_ERR_UNSUPPORTED, "aggregates over computed columns are not supported yet");
+        if (p.kind != PJ_COL) {
+            // a computed column: the VM value of every selected row, folded into the same per-unit partials
+            cls = p.e.prog.result_class;
+            if (cls == VC_NONE || cls == VC_STR) return fail(DFDB_ERR_UNSUPPORTED, "aggregate over a computed String column");
+            rc = run_selection(s);
+            if (rc) return rc;
+            rc = ensure_decoded(t, p.e.col_ids);
+            if (rc) return rc;
+            AggVmArgs va;
+            memset(&va, 0, sizeof va);
+            va.g = g;
+            rc = fill_slots(s, va.slot);
+            if (rc) return rc;
+            DevProg prog;
+            rc = prog.upload(p.e.prog);
+            if (rc) return rc;
+            va.prog = prog.d;
+            va.mask = s->d_mask;
+            va.partials = static_cast<AggPartial *>(s->d_partials);
+            va.cls = cls;
+            va.error_flag = rt.d_error;
+            const int nu = g.nblocks * g.segs_per_block;
+            {
+                int64_t bytes = 0;
+                for (int64_t id : p.e.col_ids) for (int64_t b = t->blk_lo; b < t->blk_hi; b++) bytes += t->find(id)->blocks[(size_t)b].origin;
+                PhaseScope ps(PH_CONSUME, bytes);
+                CUDA_TRY(cudaMemsetAsync(s->d_partials, 0, (size_t)std::max(nu, 1) * sizeof(AggPartial), rt.stream));
+                if (nu > 0) LAUNCH(launch_agg_vm(va, rt.sm_count, rt.stream));
+                LAUNCH(launch_agg_finalize(static_cast<AggPartial *>(s->d_partials), nu, cls, static_cast<AggPartial *>(s->d_result), rt.stream));
+            }
+            CUDA_TRY(cudaMemcpyAsync(s->h_result, s->d_result, sizeof(AggPartial), cudaMemcpyDeviceToHost, rt.stream));
+            CUDA_TRY(cudaStreamSynchronize(rt.stream));   // (the program buffer is freed on scope exit)
+            rc = check_device_error();                    // DivideError etc. raised by the expression
+            if (rc) return rc;
+            *host_out = *static_cast<AggPartial *>(s->h_result);
+            *cls_out = cls;
+            return DFDB_OK;
+        }
         ac = t->find(p.col);
         cls = value_class(ac->type.kind);
         if (cls == VC_NONE || cls == VC_STR) return fail(DFDB_ERR_UNSUPPORTED, "aggregate over column %s of type %s", ac->name.c_str(), ac->typestr.c_str());

@@ -164,4 +164,17 @@ struct ProjVmArgs {
 };
 int launch_proj_vm(const ProjVmArgs &a, cudaStream_t stream);
 
+// aggregates over a computed column (sum(t.a .* t.c), maximum(v.price .* 2) ...): VM value of every selected row folded
+// into the per-unit partials of K7 (same units, same fixed combination order, same finalize kernel)
+struct AggVmArgs {
+    Geometry g;
+    ColView slot[MAX_SLOTS];
+    const VmProgram *prog;
+    const uint32_t *mask;
+    AggPartial *partials;
+    int cls;                      // VC_* of the program's result
+    int *error_flag;
+};
+int launch_agg_vm(const AggVmArgs &a, int sm_count, cudaStream_t stream);
+
 }  // namespace dfdb

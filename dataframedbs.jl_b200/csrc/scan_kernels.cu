@@ -1032,6 +1032,62 @@ __global__ void __launch_bounds__(SCAN_THREADS) proj_vm_kernel(const ProjVmArgs 
     }
 }
 
+// reductions over a computed column (Base folds over iterate(::DFColumn), /root/reference/src/tables/column.jl:102-126, for
+// a column that is a BlockBroadcasting, columnbroadcast.jl:35-62): one CTA per work unit like K3+K7, thread t takes rows
+// t, t + 256, ... of a tile in that order, then the fixed block reduction
+__global__ void __launch_bounds__(SCAN_THREADS) agg_vm_kernel(const AggVmArgs A)
+{
+    __shared__ AggPartial red[SCAN_THREADS / 32];
+    const Geometry g = A.g;
+    const int tid = threadIdx.x, cls = A.cls;
+    const int nunits = g.nblocks * g.segs_per_block;
+    for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        const int lb = unit / g.segs_per_block;
+        const int seg = unit - lb * g.segs_per_block;
+        const int64_t rows_b = block_rows(g, lb);
+        const int64_t row0 = (int64_t)seg * g.seg_rows;
+        int64_t row1 = row0 + g.seg_rows;
+        if (row1 > rows_b) row1 = rows_b;
+        AggPartial acc;
+        agg_init(acc);
+        for (int64_t tile0 = row0; tile0 < row1; tile0 += TILE_ROWS) {
+#pragma unroll 1
+            for (int k = 0; k < 8; k++) {
+                const int64_t r = tile0 + (int64_t)k * SCAN_THREADS + tid;
+                if (r >= row1) continue;
+                if (!((__ldg(A.mask + (int64_t)lb * g.wpb + (r >> 5)) >> (r & 31)) & 1u)) continue;
+                unsigned long long v;
+                bool ms;
+                vm_eval(A.prog, A.slot, g, lb, rows_b, r, v, ms, A.error_flag);
+                acc.count++;
+                if (ms) { acc.nmissing++; continue; }
+                if (cls == VC_FLT) {
+                    const double x = __longlong_as_double((long long)v);
+                    if (x != x) acc.has_nan = 1;
+                    else {
+                        two_sum_add(acc.sum_f, acc.sum_lo, x);
+                        if (!acc.has_value) { acc.min_f = x; acc.max_f = x; acc.has_value = 1; }
+                        else { acc.min_f = jl_min(acc.min_f, x); acc.max_f = jl_max(acc.max_f, x); }
+                    }
+                } else {
+                    const long long x = (long long)v;
+                    acc.sum_i = (long long)((unsigned long long)acc.sum_i + (unsigned long long)x);
+                    if (!acc.has_value) { acc.min_i = x; acc.max_i = x; acc.has_value = 1; }
+                    else if (cls == VC_UINT) {
+                        if ((unsigned long long)x < (unsigned long long)acc.min_i) acc.min_i = x;
+                        if ((unsigned long long)x > (unsigned long long)acc.max_i) acc.max_i = x;
+                    } else {
+                        if (x < acc.min_i) acc.min_i = x;
+                        if (x > acc.max_i) acc.max_i = x;
+                    }
+                }
+            }
+        }
+        agg_block_reduce(acc, cls, red);
+        if (tid == 0) A.partials[unit] = acc;
+    }
+}
+
 int grid_for(int64_t work, int sm_count, int per_sm)
 {
     int64_t g = (int64_t)sm_count * per_sm;
@@ -1143,6 +1199,14 @@ int launch_gather_strings(const GatherArgs &a, cudaStream_t stream)
 {
     if (a.g.nblocks <= 0) return 0;
     gather_strings_kernel<<<grid_for(a.g.nblocks, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(a);
+    return CHECK_LAUNCH();
+}
+
+int launch_agg_vm(const AggVmArgs &a, int sm_count, cudaStream_t stream)
+{
+    const int nunits = a.g.nblocks * a.g.segs_per_block;
+    if (nunits <= 0) return 0;
+    agg_vm_kernel<<<grid_for(nunits, sm_count, 8), SCAN_THREADS, 0, stream>>>(a);
     return CHECK_LAUNCH();
 }
 

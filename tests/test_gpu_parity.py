@@ -330,6 +330,39 @@ def test_synthetic_aggregates_match_oracle(synth):
     assert D.sum(D.ismissing(t.ms)) == int(ot.mask(D.plan_bytes(t[D.ismissing(t.ms), :])).sum())
 
 
+def test_aggregates_over_computed_columns(synth, tmp_path, oracle):
+    """sum / minimum / maximum / count of a broadcast column (test/columnbroadcast.jl:28-33,55-60: `sum(t.a .* t.c)`,
+    reductions over `v.price .* 2`): the Base folds run over the VM values of the selected rows."""
+    t, ot, nrows = synth
+    v = t[(t.a > 25) & (t.a <= 75), :]
+    vm = t[D.coalesce(t.ma > 50, False), :]
+    cols = {
+        "int_arith": v.a * 2 + v.q,
+        "flt_arith": v.b * 2.5 - 1.0,
+        "mixed": v.a * v.b,
+        "bool": v.b < 0.5,
+        "missing_int": t.ma + t.a,                                                  # missing where ma is
+        "missing_flt": vm.mb * 2.0,
+        "all_rows": t.a % 7,
+        "none": t[t.a > 1000, :].a * 3,
+    }
+    for name, c in cols.items():
+        got, ref = D.aggregate(c), ot.aggregate(D.plan_bytes(c), 0)
+        _check_agg(got, ref, name)
+        again = D.aggregate(c)
+        assert (got.sum_f64, got.sum_f64_lo, got.sum_i64) == (again.sum_f64, again.sum_f64_lo, again.sum_i64), name
+    assert D.sum(cols["int_arith"]) == int(ot.aggregate(D.plan_bytes(cols["int_arith"]), 0).sum_i64)
+    assert D.maximum(cols["flt_arith"]) == ot.aggregate(D.plan_bytes(cols["flt_arith"]), 0).max_f64
+    assert D.sum(cols["missing_int"]) is None                                         # missing + x == missing
+    # DivideError raised by the expression surfaces from the reduction as well (broadcast.jl:96-133 evaluates it per row)
+    p = str(tmp_path / "div")
+    oracle.write_table(p, [("x", "Int64", np.arange(-3, 4, dtype=np.int64))], block_size=4)
+    td = D.open_table(p)
+    with pytest.raises(ZeroDivisionError):
+        D.sum(10 % td.x)                                                           # rem(10, 0)
+    td.close()
+
+
 def test_residency_modes_and_kernel_variants_agree(synth, oracle):
     t, ot, nrows = synth
     v = t[(t.a > 25) & (t.a <= 75), ["b"]]
