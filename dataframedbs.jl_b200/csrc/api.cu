@@ -36,6 +36,7 @@ struct Runtime {
                                                                       // decode that the scan of the earlier rounds runs beside (ensure_decoded)
     unsigned int *d_counter = nullptr;
     int *d_error = nullptr;
+    int win_lo = 0, win_hi = 0x7fffffff;   // local block window of the scan being served (BlockWindow): blocks outside hold no selected row
     std::atomic<int64_t> launches{0};
     // options
     int64_t lz4_simple = 0;   // one sequence at a time (baseline)
@@ -227,7 +228,7 @@ void column_release(Column &c)
     c.d_skip = nullptr; c.h_skip.clear(); c.stored_blocks = 0;
     c.h_comp = nullptr; c.d_comp = nullptr; c.d_decoded = nullptr; c.d_comp_off = nullptr; c.d_comp_len = nullptr;
     c.d_dec_off = nullptr; c.d_origin = nullptr; c.d_status = nullptr; c.d_str_off = nullptr;
-    c.loaded = false; c.decoded_valid = false; c.str_off_valid = false;
+    c.loaded = false; c.decoded_valid = false; c.dec_lo = c.dec_hi = 0; c.str_off_valid = false;
 }
 
 Geometry make_geometry(const dfdb_table *t)
@@ -333,23 +334,29 @@ using PartFn = std::function<int(int, int, int)>;
 
 int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const PartFn *on_part = nullptr)
 {
+    // Only the blocks inside the scan's window are decoded (skip_block / skipblocks in the reference,
+    // src/io/blocksiterator.jl:69-78, src/tables/selection.jl:177-184: blocks that a leading range stage rules out are
+    // seeked over, not decompressed).  A column remembers which block range of it is currently decoded.
+    const int nblocks = (int)(t->blk_hi - t->blk_lo);
+    const int wlo = std::min(std::max(0, rt.win_lo), nblocks), whi = std::max(wlo, std::min(nblocks, rt.win_hi));
     std::vector<Column *> todo;
     for (int64_t id : col_ids) {
         Column *c = t->find(id);
         if (!c) return fail(DFDB_ERR_KEY, "unknown column id %lld", (long long)id);
         if (!c->loaded) return fail(DFDB_ERR_STATE, "column %s is not loaded (call dfdb_table_load first)", c->name.c_str());
-        if (!c->decoded_valid && std::find(todo.begin(), todo.end(), c) == todo.end()) todo.push_back(c);
+        const bool have = c->decoded_valid || (c->dec_lo <= wlo && whi <= c->dec_hi);
+        if (!have && std::find(todo.begin(), todo.end(), c) == todo.end()) todo.push_back(c);
     }
-    const int nblocks = (int)(t->blk_hi - t->blk_lo);
-    if (todo.empty() || nblocks == 0) return DFDB_OK;
+    if (todo.empty() || whi == wlo) return DFDB_OK;
     // Transfer-inclusive mode: the compressed blocks live in pinned host memory.  They are copied H2D in
     // block-range chunks on a second stream while the previous chunk is being decoded on the scan stream.
     int64_t host_bytes = 0;
-    for (Column *c : todo) if (c->mode == DFDB_LOAD_HOST) host_bytes += (int64_t)c->comp_bytes;
+    for (Column *c : todo)
+        if (c->mode == DFDB_LOAD_HOST) host_bytes += (whi < nblocks ? c->h_comp_off[(size_t)whi] : (int64_t)c->comp_bytes) - c->h_comp_off[(size_t)wlo];
     int nchunks = 1;
     if (host_bytes > 0) {
         nchunks = (int)std::min<int64_t>(16, std::max<int64_t>(1, host_bytes / (64ll << 20)));
-        if (nchunks > nblocks) nchunks = nblocks;
+        if (nchunks > whi - wlo) nchunks = whi - wlo;
     }
     std::vector<cudaEvent_t> copied;
     if (host_bytes > 0) {
@@ -360,7 +367,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
         cudaEventDestroy(start);
         PhaseScope ps(PH_H2D, host_bytes, rt.copy_stream);
         for (int k = 0; k < nchunks; k++) {
-            const int b0 = (int)((int64_t)nblocks * k / nchunks), b1 = (int)((int64_t)nblocks * (k + 1) / nchunks);
+            const int b0 = wlo + (int)((int64_t)(whi - wlo) * k / nchunks), b1 = wlo + (int)((int64_t)(whi - wlo) * (k + 1) / nchunks);
             for (Column *c : todo) {
                 if (c->mode != DFDB_LOAD_HOST) continue;
                 const int64_t lo = c->h_comp_off[(size_t)b0];
@@ -380,18 +387,18 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
         for (Column *c : todo) one_flavour = one_flavour && c->lz4_general == todo[0]->lz4_general;
         const int64_t wave = (int64_t)rt.sm_count * LZ4_SLOTS_PER_SM;
         int64_t real = 0;
-        for (Column *c : todo) for (int b = 0; b < nblocks; b++) real += c->h_skip[(size_t)b] ? 0 : 1;
+        for (Column *c : todo) for (int b = wlo; b < whi; b++) real += c->h_skip[(size_t)b] ? 0 : 1;
         // the last round: what is left after the full rounds
         int split = 0;
         int64_t last_real = real % wave, acc = 0;
         if (one_flavour && real > wave && last_real > 0) {
-            for (int b = 0; b < nblocks && acc < real - last_real; b++) {
+            for (int b = wlo; b < whi && acc < real - last_real; b++) {
                 for (Column *c : todo) acc += c->h_skip[(size_t)b] ? 0 : 1;
                 split = b + 1;
             }
         }
         const int last_ctas = (int)((last_real + LZ4_SLOTS_PER_SM - 1) / LZ4_SLOTS_PER_SM);
-        if (split > 0 && split < nblocks && rt.sm_count - last_ctas >= 8) {
+        if (split > wlo && split < whi && rt.sm_count - last_ctas >= 8) {
             // The full rounds go to one launch (its slots pick up blocks as they finish: no barrier between rounds); the last
             // round is a launch of its own on a second stream, so that its CTAs move in as the first launch's CTAs run out
             // of blocks -- again no barrier -- and it is limited to the SMs it can fill.
@@ -422,17 +429,17 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
             CUDA_TRY(cudaStreamWaitEvent(rt.decode_stream, e0, 0));
             CUDA_TRY(cudaStreamWaitEvent(rt.decode_stream2, e0, 0));
             if (pr.a) cudaEventRecord(pr.a, rt.decode_stream);
-            int rc = decode_range(0, split, 0, rt.decode_stream, 0);
-            if (!rc) { CUDA_TRY(cudaEventRecord(e1, rt.decode_stream)); rc = decode_range(split, nblocks, last_ctas, rt.decode_stream2, 1); }
+            int rc = decode_range(wlo, split, 0, rt.decode_stream, 0);
+            if (!rc) { CUDA_TRY(cudaEventRecord(e1, rt.decode_stream)); rc = decode_range(split, whi, last_ctas, rt.decode_stream2, 1); }
             if (pr.a) { cudaEventRecord(pr.b, rt.decode_stream2); pr.bytes = bytes; rt.recs.push_back(pr); }
             if (!rc) {
                 CUDA_TRY(cudaEventRecord(e2, rt.decode_stream2));
                 CUDA_TRY(cudaStreamWaitEvent(rt.stream, e1, 0));
-                rc = (*on_part)(0, split, rt.sm_count - last_ctas);
+                rc = (*on_part)(wlo, split, rt.sm_count - last_ctas);
             }
             if (!rc) {
                 CUDA_TRY(cudaStreamWaitEvent(rt.stream, e2, 0));
-                rc = (*on_part)(split, nblocks, rt.sm_count);
+                rc = (*on_part)(split, whi, rt.sm_count);
             }
             cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
             if (rc) return rc;
@@ -440,7 +447,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
         }
     }
     for (int k = 0; k < nchunks && !parted; k++) {
-        const int b0 = (int)((int64_t)nblocks * k / nchunks), b1 = (int)((int64_t)nblocks * (k + 1) / nchunks);
+        const int b0 = wlo + (int)((int64_t)(whi - wlo) * k / nchunks), b1 = wlo + (int)((int64_t)(whi - wlo) * (k + 1) / nchunks);
         if (!copied.empty()) {
             CUDA_TRY(cudaStreamWaitEvent(rt.stream, copied[(size_t)k], 0));
             cudaEventDestroy(copied[(size_t)k]);
@@ -470,7 +477,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
         }
     }
     if (on_part && !parted) {
-        const int rc = (*on_part)(0, nblocks, rt.sm_count);
+        const int rc = (*on_part)(wlo, whi, rt.sm_count);
         if (rc) return rc;
     }
     const Geometry g = make_geometry(t);
@@ -484,11 +491,13 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
     for (Column *c : todo) {
         CUDA_TRY(cudaMemcpyAsync(st.data(), c->d_status, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, rt.stream));
         CUDA_TRY(cudaStreamSynchronize(rt.stream));
-        for (int b = 0; b < nblocks; b++)
+        for (int b = wlo; b < whi; b++)
             if (st[(size_t)b] != 0)
                 return fail(DFDB_ERR_CORRUPT, "decompression error in column %s block %lld (code %d)", c->name.c_str(),
                             (long long)(t->blk_lo + b), st[(size_t)b]);
-        c->decoded_valid = true;
+        c->dec_lo = wlo;
+        c->dec_hi = whi;
+        c->decoded_valid = wlo == 0 && whi == nblocks;
     }
     return DFDB_OK;
 }
@@ -496,8 +505,30 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
 void invalidate_decoded(dfdb_table *t)
 {
     for (auto &c : t->cols)
-        if (c.mode != DFDB_LOAD_DECODED) c.decoded_valid = false;
+        if (c.mode != DFDB_LOAD_DECODED) { c.decoded_valid = false; c.dec_lo = c.dec_hi = 0; }
 }
+
+// The local blocks that can hold selected rows of a scan: a leading range / index-vector stage works on table row numbers
+// (selection.jl:94-111 with offset 0), so the blocks before its first and behind its last row are never decoded.  Scope
+// guard: ensure_decoded reads the window of the scan being served.
+struct BlockWindow {
+    int lo0, hi0;
+    explicit BlockWindow(const dfdb_scan *s) : lo0(rt.win_lo), hi0(rt.win_hi)
+    {
+        const dfdb_table *t = s->tbl;
+        int64_t lo = 0, hi = t->blk_hi - t->blk_lo;
+        if (!s->stages.empty() && s->stages[0].kind != ST_PRED && t->block_size > 0) {
+            const int64_t tb_lo = (s->stages[0].first - 1) / t->block_size, tb_hi = (s->stages[0].last - 1) / t->block_size + 1;
+            lo = std::max<int64_t>(lo, tb_lo - t->blk_lo);
+            hi = std::min<int64_t>(hi, tb_hi - t->blk_lo);
+            if (s->stages[0].first < 1) lo = 0;          // (rows below 1 select nothing; keep the arithmetic simple)
+            if (hi < lo) hi = lo;
+        }
+        rt.win_lo = (int)lo;
+        rt.win_hi = (int)hi;
+    }
+    ~BlockWindow() { rt.win_lo = lo0; rt.win_hi = hi0; }
+};
 
 // ---- scan helpers ---------------------------------------------------------------------------------------
 int scan_alloc(dfdb_scan *s)
@@ -588,6 +619,7 @@ void fill_terms(dfdb_scan *s, const Expr &e, FusedArgs *a)
 // The rank of a surviving row for range stages is global (selection.jl:94-111 running offsets).
 int run_selection(dfdb_scan *s)
 {
+    BlockWindow win(s);
     dfdb_table *t = s->tbl;
     int rc = scan_alloc(s);
     if (rc) return rc;
@@ -811,6 +843,7 @@ void agg_to_public(const AggPartial &p, int cls, dfdb_agg *out)
 
 int run_aggregate(dfdb_scan *s, int32_t proj_idx, bool count_only, AggPartial *host_out, int *cls_out)
 {
+    BlockWindow win(s);
     dfdb_table *t = s->tbl;
     int rc = scan_alloc(s);
     if (rc) return rc;
@@ -1258,13 +1291,14 @@ int32_t dfdb_table_load(dfdb_table *t, const int64_t *col_ids, int32_t n, int32_
         c->mode = mode;
         c->loaded = true;
         c->decoded_valid = false;
+        c->dec_lo = c->dec_hi = 0;
     }
     return DFDB_OK;
 }
 
 int32_t dfdb_table_drop_decoded(dfdb_table *t)
 {
-    for (auto &c : t->cols) c.decoded_valid = false;
+    for (auto &c : t->cols) { c.decoded_valid = false; c.dec_lo = c.dec_hi = 0; }
     return DFDB_OK;
 }
 
@@ -1489,6 +1523,7 @@ int32_t dfdb_scan_materialize_sizes(dfdb_scan *s, int64_t *nrows, int64_t *str_b
 {
     int rc = need_init();
     if (rc) return rc;
+    BlockWindow win(s);
     dfdb_table *t = s->tbl;
     invalidate_decoded(t);
     rc = run_selection(s);
@@ -1525,6 +1560,7 @@ int32_t dfdb_scan_materialize(dfdb_scan *s, dfdb_outcol *cols, int32_t ncols)
 {
     int rc = need_init();
     if (rc) return rc;
+    BlockWindow win(s);
     dfdb_table *t = s->tbl;
     if ((size_t)ncols != s->projs.size()) return fail(DFDB_ERR_ARGUMENT, "expected %zu output columns, got %d", s->projs.size(), ncols);
     if (!s->mask_valid || s->selected < 0) {

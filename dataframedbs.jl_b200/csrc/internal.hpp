@@ -55,6 +55,7 @@ struct Column {
     uint8_t *d_decoded = nullptr;    // decoded bodies, one 256B-aligned slot per block
     size_t decoded_bytes = 0;
     bool decoded_valid = false;
+    int dec_lo = 0, dec_hi = 0;      // local block range whose decoded bodies are current (decoded_valid: all of them)
     // per local block device arrays
     int64_t *d_comp_off = nullptr;   // offset of payload in (h|d)_comp
     int32_t *d_comp_len = nullptr;

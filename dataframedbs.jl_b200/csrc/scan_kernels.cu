@@ -916,6 +916,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) gather_strings_kernel(const Gath
         const uint8_t *body = col_body(A.col, lb);
         const int32_t *sizes = reinterpret_cast<const int32_t *>(body + 4);
         const uint8_t *chars = body + 4 + 4 * rows_b;
+        if (A.blk_base[lb + 1] == A.blk_base[lb]) continue;   // no selected row in this block (it may not even be decoded)
         int64_t row_pos = A.blk_base[lb];          // output row / output byte / source byte position of the tile (uniform)
         int64_t byte_pos = A.blk_char_base[lb];
         int64_t char_pos = 0;

@@ -428,6 +428,44 @@ def test_decode_scan_overlap_matches_the_plain_path(tmp_path, oracle):
     ot.close()
 
 
+def test_leading_range_stage_prunes_the_decode(synth):
+    """skip_block / skipblocks (blocksiterator.jl:69-78, selection.jl:177-184): blocks that a leading range stage rules out
+    are not decompressed -- and the result is the same as when they are."""
+    t, ot, nrows = synth
+    L = _capi.lib()
+
+    def decoded_bytes(view, fn):
+        L.dfdb_profile_reset()
+        L.dfdb_profile_enable(1)
+        out = fn(view)
+        L.dfdb_profile_enable(0)
+        ms, n, b = C.c_double(), C.c_int64(), C.c_int64()
+        L.dfdb_profile_get(b"decode", C.byref(ms), C.byref(n), C.byref(b))
+        return out, b.value
+
+    cols = ["a", "s", "ma"]
+    full = t[t.a > 50, cols]
+    _, full_bytes = decoded_bytes(full, D.materialize)
+    for lo, hi in [(70_000, 140_000), (1, 10), (nrows - 5, nrows), (65_536, 65_537)]:
+        v = t[R(lo, hi), :][t.a > 50, cols]
+        fr, part_bytes = decoded_bytes(v, D.materialize)
+        exp = ot.materialize(D.plan_bytes(v))
+        got = fr.to_dict()
+        assert got["a"] == exp[0].tolist() and got["s"] == exp[1].tolist(), (lo, hi)
+        assert got["ma"] == [None if m else x for x, m in zip(exp[2][0].tolist(), exp[2][1].tolist())], (lo, hi)
+        nblk = (hi - 1) // 65536 - (lo - 1) // 65536 + 1
+        assert 0 < part_bytes <= full_bytes * (nblk + 0.5) / 6, (lo, hi, part_bytes, full_bytes)
+        assert D.nrow(v) == len(exp[0])
+        c = v.ma
+        _check_agg(D.aggregate(c), ot.aggregate(D.plan_bytes(c), 0), (lo, hi))
+    # an index vector and a single row are windows too
+    v = t[[5, 70_000, 70_001], cols]
+    assert D.materialize(v).to_dict()["a"] == ot.materialize(D.plan_bytes(v))[0].tolist()
+    # and a scan over everything afterwards still sees every block
+    fr, again_bytes = decoded_bytes(full, D.materialize)
+    assert again_bytes == full_bytes and fr.to_dict()["a"] == ot.materialize(D.plan_bytes(full))[0].tolist()
+
+
 def test_result_arena(synth):
     """dfdb_host_alloc / dfdb_host_free: page-locked result buffers, reused after they are freed; materialize fills both
     arena buffers (direct copy) and ordinary memory (bounce buffers) with the same bytes."""
