@@ -25,4 +25,8 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:lz4_
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gather_strings -s 1 -c 1 -o $OUT/prof_gather_str -f \
     python bench_configs.py --config 3 --reps 1 > $OUT/prof_gather_str.log 2>&1
 timeout 600 python scripts/decode_kinds.py --rows 200000000 > $OUT/kinds.json 2> $OUT/kinds.err
+# configs[0] (the reference's own CPU-runnable case): 10M rows, same query, for the record
+timeout 300 python bench.py --rows 10000000 --steps 20 --warmup 3 --no-e2e > $OUT/bench_10M.json 2> $OUT/bench_10M.err
+timeout 400 python bench_configs.py --config 3 > $OUT/c3.json 2> $OUT/c3.err
+timeout 400 python bench_configs.py --config 4 > $OUT/c4.json 2> $OUT/c4.err
 ls -la $OUT
