@@ -36,6 +36,7 @@ struct Runtime {
                                                                       // decode that the scan of the earlier rounds runs beside (ensure_decoded)
     unsigned int *d_counter = nullptr;
     int *d_error = nullptr;
+    const std::vector<int64_t> *blk_live = nullptr;   // set while projection columns of a scan are decoded: blocks without a selected row are skipped
     int win_lo = 0, win_hi = 0x7fffffff;   // local block window of the scan being served (BlockWindow): blocks outside hold no selected row
     std::atomic<int64_t> launches{0};
     // options
@@ -228,7 +229,7 @@ void column_release(Column &c)
     c.d_skip = nullptr; c.h_skip.clear(); c.stored_blocks = 0;
     c.h_comp = nullptr; c.d_comp = nullptr; c.d_decoded = nullptr; c.d_comp_off = nullptr; c.d_comp_len = nullptr;
     c.d_dec_off = nullptr; c.d_origin = nullptr; c.d_status = nullptr; c.d_str_off = nullptr;
-    c.loaded = false; c.decoded_valid = false; c.dec_lo = c.dec_hi = 0; c.str_off_valid = false;
+    c.loaded = false; c.decoded_valid = false; c.dec_lo = c.dec_hi = 0; c.dec_live = nullptr; c.str_off_valid = false;
 }
 
 Geometry make_geometry(const dfdb_table *t)
@@ -344,10 +345,45 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
         Column *c = t->find(id);
         if (!c) return fail(DFDB_ERR_KEY, "unknown column id %lld", (long long)id);
         if (!c->loaded) return fail(DFDB_ERR_STATE, "column %s is not loaded (call dfdb_table_load first)", c->name.c_str());
-        const bool have = c->decoded_valid || (c->dec_lo <= wlo && whi <= c->dec_hi);
+        const bool have = c->decoded_valid || (c->dec_lo <= wlo && whi <= c->dec_hi) || (rt.blk_live && c->dec_live == rt.blk_live);
         if (!have && std::find(todo.begin(), todo.end(), c) == todo.end()) todo.push_back(c);
     }
     if (todo.empty() || whi == wlo) return DFDB_OK;
+    // Projection columns: a block without a selected row is skipped like a block outside the window (skip_cols,
+    // blocksiterator.jl:84-95,112-115: `isempty(range) ? skip_cols(proj_cols) : read_cols(proj_cols)`).  The stored-block
+    // flags and the scan's per-block survivor counts are merged into one skip array per column for this call.
+    const std::vector<int64_t> *live = rt.blk_live && (int)rt.blk_live->size() == nblocks ? rt.blk_live : nullptr;
+    struct SkipSet {
+        std::vector<std::vector<uint8_t>> h;
+        std::vector<uint8_t *> d;
+        ~SkipSet() { for (uint8_t *p : d) scratch_free(p); }
+    } skips;
+    bool filtered = false;
+    uint8_t *d_dead = nullptr;           // blocks without a selected row (any column)
+    if (live) {
+        std::vector<uint8_t> dead((size_t)nblocks);
+        for (int b = 0; b < nblocks; b++) dead[(size_t)b] = (*live)[(size_t)b] == 0;
+        if (scratch_alloc(reinterpret_cast<void **>(&d_dead), (size_t)nblocks) != cudaSuccess) return fail(DFDB_ERR_NOMEM, "out of device memory for the block skip list");
+        skips.d.push_back(d_dead);       // (freed with the others)
+        CUDA_TRY(cudaMemcpyAsync(d_dead, dead.data(), (size_t)nblocks, cudaMemcpyHostToDevice, rt.stream));
+        for (Column *c : todo) {
+            std::vector<uint8_t> sk(c->h_skip);
+            for (int b = 0; b < nblocks; b++) if ((*live)[(size_t)b] == 0 && !sk[(size_t)b]) { sk[(size_t)b] = 1; filtered = true; }
+            uint8_t *dp = nullptr;
+            if (scratch_alloc(reinterpret_cast<void **>(&dp), (size_t)nblocks) != cudaSuccess) return fail(DFDB_ERR_NOMEM, "out of device memory for the block skip list");
+            skips.d.push_back(dp);
+            skips.h.push_back(std::move(sk));
+            CUDA_TRY(cudaMemcpyAsync(dp, skips.h.back().data(), (size_t)nblocks, cudaMemcpyHostToDevice, rt.stream));
+        }
+    }
+    auto h_skip_of = [&](Column *c) -> const std::vector<uint8_t> & {
+        if (live) for (size_t i = 0; i < todo.size(); i++) if (todo[i] == c) return skips.h[i];
+        return c->h_skip;
+    };
+    auto d_skip_of = [&](Column *c) -> const uint8_t * {
+        if (live) for (size_t i = 0; i < todo.size(); i++) if (todo[i] == c) return skips.d[i + 1];   // ([0] is the column-independent list of dead blocks)
+        return c->d_skip;
+    };
     // Transfer-inclusive mode: the compressed blocks live in pinned host memory.  They are copied H2D in
     // block-range chunks on a second stream while the previous chunk is being decoded on the scan stream.
     int64_t host_bytes = 0;
@@ -387,13 +423,13 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
         for (Column *c : todo) one_flavour = one_flavour && c->lz4_general == todo[0]->lz4_general;
         const int64_t wave = (int64_t)rt.sm_count * LZ4_SLOTS_PER_SM;
         int64_t real = 0;
-        for (Column *c : todo) for (int b = wlo; b < whi; b++) real += c->h_skip[(size_t)b] ? 0 : 1;
+        for (Column *c : todo) for (int b = wlo; b < whi; b++) real += h_skip_of(c)[(size_t)b] ? 0 : 1;
         // the last round: what is left after the full rounds
         int split = 0;
         int64_t last_real = real % wave, acc = 0;
         if (one_flavour && real > wave && last_real > 0) {
             for (int b = wlo; b < whi && acc < real - last_real; b++) {
-                for (Column *c : todo) acc += c->h_skip[(size_t)b] ? 0 : 1;
+                for (Column *c : todo) acc += h_skip_of(c)[(size_t)b] ? 0 : 1;
                 split = b + 1;
             }
         }
@@ -411,9 +447,9 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
                 for (Column *c : todo) {
                     DecodeCol &d = a.col[a.ncols++];
                     d.comp = c->d_comp; d.comp_off = c->d_comp_off; d.comp_len = c->d_comp_len; d.dec_off = c->d_dec_off;
-                    d.origin = c->d_origin; d.out = c->d_decoded; d.status = c->d_status; d.skip = c->d_skip;
+                    d.origin = c->d_origin; d.out = c->d_decoded; d.status = c->d_status; d.skip = d_skip_of(c);
                     for (int64_t b = b0; b < b1; b++)
-                        if (!c->h_skip[(size_t)b]) bytes += c->blocks[(size_t)(t->blk_lo + b)].compressed + c->blocks[(size_t)(t->blk_lo + b)].origin;
+                        if (!h_skip_of(c)[(size_t)b]) bytes += c->blocks[(size_t)(t->blk_lo + b)].compressed + c->blocks[(size_t)(t->blk_lo + b)].origin;
                 }
                 LAUNCH(launch_decode(a, todo[0]->lz4_general, stream, cta_limit, counter_slot));
                 return DFDB_OK;
@@ -467,9 +503,9 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
                 Column *c = grp[q];
                 DecodeCol &d = a.col[a.ncols++];
                 d.comp = c->d_comp; d.comp_off = c->d_comp_off; d.comp_len = c->d_comp_len; d.dec_off = c->d_dec_off;
-                d.origin = c->d_origin; d.out = c->d_decoded; d.status = c->d_status; d.skip = c->d_skip;
+                d.origin = c->d_origin; d.out = c->d_decoded; d.status = c->d_status; d.skip = d_skip_of(c);
                 for (int64_t b = b0; b < b1; b++)
-                    if (!c->h_skip[(size_t)b]) bytes += c->blocks[(size_t)(t->blk_lo + b)].compressed + c->blocks[(size_t)(t->blk_lo + b)].origin;
+                    if (!h_skip_of(c)[(size_t)b]) bytes += c->blocks[(size_t)(t->blk_lo + b)].compressed + c->blocks[(size_t)(t->blk_lo + b)].origin;
             }
             PhaseScope ps(PH_DECODE, bytes);
             LAUNCH(launch_decode(a, general != 0));
@@ -484,7 +520,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
     for (Column *c : todo)
         if (c->type.kind == DFDB_STRING) {
             PhaseScope ps(PH_UNPACK, 0);
-            LAUNCH(launch_str_offsets(g, make_view(*c), c->d_str_off, c->d_status, rt.stream));
+            LAUNCH(launch_str_offsets(g, make_view(*c), c->d_str_off, c->d_status, rt.stream, wlo, whi, d_dead));
         }
     // integrity gate (the reference asserts after every block, BlockStreams.jl:112)
     std::vector<int32_t> st((size_t)nblocks);
@@ -495,9 +531,11 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
             if (st[(size_t)b] != 0)
                 return fail(DFDB_ERR_CORRUPT, "decompression error in column %s block %lld (code %d)", c->name.c_str(),
                             (long long)(t->blk_lo + b), st[(size_t)b]);
-        c->dec_lo = wlo;
-        c->dec_hi = whi;
-        c->decoded_valid = wlo == 0 && whi == nblocks;
+        // (a decode that skipped blocks without selected rows leaves nothing another scan could rely on)
+        c->dec_lo = filtered ? 0 : wlo;
+        c->dec_hi = filtered ? 0 : whi;
+        c->dec_live = filtered ? rt.blk_live : nullptr;
+        c->decoded_valid = !filtered && wlo == 0 && whi == nblocks;
     }
     return DFDB_OK;
 }
@@ -505,12 +543,19 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
 void invalidate_decoded(dfdb_table *t)
 {
     for (auto &c : t->cols)
-        if (c.mode != DFDB_LOAD_DECODED) { c.decoded_valid = false; c.dec_lo = c.dec_hi = 0; }
+        if (c.mode != DFDB_LOAD_DECODED) { c.decoded_valid = false; c.dec_lo = c.dec_hi = 0; c.dec_live = nullptr; }
 }
 
 // The local blocks that can hold selected rows of a scan: a leading range / index-vector stage works on table row numbers
 // (selection.jl:94-111 with offset 0), so the blocks before its first and behind its last row are never decoded.  Scope
 // guard: ensure_decoded reads the window of the scan being served.
+// Scope guard: while the projection columns of a scan are decoded, blocks without a selected row are skipped.
+struct LiveBlocks {
+    const std::vector<int64_t> *prev;
+    explicit LiveBlocks(const dfdb_scan *s) : prev(rt.blk_live) { rt.blk_live = s->mask_valid && s->selected >= 0 ? &s->blk_live : nullptr; }
+    ~LiveBlocks() { rt.blk_live = prev; }
+};
+
 struct BlockWindow {
     int lo0, hi0;
     explicit BlockWindow(const dfdb_scan *s) : lo0(rt.win_lo), hi0(rt.win_hi)
@@ -721,8 +766,10 @@ int count_mask(dfdb_scan *s, int64_t *total)
         LAUNCH(launch_block_counts(g, s->d_mask, s->d_blk_counts, rt.stream));
         LAUNCH(launch_exclusive_scan(s->d_blk_counts, s->d_blk_base, g.nblocks, rt.stream));
     }
-    PhaseScope ps(PH_D2H, 8);
+    PhaseScope ps(PH_D2H, 8 + (int64_t)g.nblocks * 8);
+    s->blk_live.assign((size_t)g.nblocks, 0);
     CUDA_TRY(cudaMemcpyAsync(s->h_result, s->d_blk_base + g.nblocks, 8, cudaMemcpyDeviceToHost, rt.stream));
+    if (g.nblocks > 0) CUDA_TRY(cudaMemcpyAsync(s->blk_live.data(), s->d_blk_counts, (size_t)g.nblocks * 8, cudaMemcpyDeviceToHost, rt.stream));
     CUDA_TRY(cudaStreamSynchronize(rt.stream));
     *total = *static_cast<int64_t *>(s->h_result);
     s->selected = *total;
@@ -1292,13 +1339,14 @@ int32_t dfdb_table_load(dfdb_table *t, const int64_t *col_ids, int32_t n, int32_
         c->loaded = true;
         c->decoded_valid = false;
         c->dec_lo = c->dec_hi = 0;
+        c->dec_live = nullptr;
     }
     return DFDB_OK;
 }
 
 int32_t dfdb_table_drop_decoded(dfdb_table *t)
 {
-    for (auto &c : t->cols) { c.decoded_valid = false; c.dec_lo = c.dec_hi = 0; }
+    for (auto &c : t->cols) { c.decoded_valid = false; c.dec_lo = c.dec_hi = 0; c.dec_live = nullptr; }
     return DFDB_OK;
 }
 
@@ -1534,6 +1582,7 @@ int32_t dfdb_scan_materialize_sizes(dfdb_scan *s, int64_t *nrows, int64_t *str_b
     if (nrows) *nrows = total;
     s->str_bytes.assign(s->projs.size(), 0);
     const Geometry g = make_geometry(t);
+    LiveBlocks live(s);
     for (size_t i = 0; i < s->projs.size(); i++) {
         const Proj &p = s->projs[i];
         if (p.kind == PJ_COL && p.type.kind == DFDB_STRING && total > 0) {
@@ -1570,6 +1619,7 @@ int32_t dfdb_scan_materialize(dfdb_scan *s, dfdb_outcol *cols, int32_t ncols)
     const int64_t total = s->selected;
     const Geometry g = make_geometry(t);
     if (total == 0) return DFDB_OK;
+    LiveBlocks live(s);
     struct CopyDrain { ~CopyDrain() { cudaStreamSynchronize(rt.copy_stream); } } drain;   // no queued copy outlives this call, on any path
     for (size_t i = 0; i < s->projs.size(); i++) {
         const Proj &p = s->projs[i];

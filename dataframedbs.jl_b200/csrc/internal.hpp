@@ -56,6 +56,7 @@ struct Column {
     size_t decoded_bytes = 0;
     bool decoded_valid = false;
     int dec_lo = 0, dec_hi = 0;      // local block range whose decoded bodies are current (decoded_valid: all of them)
+    const void *dec_live = nullptr;  // the blocks with selected rows of the scan whose survivor counts live here are decoded (skip_cols)
     // per local block device arrays
     int64_t *d_comp_off = nullptr;   // offset of payload in (h|d)_comp
     int32_t *d_comp_len = nullptr;
@@ -208,6 +209,7 @@ struct dfdb_scan {
     bool mask_valid = false;
     int64_t selected = -1;
     std::vector<int64_t> str_bytes;    // per projection
+    std::vector<int64_t> blk_live;     // selected rows per local block (host copy of the counts behind d_blk_base), valid with `selected`
     // sharded tables: survivors of lower-ranked shards entering each range stage that follows a predicate
     std::vector<int64_t> rank_offsets;
     int64_t exchange_count = -1;       // this shard's count at the first stage whose offset is missing

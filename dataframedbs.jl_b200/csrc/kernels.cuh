@@ -130,7 +130,8 @@ int launch_range_stage(const RangeArgs &a, cudaStream_t stream);
 int launch_fill_mask(const Geometry &g, uint32_t *mask, cudaStream_t stream);
 
 // ---- K2: String bodies: per-row char offsets (unsafe_remake_offsets!) --------------------------------
-int launch_str_offsets(const Geometry &g, const ColView &col, int32_t *str_off, int32_t *status, cudaStream_t stream);
+int launch_str_offsets(const Geometry &g, const ColView &col, int32_t *str_off, int32_t *status, cudaStream_t stream, int lo = 0, int hi = 0x7fffffff,
+                       const uint8_t *dead = nullptr);   // local blocks [lo, hi) except those flagged in `dead`
 
 // ---- K5/K6: stream compaction / gathers ---------------------------------------------------------------
 struct GatherArgs {

@@ -734,10 +734,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) range_stage_kernel(const RangeAr
 
 // ---- K2: string offsets -------------------------------------------------------------------------------------
 // one warp per block: exclusive prefix sum of max(size, 0) in row order
-__global__ void __launch_bounds__(SCAN_THREADS) str_offsets_kernel(const Geometry g, const ColView col, int32_t *str_off, int32_t *status)
+// (blocks outside [lo, hi) and blocks flagged in `dead` were not decoded for this scan: their bodies are stale)
+__global__ void __launch_bounds__(SCAN_THREADS) str_offsets_kernel(const Geometry g, const ColView col, int32_t *str_off, int32_t *status,
+                                                                  int lo, int hi, const uint8_t *dead)
 {
     const int warps = gridDim.x * (SCAN_THREADS / 32);
-    for (int lb = blockIdx.x * (SCAN_THREADS / 32) + warp_id(); lb < g.nblocks; lb += warps) {
+    for (int lb = lo + blockIdx.x * (SCAN_THREADS / 32) + warp_id(); lb < hi; lb += warps) {
+        if (dead && dead[lb]) continue;
         const uint8_t *body = col_body(col, lb);
         const int64_t rows_b = block_rows(g, lb);
         const int32_t datasize = *reinterpret_cast<const int32_t *>(body);
@@ -1168,10 +1171,13 @@ int launch_fill_mask(const Geometry &g, uint32_t *mask, cudaStream_t stream)
     return CHECK_LAUNCH();
 }
 
-int launch_str_offsets(const Geometry &g, const ColView &col, int32_t *str_off, int32_t *status, cudaStream_t stream)
+int launch_str_offsets(const Geometry &g, const ColView &col, int32_t *str_off, int32_t *status, cudaStream_t stream, int lo, int hi,
+                       const uint8_t *dead)
 {
-    if (g.nblocks <= 0) return 0;
-    str_offsets_kernel<<<grid_for((g.nblocks + 7) / 8, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(g, col, str_off, status);
+    if (hi > g.nblocks) hi = g.nblocks;
+    if (lo < 0) lo = 0;
+    if (hi <= lo) return 0;
+    str_offsets_kernel<<<grid_for((hi - lo + 7) / 8, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(g, col, str_off, status, lo, hi, dead);
     return CHECK_LAUNCH();
 }
 
