@@ -77,8 +77,13 @@ enum { ST_W_ROUNDS = 0, ST_W_COMMITS, ST_W_RINGFULL, ST_W_WINEMPTY, ST_W_PARKED,
 __device__ unsigned long long *g_stats;
 #define STAT_ADD(i, v) do { if (g_stats) atomicAdd(&g_stats[i], (unsigned long long)(v)); } while (0)
 #define STATS_ON (g_stats != nullptr)
+// per-batch counters are kept per warp and added to the global totals once, when the warp retires: a global atomic per
+// batch from every warp perturbs what it measures
+__device__ unsigned long long g_warp_stats[148 * 32][8];
+#define WSTAT_ADD(k, v) do { if (g_stats) g_warp_stats[blockIdx.x * 32 + (threadIdx.x >> 5)][k] += (unsigned long long)(v); } while (0)
 #else
 #define STAT_ADD(i, v) do { } while (0)
+#define WSTAT_ADD(k, v) do { } while (0)
 #define STATS_ON false
 #endif
 
@@ -445,72 +450,50 @@ __device__ __forceinline__ int generic_batch(const uint8_t *win, uint8_t *stg, c
     if (active)
         for (uint32_t i = 0; i < L; i++) stg[(int32_t)o - stg_base + (int32_t)i] = win[(p + 1 + i) & WM];
     __syncwarp();
-    // Frontier F: every output byte < F is final.  A lane runs when all its source bytes are below F, or when it
-    // is the first pending lane (then every earlier sequence is complete).
-    const int32_t src_end = (m_src + (int32_t)M < m_dst) ? m_src + (int32_t)M : m_dst;
-    uint32_t pending = g >= 32 ? FULL : ((1u << g) - 1u);
-    int P = 0;
-    int32_t F = __shfl_sync(FULL, m_dst, 0);
-    while (pending) {
-        const bool mine = (pending >> lane) & 1u;
-        const bool ready = mine && (src_end <= F || (int)lane == P);
-        const bool far = m_src + (int32_t)M <= stg_base;            // whole source below the staging area: in global memory
-        const bool near = m_src >= stg_base && off >= M;            // whole source in the staging area, not overlapping the destination
-        if (ready && (far || near)) {
-            // aligned 8-byte loads, all in flight at once (only the words that hold source bytes, so nothing beyond
-            // the bytes already written is touched), then the bytes are stored from registers
-            const int32_t sd = m_dst - stg_base;
-            const uint32_t sh = (uint32_t)m_src & 7u, span = sh + M;                      // M <= 18: span <= 25
-            unsigned long long w0, w1 = 0, w2 = 0, w3 = 0;
-            if (far) {
-                const unsigned long long *g8 = reinterpret_cast<const unsigned long long *>(J.dst + (m_src - (int32_t)sh));
-                w0 = __ldcg(g8);
-                if (span > 8u) w1 = __ldcg(g8 + 1);
-                if (span > 16u) w2 = __ldcg(g8 + 2);
-                if (span > 24u) w3 = __ldcg(g8 + 3);
-            } else {
-                const unsigned long long *s8 = reinterpret_cast<const unsigned long long *>(stg + (m_src - stg_base - (int32_t)sh));
-                w0 = s8[0];
-                if (span > 8u) w1 = s8[1];
-                if (span > 16u) w2 = s8[2];
-                if (span > 24u) w3 = s8[3];
-            }
-            const uint32_t s8b = sh * 8;
-            if (s8b) {
-                w0 = (w0 >> s8b) | (w1 << (64 - s8b));
-                w1 = (w1 >> s8b) | (w2 << (64 - s8b));
-                w2 = (w2 >> s8b) | (w3 << (64 - s8b));
-            }
+    // Matches.  (1) Every sequence whose source lies wholly below the staging area copies it from global memory, all of
+    // them at once: aligned 8-byte loads issued together (only the words that hold source bytes, so nothing beyond the
+    // bytes already written is touched), bytes stored from registers.  (2) The others -- sources inside the batch or
+    // straddling its start -- go in stream order, the whole warp on one sequence, lane = byte: no dependency analysis, no
+    // waves in which a handful of lanes work while 32 pay, and a self-overlapping match is just a source index modulo
+    // its offset.
+    const bool far = active && m_src + (int32_t)M <= stg_base;
+    if (far) {
+        const int32_t sd = m_dst - stg_base;
+        const uint32_t sh = (uint32_t)m_src & 7u, span = sh + M;                          // M <= 18: span <= 25
+        const unsigned long long *g8 = reinterpret_cast<const unsigned long long *>(J.dst + (m_src - (int32_t)sh));
+        unsigned long long w0 = __ldcg(g8), w1 = 0, w2 = 0, w3 = 0;
+        if (span > 8u) w1 = __ldcg(g8 + 1);
+        if (span > 16u) w2 = __ldcg(g8 + 2);
+        if (span > 24u) w3 = __ldcg(g8 + 3);
+        const uint32_t s8b = sh * 8;
+        if (s8b) {
+            w0 = (w0 >> s8b) | (w1 << (64 - s8b));
+            w1 = (w1 >> s8b) | (w2 << (64 - s8b));
+            w2 = (w2 >> s8b) | (w3 << (64 - s8b));
+        }
 #pragma unroll
-            for (int i = 0; i < 18; i++) {
-                const unsigned long long w = i < 8 ? w0 : (i < 16 ? w1 : w2);
-                if ((uint32_t)i < M) stg[sd + i] = (uint8_t)(w >> (8 * (i & 7)));
-            }
-        } else if (ready) {
-            const int32_t sd = m_dst - stg_base;
-            uint32_t i = 0;
-            if (off >= 8 && ((m_dst | m_src) & 7) == 0) {
-                for (; i + 8 <= M; i += 8) {
-                    unsigned long long v;
-                    const int32_t x = m_src + (int32_t)i;
-                    if (x >= stg_base) v = *reinterpret_cast<const unsigned long long *>(stg + (x - stg_base));
-                    else v = __ldcg(reinterpret_cast<const unsigned long long *>(J.dst + x));
-                    *reinterpret_cast<unsigned long long *>(stg + sd + i) = v;
-                }
-            }
-            // byte-serial per lane: correct for self-overlapping matches (off < M) as well
-            for (; i < M; i++) {
-                const int32_t x = m_src + (int32_t)i;
-                stg[sd + i] = x >= stg_base ? stg[x - stg_base] : __ldcg(J.dst + x);
-            }
+        for (int i = 0; i < 18; i++) {
+            const unsigned long long w = i < 8 ? w0 : (i < 16 ? w1 : w2);
+            if ((uint32_t)i < M) stg[sd + i] = (uint8_t)(w >> (8 * (i & 7)));
+        }
+    }
+    __syncwarp();
+    uint32_t rest = __ballot_sync(FULL, active && !far);
+    const uint32_t pk = (uint32_t)(m_dst - stg_base) | (M << 11) | (off << 16);           // staging index < 2048, M <= 18
+    while (rest) {
+        const int k = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const uint32_t q = __shfl_sync(FULL, pk, k);
+        const uint32_t kM = (q >> 11) & 31u, koff = q >> 16;
+        const int32_t kdst = (int32_t)(q & 2047u);
+        if (lane < kM) {
+            uint32_t r = lane;
+            if (koff < kM) while (r >= koff) r -= koff;               // self-overlapping: the source repeats with period off
+            const int32_t x = kdst - (int32_t)koff + (int32_t)r;      // staging index of the source byte (negative: below the staging area)
+            stg[kdst + (int32_t)lane] = x >= 0 ? stg[x] : __ldcg(J.dst + (stg_base + x));
         }
         __syncwarp();
-        if (STATS_ON && lane == 0) STAT_ADD(ST_G_WAVES, 1);
-        pending &= ~__ballot_sync(FULL, ready);
-        if (pending) {
-            P = __ffs(pending) - 1;
-            F = __shfl_sync(FULL, m_dst, P);
-        }
+        if (STATS_ON && lane == 0) WSTAT_ADD(5, 1);
     }
     *new_op = end;
     return E_OK;
@@ -789,7 +772,7 @@ __device__ __noinline__ int process_slot(V2Smem &S, int s, SlotJob &J, uint8_t *
             const uint32_t cand = run16 & ~1u & (nv >= 32 ? FULL : ((1u << nv) - 1u));
             nproc = cand ? (__ffs(cand) - 1) : nv;
             generic = true;
-            if (STATS_ON && lane == 0) { STAT_ADD(ST_C_GEN, 1); STAT_ADD(ST_C_GENSEQ, nproc); }
+
             const long long tp1 = STATS_ON ? clock64() : 0;
             // the staging area starts at the 16-byte chunk that holds o0; its bytes below o0 are still there when the
             // warp's last generic batch was this slot's previous one, else they come back from memory
@@ -811,7 +794,7 @@ __device__ __noinline__ int process_slot(V2Smem &S, int s, SlotJob &J, uint8_t *
             }
             if (STATS_ON) {
                 tp4 = clock64();
-                if (lane == 0) { STAT_ADD(ST_G_PRO, tp1 - tp0); STAT_ADD(ST_G_HEAD, tp2 - tp1); STAT_ADD(ST_G_BATCH, tp3 - tp2); STAT_ADD(ST_G_FLUSH, tp4 - tp3); }
+                if (lane == 0) { WSTAT_ADD(0, tp1 - tp0); WSTAT_ADD(1, tp2 - tp1); WSTAT_ADD(2, tp3 - tp2); WSTAT_ADD(3, tp4 - tp3); WSTAT_ADD(6, 1); WSTAT_ADD(7, nproc); }
             }
         }
     }
@@ -820,7 +803,7 @@ __device__ __noinline__ int process_slot(V2Smem &S, int s, SlotJob &J, uint8_t *
     if (lane == 0) { J.op = new_op; J.ip = next_ip; J.tail += (uint32_t)nproc; st_rlx(&S.tail[s], J.tail); }
     __syncwarp();
     refill_issue(S, s, J, 256);
-    if (STATS_ON && tp4 && lane == 0) STAT_ADD(ST_G_EPI, clock64() - tp4);
+    if (STATS_ON && tp4 && lane == 0) WSTAT_ADD(4, clock64() - tp4);
     return generic ? 3 : 1;
 }
 
@@ -1143,6 +1126,14 @@ __device__ void consumer(V2Smem &S, const DecodeArgs &args, unsigned int *counte
             }
         }
     }
+#ifdef DFDB_LZ4_STATS
+    if (STATS_ON && lane == 0) {
+        unsigned long long *w = g_warp_stats[blockIdx.x * 32 + (threadIdx.x >> 5)];
+        STAT_ADD(ST_G_PRO, w[0]); STAT_ADD(ST_G_HEAD, w[1]); STAT_ADD(ST_G_BATCH, w[2]); STAT_ADD(ST_G_FLUSH, w[3]); STAT_ADD(ST_G_EPI, w[4]);
+        STAT_ADD(ST_G_WAVES, w[5]); STAT_ADD(ST_C_GEN, w[6]); STAT_ADD(ST_C_GENSEQ, w[7]);
+        for (int k = 0; k < 8; k++) w[k] = 0;
+    }
+#endif
     if (STATS_ON && lane == 0) { STAT_ADD(ST_C_POLLS, st_polls); STAT_ADD(ST_C_SLEEPS, st_sleeps); STAT_ADD(ST_C_LOOP_CYCLES, clock64() - st_t0); STAT_ADD(ST_C_SLEEP_CYCLES, st_sleep_cycles); }
 }
 
