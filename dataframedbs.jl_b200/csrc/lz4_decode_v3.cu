@@ -744,8 +744,9 @@ __device__ __noinline__ int process_slot(V2Smem &S, int s, SlotJob &J, uint8_t *
     int err = E_OK;
     // the stream bytes of the whole batch must be in the window
     const uint32_t need = __shfl_sync(FULL, p + 3 + L, nv - 1);
+    // (a refill that was in flight may land inside refill() and fill the window: no new one can be issued then, and none is needed)
     while (!err && J.whi < need)
-        if (!refill(S, s, J, 16)) err = E_INTERNAL;
+        if (!refill(S, s, J, 16) && J.whi < need) err = E_INTERNAL;
     int nproc = 0;
     bool generic = false;
     uint32_t new_op = o0;
