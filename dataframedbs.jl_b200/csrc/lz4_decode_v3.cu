@@ -435,20 +435,29 @@ __device__ __forceinline__ int regular_batch(const SlotJob &J, uint32_t o0, uint
 }
 
 // ---- generic batch: lanes [0, g) hold simple sequences of any alignment; byte-granular dependency waves ----
-__device__ __forceinline__ int generic_batch(const uint8_t *win, uint8_t *stg, const SlotJob &J, uint32_t o0, uint32_t p, uint32_t o,
-                                             uint32_t L, uint32_t M, int g, uint32_t *new_op)
+__device__ __forceinline__ int generic_batch(const uint8_t *win, uint8_t *stg, const SlotJob &J, uint32_t o0, uint32_t lit_pos, uint32_t off_pos,
+                                             uint32_t o, uint32_t L, uint32_t M, int g, uint32_t *new_op)
 {
     const uint32_t lane = lane_id();
     const bool active = (int)lane < g;
     const int32_t stg_base = (int32_t)(o0 & ~15u);
-    const uint32_t off = active ? ((uint32_t)win[(p + 1 + L) & WM] | ((uint32_t)win[(p + 2 + L) & WM] << 8)) : 1u;
+    const uint32_t off = active ? ((uint32_t)win[off_pos & WM] | ((uint32_t)win[(off_pos + 1) & WM] << 8)) : 1u;
     const uint32_t end = __shfl_sync(FULL, o + L + M, g - 1);
     if (end > J.origin) return E_OVERFLOW;
     const int32_t m_dst = (int32_t)(o + L), m_src = m_dst - (int32_t)off;
     const bool bad = active && (off == 0 || m_src < 0);
     if (__any_sync(FULL, bad)) return E_OFFSET;
-    if (active)
-        for (uint32_t i = 0; i < L; i++) stg[(int32_t)o - stg_base + (int32_t)i] = win[(p + 1 + i) & WM];
+    // Literals: short runs (no length extension) lane by lane, long ones by the whole warp, one sequence after the other.
+    if (active && L < 15u)
+        for (uint32_t i = 0; i < L; i++) stg[(int32_t)o - stg_base + (int32_t)i] = win[(lit_pos + i) & WM];
+    uint32_t longl = __ballot_sync(FULL, active && L >= 15u);
+    while (longl) {
+        const int k = __ffs(longl) - 1;
+        longl &= longl - 1;
+        const uint32_t kL = __shfl_sync(FULL, L, k), kpos = __shfl_sync(FULL, lit_pos, k);
+        const int32_t kd = __shfl_sync(FULL, (int32_t)o - stg_base, k);
+        for (uint32_t i = lane; i < kL; i += 32) stg[kd + (int32_t)i] = win[(kpos + i) & WM];
+    }
     __syncwarp();
     // Matches.  (1) Every sequence whose source lies wholly below the staging area copies it from global memory, all of
     // them at once: aligned 8-byte loads issued together (only the words that hold source bytes, so nothing beyond the
@@ -456,7 +465,7 @@ __device__ __forceinline__ int generic_batch(const uint8_t *win, uint8_t *stg, c
     // straddling its start -- go in stream order, the whole warp on one sequence, lane = byte: no dependency analysis, no
     // waves in which a handful of lanes work while 32 pay, and a self-overlapping match is just a source index modulo
     // its offset.
-    const bool far = active && m_src + (int32_t)M <= stg_base;
+    const bool far = active && M <= 18u && m_src + (int32_t)M <= stg_base;
     if (far) {
         const int32_t sd = m_dst - stg_base;
         const uint32_t sh = (uint32_t)m_src & 7u, span = sh + M;                          // M <= 18: span <= 25
@@ -479,18 +488,18 @@ __device__ __forceinline__ int generic_batch(const uint8_t *win, uint8_t *stg, c
     }
     __syncwarp();
     uint32_t rest = __ballot_sync(FULL, active && !far);
-    const uint32_t pk = (uint32_t)(m_dst - stg_base) | (M << 11) | (off << 16);           // staging index < 2048, M <= 18
+    const uint32_t pk = (uint32_t)(m_dst - stg_base) | (M << 16);                         // staging index < 2048, M < 512
     while (rest) {
         const int k = __ffs(rest) - 1;
         rest &= rest - 1;
-        const uint32_t q = __shfl_sync(FULL, pk, k);
-        const uint32_t kM = (q >> 11) & 31u, koff = q >> 16;
-        const int32_t kdst = (int32_t)(q & 2047u);
-        if (lane < kM) {
-            uint32_t r = lane;
-            if (koff < kM) while (r >= koff) r -= koff;               // self-overlapping: the source repeats with period off
+        const uint32_t q = __shfl_sync(FULL, pk, k), koff = __shfl_sync(FULL, off, k);
+        const uint32_t kM = q >> 16;
+        const int32_t kdst = (int32_t)(q & 0xffffu);
+        // the bytes [m_src, m_src + min(off, M)) are final, and byte i of the match is byte i mod off of them
+        for (uint32_t i = lane; i < kM; i += 32) {
+            const uint32_t r = koff < kM ? i % koff : i;
             const int32_t x = kdst - (int32_t)koff + (int32_t)r;      // staging index of the source byte (negative: below the staging area)
-            stg[kdst + (int32_t)lane] = x >= 0 ? stg[x] : __ldcg(J.dst + (stg_base + x));
+            stg[kdst + (int32_t)i] = x >= 0 ? stg[x] : __ldcg(J.dst + (stg_base + x));
         }
         __syncwarp();
         if (STATS_ON && lane == 0) WSTAT_ADD(5, 1);
@@ -724,26 +733,52 @@ __device__ __noinline__ int process_slot(V2Smem &S, int s, SlotJob &J, uint8_t *
     if (navail == 0) return 0;
     const uint32_t p = (int)lane < navail ? S.ring[s][(J.tail + lane) & RM] : 0u;
     const uint32_t tok = (int)lane < navail ? S.win[s][p & WM] : 0u;   // the walker only emits tokens that are in the window
-    // special entries: tokens with length extensions, and the last entry of a parked walker whatever its nibbles say
+    // Every lane parses its sequence header.  A length extension of one byte (lengths up to 269 / 273) is read here --
+    // the walker got past such a token because its extension bytes are in the window -- and the sequence stays in the
+    // batch; longer extensions, and the last entry of a parked walker whatever its nibbles say, are "big": done one at
+    // a time by special_step.
     const bool parked_last = (h & H_PARKED) && avail <= 32u;
-    uint32_t sm = __ballot_sync(FULL, (int)lane < navail && (tok >= 0xf0u || (tok & 15u) == 15u));
-    if (parked_last) sm |= 1u << (navail - 1);
-    const int nv = sm ? __ffs(sm) - 1 : navail;                // leading plain entries
+    const bool ext = tok >= 0xf0u || (tok & 15u) == 15u;
+    uint32_t L = tok >> 4, M = (tok & 15u) + 4, lit_pos = p + 1;
+    bool big = parked_last && (int)lane == navail - 1;
+    if ((int)lane < navail && L == 15u) {
+        const uint32_t e = S.win[s][lit_pos & WM];
+        lit_pos++;
+        L += e;
+        big |= e == 255u;
+    }
+    const uint32_t off_pos = lit_pos + L;
+    uint32_t nxt = off_pos + 2;
+    if ((int)lane < navail && !big && (tok & 15u) == 15u) {
+        const uint32_t e = S.win[s][nxt & WM];
+        nxt++;
+        M += e;
+        big |= e == 255u;
+    }
+    const uint32_t len = L + M;
+    const uint32_t sm = __ballot_sync(FULL, (int)lane < navail && big);
+    int nv = sm ? __ffs(sm) - 1 : navail;                      // leading entries a batch can take
+    // wait for a full batch unless the run ends in a big entry, or the walker cannot go on before this warp has made
+    // room in the window
+    if (nv > 0 && nv < 32 && sm == 0 && !force) return 0;
+    const uint32_t o0 = J.op;
+    const uint32_t o = o0 + warp_incl_scan((int)lane < nv ? len : 0u) - ((int)lane < nv ? len : 0u);
+    {
+        // ... and only as many as fit the staging area and the window (sequences with long literal runs are big in bytes)
+        const bool fits = (int)lane < nv && o + len - (o0 & ~15u) <= (uint32_t)(STG - 48) && nxt - (J.ip & ~15u) <= (uint32_t)(W - 32);
+        const uint32_t fm = __ballot_sync(FULL, fits);
+        const int nfit = fm == FULL ? 32 : __ffs(~fm) - 1;
+        if (nfit < nv) nv = nfit;
+    }
     if (nv == 0) {
         const long long t0 = STATS_ON ? clock64() : 0;
         special_step(S, s, J, __shfl_sync(FULL, p, 0), parked_last && navail == 1);
         if (STATS_ON && lane == 0) { STAT_ADD(ST_C_SPECIAL, 1); STAT_ADD(ST_C_SPECIAL_CYCLES, clock64() - t0); }
         return 3;
     }
-    const uint32_t L = tok >> 4, M = (tok & 15u) + 4, len = L + M;
-    // wait for a full batch unless the run ends in a special entry, or the walker cannot go on before this warp has
-    // made room in the window
-    if (nv < 32 && sm == 0 && !force) return 0;
-    const uint32_t o0 = J.op;
-    const uint32_t o = o0 + warp_incl_scan((int)lane < nv ? len : 0u) - ((int)lane < nv ? len : 0u);
     int err = E_OK;
     // the stream bytes of the whole batch must be in the window
-    const uint32_t need = __shfl_sync(FULL, p + 3 + L, nv - 1);
+    const uint32_t need = __shfl_sync(FULL, nxt, nv - 1);
     // (a refill that was in flight may land inside refill() and fill the window: no new one can be issued then, and none is needed)
     while (!err && J.whi < need)
         if (!refill(S, s, J, 16) && J.whi < need) err = E_INTERNAL;
@@ -759,7 +794,7 @@ __device__ __noinline__ int process_slot(V2Smem &S, int s, SlotJob &J, uint8_t *
         const uint32_t lo = __funnelshift_r(w32[(a4 & WM) >> 2], w32[((a4 + 4) & WM) >> 2], (a & 3u) * 8);
         const uint32_t offv = (lo >> (8 * (L & 3u))) & 0xffffu;
         const uint32_t lit = lo & ~(0xffffffffu << (8 * (L & 3u)));
-        const bool wr = (int)lane < nv && L <= 2 && ((len | offv | o) & 7u) == 0 && (offv - 1u) < o;
+        const bool wr = (int)lane < nv && !ext && L <= 2 && ((len | offv | o) & 7u) == 0 && (offv - 1u) < o;
         const uint32_t rm = __ballot_sync(FULL, wr && ((o - o0) >> 3) + (len >> 3) <= 32u);
         const int nreg = rm == FULL ? 32 : (__ffs(~rm) - 1);
         if (nreg >= REG_MIN || (nreg == nv)) {
@@ -782,7 +817,7 @@ __device__ __noinline__ int process_slot(V2Smem &S, int s, SlotJob &J, uint8_t *
                 *reinterpret_cast<uint4 *>(stg) = __ldcg(reinterpret_cast<const uint4 *>(J.dst + (o0 & ~15u)));
             __syncwarp();
             const long long tp2 = STATS_ON ? clock64() : 0;
-            err = generic_batch(win, stg, J, o0, p, o, L, M, nproc, &new_op);
+            err = generic_batch(win, stg, J, o0, lit_pos, off_pos, o, L, M, nproc, &new_op);
             const long long tp3 = STATS_ON ? clock64() : 0;
             if (!err) {
                 flush(J, stg, o0 & ~15u, new_op);
@@ -800,7 +835,7 @@ __device__ __noinline__ int process_slot(V2Smem &S, int s, SlotJob &J, uint8_t *
         }
     }
     if (err) { finish_block(J, err); return 1; }   // dropped where it stands; the next block's command flushes the ring
-    const uint32_t next_ip = __shfl_sync(FULL, p + 3 + L, nproc - 1);
+    const uint32_t next_ip = __shfl_sync(FULL, nxt, nproc - 1);
     if (lane == 0) { J.op = new_op; J.ip = next_ip; J.tail += (uint32_t)nproc; st_rlx(&S.tail[s], J.tail); }
     __syncwarp();
     refill_issue(S, s, J, 256);
