@@ -489,14 +489,29 @@ __device__ __forceinline__ int generic_batch(const uint8_t *win, uint8_t *stg, c
     __syncwarp();
     uint32_t rest = __ballot_sync(FULL, active && !far);
     const uint32_t pk = (uint32_t)(m_dst - stg_base) | (M << 16);                         // staging index < 2048, M < 512
+    // Two short sequences go in one step (lanes 0-15 / 16-31) when the second does not read what the first writes: every
+    // lane checks that against its predecessor among the sequences left.
+    uint32_t pairable;
+    {
+        const uint32_t below = rest & ((1u << lane) - 1u);
+        const int prev = below ? 31 - __clz(below) : 0;
+        const uint32_t qp = __shfl_sync(FULL, pk, prev);
+        const int32_t pdst = (int32_t)(qp & 0xffffu), pM = (int32_t)(qp >> 16);
+        const int32_t s0 = m_src - stg_base, s1 = s0 + (int32_t)(off < M ? off : M);          // my source bytes (staging indices)
+        pairable = __ballot_sync(FULL, below && M <= 16u && pM <= 16 && (s1 <= pdst || s0 >= pdst + pM));
+    }
     while (rest) {
         const int k = __ffs(rest) - 1;
         rest &= rest - 1;
-        const uint32_t q = __shfl_sync(FULL, pk, k), koff = __shfl_sync(FULL, off, k);
+        const int k2 = rest ? __ffs(rest) - 1 : 0;
+        const bool pair = rest && ((pairable >> k2) & 1u);
+        if (pair) rest &= rest - 1;
+        const int sel = pair && lane >= 16 ? k2 : k;
+        const uint32_t q = __shfl_sync(FULL, pk, sel), koff = __shfl_sync(FULL, off, sel);
         const uint32_t kM = q >> 16;
         const int32_t kdst = (int32_t)(q & 0xffffu);
         // the bytes [m_src, m_src + min(off, M)) are final, and byte i of the match is byte i mod off of them
-        for (uint32_t i = lane; i < kM; i += 32) {
+        for (uint32_t i = pair ? (lane & 15u) : lane; i < kM; i += pair ? 16u : 32u) {
             const uint32_t r = koff < kM ? i % koff : i;
             const int32_t x = kdst - (int32_t)koff + (int32_t)r;      // staging index of the source byte (negative: below the staging area)
             stg[kdst + (int32_t)i] = x >= 0 ? stg[x] : __ldcg(J.dst + (stg_base + x));
