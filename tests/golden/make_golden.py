@@ -114,6 +114,14 @@ def main():
     sel = [i for i in range(n) if mixed["a"][i] > 50]
     add("docs_example", "mixed", t[t.a > 50, ["b"]], sel, {"b": [mixed["b"][i] for i in sel]},
         {"count": len(sel), "sum": math.fsum(mixed["b"][i] for i in sel)})
+    # reductions over computed columns (test/columnbroadcast.jl:28-33,55-60): sum / extrema of a broadcast expression
+    sel = [i for i in range(n) if mixed["a"][i] > 50]
+    vals = [mixed["a"][i] * 2 + 1 for i in sel]
+    add("computed_int_aggregate", "mixed", t[t.a > 50, ["a"]], sel, {"a": [mixed["a"][i] for i in sel]},
+        {"expr": "a*2+1", "count": len(vals), "sum_i": sum(vals), "min_i": min(vals), "max_i": max(vals)})
+    fvals = [mixed["a"][i] * mixed["b"][i] for i in sel]
+    add("computed_float_aggregate", "mixed", t[t.a > 50, ["b"]], sel, {"b": [mixed["b"][i] for i in sel]},
+        {"expr": "a*b", "count": len(fvals), "sum": math.fsum(fvals), "min": min(fvals), "max": max(fvals)})
     # configs[2]: string equality / prefix + projection
     sel = [i for i in range(n) if mixed["s"][i] == "sony"]
     add("string_equality", "mixed", t[t.s == "sony", ["s", "a"]], sel, {"s": [mixed["s"][i] for i in sel], "a": [mixed["a"][i] for i in sel]})

@@ -32,12 +32,37 @@ def _same(got, exp):
         assert (g is None) == (e is None) and (g is None or g == e), (g, e)
 
 
+def _agg_column(q, t, v):
+    """the column a query's `aggregate` expectation is about: `b`, or a computed one"""
+    expr = q["aggregate"].get("expr")
+    if expr == "a*2+1":
+        return v.a * 2 + 1
+    if expr == "a*b":
+        w = t[t.a > 50, :]
+        return w.a * w.b
+    return v.b
+
+
+def _check_aggregate(a, e, sum_f):
+    assert a.count == e["count"]
+    if "sum_i" in e:
+        assert a.sum_i64 == e["sum_i"] and a.min_i64 == e["min_i"] and a.max_i64 == e["max_i"]
+        return
+    assert abs(sum_f - e["sum"]) <= 1e-12 * abs(e["sum"])                                   # BASELINE.json: 1e-12 relative
+    if "min" in e:
+        assert a.min_f64 == e["min"] and a.max_f64 == e["max"]
+
+
 def _rebuild_view(q, t):
     """the query again through the host-side plan algebra: pins the plan serialisation to the committed bytes"""
     n = q["name"]
     if n == "range_predicate_aggregate":
         return t[(t.a > 25) & (t.a <= 75), ["b"]]
     if n == "docs_example":
+        return t[t.a > 50, ["b"]]
+    if n == "computed_int_aggregate":
+        return t[t.a > 50, ["a"]]
+    if n == "computed_float_aggregate":
         return t[t.a > 50, ["b"]]
     if n == "string_equality":
         return t[t.s == "sony", ["s", "a"]]
@@ -81,12 +106,8 @@ def test_oracle_matches_golden_queries(oracle, q):
         for name, c in zip(v.projection.keys(), cols):
             _same(_norm_col(c), q["columns"][name])
         if "aggregate" in q:
-            a = ot.aggregate(D.plan_bytes(v.b), 0)
-            e = q["aggregate"]
-            assert a.count == e["count"]
-            assert abs(a.sum_kahan - e["sum"]) <= 1e-12 * abs(e["sum"])
-            if "min" in e:
-                assert a.min_f64 == e["min"] and a.max_f64 == e["max"]
+            a = ot.aggregate(D.plan_bytes(_agg_column(q, t, v)), 0)
+            _check_aggregate(a, q["aggregate"], a.sum_kahan)
     finally:
         ot.close()
         t.close()
@@ -148,11 +169,7 @@ def test_gpu_matches_golden_queries(q):
         for name in v.projection.keys():
             _same(fr[name], q["columns"][name])
         if "aggregate" in q:
-            a = D.aggregate(v.b)
-            e = q["aggregate"]
-            assert a.count == e["count"]
-            assert abs((a.sum_f64 + a.sum_f64_lo) - e["sum"]) <= 1e-12 * abs(e["sum"])      # BASELINE.json: 1e-12 relative
-            if "min" in e:
-                assert a.min_f64 == e["min"] and a.max_f64 == e["max"]
+            a = D.aggregate(_agg_column(q, t, v))
+            _check_aggregate(a, q["aggregate"], a.sum_f64 + a.sum_f64_lo)
     finally:
         t.close()
