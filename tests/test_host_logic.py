@@ -149,3 +149,30 @@ def test_agg_fold_is_a_fixed_order_host_fold():
     f = D.fold(parts)
     assert f.count == 5 and f.min_f64 == 0.0 and np.signbit(f.min_f64) and f.max_f64 == 0.75
     assert f.sum_f64 + f.sum_f64_lo == 1.5 + 1e-17 or abs((f.sum_f64 + f.sum_f64_lo) - 1.5) < 1e-15
+
+
+def test_flat_strings_vector_views():
+    """FlatStringsVector (src/FlatStringsVectors.jl:5-9,61-70,83-85): sizes + flat chars, offsets = exclusive scan of max(size, 0)
+    built on first use; the char buffer may be bytes or a zero-copy view of a result array."""
+    import numpy as np
+    sizes = np.array([4, -1, 0, 5, 3], dtype=np.int32)
+    chars = b"sonyapplexyz"
+    a = D.FlatStringsVector(sizes, chars)
+    b = D.FlatStringsVector(sizes, np.frombuffer(chars, dtype=np.uint8))
+    assert a._offsets is None and len(a) == 5
+    assert a.tolist() == ["sony", None, "", "apple", "xyz"] == b.tolist()
+    assert a.offsets.tolist() == [0, 4, 4, 4, 9]
+    assert a == b and a == ["sony", None, "", "apple", "xyz"] and a[3] == "apple" and a[1] is None
+    assert a[np.array([True, False, False, True, False])] == ["sony", "apple"]
+    assert len(b.data) == len(chars) and bytes(b.data) == chars
+    empty = D.FlatStringsVector(np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.uint8))
+    assert len(empty) == 0 and empty.tolist() == []
+
+
+def test_result_array_small_results_stay_in_ordinary_memory():
+    """results below _capi.PINNED_MIN_BYTES do not touch the (GPU-side) result arena"""
+    import numpy as np
+    from dfdb_b200 import _capi
+    a = _capi.result_array(10, np.int64)
+    assert a.dtype == np.int64 and a.shape == (10,) and not a.any()
+    assert _capi.result_array(0, np.uint8).shape == (1,)
