@@ -80,6 +80,14 @@ SYMBOLS = {
     "dfdb_scan_exchange_count": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "dfdb_scan_exchange_offset": (C.c_int32, [C.c_void_p, C.c_int64]),
     "dfdb_scan_aggregate_device": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "dfdb_comm_unique_id": (C.c_int32, [C.c_void_p]),
+    "dfdb_comm_init": (C.c_int32, [C.c_int32, C.c_int32, C.c_void_p]),
+    "dfdb_comm_destroy": (C.c_int32, []),
+    "dfdb_comm_info": (C.c_int32, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "dfdb_scan_aggregate_all": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(Agg)]),
+    "dfdb_scan_count_all": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "dfdb_scan_resolve_exchange": (C.c_int32, [C.c_void_p]),
+    "dfdb_scan_row_offset_all": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dfdb_lz4_decode_blocks": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
 }
 

@@ -709,6 +709,31 @@ def aggregate(col: DFColumn) -> _capi.Agg:
     return out
 
 
+def aggregate_all(col: DFColumn) -> _capi.Agg:
+    """dfdb_scan_aggregate_all: every rank aggregates its shard, the partials are all-gathered over the library's NCCL
+    communicator (dist.comm_init_from_torch / dfdb_comm_init) and folded in rank order; every rank gets the same bits."""
+    out = _capi.Agg()
+    try:
+        _capi.check(_capi.lib().dfdb_scan_aggregate_all(_scan_handle(col.view), 0, C.byref(out)))
+    except DfdbError as e:
+        _raise(e)
+    return out
+
+
+def nrow_all(v) -> int:
+    """dfdb_scan_count_all: nrow(v) over all shards (survivor-count exchanges resolved over the communicator first)."""
+    if isinstance(v, DFTable):
+        v = DFView(v)
+    if isinstance(v, DFColumn):
+        v = v.view
+    n = C.c_int64()
+    try:
+        _capi.check(_capi.lib().dfdb_scan_count_all(_scan_handle(v), C.byref(n)))
+    except DfdbError as e:
+        _raise(e)
+    return n.value
+
+
 def fold(partials) -> _capi.Agg:
     """dfdb_agg_fold: fixed rank-order combination of per-shard partials."""
     arr = (_capi.Agg * len(partials))(*partials)

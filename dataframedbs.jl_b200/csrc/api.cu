@@ -5,6 +5,7 @@
 // projection columns -> project), this driver decodes every needed column block of the shard with one
 // K1 launch and then runs each selection stage / consumer as one kernel over all blocks.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <unistd.h>
 
@@ -37,6 +38,8 @@ struct Runtime {
     unsigned int *d_counter = nullptr;
     int *d_error = nullptr;
     const std::vector<int64_t> *blk_live = nullptr;   // set while projection columns of a scan are decoded: blocks without a selected row are skipped
+    uint64_t blk_live_gen = 0;                        // ... and the generation of those counts (the key of a column's filtered decode)
+    uint64_t next_gen = 1;
     int win_lo = 0, win_hi = 0x7fffffff;   // local block window of the scan being served (BlockWindow): blocks outside hold no selected row
     std::atomic<int64_t> launches{0};
     // options
@@ -45,7 +48,7 @@ struct Runtime {
     int64_t no_wide = 0;
     int64_t no_fused = 0;
     int64_t no_tma = 0;
-    int64_t lz4_flavour = 0;  // K1 flavour: 0 = per column from a token sample at load, 1 = word-regular decoder (v2), 2 = general decoder (v3)
+    int64_t lz4_flavour = 0;  // K1 flavour: 0 = per column from a token sample at load, 1 = word-regular decoder (v2), 2 = general decoder (v3), 3 = lane-per-block decoder
     int64_t no_overlap = 0;   // do not run the scan of the decoded part of a shard beside the decode of its last part
     int64_t no_alias = 0;     // copy stored (incompressible) blocks like any other block instead of referencing them in place
     // profiling
@@ -229,7 +232,7 @@ void column_release(Column &c)
     c.d_skip = nullptr; c.h_skip.clear(); c.stored_blocks = 0;
     c.h_comp = nullptr; c.d_comp = nullptr; c.d_decoded = nullptr; c.d_comp_off = nullptr; c.d_comp_len = nullptr;
     c.d_dec_off = nullptr; c.d_origin = nullptr; c.d_status = nullptr; c.d_str_off = nullptr;
-    c.loaded = false; c.decoded_valid = false; c.dec_lo = c.dec_hi = 0; c.dec_live = nullptr; c.str_off_valid = false;
+    c.loaded = false; c.decoded_valid = false; c.dec_lo = c.dec_hi = 0; c.dec_live_gen = 0; c.str_off_valid = false;
 }
 
 Geometry make_geometry(const dfdb_table *t)
@@ -282,6 +285,7 @@ int launch_decode(const DecodeArgs &a, bool general, cudaStream_t stream = nullp
     if (!stream) stream = rt.stream;
     unsigned int *counter = rt.d_counter + 4 * counter_slot;   // launches that may run at the same time need their own job counter
     if (rt.lz4_simple || rt.lz4_v1) return launch_lz4_decode(a, counter, rt.sm_count, (int)rt.lz4_simple, stream);
+    if (rt.lz4_flavour == 3) return launch_lz4_decode_lane(a, nullptr, counter, rt.sm_count, stream, cta_limit);
     if (rt.lz4_flavour == 1) general = false;
     if (rt.lz4_flavour == 2) general = true;
     return general ? launch_lz4_decode_v3(a, counter, rt.sm_count, stream, cta_limit) : launch_lz4_decode_v2(a, counter, rt.sm_count, stream, cta_limit);
@@ -345,7 +349,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
         Column *c = t->find(id);
         if (!c) return fail(DFDB_ERR_KEY, "unknown column id %lld", (long long)id);
         if (!c->loaded) return fail(DFDB_ERR_STATE, "column %s is not loaded (call dfdb_table_load first)", c->name.c_str());
-        const bool have = c->decoded_valid || (c->dec_lo <= wlo && whi <= c->dec_hi) || (rt.blk_live && c->dec_live == rt.blk_live);
+        const bool have = c->decoded_valid || (c->dec_lo <= wlo && whi <= c->dec_hi) || (rt.blk_live && rt.blk_live_gen != 0 && c->dec_live_gen == rt.blk_live_gen);
         if (!have && std::find(todo.begin(), todo.end(), c) == todo.end()) todo.push_back(c);
     }
     if (todo.empty() || whi == wlo) return DFDB_OK;
@@ -520,7 +524,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
     for (Column *c : todo)
         if (c->type.kind == DFDB_STRING) {
             PhaseScope ps(PH_UNPACK, 0);
-            LAUNCH(launch_str_offsets(g, make_view(*c), c->d_str_off, c->d_status, rt.stream, wlo, whi, d_dead));
+            LAUNCH(launch_str_offsets(g, make_view(*c), c->d_str_off, c->d_status, c->d_origin, rt.stream, wlo, whi, d_dead));
         }
     // integrity gate (the reference asserts after every block, BlockStreams.jl:112)
     std::vector<int32_t> st((size_t)nblocks);
@@ -534,7 +538,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
         // (a decode that skipped blocks without selected rows leaves nothing another scan could rely on)
         c->dec_lo = filtered ? 0 : wlo;
         c->dec_hi = filtered ? 0 : whi;
-        c->dec_live = filtered ? rt.blk_live : nullptr;
+        c->dec_live_gen = filtered ? rt.blk_live_gen : 0;
         c->decoded_valid = !filtered && wlo == 0 && whi == nblocks;
     }
     return DFDB_OK;
@@ -543,17 +547,26 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
 void invalidate_decoded(dfdb_table *t)
 {
     for (auto &c : t->cols)
-        if (c.mode != DFDB_LOAD_DECODED) { c.decoded_valid = false; c.dec_lo = c.dec_hi = 0; c.dec_live = nullptr; }
+        if (c.mode != DFDB_LOAD_DECODED) { c.decoded_valid = false; c.dec_lo = c.dec_hi = 0; c.dec_live_gen = 0; }
 }
 
 // The local blocks that can hold selected rows of a scan: a leading range / index-vector stage works on table row numbers
 // (selection.jl:94-111 with offset 0), so the blocks before its first and behind its last row are never decoded.  Scope
 // guard: ensure_decoded reads the window of the scan being served.
 // Scope guard: while the projection columns of a scan are decoded, blocks without a selected row are skipped.
+// a mask (and the counts derived from it) is only good for the shard it was computed on
+bool mask_current(const dfdb_scan *s) { return s->mask_valid && s->mask_epoch == s->tbl->epoch; }
+
 struct LiveBlocks {
     const std::vector<int64_t> *prev;
-    explicit LiveBlocks(const dfdb_scan *s) : prev(rt.blk_live) { rt.blk_live = s->mask_valid && s->selected >= 0 ? &s->blk_live : nullptr; }
-    ~LiveBlocks() { rt.blk_live = prev; }
+    uint64_t prev_gen;
+    explicit LiveBlocks(const dfdb_scan *s) : prev(rt.blk_live), prev_gen(rt.blk_live_gen)
+    {
+        const bool ok = mask_current(s) && s->selected >= 0 && s->live_gen != 0;
+        rt.blk_live = ok ? &s->blk_live : nullptr;
+        rt.blk_live_gen = ok ? s->live_gen : 0;
+    }
+    ~LiveBlocks() { rt.blk_live = prev; rt.blk_live_gen = prev_gen; }
 };
 
 struct BlockWindow {
@@ -754,6 +767,7 @@ int run_selection(dfdb_scan *s)
         if (rc) return rc;
     }
     s->mask_valid = true;
+    s->mask_epoch = t->epoch;
     return DFDB_OK;
 }
 
@@ -773,6 +787,7 @@ int count_mask(dfdb_scan *s, int64_t *total)
     CUDA_TRY(cudaStreamSynchronize(rt.stream));
     *total = *static_cast<int64_t *>(s->h_result);
     s->selected = *total;
+    s->live_gen = rt.next_gen++;       // new counts: a filtered decode keyed on the old ones is not reused
     return DFDB_OK;
 }
 
@@ -1072,6 +1087,7 @@ int32_t dfdb_shutdown(void)
 {
     if (!rt.inited) return DFDB_OK;
     cudaStreamSynchronize(rt.stream);
+    dfdb_comm_destroy();
     profile_collect();
     cudaFree(rt.d_counter);
     cudaFree(rt.d_error);
@@ -1203,6 +1219,7 @@ int32_t dfdb_table_set_shard(dfdb_table *t, int32_t rank, int32_t world)
     for (auto &c : t->cols) if (c.loaded) column_release(c);
     t->rank = rank;
     t->world = world;
+    t->epoch++;                        // masks, survivor counts and filtered decodes of the old shard are stale
     t->blk_lo = t->nblocks * rank / world;
     t->blk_hi = t->nblocks * (rank + 1) / world;
     return DFDB_OK;
@@ -1339,14 +1356,14 @@ int32_t dfdb_table_load(dfdb_table *t, const int64_t *col_ids, int32_t n, int32_
         c->loaded = true;
         c->decoded_valid = false;
         c->dec_lo = c->dec_hi = 0;
-        c->dec_live = nullptr;
+        c->dec_live_gen = 0;
     }
     return DFDB_OK;
 }
 
 int32_t dfdb_table_drop_decoded(dfdb_table *t)
 {
-    for (auto &c : t->cols) { c.decoded_valid = false; c.dec_lo = c.dec_hi = 0; c.dec_live = nullptr; }
+    for (auto &c : t->cols) { c.decoded_valid = false; c.dec_lo = c.dec_hi = 0; c.dec_live_gen = 0; }
     return DFDB_OK;
 }
 
@@ -1502,6 +1519,8 @@ int32_t dfdb_scan_exchange_offset(dfdb_scan *s, int64_t survivors_in_lower_ranks
     s->rank_offsets.push_back(survivors_in_lower_ranks);
     s->exchange_count = -1;
     s->mask_valid = false;
+    s->selected = -1;
+    s->live_gen = 0;
     return DFDB_OK;
 }
 
@@ -1612,7 +1631,7 @@ int32_t dfdb_scan_materialize(dfdb_scan *s, dfdb_outcol *cols, int32_t ncols)
     BlockWindow win(s);
     dfdb_table *t = s->tbl;
     if ((size_t)ncols != s->projs.size()) return fail(DFDB_ERR_ARGUMENT, "expected %zu output columns, got %d", s->projs.size(), ncols);
-    if (!s->mask_valid || s->selected < 0) {
+    if (!mask_current(s) || s->selected < 0) {
         rc = dfdb_scan_materialize_sizes(s, nullptr, nullptr);
         if (rc) return rc;
     }
@@ -1738,6 +1757,206 @@ int32_t dfdb_scan_materialize(dfdb_scan *s, dfdb_outcol *cols, int32_t ncols)
     if (e == cudaSuccess) e = cudaStreamSynchronize(rt.stream);
     if (e != cudaSuccess) return fail(DFDB_ERR_CUDA, "materialize failed: %s", cudaGetErrorString(e));
     return DFDB_OK;
+}
+
+// ---- communicator: NCCL, bound at run time -------------------------------------------------------------
+// (declarations restated from nccl.h so that the library builds without it; the ABI of these five entry points is stable
+// across NCCL 2.x: ncclUniqueId is 128 bytes passed by value, ncclInt8 = 0)
+namespace {
+struct NcclId { char internal[DFDB_COMM_ID_BYTES]; };
+struct Nccl {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    void *comm = nullptr;
+    int rank = 0, world = 0;
+    uint8_t *d_buf = nullptr;      // world + 1 slots of 128 bytes: [0] = this rank's contribution, [1..] = gathered
+    uint8_t *h_buf = nullptr;      // pinned mirror
+} nccl;
+
+int nccl_bind()
+{
+    if (nccl.lib) return DFDB_OK;
+    const char *names[] = {getenv("DFDB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        if (!n || !*n) continue;
+        nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (nccl.lib) break;
+    }
+    if (!nccl.lib) return fail(DFDB_ERR_STATE, "cannot open libnccl.so.2 (%s); set DFDB_NCCL_LIB", dlerror());
+    nccl.GetUniqueId = reinterpret_cast<decltype(nccl.GetUniqueId)>(dlsym(nccl.lib, "ncclGetUniqueId"));
+    nccl.CommInitRank = reinterpret_cast<decltype(nccl.CommInitRank)>(dlsym(nccl.lib, "ncclCommInitRank"));
+    nccl.AllGather = reinterpret_cast<decltype(nccl.AllGather)>(dlsym(nccl.lib, "ncclAllGather"));
+    nccl.CommDestroy = reinterpret_cast<decltype(nccl.CommDestroy)>(dlsym(nccl.lib, "ncclCommDestroy"));
+    nccl.GetErrorString = reinterpret_cast<decltype(nccl.GetErrorString)>(dlsym(nccl.lib, "ncclGetErrorString"));
+    if (!nccl.GetUniqueId || !nccl.CommInitRank || !nccl.AllGather || !nccl.CommDestroy) {
+        dlclose(nccl.lib);
+        nccl.lib = nullptr;
+        return fail(DFDB_ERR_STATE, "libnccl does not export the expected entry points");
+    }
+    return DFDB_OK;
+}
+
+#define NCCL_TRY(expr)                                                                                              \
+    do {                                                                                                            \
+        int _r = (expr);                                                                                            \
+        if (_r != 0) return fail(DFDB_ERR_CUDA, "%s failed: %s", #expr, nccl.GetErrorString ? nccl.GetErrorString(_r) : "?"); \
+    } while (0)
+
+constexpr size_t COMM_SLOT = 128;   // bytes per rank in an exchange (>= sizeof(dfdb_agg))
+static_assert(sizeof(dfdb_agg) <= COMM_SLOT, "a partial fits one exchange slot");
+
+// all-gather of one COMM_SLOT-byte record per rank on the scan stream; result in nccl.h_buf + COMM_SLOT * (1 + rank)
+int comm_allgather(const void *mine, size_t n)
+{
+    if (!nccl.comm) return fail(DFDB_ERR_STATE, "no communicator (call dfdb_comm_init first)");
+    memset(nccl.h_buf, 0, COMM_SLOT);
+    memcpy(nccl.h_buf, mine, n);
+    CUDA_TRY(cudaMemcpyAsync(nccl.d_buf, nccl.h_buf, COMM_SLOT, cudaMemcpyHostToDevice, rt.stream));
+    NCCL_TRY(nccl.AllGather(nccl.d_buf, nccl.d_buf + COMM_SLOT, COMM_SLOT, /*ncclInt8*/ 0, nccl.comm, rt.stream));
+    CUDA_TRY(cudaMemcpyAsync(nccl.h_buf + COMM_SLOT, nccl.d_buf + COMM_SLOT, COMM_SLOT * (size_t)nccl.world, cudaMemcpyDeviceToHost, rt.stream));
+    CUDA_TRY(cudaStreamSynchronize(rt.stream));
+    return DFDB_OK;
+}
+}  // namespace
+
+int32_t dfdb_comm_unique_id(uint8_t *id)
+{
+    if (!id) return fail(DFDB_ERR_ARGUMENT, "null argument");
+    int rc = nccl_bind();
+    if (rc) return rc;
+    NcclId u;
+    NCCL_TRY(nccl.GetUniqueId(&u));
+    memcpy(id, u.internal, DFDB_COMM_ID_BYTES);
+    return DFDB_OK;
+}
+
+int32_t dfdb_comm_init(int32_t rank, int32_t world, const uint8_t *id)
+{
+    int rc = need_init();
+    if (rc) return rc;
+    if (!id || world < 1 || rank < 0 || rank >= world) return fail(DFDB_ERR_ARGUMENT, "bad communicator arguments (rank %d of %d)", rank, world);
+    if (nccl.comm) return fail(DFDB_ERR_STATE, "a communicator already exists (dfdb_comm_destroy first)");
+    rc = nccl_bind();
+    if (rc) return rc;
+    NcclId u;
+    memcpy(u.internal, id, DFDB_COMM_ID_BYTES);
+    CUDA_TRY(cudaSetDevice(rt.device));
+    NCCL_TRY(nccl.CommInitRank(&nccl.comm, world, u, rank));
+    nccl.rank = rank;
+    nccl.world = world;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&nccl.d_buf), COMM_SLOT * (size_t)(world + 1)));
+    CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&nccl.h_buf), COMM_SLOT * (size_t)(world + 1)));
+    return DFDB_OK;
+}
+
+int32_t dfdb_comm_destroy(void)
+{
+    if (!nccl.comm) return DFDB_OK;
+    if (rt.inited) cudaStreamSynchronize(rt.stream);
+    nccl.CommDestroy(nccl.comm);
+    nccl.comm = nullptr;
+    nccl.world = 0;
+    cudaFree(nccl.d_buf);
+    cudaFreeHost(nccl.h_buf);
+    nccl.d_buf = nccl.h_buf = nullptr;
+    return DFDB_OK;
+}
+
+int32_t dfdb_comm_info(int32_t *rank, int32_t *world)
+{
+    if (rank) *rank = nccl.comm ? nccl.rank : 0;
+    if (world) *world = nccl.comm ? nccl.world : 0;
+    return DFDB_OK;
+}
+
+int32_t dfdb_scan_resolve_exchange(dfdb_scan *s)
+{
+    int rc = need_init();
+    if (rc) return rc;
+    if (!s) return fail(DFDB_ERR_ARGUMENT, "null argument");
+    if (s->tbl->world <= 1) return DFDB_OK;
+    if (!nccl.comm || nccl.world != s->tbl->world || nccl.rank != s->tbl->rank)
+        return fail(DFDB_ERR_STATE, "the table is shard %d of %d but the communicator is rank %d of %d", s->tbl->rank, s->tbl->world, nccl.rank, nccl.world);
+    for (int stage = 0; stage < 64; stage++) {
+        int64_t local = 0;
+        int32_t pending = 0;
+        rc = dfdb_scan_exchange_count(s, &local, &pending);
+        if (rc) return rc;
+        // every rank runs the same plan, so every rank has the same number of pending stages; the flag travels with the
+        // count all the same so that a disagreement is an error, not a hang
+        int64_t rec[2] = {local, pending};
+        rc = comm_allgather(rec, sizeof rec);
+        if (rc) return rc;
+        int64_t lower = 0;
+        for (int r = 0; r < nccl.world; r++) {
+            int64_t theirs[2];
+            memcpy(theirs, nccl.h_buf + COMM_SLOT * (size_t)(1 + r), sizeof theirs);
+            if (theirs[1] != pending) return fail(DFDB_ERR_STATE, "ranks disagree on the plan: rank %d has %s exchange pending", r, theirs[1] ? "an" : "no");
+            if (r < nccl.rank) lower += theirs[0];
+        }
+        if (!pending) return DFDB_OK;
+        rc = dfdb_scan_exchange_offset(s, lower);
+        if (rc) return rc;
+    }
+    return fail(DFDB_ERR_STATE, "too many exchange stages");
+}
+
+int32_t dfdb_scan_aggregate_all(dfdb_scan *s, int32_t proj_idx, dfdb_agg *out)
+{
+    int rc = need_init();
+    if (rc) return rc;
+    if (!s || !out) return fail(DFDB_ERR_ARGUMENT, "null argument");
+    if (s->tbl->world <= 1) return dfdb_scan_aggregate(s, proj_idx, out);
+    rc = dfdb_scan_resolve_exchange(s);
+    if (rc) return rc;
+    dfdb_agg mine;
+    rc = dfdb_scan_aggregate(s, proj_idx, &mine);
+    if (rc) return rc;
+    rc = comm_allgather(&mine, sizeof mine);
+    if (rc) return rc;
+    std::vector<dfdb_agg> parts((size_t)nccl.world);
+    for (int r = 0; r < nccl.world; r++) memcpy(&parts[(size_t)r], nccl.h_buf + COMM_SLOT * (size_t)(1 + r), sizeof(dfdb_agg));
+    return dfdb_agg_fold(parts.data(), nccl.world, out);
+}
+
+int32_t dfdb_scan_row_offset_all(dfdb_scan *s, int64_t *local, int64_t *row_offset, int64_t *total)
+{
+    int rc = need_init();
+    if (rc) return rc;
+    if (!s) return fail(DFDB_ERR_ARGUMENT, "null argument");
+    int64_t n = 0;
+    if (s->tbl->world > 1) {
+        rc = dfdb_scan_resolve_exchange(s);
+        if (rc) return rc;
+    }
+    rc = dfdb_scan_count(s, &n);
+    if (rc) return rc;
+    int64_t lower = 0, all = n;
+    if (s->tbl->world > 1) {
+        rc = comm_allgather(&n, sizeof n);
+        if (rc) return rc;
+        all = 0;
+        for (int r = 0; r < nccl.world; r++) {
+            int64_t c;
+            memcpy(&c, nccl.h_buf + COMM_SLOT * (size_t)(1 + r), sizeof c);
+            if (r < nccl.rank) lower += c;
+            all += c;
+        }
+    }
+    if (local) *local = n;
+    if (row_offset) *row_offset = lower;
+    if (total) *total = all;
+    return DFDB_OK;
+}
+
+int32_t dfdb_scan_count_all(dfdb_scan *s, int64_t *n)
+{
+    if (!n) return fail(DFDB_ERR_ARGUMENT, "null argument");
+    return dfdb_scan_row_offset_all(s, nullptr, nullptr, n);
 }
 
 // ---- result arena ------------------------------------------------------------------------------------

@@ -56,7 +56,7 @@ struct Column {
     size_t decoded_bytes = 0;
     bool decoded_valid = false;
     int dec_lo = 0, dec_hi = 0;      // local block range whose decoded bodies are current (decoded_valid: all of them)
-    const void *dec_live = nullptr;  // the blocks with selected rows of the scan whose survivor counts live here are decoded (skip_cols)
+    uint64_t dec_live_gen = 0;       // generation of the survivor counts (dfdb_scan::live_gen) whose live blocks are the ones decoded (skip_cols); 0 = none
     // per local block device arrays
     int64_t *d_comp_off = nullptr;   // offset of payload in (h|d)_comp
     int32_t *d_comp_len = nullptr;
@@ -80,6 +80,7 @@ struct dfdb_table {
     std::vector<dfdb::Column> cols;
     int64_t nrows = 0, nblocks = 0;
     int32_t rank = 0, world = 1;
+    uint64_t epoch = 1;                // bumped whenever the shard changes: masks and counts of older epochs are stale
     int64_t blk_lo = 0, blk_hi = 0;    // shard
     dfdb::Column *find(int64_t id)
     {
@@ -207,6 +208,8 @@ struct dfdb_scan {
     void *d_result = nullptr;          // final dfdb_agg (+ scalars) on device
     void *h_result = nullptr;          // pinned host mirror
     bool mask_valid = false;
+    uint64_t mask_epoch = 0;           // table epoch the mask was computed in
+    uint64_t live_gen = 0;             // generation of blk_live (a new one every time the survivor counts are recomputed)
     int64_t selected = -1;
     std::vector<int64_t> str_bytes;    // per projection
     std::vector<int64_t> blk_live;     // selected rows per local block (host copy of the counts behind d_blk_base), valid with `selected`

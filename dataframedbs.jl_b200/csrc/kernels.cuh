@@ -101,6 +101,21 @@ struct TmaScanArgs {
 };
 int launch_fused_tma(const TmaScanArgs &a, int agg, int sm_count, cudaStream_t stream);
 
+// ---- K1 lane-per-block decoder (lz4_decode_lane.cu), optionally with K3 + K7 fused into its flush -----------------
+// The predicate is one closed interval (+ != constants) on the 8-byte, non-nullable column DecodeArgs::col[pred_col];
+// the selected rows of `agg` (8-byte, non-nullable, body resident: stored in place or decoded earlier) are folded into
+// one partial per block, written at partials[(local block - part_blk0) * segs_per_block].
+struct LaneFused {
+    int pred_col;                 // index into DecodeArgs::col
+    ColTest test;
+    ColView agg;                  // base == nullptr: count only
+    int agg_kind;                 // 0 = count, 1 = integer aggregate, 2 = Float64 aggregate
+    int agg_cls;
+    AggPartial *partials;
+    int part_blk0, segs_per_block;
+};
+int launch_lz4_decode_lane(const DecodeArgs &args, const LaneFused *fused, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit = 0);
+
 // ---- K3 generic: VM predicate -> mask ------------------------------------------------------------------
 struct VmArgs {
     Geometry g;
@@ -130,7 +145,7 @@ int launch_range_stage(const RangeArgs &a, cudaStream_t stream);
 int launch_fill_mask(const Geometry &g, uint32_t *mask, cudaStream_t stream);
 
 // ---- K2: String bodies: per-row char offsets (unsafe_remake_offsets!) --------------------------------
-int launch_str_offsets(const Geometry &g, const ColView &col, int32_t *str_off, int32_t *status, cudaStream_t stream, int lo = 0, int hi = 0x7fffffff,
+int launch_str_offsets(const Geometry &g, const ColView &col, int32_t *str_off, int32_t *status, const int32_t *origin, cudaStream_t stream, int lo = 0, int hi = 0x7fffffff,
                        const uint8_t *dead = nullptr);   // local blocks [lo, hi) except those flagged in `dead`
 
 // ---- K5/K6: stream compaction / gathers ---------------------------------------------------------------

@@ -735,8 +735,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) range_stage_kernel(const RangeAr
 // ---- K2: string offsets -------------------------------------------------------------------------------------
 // one warp per block: exclusive prefix sum of max(size, 0) in row order
 // (blocks outside [lo, hi) and blocks flagged in `dead` were not decoded for this scan: their bodies are stale)
+// A body whose size table does not describe exactly the bytes that follow it is corrupt (the reference's unsafe_read on the
+// block's IOBuffer throws EOFError there, src/io/blocks.jl:62-71): status 5 unless 4 + 4 * rows + datasize == origin and the
+// sizes add up to datasize -- no consumer kernel then reads past the decoded slot.
 __global__ void __launch_bounds__(SCAN_THREADS) str_offsets_kernel(const Geometry g, const ColView col, int32_t *str_off, int32_t *status,
-                                                                  int lo, int hi, const uint8_t *dead)
+                                                                  const int32_t *origin, int lo, int hi, const uint8_t *dead)
 {
     const int warps = gridDim.x * (SCAN_THREADS / 32);
     for (int lb = lo + blockIdx.x * (SCAN_THREADS / 32) + warp_id(); lb < hi; lb += warps) {
@@ -748,9 +751,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) str_offsets_kernel(const Geometr
         int32_t *out = str_off + (int64_t)lb * g.block_size;
         long long run = 0;
         // each lane takes 4 consecutive rows per step (one 16-byte load when aligned is not guaranteed: body+4)
+        if (datasize < 0 || 4 + 4 * rows_b + (int64_t)datasize != (int64_t)origin[lb]) {
+            if (lane_id() == 0) status[lb] = 5;
+            continue;
+        }
         for (int64_t r0 = 0; r0 < rows_b; r0 += 128) {
             int s[4];
-            int local = 0;
+            long long local = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int64_t r = r0 + lane_id() * 4 + j;
@@ -758,10 +765,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) str_offsets_kernel(const Geometr
                 if (s[j] < 0) s[j] = 0;
                 local += s[j];
             }
-            int incl = local;
+            long long incl = local;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const int v = __shfl_up_sync(FULL, incl, d);
+                const long long v = __shfl_up_sync(FULL, incl, d);
                 if (lane_id() >= d) incl += v;
             }
             long long o = run + (incl - local);
@@ -1171,13 +1178,13 @@ int launch_fill_mask(const Geometry &g, uint32_t *mask, cudaStream_t stream)
     return CHECK_LAUNCH();
 }
 
-int launch_str_offsets(const Geometry &g, const ColView &col, int32_t *str_off, int32_t *status, cudaStream_t stream, int lo, int hi,
-                       const uint8_t *dead)
+int launch_str_offsets(const Geometry &g, const ColView &col, int32_t *str_off, int32_t *status, const int32_t *origin, cudaStream_t stream, int lo,
+                       int hi, const uint8_t *dead)
 {
     if (hi > g.nblocks) hi = g.nblocks;
     if (lo < 0) lo = 0;
     if (hi <= lo) return 0;
-    str_offsets_kernel<<<grid_for((hi - lo + 7) / 8, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(g, col, str_off, status, lo, hi, dead);
+    str_offsets_kernel<<<grid_for((hi - lo + 7) / 8, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(g, col, str_off, status, origin, lo, hi, dead);
     return CHECK_LAUNCH();
 }
 

@@ -11,6 +11,32 @@ import ctypes as C
 
 from . import _capi
 
+COMM_ID_BYTES = 128
+
+
+def comm_init_from_torch(rank: int, world: int, device=None):
+    """Create the LIBRARY's NCCL communicator (dfdb_comm_init): rank 0 makes the 128-byte id (dfdb_comm_unique_id) and
+    torch.distributed only carries it to the other ranks.  After this the combine step runs inside the C ABI
+    (dfdb_scan_aggregate_all: ncclAllGather on the scan stream + dfdb_agg_fold), with no torch call per scan."""
+    import torch
+    import torch.distributed as dist
+
+    L = _capi.lib()
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    if rank == 0:
+        _capi.check(L.dfdb_comm_unique_id(buf))
+    t = torch.tensor(list(buf), dtype=torch.uint8)
+    if device is not None:
+        t = t.to(device)
+    dist.broadcast(t, 0)
+    raw = bytes(t.cpu().tolist())
+    buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(raw)
+    _capi.check(L.dfdb_comm_init(rank, world, buf))
+
+
+def comm_destroy():
+    _capi.check(_capi.lib().dfdb_comm_destroy())
+
 
 def allgather_fold(agg: _capi.Agg, device=None) -> _capi.Agg:
     """All-gather one dfdb_agg per rank and fold them in rank order.  `device`: torch device of the exchange buffers."""

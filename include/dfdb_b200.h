@@ -152,6 +152,28 @@ DFDB_API int32_t dfdb_scan_exchange_offset(dfdb_scan *s, int64_t survivors_in_lo
 /* device-resident copy of the last dfdb_scan_aggregate result (sizeof(dfdb_agg) bytes), for NCCL */
 DFDB_API int32_t dfdb_scan_aggregate_device(dfdb_scan *s, int32_t proj_idx, void *device_out);
 
+/* ---- multi-GPU inside the library: one process per GPU, NCCL over NVLink / NVSwitch.  The library opens libnccl.so.2 at
+ *      dfdb_comm_init (no NCCL dependency until then).  Rank 0 creates the 128-byte id with dfdb_comm_unique_id, the host
+ *      distributes it by whatever means it has (MPI, a file, torch.distributed), every rank calls dfdb_comm_init on the device
+ *      it gave dfdb_init.  No reference counterpart: the reference is a single process. ---------------------------------- */
+#define DFDB_COMM_ID_BYTES 128
+DFDB_API int32_t dfdb_comm_unique_id(uint8_t *id);                                   /* ncclGetUniqueId                    */
+DFDB_API int32_t dfdb_comm_init(int32_t rank, int32_t world, const uint8_t *id);     /* ncclCommInitRank                   */
+DFDB_API int32_t dfdb_comm_destroy(void);
+DFDB_API int32_t dfdb_comm_info(int32_t *rank, int32_t *world);                      /* world = 0: no communicator          */
+/* Reductions over a block-range sharded table (Base folds over iterate(::DFColumn), src/tables/column.jl:102-126): every rank
+ * aggregates its shard, the 88-byte partials are all-gathered with ncclAllGather on the scan stream and folded in rank order
+ * (dfdb_agg_fold) -- every rank returns the same bits.  Survivor-count exchanges that the plan needs (range stage behind a
+ * predicate, see dfdb_scan_exchange_count) are resolved over the same communicator first. */
+DFDB_API int32_t dfdb_scan_aggregate_all(dfdb_scan *s, int32_t proj_idx, dfdb_agg *out);
+/* nrow(v) over all shards (src/tables/view.jl:192-206): all-gather of the per-shard counts */
+DFDB_API int32_t dfdb_scan_count_all(dfdb_scan *s, int64_t *n);
+/* resolves every pending survivor-count exchange of the scan over the communicator (dfdb_scan_exchange_count / _offset) */
+DFDB_API int32_t dfdb_scan_resolve_exchange(dfdb_scan *s);
+/* materialize over all shards: *row_offset = selected rows of the lower-ranked shards, *total = selected rows of the whole
+ * table; this rank's rows go to [row_offset, row_offset + local) of the result (dfdb_scan_materialize fills the local part) */
+DFDB_API int32_t dfdb_scan_row_offset_all(dfdb_scan *s, int64_t *local, int64_t *row_offset, int64_t *total);
+
 /* ---- result buffers.  materialize(::DFView) allocates its result vectors (`sizehint!` + `append!`,
  *      src/tables/materialization.jl:1-25,29-37); a caller that takes them from here gets page-locked memory, which
  *      dfdb_scan_materialize recognises and fills with one device-to-host copy at full PCIe rate (ordinary pageable

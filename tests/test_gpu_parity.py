@@ -81,11 +81,13 @@ def _set_variant(variant):
         _capi.check(L.dfdb_set_option(b"lz4_flavour", 1))
     elif variant == "v3":
         _capi.check(L.dfdb_set_option(b"lz4_flavour", 2))
+    elif variant == "lane":
+        _capi.check(L.dfdb_set_option(b"lz4_flavour", 3))
     elif variant is not None:
         _capi.check(L.dfdb_set_option(variant.encode(), 1))
 
 
-@pytest.mark.parametrize("variant", ["v2", "v3", "lz4_v1", "lz4_simple"], ids=["walker_regular", "walker_general", "warp_per_block", "sequential"])
+@pytest.mark.parametrize("variant", ["lane", "v2", "v3", "lz4_v1", "lz4_simple"], ids=["lane_per_block", "walker_regular", "walker_general", "warp_per_block", "sequential"])
 def test_lz4_decode_matches_reference_codec(oracle, variant):
     """read_block BlockStreams.jl:101-119: decoded bytes are determined by the LZ4 block format."""
     bodies = _bodies(oracle)
@@ -102,7 +104,7 @@ def test_lz4_decode_matches_reference_codec(oracle, variant):
         assert got[i] == bodies[k], f"decoded bytes differ for {k} (first diff at {next(j for j in range(len(got[i])) if got[i][j] != bodies[k][j])})"
 
 
-@pytest.mark.parametrize("variant", ["v2", "v3"], ids=["walker_regular", "walker_general"])
+@pytest.mark.parametrize("variant", ["lane", "v2", "v3"], ids=["lane_per_block", "walker_regular", "walker_general"])
 def test_lz4_decode_many_small_blocks(oracle, variant):
     """More blocks than the persistent decoder has slots (148 SMs x 87), ragged sizes, every body kind: slots are
     reused, rings wrap, windows re-base after long literal / match runs."""
@@ -128,7 +130,7 @@ def test_lz4_decode_many_small_blocks(oracle, variant):
     assert not bad, f"{len(bad)} of {len(idx)} blocks differ, first: block {bad[0]} (pool {idx[bad[0]]}, origin {origins[bad[0]]}, status {status[bad[0]]})"
 
 
-@pytest.mark.parametrize("variant", ["v2", "v3"], ids=["walker_regular", "walker_general"])
+@pytest.mark.parametrize("variant", ["lane", "v2", "v3"], ids=["lane_per_block", "walker_regular", "walker_general"])
 def test_lz4_decode_rejects_corrupt_blocks(oracle, variant):
     """@assert size == sizes.origin "decompression error" (BlockStreams.jl:112)"""
     body = np.random.default_rng(3).integers(1, 101, 4096).astype(np.int64).tobytes()
@@ -148,7 +150,7 @@ def test_lz4_decode_rejects_corrupt_blocks(oracle, variant):
             oracle.lz4_decompress(blk, org)
 
 
-@pytest.mark.parametrize("variant", ["v2", "v3"], ids=["walker_regular", "walker_general"])
+@pytest.mark.parametrize("variant", ["lane", "v2", "v3"], ids=["lane_per_block", "walker_regular", "walker_general"])
 def test_lz4_decode_fuzzed_streams(oracle, variant):
     """LZ4_decompress_safe contract on damaged streams: no crash, no out-of-bounds write, and whatever the CPU codec
     accepts decodes to the same bytes.  (The GPU decoders do not enforce liblz4's end-of-block rules, so they may accept
@@ -183,6 +185,9 @@ def test_lz4_decode_fuzzed_streams(oracle, variant):
     for k, ref in enumerate(expect):
         if ref is not None:
             assert status[k] == 0 and got[k] == ref, f"stream {k}: the CPU codec accepts it, GPU status {status[k]}"
+        elif variant == "lane":
+            # the lane-per-block decoder enforces liblz4's end-of-block rules: identical accept / reject
+            assert status[k] != 0, f"stream {k}: the CPU codec rejects it, the GPU decoder accepted it"
 
 
 # ---- reference known-answer cases through the C ABI -----------------------------------------------------------
