@@ -10,8 +10,11 @@ throughput beside its algorithmic bytes:
              `coalesce.(a .> 50, false) .& coalesce.(b .< 0.5, false)`, materialize [a, b, c, d]
 
 Per query: rows/s through the public API (open table resident in HBM -> decode -> predicate -> gather -> host arrays),
-the device time of every phase (CUDA events inside the library), and a check of the result against the CPU oracle on a
-prefix of the table.  One JSON line per query.
+the device time of every phase (CUDA events inside the library), and a check of the WHOLE result against the CPU oracle:
+the oracle materializes the same plan over block ranges on every host thread and reduces each output column to a 64-bit
+content hash (oracle/dfdb_oracle.c: orc_materialize_hash_blocks); the GPU result is hashed the same way and must agree in
+row count and in every column hash (`--check prefix` restores the cheap bit-exact comparison on a leading row range).
+One JSON line per query.  bench.py imports run_config() for its `variants`.
 """
 import argparse
 import ctypes as C
@@ -95,33 +98,45 @@ def run_query(D, L, name, make_view, rows, reps, check):
             "device_ms": round(sum(ph[k]["ms"] for k in ph), 2),
             "decode_gbs": round(ph["decode"]["bytes"] / max(ph["decode"]["ms"], 1e-9) / 1e6, 1),
             "verified": check(v, fr)}
-    print(json.dumps(line), flush=True)
+    if not getattr(run_query, "quiet", False):
+        print(json.dumps(line), flush=True)
     return line
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, default=3, choices=[3, 4])
-    ap.add_argument("--rows", type=int, default=0)
-    ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--check-rows", type=int, default=2_000_000)
-    args = ap.parse_args()
+def frame_columns(D, np, fr):
+    """The result frame as the column list oracle.hash_columns takes."""
+    cols = []
+    for n in fr.names:
+        c = fr[n]
+        if isinstance(c, D.FlatStringsVector):
+            cols.append(("str", c.sizes, np.frombuffer(c.data, dtype=np.uint8) if not isinstance(c.data, np.ndarray) else c.data))
+        elif isinstance(c, np.ma.MaskedArray):
+            m = np.ma.getmaskarray(c)
+            cols.append((np.where(m, np.zeros((), dtype=c.dtype), c.data), m))
+        else:
+            cols.append(c)
+    return cols
+
+
+def run_config(config, rows=0, reps=3, check="full", check_rows=2_000_000, quiet=False):
+    """Runs the queries of BASELINE.json configs[2] (config=3) / configs[3] (config=4); returns the JSON-able lines."""
     import numpy as np
     import torch
     import dfdb_b200 as D
     from dfdb_b200 import R, _capi
     from oracle import oracle as O
 
-    cfg = CONFIGS[args.config]
-    rows = args.rows or cfg["rows"]
+    cfg = CONFIGS[config]
+    rows = rows or cfg["rows"]
     threads = os.cpu_count() or 1
     path, info = ensure_table(cfg, rows, threads)
-    torch.cuda.set_device(0)
-    _capi.init(0)
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    _capi.init(int(os.environ.get("LOCAL_RANK", "0")))
     L = _capi.lib()
-    t = D.open_table(path, mode=D.LOAD_HBM, device=0)
+    t = D.open_table(path, mode=D.LOAD_HBM, device=int(os.environ.get("LOCAL_RANK", "0")))
     ot = O.OracleTable(path)
-    nchk = min(rows, args.check_rows)
+    nchk = min(rows, check_rows)
+    nblocks = t.nblocks()
 
     def check_prefix(make_prefixed):
         """Same query behind a leading range stage 1:nchk, GPU against the CPU oracle (bit-exact)."""
@@ -138,24 +153,50 @@ def main():
                     ok &= bool(np.array_equal(np.ma.getmaskarray(g), em) and np.array_equal(g.data[~em], ev[~em]))
                 else:
                     ok &= bool(np.array_equal(g, e))
-            return {"ok": ok, "prefix_rows": nchk, "prefix_selected": got.nrow()}
+            return {"ok": ok, "kind": "prefix", "prefix_rows": nchk, "prefix_selected": got.nrow()}
         return chk
 
-    log(f"[cfg] config {args.config}: {rows} rows, {info['uncompressed'] / 1e9:.2f} GB decoded, {info['compressed'] / 1e9:.2f} GB compressed")
-    if args.config == 3:
-        run_query(D, L, 's .== "sony" -> materialize [s]', lambda: t[t.s == "sony", ["s"]], rows, args.reps,
-                  check_prefix(lambda: t[R(1, nchk), :][t.s == "sony", ["s"]]))
-        run_query(D, L, 'startswith.(s, "s") -> materialize [s, k]', lambda: t[D.startswith(t.s, "s"), ["s", "k"]], rows, args.reps,
-                  check_prefix(lambda: t[R(1, nchk), :][D.startswith(t.s, "s"), ["s", "k"]]))
+    def check_full(v, fr):
+        """Whole table: row count and a content hash of every output column, oracle (all host threads) against the GPU result."""
+        t0 = time.time()
+        exp, nexp = ot.materialize_hash_mt(D.plan_bytes(v), nblocks, threads, len(fr.names))
+        t1 = time.time()
+        got = O.hash_columns(frame_columns(D, np, fr), threads)
+        ok = nexp == fr.nrow() and [tuple(x) for x in exp] == [tuple(x) for x in got]
+        return {"ok": bool(ok), "kind": "full", "rows": rows, "selected_oracle": nexp, "selected_gpu": fr.nrow(),
+                "column_hashes": [f"{a:016x}" for a, _ in got], "oracle_s": round(t1 - t0, 1), "oracle_threads": threads}
+
+    def checker(make_prefixed):
+        return check_full if check == "full" else check_prefix(make_prefixed)
+
+    if not quiet:
+        log(f"[cfg] config {config}: {rows} rows, {info['uncompressed'] / 1e9:.2f} GB decoded, {info['compressed'] / 1e9:.2f} GB compressed")
+    lines = []
+    if config == 3:
+        lines.append(run_query(D, L, 's .== "sony" -> materialize [s]', lambda: t[t.s == "sony", ["s"]], rows, reps,
+                               checker(lambda: t[R(1, nchk), :][t.s == "sony", ["s"]])))
+        lines.append(run_query(D, L, 'startswith.(s, "s") -> materialize [s, k]', lambda: t[D.startswith(t.s, "s"), ["s", "k"]], rows, reps,
+                               checker(lambda: t[R(1, nchk), :][D.startswith(t.s, "s"), ["s", "k"]])))
     else:
-        pred = lambda: D.coalesce(t.ma > 50, False) & D.coalesce(t.mb < 0.5, False)   # noqa: E731
         names = [m.name for m in t.meta]
         a, b = names[0], names[1]
         pred = lambda: D.coalesce(getattr(t, a) > 50, False) & D.coalesce(getattr(t, b) < 0.5, False)   # noqa: E731
-        run_query(D, L, "coalesce.(a .> 50, false) .& coalesce.(b .< 0.5, false) -> materialize [a, b, c, d]",
-                  lambda: t[pred(), names], rows, args.reps, check_prefix(lambda: t[R(1, nchk), :][pred(), names]))
+        lines.append(run_query(D, L, "coalesce.(a .> 50, false) .& coalesce.(b .< 0.5, false) -> materialize [a, b, c, d]",
+                               lambda: t[pred(), names], rows, reps, checker(lambda: t[R(1, nchk), :][pred(), names])))
     t.close()
     ot.close()
+    return lines
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4])
+    ap.add_argument("--rows", type=int, default=0)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--check", default="full", choices=["full", "prefix"])
+    ap.add_argument("--check-rows", type=int, default=2_000_000)
+    args = ap.parse_args()
+    run_config(args.config, args.rows, args.reps, args.check, args.check_rows)
     return 0
 
 

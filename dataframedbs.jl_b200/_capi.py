@@ -1,6 +1,6 @@
 """ctypes binding of libdfdb_b200.so (include/dfdb_b200.h).
 
-This is the Python twin of the `ccall` methods in julia/DataFrameDBsB200.jl / INTEGRATION.md.  There is
+This is the Python twin of the `ccall` methods in julia/b200.jl / INTEGRATION.md.  There is
 no CPU fallback: if the CUDA library is missing or no B200 is usable, every scan raises.
 """
 from __future__ import annotations

@@ -51,6 +51,8 @@ struct Runtime {
     int64_t lz4_flavour = 0;  // K1 flavour: 0 = per column from a token sample at load, 1 = word-regular decoder (v2), 2 = general decoder (v3), 3 = lane-per-block decoder
     int64_t no_overlap = 0;   // do not run the scan of the decoded part of a shard beside the decode of its last part
     int64_t no_alias = 0;     // copy stored (incompressible) blocks like any other block instead of referencing them in place
+    int64_t no_validate = 0;  // skip the acceptance pass of dfdb_table_load (A/B, load-time measurements)
+    int64_t lane_hot = -1;    // lane decoder: -1 = hot-step schedule per column from the token sample, 0 / 1 = force off / on (A/B, tests)
     // profiling
     bool profiling = false;
     std::vector<PhaseRec> recs;
@@ -229,7 +231,7 @@ void column_release(Column &c)
     if (c.h_comp) cudaFreeHost(c.h_comp);
     cudaFree(c.d_comp); cudaFree(c.d_decoded); cudaFree(c.d_comp_off); cudaFree(c.d_comp_len); cudaFree(c.d_dec_off);
     cudaFree(c.d_origin); cudaFree(c.d_status); cudaFree(c.d_str_off); cudaFree(c.d_skip);
-    c.d_skip = nullptr; c.h_skip.clear(); c.stored_blocks = 0;
+    c.d_skip = nullptr; c.h_skip.clear(); c.h_corrupt.clear(); c.stored_blocks = 0;
     c.h_comp = nullptr; c.d_comp = nullptr; c.d_decoded = nullptr; c.d_comp_off = nullptr; c.d_comp_len = nullptr;
     c.d_dec_off = nullptr; c.d_origin = nullptr; c.d_status = nullptr; c.d_str_off = nullptr;
     c.loaded = false; c.decoded_valid = false; c.dec_lo = c.dec_hi = 0; c.dec_live_gen = 0; c.str_off_valid = false;
@@ -285,7 +287,12 @@ int launch_decode(const DecodeArgs &a, bool general, cudaStream_t stream = nullp
     if (!stream) stream = rt.stream;
     unsigned int *counter = rt.d_counter + 4 * counter_slot;   // launches that may run at the same time need their own job counter
     if (rt.lz4_simple || rt.lz4_v1) return launch_lz4_decode(a, counter, rt.sm_count, (int)rt.lz4_simple, stream);
-    if (rt.lz4_flavour == 3) return launch_lz4_decode_lane(a, nullptr, counter, rt.sm_count, stream, cta_limit);
+    if (rt.lz4_flavour == 3) {
+        DecodeArgs la = a;
+        la.hot = general ? 0 : 1;      // word-regular columns (the token sample at load) run the hot-step schedule
+        if (rt.lane_hot >= 0) la.hot = (int)rt.lane_hot;
+        return launch_lz4_decode_lane(la, nullptr, counter, rt.sm_count, stream, cta_limit);
+    }
     if (rt.lz4_flavour == 1) general = false;
     if (rt.lz4_flavour == 2) general = true;
     return general ? launch_lz4_decode_v3(a, counter, rt.sm_count, stream, cta_limit) : launch_lz4_decode_v2(a, counter, rt.sm_count, stream, cta_limit);
@@ -422,7 +429,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
     }
     // ---- decode / scan overlap (compressed blocks resident, one flavour, more than one round of blocks) ----
     bool parted = false;
-    if (on_part && host_bytes == 0 && !rt.no_overlap && !rt.lz4_simple && !rt.lz4_v1 && todo.size() <= (size_t)DECODE_MAX_COLS) {
+    if (on_part && host_bytes == 0 && !rt.no_overlap && !rt.lz4_simple && !rt.lz4_v1 && rt.lz4_flavour != 3 && todo.size() <= (size_t)DECODE_MAX_COLS) {
         bool one_flavour = true;
         for (Column *c : todo) one_flavour = one_flavour && c->lz4_general == todo[0]->lz4_general;
         const int64_t wave = (int64_t)rt.sm_count * LZ4_SLOTS_PER_SM;
@@ -531,10 +538,13 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
     for (Column *c : todo) {
         CUDA_TRY(cudaMemcpyAsync(st.data(), c->d_status, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, rt.stream));
         CUDA_TRY(cudaStreamSynchronize(rt.stream));
-        for (int b = wlo; b < whi; b++)
-            if (st[(size_t)b] != 0)
+        for (int b = wlo; b < whi; b++) {
+            // a block the decoder was told to skip (no selected row: skip_cols seeks over it) is not decompressed, hence not judged
+            const int32_t verdict = st[(size_t)b] != 0 ? st[(size_t)b] : (!c->h_corrupt.empty() && !h_skip_of(c)[(size_t)b] ? c->h_corrupt[(size_t)b] : 0);
+            if (verdict != 0)
                 return fail(DFDB_ERR_CORRUPT, "decompression error in column %s block %lld (code %d)", c->name.c_str(),
-                            (long long)(t->blk_lo + b), st[(size_t)b]);
+                            (long long)(t->blk_lo + b), verdict);
+        }
         // (a decode that skipped blocks without selected rows leaves nothing another scan could rely on)
         c->dec_lo = filtered ? 0 : wlo;
         c->dec_hi = filtered ? 0 : whi;
@@ -1130,6 +1140,8 @@ int32_t dfdb_set_option(const char *name, int64_t value)
     else if (n == "lz4_flavour") rt.lz4_flavour = value;
     else if (n == "no_overlap") rt.no_overlap = value;
     else if (n == "no_alias") rt.no_alias = value;
+    else if (n == "lane_hot") rt.lane_hot = value;
+    else if (n == "no_validate") rt.no_validate = value;
     else if (n == "host_arena_cap_mb") { std::lock_guard<std::mutex> lk(arena.mu); arena.cap_bytes = (size_t)std::max<int64_t>(value, 0) << 20; arena.trim(arena.cap_bytes); }
     else return fail(DFDB_ERR_ARGUMENT, "unknown option %s", n.c_str());
     return DFDB_OK;
@@ -1347,8 +1359,29 @@ int32_t dfdb_table_load(dfdb_table *t, const int64_t *col_ids, int32_t n, int32_
         if ((rc = dev_upload(&c->d_dec_off, dec_off))) return rc;
         if (c->type.kind == DFDB_STRING)
             CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&c->d_str_off), (size_t)std::max<int64_t>(nb, 1) * (size_t)t->block_size * 4));
+        CUDA_TRY(cudaMemcpy(c->d_comp, c->h_comp, c->comp_bytes, cudaMemcpyHostToDevice));
+        // Acceptance.  The reference asserts the result of LZ4_decompress_safe for every block it reads (BlockStreams.jl:110-112);
+        // the walker / consumer decoders are memory-safe but do not enforce liblz4's end-of-block rules, so the verdict for every
+        // block is taken once, here, from the lane-per-block decoder (lz4_decode_lane.cu), which implements those rules exactly
+        // (tests: identical accept / reject with the CPU codec on fuzzed streams).  Scans consult it in their integrity gate.
+        c->h_corrupt.clear();
+        if (!rt.no_validate && nb > 0) {
+            DecodeArgs va;
+            memset(&va, 0, sizeof va);
+            va.ncols = 1;
+            va.nblocks = (int)nb;
+            va.hot = c->lz4_general ? 0 : 1;
+            va.col[0] = DecodeCol{c->d_comp, c->d_comp_off, c->d_comp_len, c->d_dec_off, c->d_origin, c->d_decoded, c->d_status, c->d_skip};
+            LAUNCH(launch_lz4_decode_lane(va, nullptr, rt.d_counter, rt.sm_count, rt.stream));
+            c->h_corrupt.assign((size_t)nb, 0);
+            CUDA_TRY(cudaMemcpyAsync(c->h_corrupt.data(), c->d_status, (size_t)nb * 4, cudaMemcpyDeviceToHost, rt.stream));
+            CUDA_TRY(cudaMemsetAsync(c->d_status, 0, (size_t)nb * 4, rt.stream));
+            CUDA_TRY(cudaStreamSynchronize(rt.stream));
+            // (blocks beyond the lane decoder's 32 MB position range are not judged here; the walker decoders' own checks apply)
+            for (int64_t b = 0; b < nb; b++)
+                if (origin[(size_t)b] >= (1 << 25) || comp_len[(size_t)b] >= (1 << 25)) c->h_corrupt[(size_t)b] = 0;
+        }
         if (mode != DFDB_LOAD_HOST) {
-            CUDA_TRY(cudaMemcpy(c->d_comp, c->h_comp, c->comp_bytes, cudaMemcpyHostToDevice));
             cudaFreeHost(c->h_comp);
             c->h_comp = nullptr;
         }
@@ -2049,6 +2082,16 @@ int32_t dfdb_lz4_decode_blocks(const uint8_t *comp, const int64_t *comp_off, con
     a.ncols = 1;
     a.nblocks = n;
     a.col[0] = DecodeCol{d_comp, d_coff, d_clen, d_doff, d_orig, d_out, d_status, nullptr};
+    // acceptance first (the lane-per-block decoder: LZ4_decompress_safe's rules exactly), then the flavour under test decodes
+    std::vector<int32_t> verdict((size_t)n, 0);
+    if (rt.lz4_flavour != 3 && !rt.no_validate) {
+        DecodeArgs va = a;
+        if (launch_lz4_decode_lane(va, nullptr, rt.d_counter, rt.sm_count, rt.stream) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "decode launch failed"); }
+        rt.launches++;
+        cudaMemcpyAsync(verdict.data(), d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, rt.stream);
+        cudaMemsetAsync(d_status, 0xff, (size_t)n * 4, rt.stream);
+        cudaStreamSynchronize(rt.stream);
+    }
     if (launch_decode(a, true) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "decode launch failed"); }
     rt.launches++;
     std::vector<uint8_t> hout((size_t)dpos + 256);
@@ -2058,7 +2101,7 @@ int32_t dfdb_lz4_decode_blocks(const uint8_t *comp, const int64_t *comp_off, con
     cleanup();
     if (e != cudaSuccess) return fail(DFDB_ERR_CUDA, "decode failed: %s", cudaGetErrorString(e));
     for (int i = 0; i < n; i++) {
-        if (status[i] == 0) memcpy(out + out_off[i], hout.data() + doff[(size_t)i], (size_t)origin[i]);
+        if (status[i] == 0 && verdict[(size_t)i] == 0) memcpy(out + out_off[i], hout.data() + doff[(size_t)i], (size_t)origin[i]);
         else status[i] = DFDB_ERR_CORRUPT;
     }
     return DFDB_OK;

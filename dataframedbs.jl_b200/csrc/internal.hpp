@@ -65,6 +65,7 @@ struct Column {
     int32_t *d_status = nullptr;     // decode status per block
     uint8_t *d_skip = nullptr;       // 1 = stored block (one literal run): its body is referenced in place inside d_comp
     std::vector<uint8_t> h_skip;
+    std::vector<int32_t> h_corrupt;  // per local block: LZ4_decompress_safe's verdict (0 = accepted), decided once at load by the lane-per-block decoder
     int64_t stored_blocks = 0;
     bool lz4_general = false;        // K1 flavour: general decoder (v3) instead of the word-regular one (v2), decided at load
     int32_t *d_str_off = nullptr;    // String columns: per-row char offset inside the block's char area

@@ -24,6 +24,7 @@ struct DecodeArgs {
     int nblocks;   // blocks per column in this launch
     int blk0;      // first local block of the launch (chunked, copy-overlapped decode)
     unsigned long long *stats;   // optional diagnostics counters (null = off), see lz4_decode_v2.cu
+    int hot;       // lane decoder: the columns are word-regular (nearly every token is 0x04 with an offset that is a multiple of 8): hot-step schedule
 };
 int launch_lz4_decode(const DecodeArgs &args, unsigned int *d_counter, int sm_count, int simple_mode, cudaStream_t stream);      // v1: warp per block
 constexpr int LZ4_SLOTS_PER_SM = 60;   // column blocks one decoder CTA keeps in flight (NSLOT of both walker/consumer flavours)

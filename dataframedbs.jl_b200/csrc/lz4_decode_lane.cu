@@ -53,7 +53,8 @@ constexpr unsigned FULL = 0xffffffffu;
 struct LaneSmem {
     __align__(16) uint8_t win[LANE_THREADS][WIN_BYTES];
     uint64_t ring[LANE_THREADS][RING_STRIDE];
-    uint64_t qd[LANE_WARPS][DEPTH][32];   // piece queue: the data bytes of K_DATA pieces (literals, far sources)
+    uint64_t qd[LANE_WARPS][SUBS * DEPTH][32];   // piece queue: the data bytes of K_DATA / K_WORDQ pieces and the literal bytes of K_WORD pieces
+    uint32_t qm[LANE_WARPS][SUBS * DEPTH][32];   // piece queue: the descriptors
     // per-warp mailboxes of the cooperative rounds (owner lane writes, the 8 serving lanes read)
     uint64_t fl_addr[LANE_WARPS][32];     // global address of the unit to flush (0 = none)
     uint64_t fl_aux[LANE_WARPS][32];      // fused: global address of the aggregated column's values for the same rows (0 = not a predicate block)
@@ -71,6 +72,13 @@ __device__ __forceinline__ uint64_t lds64(uint32_t sa)
     return v;
 }
 __device__ __forceinline__ void sts64(uint32_t sa, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(sa), "l"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t sa)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t sa, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(v) : "memory"); }
 __device__ __forceinline__ void cp_async16(uint32_t dst_sa, const void *src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_sa), "l"(src) : "memory");
@@ -227,9 +235,9 @@ __global__ void __launch_bounds__(LANE_THREADS, 1) lz4_decode_lane_kernel(const 
     P.reset(0, 0);
     P.st = PS_IDLE;
     E.reset();
-    uint32_t desc[DEPTH];                  // the queue's descriptors: desc[0] is the piece parsed DEPTH steps ago
+    const uint32_t qm_sa = smem_u32(&S.qm[warp][0][lane]);
 #pragma unroll
-    for (int u = 0; u < DEPTH; u++) desc[u] = K_NONE;
+    for (int u = 0; u < SUBS * DEPTH; u++) sts32(qm_sa + u * 128u, K_NONE);
 
     const uint8_t *comp = nullptr;
     int32_t *status = nullptr;
@@ -295,6 +303,7 @@ __global__ void __launch_bounds__(LANE_THREADS, 1) lz4_decode_lane_kernel(const 
     }
 
     const int grp = lane >> 3, pc = lane & 7;
+    const bool hot = A.hot != 0;
     const uint32_t ring_warp_sa = smem_u32(&S.ring[warp * 32][0]);
     const uint32_t win_warp_sa = smem_u32(&S.win[warp * 32][0]);
 
@@ -329,14 +338,34 @@ __global__ void __launch_bounds__(LANE_THREADS, 1) lz4_decode_lane_kernel(const 
             }
         }
         // ---- ROUND steps of the two-stage pipeline ----
+        //      Each step emits the two pieces parsed DEPTH steps ago and parses two new ones into the same queue slots.  Word pieces
+        //      take the straight-line fast path, lane by lane; the general step runs only when some lane of the warp needs it.
 #pragma unroll 1
         for (uint32_t v = 0; v < (uint32_t)ROUND; v++) {
-            const uint32_t slot = v & (uint32_t)(DEPTH - 1);
-            cp_async_wait<DEPTH - 1>();            // the far source fetched when desc[0] was parsed has landed
-            E.step(mem, desc[0], slot);
-#pragma unroll
-            for (int u = 0; u + 1 < DEPTH; u++) desc[u] = desc[u + 1];
-            desc[DEPTH - 1] = P.step(mem, E.flushed, slot);
+            const uint32_t slotA = (uint32_t)SUBS * (v & (uint32_t)(DEPTH - 1)), slotB = slotA + 1;
+            cp_async_wait<DEPTH - 1>();            // the far sources fetched when these two pieces were parsed have landed
+            const uint32_t mA = lds32(qm_sa + slotA * 128u), mB = lds32(qm_sa + slotB * 128u);
+            if (hot && (v & (uint32_t)(HOT_PERIOD - 1)) != (uint32_t)(HOT_PERIOD - 1)) {
+                // hot step (word-regular columns): two plain tokens per lane or nothing; a lane that meets anything else waits for the next full step
+                uint32_t nA, nB;
+                E.fast2(mem, mA, mB, slotA, slotB);
+                P.fast2(mem, E.flushed, slotA, slotB, nA, nB);
+                sts32(qm_sa + slotA * 128u, nA);
+                sts32(qm_sa + slotB * 128u, nB);
+                cp_async_commit();
+                continue;
+            }
+            const bool eA = E.fast(mem, mA, slotA);
+            if (__any_sync(FULL, !eA)) { if (!eA) E.step(mem, mA, slotA); }
+            const bool eB = E.fast(mem, mB, slotB);
+            if (__any_sync(FULL, !eB)) { if (!eB) E.step(mem, mB, slotB); }
+            uint32_t nA = K_NONE, nB = K_NONE;
+            const bool pA = P.fast(mem, E.flushed, slotA, nA);
+            if (__any_sync(FULL, !pA)) { if (!pA) nA = P.step(mem, E.flushed, slotA); }
+            const bool pB = P.fast(mem, E.flushed, slotB, nB);
+            if (__any_sync(FULL, !pB)) { if (!pB) nB = P.step(mem, E.flushed, slotB); }
+            sts32(qm_sa + slotA * 128u, nA);
+            sts32(qm_sa + slotB * 128u, nB);
             cp_async_commit();
         }
         const bool fin = active && (P.st == PS_ERR || (P.st == PS_END && E.op == P.opp));
@@ -410,7 +439,7 @@ __global__ void __launch_bounds__(LANE_THREADS, 1) lz4_decode_lane_kernel(const 
             active = false;
             P.st = PS_IDLE;
 #pragma unroll
-            for (int u = 0; u < DEPTH; u++) desc[u] = K_NONE;   // (pieces of a block that failed are dropped)
+            for (int u = 0; u < SUBS * DEPTH; u++) sts32(qm_sa + u * 128u, K_NONE);   // (pieces of a block that failed are dropped)
         }
         if (!active && !exhausted) pickup();
     }

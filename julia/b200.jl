@@ -268,9 +268,10 @@ maximum(c::DFColumn) = _extreme(c, a -> a.max_i64, a -> a.max_f64)
 end # module B200
 
 # ---- the hooks: methods of the package's own generic functions (this file is part of the package) --------------------------
-# Each consumer asks whether the view's table lives on the GPU; otherwise the reference's own method body runs (the patch
-# in INTEGRATION.md renames it `_cpu`).
-Base.length(c::DFColumn) = B200.enabled(c.view.table) ? B200.nrow(c.view) : _length_cpu(c)
+# nrow(::DFView) and materialize(::DFView) get their one-line hooks from the patch in INTEGRATION.md; length / size of a
+# DFColumn go through nrow (column.jl:46-52) and need nothing.  The reductions do not exist in the reference at all (they are
+# Base's generic folds over iterate(::DFColumn), column.jl:102-126), so these methods are new, not overwritten; off the GPU
+# they fall through to the same generic fold.
 Base.sum(c::DFColumn) = B200.enabled(c.view.table) ? B200.sum(c) : invoke(Base.sum, Tuple{Any}, c)
 Base.minimum(c::DFColumn) = B200.enabled(c.view.table) ? B200.minimum(c) : invoke(Base.minimum, Tuple{Any}, c)
 Base.maximum(c::DFColumn) = B200.enabled(c.view.table) ? B200.maximum(c) : invoke(Base.maximum, Tuple{Any}, c)

@@ -1306,8 +1306,9 @@ static int append_val(orc_col *c, val_t *v, int64_t n)
     return ORC_OK;
 }
 
-/* materialize(v::DFView): materialization.jl:27-40 (pass 1 = nrow for sizehint!, pass 2 = append!) */
-ORC_API int orc_materialize(orc_table *tbl, const uint8_t *plan_bytes, int64_t plan_len, orc_mat **out)
+/* materialize(v::DFView): materialization.jl:27-40 (pass 1 = nrow for sizehint!, pass 2 = append!);
+ * blk_hi >= 0: only blocks [blk_lo, blk_hi) (row-local plans only) -- the thread-per-range driver of the full-size checks */
+static int materialize_impl(orc_table *tbl, const uint8_t *plan_bytes, int64_t plan_len, int64_t blk_lo, int64_t blk_hi, orc_mat **out)
 {
     plan_t plan;
     int rc = plan_parse(plan_bytes, plan_len, &plan);
@@ -1325,6 +1326,14 @@ ORC_API int orc_materialize(orc_table *tbl, const uint8_t *plan_bytes, int64_t p
     blkiter *it = malloc(sizeof *it);
     rc = iter_open(it, tbl, &plan, 0);
     if (rc) { free(it); orc_mat_free(m); plan_free(&plan); return rc; }
+    if (blk_hi >= 0) {
+        for (uint32_t i = 0; i < plan.nstages && !rc; i++) if (plan.stages[i].kind != ST_PRED) rc = fail(ORC_ERR_UNSUPPORTED, "block ranges need a predicate-only selection");
+        for (int64_t b = 0; b < blk_lo && !rc; b++)
+            for (int i = 0; i < it->nreq && !rc; i++) { bsizes z; if (bs_eof(&it->streams[i])) break; rc = skip_block(&it->streams[i], &z); }
+        if (rc) { iter_close(it); free(it); orc_mat_free(m); plan_free(&plan); return rc; }
+        it->next_block = blk_lo;
+        it->blk_hi = blk_hi;
+    }
     int st;
     while ((st = iter_next(it)) == 1) {
         blockdata bd = { tbl, it->nreq, it->req, it->bufs };
@@ -1342,6 +1351,75 @@ ORC_API int orc_materialize(orc_table *tbl, const uint8_t *plan_bytes, int64_t p
     if (!rc && st < 0) rc = -st;
     if (rc) { orc_mat_free(m); return rc; }
     *out = m;
+    return ORC_OK;
+}
+
+ORC_API int orc_materialize(orc_table *tbl, const uint8_t *plan_bytes, int64_t plan_len, orc_mat **out)
+{
+    return materialize_impl(tbl, plan_bytes, plan_len, 0, -1, out);
+}
+
+/* ---- content hash of a materialized result, composable over row ranges -------------------------------------------
+ * Full-size checks (1e8..1e9 rows) cannot hold both results side by side, so the oracle and the checked result are
+ * each reduced to two 64-bit sums per column,  A = sum_i mix(row_i) * (2 i + 1),  B = sum_i mix(row_i)  (mod 2^64),
+ * i = position in the result.  A range hashed with local positions re-bases with  A + 2 * base * B,  so a
+ * thread-per-block-range driver needs one pass.  mix(row) covers the value bits (0 under a missing flag, as
+ * src/common/missings.jl:1 leaves them unspecified), the missing flag, and for strings the size and every byte. */
+static inline uint64_t mix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+ORC_API void orc_hash_fixed(const uint8_t *values, const uint8_t *missing, int elsize, int64_t n, int64_t base, uint64_t *A, uint64_t *B)
+{
+    uint64_t a = 0, b = 0;
+    for (int64_t i = 0; i < n; i++) {
+        uint64_t v = 0;
+        const int miss = missing ? missing[i] != 0 : 0;
+        if (!miss) memcpy(&v, values + i * elsize, (size_t)(elsize > 8 ? 8 : elsize));
+        if (!miss && elsize > 8) { uint64_t hi = 0; memcpy(&hi, values + i * elsize + 8, (size_t)(elsize - 8 > 8 ? 8 : elsize - 8)); v ^= mix64(hi); }
+        const uint64_t h = mix64(v ^ (miss ? 0xA5A5A5A5A5A5A5A5ull : 0));
+        a += h * (2 * (uint64_t)(base + i) + 1);
+        b += h;
+    }
+    *A = a; *B = b;
+}
+
+/* `chars` points at the first byte of row 0 of this range */
+ORC_API void orc_hash_strings(const int32_t *sizes, const uint8_t *chars, int64_t n, int64_t base, uint64_t *A, uint64_t *B)
+{
+    uint64_t a = 0, b = 0;
+    const uint8_t *p = chars;
+    for (int64_t i = 0; i < n; i++) {
+        uint64_t f = 0xCBF29CE484222325ull;
+        const int32_t sz = sizes[i];
+        for (int32_t k = 0; k < sz; k++) f = (f ^ p[k]) * 0x100000001B3ull;
+        if (sz > 0) p += sz;
+        const uint64_t h = mix64(f ^ ((uint64_t)(uint32_t)sz << 32));
+        a += h * (2 * (uint64_t)(base + i) + 1);
+        b += h;
+    }
+    *A = a; *B = b;
+}
+
+/* hashes of the rows that blocks [blk_lo, blk_hi) contribute to materialize(plan), positions local to the range */
+ORC_API int orc_materialize_hash_blocks(orc_table *tbl, const uint8_t *plan_bytes, int64_t plan_len, int64_t blk_lo, int64_t blk_hi,
+                                        uint64_t *A, uint64_t *B, int64_t *nrows, int32_t cap_cols)
+{
+    orc_mat *m = NULL;
+    int rc = materialize_impl(tbl, plan_bytes, plan_len, blk_lo, blk_hi, &m);
+    if (rc) return rc;
+    if (m->ncols > cap_cols) { orc_mat_free(m); return fail(ORC_ERR_ARGUMENT, "hash buffers too small"); }
+    *nrows = m->ncols ? m->cols[0].nrows : 0;
+    for (int i = 0; i < m->ncols; i++) {
+        orc_col *c = &m->cols[i];
+        if (c->kind == K_STRING) orc_hash_strings(c->sizes, c->chars, c->nrows, 0, &A[i], &B[i]);
+        else orc_hash_fixed(c->values, c->nullable ? c->missing : NULL, c->elsize, c->nrows, 0, &A[i], &B[i]);
+    }
+    orc_mat_free(m);
     return ORC_OK;
 }
 

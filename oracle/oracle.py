@@ -79,6 +79,12 @@ def lib():
         L.orc_mat_col.restype = C.POINTER(_Col)
         L.orc_aggregate.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.POINTER(Agg)]
         L.orc_aggregate_blocks.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.POINTER(Agg)]
+        L.orc_materialize_hash_blocks.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_uint64),
+                                                  C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.c_int32]
+        L.orc_hash_fixed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.orc_hash_fixed.restype = None
+        L.orc_hash_strings.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.orc_hash_strings.restype = None
         L.orc_decode_block.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]
         L.orc_decode_block.restype = C.c_int64
         L.orc_parse_type.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -316,6 +322,27 @@ class OracleTable:
         _check(lib().orc_aggregate_blocks(self._h, plan, len(plan), proj_idx, blk_lo, blk_hi, C.byref(a)))
         return a
 
+    def materialize_hash_mt(self, plan: bytes, nblocks: int, nthreads: int, ncols: int):
+        """Content hash per column of materialize(plan) over the whole table without holding the result: every thread
+        materializes one block range, hashes it with range-local positions and frees it; the ranges are re-based in block
+        order (A + 2 * base * B).  Returns ([(A, B)] per column, selected rows).  Predicate-only plans."""
+        nthreads = max(1, min(nthreads, nblocks))
+        bounds = [(nblocks * i) // nthreads for i in range(nthreads + 1)]
+
+        def job(k):
+            A, B, n = (C.c_uint64 * ncols)(), (C.c_uint64 * ncols)(), C.c_int64()
+            _check(lib().orc_materialize_hash_blocks(self._h, plan, len(plan), bounds[k], bounds[k + 1], A, B, C.byref(n), ncols))
+            return list(A), list(B), n.value
+        with ThreadPoolExecutor(nthreads) as ex:
+            parts = list(ex.map(job, range(nthreads)))
+        out, base = [[0, 0] for _ in range(ncols)], 0
+        for A, B, n in parts:
+            for c in range(ncols):
+                out[c][0] = (out[c][0] + A[c] + 2 * base * B[c]) & _M64
+                out[c][1] = (out[c][1] + B[c]) & _M64
+            base += n
+        return [tuple(x) for x in out], base
+
     def aggregate_mt(self, plan: bytes, proj_idx: int, nblocks: int, nthreads: int, blk_lo: int = 0):
         """Thread-per-block-range driver over the single-threaded oracle (predicate-only plans).
         Returns the list of per-range partials in block order."""
@@ -324,6 +351,50 @@ class OracleTable:
         with ThreadPoolExecutor(nthreads) as ex:
             futs = [ex.submit(self.aggregate_blocks, plan, proj_idx, bounds[i], bounds[i + 1]) for i in range(nthreads)]
             return [f.result() for f in futs]
+
+
+_M64 = (1 << 64) - 1
+
+
+def hash_columns(cols, nthreads: int = 1):
+    """(A, B) content hash per column of a materialized result (see orc_hash_fixed in dfdb_oracle.c): `cols` is a list of
+    numpy arrays (fixed width), (values, missing) pairs (nullable; missing = bool / uint8 per row) or (sizes, chars)
+    pairs with sizes.dtype == int32 (strings).  Chunks are hashed on `nthreads` threads and re-based."""
+    L = lib()
+    out = []
+    for col in cols:
+        if isinstance(col, tuple) and len(col) == 3 and col[0] == "str":
+            _, sizes, chars = col
+            sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+            chars = np.ascontiguousarray(np.frombuffer(chars, dtype=np.uint8) if isinstance(chars, (bytes, bytearray, memoryview)) else chars, dtype=np.uint8)
+            n = len(sizes)
+            bounds = [n * i // nthreads for i in range(nthreads + 1)]
+            coff = np.concatenate([[0], np.cumsum(np.maximum(sizes, 0), dtype=np.int64)]) if n else np.zeros(1, np.int64)
+
+            def job(k, sizes=sizes, chars=chars, coff=coff, bounds=bounds):
+                a, b = C.c_uint64(), C.c_uint64()
+                lo, hi = bounds[k], bounds[k + 1]
+                L.orc_hash_strings(sizes.ctypes.data + 4 * lo, chars.ctypes.data + int(coff[lo]), hi - lo, lo, C.byref(a), C.byref(b))
+                return a.value, b.value
+        else:
+            if isinstance(col, tuple):
+                vals, miss = col
+                miss = np.ascontiguousarray(miss, dtype=np.uint8)
+            else:
+                vals, miss = col, None
+            vals = np.ascontiguousarray(vals)
+            n, es = len(vals), vals.dtype.itemsize
+            bounds = [n * i // nthreads for i in range(nthreads + 1)]
+
+            def job(k, vals=vals, miss=miss, es=es, bounds=bounds):
+                a, b = C.c_uint64(), C.c_uint64()
+                lo, hi = bounds[k], bounds[k + 1]
+                L.orc_hash_fixed(vals.ctypes.data + es * lo, (miss.ctypes.data + lo) if miss is not None else None, es, hi - lo, lo, C.byref(a), C.byref(b))
+                return a.value, b.value
+        with ThreadPoolExecutor(max(1, nthreads)) as ex:
+            parts = list(ex.map(job, range(nthreads)))
+        out.append((sum(p[0] for p in parts) & _M64, sum(p[1] for p in parts) & _M64))
+    return out
 
 
 def decode_block(framed: bytes, cap: int):

@@ -16,7 +16,7 @@ namespace {
 struct HostMem {
     uint64_t win[WIN_BYTES / 8];
     uint64_t ring[RING_WORDS];
-    uint64_t qd[DEPTH];
+    uint64_t qd[SUBS * DEPTH];
     const uint8_t *out;
     uint32_t flushed;
     long far_loads = 0, far_bad = 0;
@@ -37,8 +37,9 @@ struct HostMem {
 };
 }  // namespace
 
+// hot_period: 1 = every step is a full step (general columns); HOT_PERIOD = the schedule of word-regular columns
 extern "C" __attribute__((visibility("default")))
-int lane_sim_decode(const uint8_t *comp, int comp_len, uint8_t *out, int origin, long *stats)
+int lane_sim_decode2(const uint8_t *comp, int comp_len, uint8_t *out, int origin, long *stats, int hot_period)
 {
     if (origin == 0) return (comp_len == 1 && comp[0] == 0) ? 0 : E_SIZE;
     if (comp_len <= 0) return E_TRUNCATED;
@@ -56,8 +57,9 @@ int lane_sim_decode(const uint8_t *comp, int comp_len, uint8_t *out, int origin,
     Emitter E;
     P.reset((uint32_t)comp_len, (uint32_t)origin);
     E.reset();
-    uint32_t desc[DEPTH];
+    uint32_t desc[SUBS * DEPTH];
     for (auto &d : desc) d = K_NONE;
+    long fast_p = 0, fast_e = 0;
     uint32_t win_req = 0;
     long rounds = 0, pieces = 0, stalls = 0;
     int status = -1;
@@ -73,12 +75,27 @@ int lane_sim_decode(const uint8_t *comp, int comp_len, uint8_t *out, int origin,
             win_req += 16 * m;
         }
         for (int v = 0; v < ROUND; v++) {
-            const int u = v % DEPTH;
-            E.step(mem, desc[u], (uint32_t)u);
-            desc[u] = P.step(mem, E.flushed, (uint32_t)u);
-            if (piece_kind(desc[u]) != K_NONE) pieces++; else if (!P.finished()) stalls++;
+            const uint32_t uA = (uint32_t)(SUBS * (v % DEPTH)), uB = uA + 1;
+            if (hot_period > 1 && (v % hot_period) != hot_period - 1) {
+                // hot step: two plain tokens or nothing
+                E.fast2(mem, desc[uA], desc[uB], uA, uB);
+                if (P.fast2(mem, E.flushed, uA, uB, desc[uA], desc[uB])) { fast_p += 2; pieces += 2; } else if (!P.finished()) stalls += 2;
+                continue;
+            }
+            // full step, two pieces: sub-slots A and B of queue position v % DEPTH; the word fast path first, the general step otherwise
+            for (int sub = 0; sub < SUBS; sub++) {
+                const uint32_t u = (uint32_t)(SUBS * (v % DEPTH) + sub);
+                if (E.fast(mem, desc[u], u)) fast_e++; else E.step(mem, desc[u], u);
+            }
+            for (int sub = 0; sub < SUBS; sub++) {
+                const uint32_t u = (uint32_t)(SUBS * (v % DEPTH) + sub);
+                uint32_t m = K_NONE;
+                if (P.fast(mem, E.flushed, u, m)) fast_p++; else m = P.step(mem, E.flushed, u);
+                desc[u] = m;
+                if (piece_kind(m) != K_NONE) pieces++; else if (!P.finished()) stalls++;
+            }
         }
-        while (E.unit_ready()) {
+        for (int k = 0; k < SUBS && E.unit_ready(); k++) {   // the kernel flushes at most SUBS units per lane and round
             const uint32_t s = E.flush_slot();
             memcpy(obuf.data() + E.flushed, &mem.ring[s], UNIT_BYTES);
             E.flushed += UNIT_BYTES;
@@ -98,6 +115,12 @@ int lane_sim_decode(const uint8_t *comp, int comp_len, uint8_t *out, int origin,
     }
     if (status == E_OK) memcpy(out, obuf.data(), (size_t)origin);
     if (mem.far_bad) status = 100;
-    if (stats) { stats[0] = rounds; stats[1] = pieces; stats[2] = stalls; stats[3] = mem.far_loads; }
+    if (stats) { stats[0] = rounds; stats[1] = pieces; stats[2] = stalls; stats[3] = mem.far_loads; stats[4] = fast_p; stats[5] = fast_e; }
     return status;
+}
+
+extern "C" __attribute__((visibility("default")))
+int lane_sim_decode(const uint8_t *comp, int comp_len, uint8_t *out, int origin, long *stats)
+{
+    return lane_sim_decode2(comp, comp_len, out, origin, stats, 1);
 }

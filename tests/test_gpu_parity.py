@@ -77,17 +77,21 @@ def _set_variant(variant):
     L.dfdb_set_option(b"lz4_simple", 0)
     L.dfdb_set_option(b"lz4_v1", 0)
     L.dfdb_set_option(b"lz4_flavour", 0)
+    L.dfdb_set_option(b"lane_hot", -1)
     if variant == "v2":
         _capi.check(L.dfdb_set_option(b"lz4_flavour", 1))
     elif variant == "v3":
         _capi.check(L.dfdb_set_option(b"lz4_flavour", 2))
     elif variant == "lane":
         _capi.check(L.dfdb_set_option(b"lz4_flavour", 3))
+    elif variant == "lane_hot":       # the lane-per-block decoder on the hot-step schedule of word-regular columns
+        _capi.check(L.dfdb_set_option(b"lz4_flavour", 3))
+        _capi.check(L.dfdb_set_option(b"lane_hot", 1))
     elif variant is not None:
         _capi.check(L.dfdb_set_option(variant.encode(), 1))
 
 
-@pytest.mark.parametrize("variant", ["lane", "v2", "v3", "lz4_v1", "lz4_simple"], ids=["lane_per_block", "walker_regular", "walker_general", "warp_per_block", "sequential"])
+@pytest.mark.parametrize("variant", ["lane", "lane_hot", "v2", "v3", "lz4_v1", "lz4_simple"], ids=["lane_per_block", "lane_hot_steps", "walker_regular", "walker_general", "warp_per_block", "sequential"])
 def test_lz4_decode_matches_reference_codec(oracle, variant):
     """read_block BlockStreams.jl:101-119: decoded bytes are determined by the LZ4 block format."""
     bodies = _bodies(oracle)
@@ -104,7 +108,7 @@ def test_lz4_decode_matches_reference_codec(oracle, variant):
         assert got[i] == bodies[k], f"decoded bytes differ for {k} (first diff at {next(j for j in range(len(got[i])) if got[i][j] != bodies[k][j])})"
 
 
-@pytest.mark.parametrize("variant", ["lane", "v2", "v3"], ids=["lane_per_block", "walker_regular", "walker_general"])
+@pytest.mark.parametrize("variant", ["lane", "lane_hot", "v2", "v3"], ids=["lane_per_block", "lane_hot_steps", "walker_regular", "walker_general"])
 def test_lz4_decode_many_small_blocks(oracle, variant):
     """More blocks than the persistent decoder has slots (148 SMs x 87), ragged sizes, every body kind: slots are
     reused, rings wrap, windows re-base after long literal / match runs."""
@@ -130,7 +134,7 @@ def test_lz4_decode_many_small_blocks(oracle, variant):
     assert not bad, f"{len(bad)} of {len(idx)} blocks differ, first: block {bad[0]} (pool {idx[bad[0]]}, origin {origins[bad[0]]}, status {status[bad[0]]})"
 
 
-@pytest.mark.parametrize("variant", ["lane", "v2", "v3"], ids=["lane_per_block", "walker_regular", "walker_general"])
+@pytest.mark.parametrize("variant", ["lane", "lane_hot", "v2", "v3"], ids=["lane_per_block", "lane_hot_steps", "walker_regular", "walker_general"])
 def test_lz4_decode_rejects_corrupt_blocks(oracle, variant):
     """@assert size == sizes.origin "decompression error" (BlockStreams.jl:112)"""
     body = np.random.default_rng(3).integers(1, 101, 4096).astype(np.int64).tobytes()
@@ -150,11 +154,11 @@ def test_lz4_decode_rejects_corrupt_blocks(oracle, variant):
             oracle.lz4_decompress(blk, org)
 
 
-@pytest.mark.parametrize("variant", ["lane", "v2", "v3"], ids=["lane_per_block", "walker_regular", "walker_general"])
+@pytest.mark.parametrize("variant", ["lane", "lane_hot", "v2", "v3"], ids=["lane_per_block", "lane_hot_steps", "walker_regular", "walker_general"])
 def test_lz4_decode_fuzzed_streams(oracle, variant):
-    """LZ4_decompress_safe contract on damaged streams: no crash, no out-of-bounds write, and whatever the CPU codec
-    accepts decodes to the same bytes.  (The GPU decoders do not enforce liblz4's end-of-block rules, so they may accept
-    a damaged stream the CPU codec refuses; they must never disagree on an accepted one.)"""
+    """LZ4_decompress_safe contract on damaged streams (@assert size == sizes.origin, BlockStreams.jl:110-112): no crash, no
+    out-of-bounds write, a stream is refused exactly when the CPU codec refuses it, and an accepted one decodes to the same
+    bytes."""
     rng = np.random.default_rng(23)
     brands = ["apple", "samsung", "huawai", "microsoft", "dell", "xbox", "sony", "intel"]
     bodies = [rng.integers(1, 101, 4096).astype(np.int64).tobytes(),
@@ -185,8 +189,9 @@ def test_lz4_decode_fuzzed_streams(oracle, variant):
     for k, ref in enumerate(expect):
         if ref is not None:
             assert status[k] == 0 and got[k] == ref, f"stream {k}: the CPU codec accepts it, GPU status {status[k]}"
-        elif variant == "lane":
-            # the lane-per-block decoder enforces liblz4's end-of-block rules: identical accept / reject
+        else:
+            # liblz4's end-of-block rules are enforced on the device (the lane-per-block decoder gives the verdict for every
+            # flavour): identical accept / reject
             assert status[k] != 0, f"stream {k}: the CPU codec rejects it, the GPU decoder accepted it"
 
 

@@ -23,12 +23,13 @@ def sim():
     if not os.path.exists(SO) or max(os.path.getmtime(SRC), os.path.getmtime(CORE)) > os.path.getmtime(SO):
         subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-shared", "-fPIC", "-o", SO, SRC], check=True)
     L = C.CDLL(SO)
-    L.lane_sim_decode.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_long)]
+    L.lane_sim_decode2.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_long), C.c_int]
 
-    def dec(comp, origin):
+    def dec(comp, origin, hot_period=1):
+        """hot_period 1: every step is a full step (general columns); 8: the hot-step schedule of word-regular columns"""
         out = C.create_string_buffer(max(origin, 1))
-        st = (C.c_long * 4)()
-        rc = L.lane_sim_decode(comp, len(comp), out, origin, st)
+        st = (C.c_long * 8)()
+        rc = L.lane_sim_decode2(comp, len(comp), out, origin, st, hot_period)
         return rc, out.raw[:origin], list(st)
     return dec
 
@@ -61,8 +62,14 @@ def test_every_body_kind_decodes_to_the_reference_bytes(sim, oracle):
         for comp in (oracle.compress_block(body), oracle.lz4_compress(body, 1)):
             rc, out, st = sim(comp, len(body))
             assert rc == 0 and out == body, (name, rc)
-            # one piece (<= 8 output bytes) per step: the step count stays within 2.5 steps per output word
+            # pieces of at most 8 output bytes: their number stays within 2.5 per output word
             assert st[1] <= 2.5 * (len(body) / 8) + 16, (name, st)
+            rc, out, st = sim(comp, len(body), 8)          # the hot-step schedule must decode anything too, only slower
+            assert rc == 0 and out == body, (name, "hot", rc)
+    # word-regular bodies take the two-plain-tokens hot path for nearly every piece
+    body = _bodies(oracle)["rand100"]
+    rc, out, st = sim(oracle.compress_block(body), len(body), 8)
+    assert rc == 0 and st[4] >= 0.98 * st[1], st
 
 
 def test_empty_and_degenerate_blocks(sim, oracle):
@@ -98,13 +105,14 @@ def test_accepts_and_rejects_exactly_what_lz4_decompress_safe_does(sim, oracle):
                 ref = oracle.lz4_decompress(bad, len(body))
             except oracle.OracleError:
                 ref = None
-            rc, out, _ = sim(bad, len(body))
-            if ref is None:
-                nrej += 1
-                assert rc != 0
-            else:
-                nacc += 1
-                assert rc == 0 and out == ref
+            for hp in (1, 8):
+                rc, out, _ = sim(bad, len(body), hp)
+                if ref is None:
+                    assert rc != 0
+                else:
+                    assert rc == 0 and out == ref
+            nrej += ref is None
+            nacc += ref is not None
         for d in (-8, -1, 1, 8, 100):
             try:
                 oracle.lz4_decompress(good, len(body) + d)
