@@ -136,39 +136,61 @@ def ncu_traffic(kernel, rows):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# The benchmark query `t[(t.a .> 25) .& (t.a .<= 75), [:b]]` -> sum / min / max / count of b, as plan bytes (wire format:
+# INTEGRATION.md).  A constant, so that the reference arm does not have to import the product package to build it;
+# tests/test_host_logic.py checks it against plan_bytes() of the Python mirror and tests/golden/queries.json.
+BENCH_PLAN = bytes.fromhex("4446503101000000030700000001010000000000000002190000000000000014010100000000000000024b00000000000000132001000000010200000000000000")
+C1_PLAN = bytes.fromhex("444650310100000003030000000101000000000000000232000000000000001401000000010200000000000000")   # t[t.a .> 50, [:b]]
+
+
+def oracle_scan(ot, plan, nblocks, threads, blk_lo=0):
+    """The CPU restatement of the reference's scan over blocks [blk_lo, blk_lo + nblocks) on `threads` host threads."""
+    t0 = time.time()
+    parts = ot.aggregate_mt(plan, 0, nblocks, threads, blk_lo)
+    return parts, time.time() - t0
+
+
 def run_reference(args):
-    """The reference's CPU implementation of the path, restated in C (oracle/): all host threads, bounded sample."""
+    """The reference's CPU implementation of the path, restated in C (oracle/): every host thread, the SAME table and query as
+    the GPU arm at N = 1 (at N > 1 rank 0 scans a 1B-row shard-sized table: one GPU's share of the workload).  Nothing of the
+    product is imported or loaded here."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from oracle import oracle as O
-    import dfdb_b200 as D
     threads = os.cpu_count() or 1
-    rows_total = args.rows * args.gpus
-    sample_rows = min(rows_total, args.ref_sample_rows)
-    path, info = ensure_table(sample_rows, threads)
-    t = D.open_table(path)
+    rows = args.rows if args.ref_sample_rows <= 0 else min(args.rows, args.ref_sample_rows)
+    avail = mem_available_bytes()
+    if rows * 11.1 * 1.3 > avail * 0.8:
+        rows = max(BLOCK, int(avail * 0.8 / (11.1 * 1.3)) // BLOCK * BLOCK)
+        log(f"[bench] host RAM {avail / 2**30:.0f} GiB: reference arm reduced to {rows} rows")
+    path, info = ensure_table(rows, threads)
     ot = O.OracleTable(path)
-    v = t[(t.a > 25) & (t.a <= 75), ["b"]]
-    pb = D.plan_bytes(v.b)
-    nblocks = t.nblocks()
+    nblocks = (rows + BLOCK - 1) // BLOCK
     times = []
+    parts = []
     for i in range(args.warmup + args.steps):
-        t0 = time.time()
-        parts = ot.aggregate_mt(pb, 0, nblocks, threads)
-        dt = time.time() - t0
+        parts, dt = oracle_scan(ot, BENCH_PLAN, nblocks, threads)
         if i >= args.warmup:
             times.append(dt)
+    # single thread on a bounded sample (BASELINE.md quotes single-thread figures for the reference)
+    nb1 = min(nblocks, 400)
+    _, dt1 = oracle_scan(ot, BENCH_PLAN, nb1, 1)
+    ot.close()
     total = sum(times)
-    value = sample_rows * len(times) / total
-    sample = f"{sample_rows} rows of the same table ({nblocks} blocks) per step, {threads} threads over block ranges"
+    value = rows * len(times) / total
+    sample = (f"the whole {rows}-row table ({nblocks} blocks) per step, {threads} threads over block ranges" if args.gpus == 1 else
+              f"{rows} rows ({nblocks} blocks) per step = one GPU's shard of the {args.gpus}-GPU workload, {threads} threads over block ranges")
     line = {
         "impl": "reference", "metric": "filtered-scan rows/s (LZ4 block decode + range predicate + sum/min/max/count)", "value": value,
         "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/f64", "data": "synthetic",
-        "config": workload_config(args, sample_rows, info),
+        "config": workload_config(args, rows, info),
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline_1t": {"value": min(rows, nb1 * BLOCK) / dt1, "unit": "rows/s", "cores": 1, "kind": "port",
+                            "sample": f"{min(rows, nb1 * BLOCK)} rows ({nb1} blocks) of the same table, one thread"},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "same_config": args.gpus == 1 and rows == args.rows,
         "note": "C restatement of the reference's per-block algorithm (oracle/dfdb_oracle.c); the Julia reference cannot run in this image",
         "selected_rows": sum(p.count for p in parts),
     }
@@ -188,6 +210,69 @@ def workload_config(args, rows_per_gpu, info):
     }
 
 
+def agg_variant(name, spec, seed, rows, plan_of, threads, local, steps=5, warmup=3):
+    """A filter + aggregate query over a generated table, HBM-resident: ms per step (CUDA events on the scan stream, whole
+    query through the public API), checked against the oracle over the WHOLE table."""
+    import math
+    import torch
+    import dfdb_b200 as D
+    from oracle import oracle as O
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
+    path = os.path.join(base, f"dfdb_b200_variant_{name}_{rows}_{seed:x}")
+    if not os.path.exists(os.path.join(path, ".complete")):
+        shutil.rmtree(path, ignore_errors=True)
+        O.gen_table(path, spec, rows, BLOCK, seed, threads)
+        open(os.path.join(path, ".complete"), "w").write("{}")
+    t = D.open_table(path, mode=D.LOAD_HBM, device=local)
+    col = plan_of(t)
+    stream = torch.cuda.current_stream()
+    for _ in range(warmup):
+        res = D.aggregate(col)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        res = D.aggregate(col)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ot = O.OracleTable(path)
+    parts, cpu_s = oracle_scan(ot, D.plan_bytes(col), t.nblocks(), threads)
+    ot.close()
+    cnt = sum(p.count for p in parts)
+    ksum = math.fsum(p.sum_kahan for p in parts)
+    gsum = res.sum_f64 + res.sum_f64_lo
+    ok = (cnt == res.count and abs(gsum - ksum) <= 1e-12 * max(abs(ksum), 1e-300)
+          and min(p.min_f64 for p in parts if p.count) == res.min_f64 and max(p.max_f64 for p in parts if p.count) == res.max_f64)
+    t.close()
+    shutil.rmtree(path, ignore_errors=True)
+    return {"rows": rows, "ms_per_step": ms, "value": rows / (ms / 1e3), "unit": "rows/s", "steps": steps, "columns": spec,
+            "verified": {"ok": bool(ok), "kind": "full", "count": cnt, "rel_err": abs(gsum - ksum) / max(abs(ksum), 1e-300)},
+            "cpu_port_rows_per_s": rows / cpu_s, "cpu_threads": threads}
+
+
+def run_variants(args, threads, local):
+    """configs[0] (the reference's own 10M-row case), configs[1] with a COMPRESSIBLE b (Float64 grid, LZ4 ratio 1.93: the
+    headline table's b is incompressible and read in place), configs[2] (string filter + materialize, 200M rows) and configs[3]
+    (missing-bearing multi-column predicate + materialize of 4 columns, 500M rows).  Every result is checked over the whole
+    table against the CPU oracle (aggregates: count / min / max exact, sum within 1e-12; materialize: row count + a 64-bit
+    content hash of every output column)."""
+    import bench_configs
+    out = {}
+    scale = args.rows / 1_000_000_000
+    out["config0_10M_gt50_sum_b"] = agg_variant("c0", "a:Int64:iuniform:1:100;b:Float64:funiform;s:String:brands", 0xDFDB0001,
+                                                max(BLOCK, int(10_000_000 * min(1.0, scale * 100))), lambda t: t[t.a > 50, ["b"]].b, threads, local, steps=10)
+    out["config1_compressible_b"] = agg_variant("c1fg", "a:Int64:iuniform:1:100;b:Float64:fgrid:1:0.1:2000", 0xDFDB0012, args.rows,
+                                                lambda t: t[(t.a > 25) & (t.a <= 75), ["b"]].b, threads, local)
+    bench_configs.run_query.quiet = True
+    for cfg, key in ((3, "config2_strings_200M"), (4, "config3_missings_500M")):
+        rows = max(BLOCK, int(bench_configs.CONFIGS[cfg]["rows"] * scale))
+        lines = bench_configs.run_config(cfg, rows=rows, reps=3, check="full", quiet=True)
+        out[key] = [{k: ln[k] for k in ("query", "rows", "selected", "ms", "rows_per_s", "out_bytes", "phases_ms", "verified")} for ln in lines]
+        shutil.rmtree(bench_configs.table_path(bench_configs.CONFIGS[cfg], rows), ignore_errors=True)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -195,7 +280,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=1_000_000_000, help="rows per GPU")
-    ap.add_argument("--ref-sample-rows", type=int, default=200_000_000)
+    ap.add_argument("--ref-sample-rows", type=int, default=0, help="reference arm: scan at most this many rows per step (0 = the whole table)")
+    ap.add_argument("--no-variants", action="store_true", help="skip the other BASELINE.json configurations (variants)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     args = ap.parse_args()
@@ -256,14 +342,15 @@ def main():
         t.load(["a", "b"])
         return t, v
 
-    from dfdb_b200.dist import allgather_fold
+    if world > 1:
+        # the LIBRARY's NCCL communicator (dfdb_comm_init): torch.distributed only carries the 128-byte id to the ranks
+        from dfdb_b200.dist import comm_init_from_torch
+        comm_init_from_torch(rank, world, device=torch.device("cuda", local))
 
     def step(v):
-        """one pass of the hot path over this rank's shard (+ the partial-aggregate exchange over NCCL)"""
-        a = D.aggregate(v.b)
-        if world == 1:
-            return a
-        return allgather_fold(a, device=torch.device("cuda", local))
+        """one pass of the hot path over this rank's shard; at N > 1 the partial aggregates are combined inside the library
+        (dfdb_scan_aggregate_all: ncclAllGather of the per-rank partials on the scan stream + fixed rank-order fold)"""
+        return D.aggregate(v.b) if world == 1 else D.aggregate_all(v.b)
 
     def timed(v, steps, warmup, profile=False):
         for _ in range(warmup):
@@ -341,10 +428,9 @@ def main():
         ot = O.OracleTable(path)
         pb = D.plan_bytes(v.b)
         nb_total = t.nblocks()
-        sample_blocks = nb_total if world == 1 else min(nb_total, (args.ref_sample_rows + BLOCK - 1) // BLOCK)
-        t0 = time.time()
-        parts = ot.aggregate_mt(pb, 0, sample_blocks, threads)
-        dt = time.time() - t0
+        assert pb == BENCH_PLAN, "bench.py's constant plan bytes no longer match the plan encoder"
+        sample_blocks = nb_total if world == 1 else min(nb_total, (1_000_000_000 + BLOCK - 1) // BLOCK)
+        parts, dt = oracle_scan(ot, pb, sample_blocks, threads)
         sample_rows = min(total_rows, sample_blocks * BLOCK)
         cpu_baseline = {"value": sample_rows / dt, "unit": "rows/s", "cores": threads, "kind": "port",
                         "sample": f"{sample_rows} rows ({sample_blocks} blocks) of the same table, one thread per block range, {dt:.2f} s"}
@@ -386,6 +472,15 @@ def main():
                "same_result": (res_e.count, res_e.sum_f64, res_e.sum_f64_lo) == (hbm_result.count, hbm_result.sum_f64, hbm_result.sum_f64_lo)}
         t.close()
 
+    # ---- the other BASELINE.json configurations and the compressible-b variant of this one, N = 1 only ----
+    variants = None
+    if world == 1 and not args.no_variants:
+        try:
+            variants = run_variants(args, threads, local)
+        except Exception as e:                      # a variant must never take the headline line down with it
+            log(f"[bench] variants failed: {e!r}")
+            variants = {"error": repr(e)}
+
     if rank == 0:
         line = {
             "metric": "filtered-scan rows/s (LZ4 block decode + range predicate + sum/min/max/count)", "value": value, "unit": "rows/s",
@@ -393,13 +488,17 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "int64/f64", "data": "synthetic", "config": workload_config(args, rows, info),
             "decoded_gbs": (shard_unc * world * args.steps / 1e9) / (ms / 1e3),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "scan_only": scan_only, "verified": verified,
+            "scan_only": scan_only, "verified": verified, "variants": variants,
+            "collective": ("NCCL, inside the library (dfdb_comm_init / dfdb_scan_aggregate_all: ncclAllGather of one 128-byte slot per rank)"
+                           if world > 1 else None),
             "phases_ms_per_step": {"decode": dec_ms / args.steps, "consume": con_ms / args.steps,
                                    "consume_gbs": scan_achieved},
             "result": {"count": hbm_result.count, "sum": hbm_result.sum_f64 + hbm_result.sum_f64_lo, "min": hbm_result.min_f64, "max": hbm_result.max_f64},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        from dfdb_b200.dist import comm_destroy
+        comm_destroy()
         dist.barrier()
         dist.destroy_process_group()
     return 0

@@ -40,10 +40,14 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def table_path(cfg, rows):
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
+    return os.path.join(base, f"dfdb_b200_cfg_{rows}_{cfg['seed']:x}")
+
+
 def ensure_table(cfg, rows, threads):
     from oracle import oracle as O
-    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
-    path = os.path.join(base, f"dfdb_b200_cfg_{rows}_{cfg['seed']:x}")
+    path = table_path(cfg, rows)
     marker = os.path.join(path, ".complete")
     if os.path.exists(marker):
         return path, json.load(open(marker))

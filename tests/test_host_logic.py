@@ -176,3 +176,19 @@ def test_result_array_small_results_stay_in_ordinary_memory():
     a = _capi.result_array(10, np.int64)
     assert a.dtype == np.int64 and a.shape == (10,) and not a.any()
     assert _capi.result_array(0, np.uint8).shape == (1,)
+
+
+def test_bench_plan_constants_match_the_plan_encoder(tmp_path, oracle):
+    """bench.py's reference arm must not import the product, so it carries the benchmark query as constant plan bytes: they
+    are the encoder's output for `t[(t.a .> 25) .& (t.a .<= 75), [:b]]` / `t[t.a .> 50, [:b]]` and the committed golden plan."""
+    import json
+    import bench
+    import dfdb_b200 as D
+    p = str(tmp_path / "t")
+    oracle.gen_table(p, bench.SPEC, 1000, 256, 1, 1)
+    t = D.open_table(p)
+    assert D.plan_bytes(t[(t.a > 25) & (t.a <= 75), ["b"]].b) == bench.BENCH_PLAN
+    assert D.plan_bytes(t[t.a > 50, ["b"]].b) == bench.C1_PLAN
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "queries.json")))
+    assert bytes.fromhex(next(q["plan"] for q in golden if q["name"] == "range_predicate_aggregate")) == bench.BENCH_PLAN
+    t.close()
