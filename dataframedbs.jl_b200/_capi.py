@@ -29,6 +29,11 @@ class Agg(C.Structure):
                 ("max_f64", C.c_double), ("has_nan", C.c_int32), ("value_class", C.c_int32)]
 
 
+class Zone(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("null_count", C.c_int64), ("min_i64", C.c_int64), ("max_i64", C.c_int64), ("min_f64", C.c_double),
+                ("max_f64", C.c_double), ("has_value", C.c_int32), ("has_nan", C.c_int32)]
+
+
 class OutCol(C.Structure):
     _fields_ = [("values", C.c_void_p), ("missing", C.c_void_p), ("str_sizes", C.c_void_p), ("str_chars", C.c_void_p)]
 
@@ -64,6 +69,9 @@ SYMBOLS = {
     "dfdb_table_shard_range": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dfdb_table_load": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_int32]),
     "dfdb_table_drop_decoded": (C.c_int32, [C.c_void_p]),
+    "dfdb_table_build_zonemaps": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
+    "dfdb_table_zonemap": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Zone)]),
+    "dfdb_scan_pruned": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dfdb_host_alloc": (C.c_int32, [C.c_int64, C.POINTER(C.c_void_p)]),
     "dfdb_host_free": (C.c_int32, [C.c_void_p]),
     "dfdb_scan_prepare": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int64, C.POINTER(C.c_void_p)]),

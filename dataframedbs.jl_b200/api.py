@@ -204,6 +204,31 @@ class DFTable:
     def drop_decoded(self):
         _capi.check(_capi.lib().dfdb_table_drop_decoded(self._h))
 
+    # ---- block index + zone maps (optional sidecar <id>.zmap; no reference counterpart) ----
+    def build_zonemaps(self, columns=None):
+        """Per-block (min, max, null count) of the given fixed-width numeric columns (default: all of them), computed on the
+        device and written beside the column files; used from then on (also by later open_table calls) to skip blocks a
+        predicate's constants rule out."""
+        L = _capi.lib()
+        self._drop_scans()
+        try:
+            if columns is None:
+                _capi.check(L.dfdb_table_build_zonemaps(self._h, None, 0))
+            else:
+                ids = [self.getmeta(n).id for n in columns]
+                _capi.check(L.dfdb_table_build_zonemaps(self._h, (C.c_int64 * len(ids))(*ids), len(ids)))
+        except DfdbError as e:
+            _raise(e)
+
+    def zonemap(self, column: str, block: int):
+        """dfdb_zone of one table block, or None when the column has no zone map."""
+        z = _capi.Zone()
+        rc = _capi.lib().dfdb_table_zonemap(self._h, self.getmeta(column).id, block, C.byref(z))
+        if rc == _capi.ERR_STATE:
+            return None
+        _capi.check(rc)
+        return z
+
     def _drop_scans(self):
         for s in self._scans.values():
             _capi.lib().dfdb_scan_free(s)
@@ -732,6 +757,15 @@ def nrow_all(v) -> int:
     except DfdbError as e:
         _raise(e)
     return n.value
+
+
+def pruned_blocks(v):
+    """(blocks the zone maps ruled out in the view's last scan, blocks of the shard)"""
+    if isinstance(v, DFColumn):
+        v = v.view
+    p, n = C.c_int64(), C.c_int64()
+    _capi.check(_capi.lib().dfdb_scan_pruned(_scan_handle(v), C.byref(p), C.byref(n)))
+    return p.value, n.value
 
 
 def fold(partials) -> _capi.Agg:

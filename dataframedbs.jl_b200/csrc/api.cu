@@ -40,6 +40,7 @@ struct Runtime {
     const std::vector<int64_t> *blk_live = nullptr;   // set while projection columns of a scan are decoded: blocks without a selected row are skipped
     uint64_t blk_live_gen = 0;                        // ... and the generation of those counts (the key of a column's filtered decode)
     uint64_t next_gen = 1;
+    const std::vector<uint8_t> *zone_dead = nullptr;  // set while a scan's columns are decoded: blocks its zone maps ruled out are skipped
     int win_lo = 0, win_hi = 0x7fffffff;   // local block window of the scan being served (BlockWindow): blocks outside hold no selected row
     std::atomic<int64_t> launches{0};
     // options
@@ -51,6 +52,7 @@ struct Runtime {
     int64_t lz4_flavour = 0;  // K1 flavour: 0 = per column from a token sample at load, 1 = word-regular decoder (v2), 2 = general decoder (v3), 3 = lane-per-block decoder
     int64_t no_overlap = 0;   // do not run the scan of the decoded part of a shard beside the decode of its last part
     int64_t no_alias = 0;     // copy stored (incompressible) blocks like any other block instead of referencing them in place
+    int64_t no_zonemap = 0;   // ignore zone maps (A/B: results must not change)
     int64_t no_validate = 0;  // skip the acceptance pass of dfdb_table_load (A/B, load-time measurements)
     int64_t lane_hot = -1;    // lane decoder: -1 = hot-step schedule per column from the token sample, 0 / 1 = force off / on (A/B, tests)
     // profiling
@@ -243,6 +245,7 @@ Geometry make_geometry(const dfdb_table *t)
     g.nrows_total = t->nrows;
     g.block_size = t->block_size;
     g.blk_lo = t->blk_lo;
+    g.dead = nullptr;
     g.nblocks = (int32_t)(t->blk_hi - t->blk_lo);
     g.wpb = (int32_t)((t->block_size + 31) / 32);
     // work units: segments of whole tiles inside a block; a fixed function of the table shape only, so the
@@ -364,6 +367,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
     // blocksiterator.jl:84-95,112-115: `isempty(range) ? skip_cols(proj_cols) : read_cols(proj_cols)`).  The stored-block
     // flags and the scan's per-block survivor counts are merged into one skip array per column for this call.
     const std::vector<int64_t> *live = rt.blk_live && (int)rt.blk_live->size() == nblocks ? rt.blk_live : nullptr;
+    const std::vector<uint8_t> *zdead = rt.zone_dead && (int)rt.zone_dead->size() == nblocks ? rt.zone_dead : nullptr;
     struct SkipSet {
         std::vector<std::vector<uint8_t>> h;
         std::vector<uint8_t *> d;
@@ -371,15 +375,15 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
     } skips;
     bool filtered = false;
     uint8_t *d_dead = nullptr;           // blocks without a selected row (any column)
-    if (live) {
+    if (live || zdead) {
         std::vector<uint8_t> dead((size_t)nblocks);
-        for (int b = 0; b < nblocks; b++) dead[(size_t)b] = (*live)[(size_t)b] == 0;
+        for (int b = 0; b < nblocks; b++) dead[(size_t)b] = (live && (*live)[(size_t)b] == 0) || (zdead && (*zdead)[(size_t)b]);
         if (scratch_alloc(reinterpret_cast<void **>(&d_dead), (size_t)nblocks) != cudaSuccess) return fail(DFDB_ERR_NOMEM, "out of device memory for the block skip list");
         skips.d.push_back(d_dead);       // (freed with the others)
         CUDA_TRY(cudaMemcpyAsync(d_dead, dead.data(), (size_t)nblocks, cudaMemcpyHostToDevice, rt.stream));
         for (Column *c : todo) {
             std::vector<uint8_t> sk(c->h_skip);
-            for (int b = 0; b < nblocks; b++) if ((*live)[(size_t)b] == 0 && !sk[(size_t)b]) { sk[(size_t)b] = 1; filtered = true; }
+            for (int b = 0; b < nblocks; b++) if (dead[(size_t)b] && !sk[(size_t)b]) { sk[(size_t)b] = 1; filtered = true; }
             uint8_t *dp = nullptr;
             if (scratch_alloc(reinterpret_cast<void **>(&dp), (size_t)nblocks) != cudaSuccess) return fail(DFDB_ERR_NOMEM, "out of device memory for the block skip list");
             skips.d.push_back(dp);
@@ -388,11 +392,11 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
         }
     }
     auto h_skip_of = [&](Column *c) -> const std::vector<uint8_t> & {
-        if (live) for (size_t i = 0; i < todo.size(); i++) if (todo[i] == c) return skips.h[i];
+        if (live || zdead) for (size_t i = 0; i < todo.size(); i++) if (todo[i] == c) return skips.h[i];
         return c->h_skip;
     };
     auto d_skip_of = [&](Column *c) -> const uint8_t * {
-        if (live) for (size_t i = 0; i < todo.size(); i++) if (todo[i] == c) return skips.d[i + 1];   // ([0] is the column-independent list of dead blocks)
+        if (live || zdead) for (size_t i = 0; i < todo.size(); i++) if (todo[i] == c) return skips.d[i + 1];   // ([0] is the column-independent list of dead blocks)
         return c->d_skip;
     };
     // Transfer-inclusive mode: the compressed blocks live in pinned host memory.  They are copied H2D in
@@ -548,7 +552,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
         // (a decode that skipped blocks without selected rows leaves nothing another scan could rely on)
         c->dec_lo = filtered ? 0 : wlo;
         c->dec_hi = filtered ? 0 : whi;
-        c->dec_live_gen = filtered ? rt.blk_live_gen : 0;
+        c->dec_live_gen = filtered && !zdead ? rt.blk_live_gen : 0;   // (a decode pruned by zone maps is good for that scan only)
         c->decoded_valid = !filtered && wlo == 0 && whi == nblocks;
     }
     return DFDB_OK;
@@ -566,6 +570,94 @@ void invalidate_decoded(dfdb_table *t)
 // Scope guard: while the projection columns of a scan are decoded, blocks without a selected row are skipped.
 // a mask (and the counts derived from it) is only good for the shard it was computed on
 bool mask_current(const dfdb_scan *s) { return s->mask_valid && s->mask_epoch == s->tbl->epoch; }
+
+// ---- zone maps: which blocks can hold a selected row -----------------------------------------------------------------
+// A predicate stage that is a conjunction of `column <cmp> constant` terms (Expr::simple; a missing value compares false)
+// selects nothing in a block whose value range [min, max] misses the constant's side for some term, or that holds no
+// non-missing value at all.  Any stage may prune: a block without survivors contributes nothing to the ranks of later
+// range stages either (selection.jl:94-111).  NaN never satisfies an ordered comparison and is kept out of the range; `!=`
+// only prunes a block whose values all equal the constant and that has no NaN.
+bool zone_term_dead(const Term &tm, const ZoneEntry &z, int64_t rows)
+{
+    if (tm.constant_result >= 0) return tm.constant_result == 0;
+    if (z.null_count >= rows) return true;
+    const bool has = (z.flags & 1) != 0, nan = (z.flags & 2) != 0;
+    if (tm.cls == VC_FLT) {
+        double mn, mx;
+        memcpy(&mn, &z.min_bits, 8);
+        memcpy(&mx, &z.max_bits, 8);
+        const double c = tm.cf;
+        if (c != c) return tm.code != 1;                       // only x != NaN is ever true
+        if (tm.code == 1) return has && !nan && mn == c && mx == c;
+        if (!has) return true;                                 // only NaN (and missing) values: every ordered comparison is false
+        switch (tm.code) {
+        case 0: return c < mn || c > mx;
+        case 2: return !(mn < c);
+        case 3: return !(mn <= c);
+        case 4: return !(mx > c);
+        default: return !(mx >= c);
+        }
+    }
+    if (!has) return true;
+    if (tm.cls == VC_UINT) {
+        const uint64_t mn = z.min_bits, mx = z.max_bits, c = (uint64_t)tm.ci;
+        switch (tm.code) {
+        case 0: return c < mn || c > mx;
+        case 1: return mn == c && mx == c;
+        case 2: return !(mn < c);
+        case 3: return !(mn <= c);
+        case 4: return !(mx > c);
+        default: return !(mx >= c);
+        }
+    }
+    const int64_t mn = (int64_t)z.min_bits, mx = (int64_t)z.max_bits, c = tm.ci;
+    switch (tm.code) {
+    case 0: return c < mn || c > mx;
+    case 1: return mn == c && mx == c;
+    case 2: return !(mn < c);
+    case 3: return !(mn <= c);
+    case 4: return !(mx > c);
+    default: return !(mx >= c);
+    }
+}
+
+// Fills s->zone_dead (+ the device copy); returns the number of pruned blocks.  Terms whose class differs from the column's
+// (Int64 column against a Float64 constant ...) are left alone: the plan folds those exactly elsewhere.
+int zone_prune(dfdb_scan *s)
+{
+    dfdb_table *t = s->tbl;
+    const int nblocks = (int)(t->blk_hi - t->blk_lo);
+    s->zone_dead.clear();
+    s->zone_pruned = 0;
+    if (rt.no_zonemap || nblocks <= 0) return 0;
+    bool any = false;
+    std::vector<uint8_t> dead((size_t)nblocks, 0);
+    for (const Stage &st : s->stages) {
+        if (st.kind != ST_PRED || !st.e.simple) continue;
+        for (int i = 0; i < st.e.nterms; i++) {
+            const Term &tm = st.e.terms[i];
+            const Column *c = t->find(s->slots[(size_t)tm.slot]);
+            if (!c || c->zones.size() != c->blocks.size() || value_class(c->type.kind) != tm.cls) continue;
+            for (int b = 0; b < nblocks; b++) {
+                const size_t tb = (size_t)(t->blk_lo + b);
+                if (!dead[(size_t)b] && zone_term_dead(tm, c->zones[tb], c->blocks[tb].rows)) { dead[(size_t)b] = 1; any = true; s->zone_pruned++; }
+            }
+        }
+    }
+    if (!any) return 0;
+    s->zone_dead.swap(dead);
+    if (!s->d_zone_dead && cudaMalloc(reinterpret_cast<void **>(&s->d_zone_dead), (size_t)nblocks) != cudaSuccess) { s->zone_dead.clear(); s->zone_pruned = 0; return 0; }
+    cudaMemcpyAsync(s->d_zone_dead, s->zone_dead.data(), (size_t)nblocks, cudaMemcpyHostToDevice, rt.stream);
+    return (int)s->zone_pruned;
+}
+
+// Scope guard: while this scan's columns are decoded and scanned, the blocks its zone maps ruled out are skipped.
+struct ZoneScope {
+    const std::vector<uint8_t> *prev;
+    explicit ZoneScope(dfdb_scan *s) : prev(rt.zone_dead) { rt.zone_dead = zone_prune(s) > 0 ? &s->zone_dead : nullptr; }
+    ~ZoneScope() { rt.zone_dead = prev; }
+};
+const uint8_t *zone_dead_dev(const dfdb_scan *s) { return !s->zone_dead.empty() ? s->d_zone_dead : nullptr; }
 
 struct LiveBlocks {
     const std::vector<int64_t> *prev;
@@ -688,10 +780,12 @@ void fill_terms(dfdb_scan *s, const Expr &e, FusedArgs *a)
 int run_selection(dfdb_scan *s)
 {
     BlockWindow win(s);
+    ZoneScope zone(s);
     dfdb_table *t = s->tbl;
     int rc = scan_alloc(s);
     if (rc) return rc;
-    const Geometry g = make_geometry(t);
+    Geometry g = make_geometry(t);
+    g.dead = zone_dead_dev(s);
     bool dense = true;   // every row of the shard survives so far and the mask is not materialised
     bool used_vm = false;
     int nondense = 0;    // range stages met so far that rank among survivors
@@ -916,10 +1010,12 @@ void agg_to_public(const AggPartial &p, int cls, dfdb_agg *out)
 int run_aggregate(dfdb_scan *s, int32_t proj_idx, bool count_only, AggPartial *host_out, int *cls_out)
 {
     BlockWindow win(s);
+    ZoneScope zone(s);
     dfdb_table *t = s->tbl;
     int rc = scan_alloc(s);
     if (rc) return rc;
-    const Geometry g = make_geometry(t);
+    Geometry g = make_geometry(t);
+    g.dead = zone_dead_dev(s);
     FusedArgs a;
     memset(&a, 0, sizeof a);
     a.g = g;
@@ -1142,6 +1238,7 @@ int32_t dfdb_set_option(const char *name, int64_t value)
     else if (n == "no_alias") rt.no_alias = value;
     else if (n == "lane_hot") rt.lane_hot = value;
     else if (n == "no_validate") rt.no_validate = value;
+    else if (n == "no_zonemap") rt.no_zonemap = value;
     else if (n == "host_arena_cap_mb") { std::lock_guard<std::mutex> lk(arena.mu); arena.cap_bytes = (size_t)std::max<int64_t>(value, 0) << 20; arena.trim(arena.cap_bytes); }
     else return fail(DFDB_ERR_ARGUMENT, "unknown option %s", n.c_str());
     return DFDB_OK;
@@ -1400,6 +1497,82 @@ int32_t dfdb_table_drop_decoded(dfdb_table *t)
     return DFDB_OK;
 }
 
+// ---- zone maps ------------------------------------------------------------------------------------------
+int32_t dfdb_table_build_zonemaps(dfdb_table *t, const int64_t *col_ids, int32_t n)
+{
+    int rc = need_init();
+    if (rc) return rc;
+    if (!t) return fail(DFDB_ERR_ARGUMENT, "null argument");
+    if (t->world != 1) return fail(DFDB_ERR_STATE, "zone maps are built on the unsharded table (the sidecar covers every block)");
+    std::vector<Column *> cols;
+    if (n <= 0) {
+        for (auto &c : t->cols) {
+            const int cls = value_class(c.type.kind);
+            if (c.type.elsize > 0 && c.type.elsize <= 8 && (cls == VC_INT || cls == VC_UINT || cls == VC_FLT || cls == VC_BOOL)) cols.push_back(&c);
+        }
+    } else {
+        for (int i = 0; i < n; i++) {
+            Column *c = t->find(col_ids[i]);
+            if (!c) return fail(DFDB_ERR_KEY, "unknown column id %lld", (long long)col_ids[i]);
+            const int cls = value_class(c->type.kind);
+            if (!(c->type.elsize > 0 && c->type.elsize <= 8 && (cls == VC_INT || cls == VC_UINT || cls == VC_FLT || cls == VC_BOOL)))
+                return fail(DFDB_ERR_UNSUPPORTED, "zone maps need a fixed-width numeric column; %s is %s", c->name.c_str(), c->typestr.c_str());
+            cols.push_back(c);
+        }
+    }
+    const Geometry g = make_geometry(t);
+    const int nb = g.nblocks;
+    ZoneOut *d_out = nullptr;
+    if (nb > 0) CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d_out), (size_t)nb * sizeof(ZoneOut)));
+    std::vector<ZoneOut> h((size_t)nb);
+    for (Column *c : cols) {
+        if (!c->loaded) { int64_t id = c->id; rc = dfdb_table_load(t, &id, 1, DFDB_LOAD_HBM); if (rc) { cudaFree(d_out); return rc; } }
+        invalidate_decoded(t);
+        rc = ensure_decoded(t, {c->id});
+        if (rc) { cudaFree(d_out); return rc; }
+        if (nb > 0) {
+            if (launch_zone_map(g, make_view(*c), d_out, rt.stream) != 0) { cudaFree(d_out); return fail(DFDB_ERR_CUDA, "zone map launch failed"); }
+            rt.launches++;
+            cudaMemcpyAsync(h.data(), d_out, (size_t)nb * sizeof(ZoneOut), cudaMemcpyDeviceToHost, rt.stream);
+            if (cudaStreamSynchronize(rt.stream) != cudaSuccess) { cudaFree(d_out); return fail(DFDB_ERR_CUDA, "zone map kernel failed"); }
+        }
+        c->zones.assign((size_t)nb, ZoneEntry());
+        for (int b = 0; b < nb; b++) {
+            c->zones[(size_t)b].min_bits = h[(size_t)b].min_bits; c->zones[(size_t)b].max_bits = h[(size_t)b].max_bits;
+            c->zones[(size_t)b].null_count = h[(size_t)b].null_count; c->zones[(size_t)b].flags = h[(size_t)b].flags;
+        }
+        rc = zonemap_write(t, *c);
+        if (rc) { cudaFree(d_out); return rc; }
+    }
+    cudaFree(d_out);
+    return DFDB_OK;
+}
+
+int32_t dfdb_table_zonemap(const dfdb_table *t, int64_t col_id, int64_t block, dfdb_zone *out)
+{
+    const Column *c = const_cast<dfdb_table *>(t)->find(col_id);
+    if (!c || !out) return fail(DFDB_ERR_KEY, "unknown column id %lld", (long long)col_id);
+    if (c->zones.size() != c->blocks.size()) return fail(DFDB_ERR_STATE, "column %s has no zone map (dfdb_table_build_zonemaps)", c->name.c_str());
+    if (block < 0 || (size_t)block >= c->zones.size()) return fail(DFDB_ERR_ARGUMENT, "block %lld out of range", (long long)block);
+    const ZoneEntry &z = c->zones[(size_t)block];
+    memset(out, 0, sizeof *out);
+    out->rows = c->blocks[(size_t)block].rows;
+    out->null_count = z.null_count;
+    out->has_value = z.flags & 1;
+    out->has_nan = (z.flags >> 1) & 1;
+    if (value_class(c->type.kind) == VC_FLT) { memcpy(&out->min_f64, &z.min_bits, 8); memcpy(&out->max_f64, &z.max_bits, 8); }
+    else { out->min_i64 = (int64_t)z.min_bits; out->max_i64 = (int64_t)z.max_bits; }
+    return DFDB_OK;
+}
+
+int32_t dfdb_scan_pruned(const dfdb_scan *s, int64_t *pruned, int64_t *blocks)
+{
+    if (!s) return fail(DFDB_ERR_ARGUMENT, "null argument");
+    if (pruned) *pruned = s->zone_pruned;
+    if (blocks) *blocks = s->tbl->blk_hi - s->tbl->blk_lo;
+    return DFDB_OK;
+}
+
 // ---- scan ---------------------------------------------------------------------------------------------
 int32_t dfdb_scan_prepare(dfdb_table *t, const uint8_t *plan, int64_t plan_len, dfdb_scan **out)
 {
@@ -1417,7 +1590,7 @@ int32_t dfdb_scan_free(dfdb_scan *s)
     if (!s) return DFDB_OK;
     if (rt.inited) cudaStreamSynchronize(rt.stream);
     cudaFree(s->d_mask); cudaFree(s->d_blk_counts); cudaFree(s->d_blk_base); cudaFree(s->d_blk_bytes);
-    cudaFree(s->d_partials); cudaFree(s->d_result);
+    cudaFree(s->d_partials); cudaFree(s->d_result); cudaFree(s->d_zone_dead);
     if (s->h_result) cudaFreeHost(s->h_result);
     for (auto &st : s->stages) cudaFree(st.d_idx);
     delete s;

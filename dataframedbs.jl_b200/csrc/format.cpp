@@ -143,6 +143,77 @@ struct File {
 };
 }  // namespace
 
+// ---- block index + zone map sidecar: <table>/<id>.zmap --------------------------------------------------------------
+// The reference's format has no index (skip_block walks the headers, BlockStreams.jl:74-78) and no per-block statistics.
+// The sidecar is OPTIONAL and lives beside the column file, which stays byte-identical, so the reference still opens the
+// table (it only ever opens meta.bin and <id>.bin).  It is trusted only while the column file has the size and the
+// modification time recorded in it; otherwise it is ignored and the headers are walked as before.
+//   char[8] "DFDBZM01" | i64 block_size | i64 nblocks | i64 col_id | i64 bin_size | i64 bin_mtime_ns | i32 kind, nullable, elsize, cls
+//   nblocks x { i64 file_off | i32 rows | i32 flags | i64 origin | i64 compressed | i64 null_count | u64 min_bits | u64 max_bits }
+namespace {
+struct __attribute__((packed)) ZmHeader { char magic[8]; int64_t block_size, nblocks, col_id, bin_size, bin_mtime_ns; int32_t kind, nullable, elsize, cls; };
+struct __attribute__((packed)) ZmEntry { int64_t file_off; int32_t rows, flags; int64_t origin, compressed, null_count; uint64_t min_bits, max_bits; };
+
+int64_t mtime_ns(const struct stat &st) { return (int64_t)st.st_mtim.tv_sec * 1000000000ll + st.st_mtim.tv_nsec; }
+
+// fills c.blocks (+ totals) and c.zones from a valid sidecar; false = no usable sidecar
+bool zonemap_read(const std::string &base, Column &c, int64_t block_size, const struct stat &bin)
+{
+    File f;
+    if (!f.open_ro(base + "/" + std::to_string(c.id) + ".zmap")) return false;
+    ZmHeader h;
+    if (!f.read(&h, sizeof h) || memcmp(h.magic, "DFDBZM01", 8) != 0) return false;
+    if (h.block_size != block_size || h.col_id != c.id || h.bin_size != (int64_t)bin.st_size || h.bin_mtime_ns != mtime_ns(bin)) return false;
+    if (h.kind != c.type.kind || h.nullable != (c.type.nullable ? 1 : 0) || h.elsize != c.type.elsize) return false;
+    if (h.nblocks < 0 || h.nblocks > (1 << 28) || f.size != (int64_t)(sizeof h + (size_t)h.nblocks * sizeof(ZmEntry))) return false;
+    std::vector<ZmEntry> e((size_t)h.nblocks);
+    if (h.nblocks && !f.read(e.data(), e.size() * sizeof(ZmEntry))) return false;
+    // the index must tile the column file exactly: data_start | 20-byte header | payload | 20-byte header | payload ...
+    int64_t pos = c.data_start;
+    for (const ZmEntry &z : e) {
+        if (z.rows < 0 || z.origin < 0 || z.compressed < 0 || z.origin > 0x7E000000LL || z.file_off != pos + 20) return false;
+        pos = z.file_off + z.compressed;
+    }
+    if (pos != (int64_t)bin.st_size) return false;
+    c.blocks.clear();
+    c.zones.clear();
+    c.total_compressed = c.total_origin = 0;
+    for (const ZmEntry &z : e) {
+        c.blocks.push_back(BlockInfo{z.file_off, z.rows, z.origin, z.compressed});
+        c.total_compressed += z.compressed;
+        c.total_origin += z.origin;
+        ZoneEntry ze;
+        ze.min_bits = z.min_bits; ze.max_bits = z.max_bits; ze.null_count = z.null_count; ze.flags = z.flags;
+        c.zones.push_back(ze);
+    }
+    c.index_from_sidecar = true;
+    return true;
+}
+}  // namespace
+
+int zonemap_write(const dfdb_table *t, const Column &c)
+{
+    if (c.zones.size() != c.blocks.size()) return fail(DFDB_ERR_STATE, "column %s has no zone maps to write", c.name.c_str());
+    const std::string bin = t->path + "/" + std::to_string(c.id) + ".bin", dst = t->path + "/" + std::to_string(c.id) + ".zmap", tmp = dst + ".tmp";
+    struct stat st;
+    if (stat(bin.c_str(), &st)) return fail(DFDB_ERR_IO, "cannot stat %s", bin.c_str());
+    ZmHeader h;
+    memcpy(h.magic, "DFDBZM01", 8);
+    h.block_size = t->block_size; h.nblocks = (int64_t)c.blocks.size(); h.col_id = c.id; h.bin_size = (int64_t)st.st_size; h.bin_mtime_ns = mtime_ns(st);
+    h.kind = c.type.kind; h.nullable = c.type.nullable ? 1 : 0; h.elsize = c.type.elsize; h.cls = value_class(c.type.kind);
+    std::vector<ZmEntry> e(c.blocks.size());
+    for (size_t b = 0; b < e.size(); b++) {
+        e[b].file_off = c.blocks[b].file_off; e[b].rows = c.blocks[b].rows; e[b].flags = c.zones[b].flags; e[b].origin = c.blocks[b].origin;
+        e[b].compressed = c.blocks[b].compressed; e[b].null_count = c.zones[b].null_count; e[b].min_bits = c.zones[b].min_bits; e[b].max_bits = c.zones[b].max_bits;
+    }
+    FILE *fp = fopen(tmp.c_str(), "wb");
+    if (!fp) return fail(DFDB_ERR_IO, "cannot write %s", tmp.c_str());
+    bool ok = fwrite(&h, sizeof h, 1, fp) == 1 && (e.empty() || fwrite(e.data(), sizeof(ZmEntry), e.size(), fp) == e.size());
+    ok = fclose(fp) == 0 && ok;
+    if (!ok || rename(tmp.c_str(), dst.c_str())) { unlink(tmp.c_str()); return fail(DFDB_ERR_IO, "cannot write %s", dst.c_str()); }
+    return DFDB_OK;
+}
+
 int table_open_host(const char *path, dfdb_table **out)
 {
     struct stat st;
@@ -194,6 +265,13 @@ int table_open_host(const char *path, dfdb_table **out)
         }
         c.data_start = f.pos;
         int64_t rows_total = 0;
+        {
+            struct stat bst;
+            if (fstat(f.fd, &bst) == 0 && zonemap_read(base, c, t->block_size, bst)) {
+                for (const BlockInfo &bi : c.blocks) rows_total += bi.rows;
+                f.pos = f.size;                           // the sidecar's index replaces the header walk
+            }
+        }
         while (f.pos < f.size) {
             struct __attribute__((packed)) { int32_t rows; int64_t origin, compressed; } h;
             if (!f.read(&h, 20)) { delete t; return fail(DFDB_ERR_CORRUPT, "truncated block header in %s", p.c_str()); }

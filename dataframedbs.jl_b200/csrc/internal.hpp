@@ -38,6 +38,14 @@ struct BlockInfo {
     int64_t compressed;
 };
 
+// zone map of one column block (sidecar <id>.zmap): range of the non-missing values as 64-bit payloads of the column's
+// value class (signed / unsigned integer bits, or double bits with NaN kept out of the range and flagged)
+struct ZoneEntry {
+    uint64_t min_bits = 0, max_bits = 0;
+    int64_t null_count = 0;
+    int32_t flags = 0;        // 1 = has a non-missing, non-NaN value, 2 = has NaN
+};
+
 struct Column {
     int64_t id = 0;
     std::string name, typestr;
@@ -45,6 +53,8 @@ struct Column {
     int64_t data_start = 0;
     std::vector<BlockInfo> blocks;
     int64_t total_compressed = 0, total_origin = 0;
+    std::vector<ZoneEntry> zones;    // per table block, empty = no (valid) sidecar
+    bool index_from_sidecar = false; // the block index came from the sidecar instead of the header walk
 
     // ---- residency of the current shard (blocks [blk_lo, blk_hi) of the table) ----
     bool loaded = false;
@@ -93,6 +103,7 @@ struct dfdb_table {
 namespace dfdb {
 
 int table_open_host(const char *path, dfdb_table **out);   // format.cpp
+int zonemap_write(const dfdb_table *t, const Column &c);    // format.cpp: <table>/<id>.zmap from c.blocks + c.zones
 
 // ------------------------------------------------------------------------------------------------
 // plan (host): parsed + typed expression programs
@@ -215,6 +226,9 @@ struct dfdb_scan {
     std::vector<int64_t> str_bytes;    // per projection
     std::vector<int64_t> blk_live;     // selected rows per local block (host copy of the counts behind d_blk_base), valid with `selected`
     // sharded tables: survivors of lower-ranked shards entering each range stage that follows a predicate
+    std::vector<uint8_t> zone_dead;    // per local block: 1 = the zone maps rule out every row for some predicate stage (never decoded)
+    uint8_t *d_zone_dead = nullptr;
+    int64_t zone_pruned = 0;           // blocks ruled out by the zone maps in the last run
     std::vector<int64_t> rank_offsets;
     int64_t exchange_count = -1;       // this shard's count at the first stage whose offset is missing
 };

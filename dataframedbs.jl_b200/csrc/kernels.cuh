@@ -31,6 +31,17 @@ constexpr int LZ4_SLOTS_PER_SM = 60;   // column blocks one decoder CTA keeps in
 int launch_lz4_decode_v2(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit = 0);                     // v2: walker / consumer warps, word-regular columns
 int launch_lz4_decode_v3(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit = 0);                     // v3: same organisation, general columns (strings, literal-heavy, chains)
 
+// ---- write path: raw LZ4 block compression (lz4_compress.cu), one warp per body ---------------------------------------
+struct CompressArgs {
+    const uint8_t *src;         // bodies, each readable 16 bytes past its end
+    const int64_t *src_off, *src_len;
+    uint8_t *dst;               // one slot of LZ4_compressBound(len) bytes per body
+    const int64_t *dst_off;
+    int64_t *dst_len;           // out: compressed size per body
+    int nblocks;
+};
+int launch_lz4_compress(const CompressArgs &a, unsigned int *d_counter, int sm_count, cudaStream_t stream);
+
 // ---- scan geometry -------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 256;
 constexpr int ROWS_PER_THREAD = 8;
@@ -44,6 +55,7 @@ struct Geometry {
     int32_t wpb;             // mask words (32 rows each) per block
     int32_t segs_per_block;  // work units per block
     int32_t seg_rows;        // rows per work unit (multiple of TILE_ROWS)
+    const uint8_t *dead;     // per local block, may be null: 1 = no row of the block can be selected (zone maps); its body is not decoded
 };
 
 __host__ __device__ inline int64_t block_rows(const Geometry &g, int lb)
@@ -148,6 +160,10 @@ int launch_fill_mask(const Geometry &g, uint32_t *mask, cudaStream_t stream);
 // ---- K2: String bodies: per-row char offsets (unsafe_remake_offsets!) --------------------------------
 int launch_str_offsets(const Geometry &g, const ColView &col, int32_t *str_off, int32_t *status, const int32_t *origin, cudaStream_t stream, int lo = 0, int hi = 0x7fffffff,
                        const uint8_t *dead = nullptr);   // local blocks [lo, hi) except those flagged in `dead`
+
+// ---- zone maps (block index sidecar): per block min / max / null count of a decoded fixed-width column ----
+struct ZoneOut { unsigned long long min_bits, max_bits; long long null_count; int flags, pad; };
+int launch_zone_map(const Geometry &g, const ColView &col, ZoneOut *out, cudaStream_t stream);
 
 // ---- K5/K6: stream compaction / gathers ---------------------------------------------------------------
 struct GatherArgs {

@@ -239,6 +239,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) fused_scan_kernel(const FusedArg
         if (row1 > rows_b) row1 = rows_b;
         AggPartial acc;
         agg_init(acc);
+        if (g.dead && g.dead[lb]) {
+            // ruled out by the zone maps: no row selected, the body was not decoded and is not read
+            if (EMIT)
+                for (int64_t r0 = row0 + (int64_t)tid * 32; r0 < row1; r0 += (int64_t)SCAN_THREADS * 32) A.mask_out[(int64_t)lb * g.wpb + (r0 >> 5)] = 0u;
+            if (tid == 0) A.partials[unit] = acc;
+            continue;
+        }
         for (int64_t tile0 = row0; tile0 < row1; tile0 += TILE_ROWS) {
             unsigned long long av[8];
             unsigned amiss = 0;
@@ -595,7 +602,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) vm_mask_kernel(const VmArgs A)
             if (r0 >= rows_b) continue;                                  // warp-uniform
             const int64_t r = r0 + lane_id();
             const int64_t widx = (int64_t)lb * g.wpb + (r0 >> 5);
-            bool sel = r < rows_b;
+            bool sel = r < rows_b && !(g.dead && g.dead[lb]);              // (zone maps: the block is not decoded, nothing is evaluated)
             if (A.mask_in) sel = sel && ((A.mask_in[widx] >> lane_id()) & 1u);
             bool res = false;
             if (sel) {
@@ -781,6 +788,74 @@ __global__ void __launch_bounds__(SCAN_THREADS) str_offsets_kernel(const Geometr
             run += __shfl_sync(FULL, incl, 31);
         }
         if (lane_id() == 0 && run != datasize) status[lb] = 5;   // sizes do not add up to datasize: corrupt body
+    }
+}
+
+// ---- zone maps: one CTA per block --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS) zone_map_kernel(const Geometry g, const ColView col, ZoneOut *out)
+{
+    __shared__ unsigned long long s_min[SCAN_THREADS / 32], s_max[SCAN_THREADS / 32];
+    __shared__ long long s_null[SCAN_THREADS / 32];
+    __shared__ int s_flags[SCAN_THREADS / 32];
+    for (int lb = blockIdx.x; lb < g.nblocks; lb += gridDim.x) {
+        const int64_t rows_b = block_rows(g, lb);
+        const uint8_t *vals = col_values(col, lb, rows_b);
+        const int cls = col.cls;
+        unsigned long long mn = 0, mx = 0;
+        long long nulls = 0;
+        int flags = 0;
+        for (int64_t r = threadIdx.x; r < rows_b; r += SCAN_THREADS) {
+            if (col_missing(col, lb, r)) { nulls++; continue; }
+            const unsigned long long v = load_widen(vals + r * col.elsize, col.kind);
+            if (cls == VC_FLT) {
+                const double x = __longlong_as_double((long long)v);
+                if (x != x) { flags |= 2; continue; }
+                if (!(flags & 1)) { mn = mx = v; flags |= 1; }
+                else {
+                    if (x < __longlong_as_double((long long)mn)) mn = v;
+                    if (x > __longlong_as_double((long long)mx)) mx = v;
+                }
+            } else if (cls == VC_UINT || cls == VC_BOOL) {
+                if (!(flags & 1)) { mn = mx = v; flags |= 1; }
+                else { if (v < mn) mn = v; if (v > mx) mx = v; }
+            } else {
+                if (!(flags & 1)) { mn = mx = v; flags |= 1; }
+                else { if ((long long)v < (long long)mn) mn = v; if ((long long)v > (long long)mx) mx = v; }
+            }
+        }
+        auto merge = [&](unsigned long long omn, unsigned long long omx, long long onull, int ofl) {
+            nulls += onull;
+            if (ofl & 1) {
+                if (!(flags & 1)) { mn = omn; mx = omx; }
+                else if (cls == VC_FLT) {
+                    if (__longlong_as_double((long long)omn) < __longlong_as_double((long long)mn)) mn = omn;
+                    if (__longlong_as_double((long long)omx) > __longlong_as_double((long long)mx)) mx = omx;
+                } else if (cls == VC_UINT || cls == VC_BOOL) {
+                    if (omn < mn) mn = omn;
+                    if (omx > mx) mx = omx;
+                } else {
+                    if ((long long)omn < (long long)mn) mn = omn;
+                    if ((long long)omx > (long long)mx) mx = omx;
+                }
+            }
+            flags |= ofl;
+        };
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const unsigned long long omn = __shfl_down_sync(FULL, mn, d), omx = __shfl_down_sync(FULL, mx, d);
+            const long long onull = __shfl_down_sync(FULL, nulls, d);
+            const int ofl = __shfl_down_sync(FULL, flags, d);
+            if (lane_id() + d < 32) merge(omn, omx, onull, ofl);
+        }
+        if (lane_id() == 0) { s_min[warp_id()] = mn; s_max[warp_id()] = mx; s_null[warp_id()] = nulls; s_flags[warp_id()] = flags; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < SCAN_THREADS / 32; w++) merge(s_min[w], s_max[w], s_null[w], s_flags[w]);
+            ZoneOut z;
+            z.min_bits = mn; z.max_bits = mx; z.null_count = nulls; z.flags = flags; z.pad = 0;
+            out[lb] = z;
+        }
+        __syncthreads();
     }
 }
 
@@ -1185,6 +1260,13 @@ int launch_str_offsets(const Geometry &g, const ColView &col, int32_t *str_off, 
     if (lo < 0) lo = 0;
     if (hi <= lo) return 0;
     str_offsets_kernel<<<grid_for((hi - lo + 7) / 8, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(g, col, str_off, status, origin, lo, hi, dead);
+    return CHECK_LAUNCH();
+}
+
+int launch_zone_map(const Geometry &g, const ColView &col, ZoneOut *out, cudaStream_t stream)
+{
+    if (g.nblocks <= 0) return 0;
+    zone_map_kernel<<<grid_for(g.nblocks, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(g, col, out);
     return CHECK_LAUNCH();
 }
 

@@ -69,6 +69,7 @@ __device__ __forceinline__ void cursor_load_unit(TileCursor &c, const Geometry &
     c.tile0 = (int64_t)seg * g.seg_rows;
     c.row1 = c.tile0 + g.seg_rows;
     if (c.row1 > c.rows_b) c.row1 = c.rows_b;
+    if (g.dead && g.dead[c.lb]) c.row1 = c.tile0;      // ruled out by the zone maps: the unit is empty (its partial stays zero)
 }
 // advance to the next non-empty tile; false when the CTA has no more work
 __device__ __forceinline__ bool cursor_next(TileCursor &c, const Geometry &g, int nunits, bool first)

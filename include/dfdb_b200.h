@@ -117,6 +117,24 @@ DFDB_API int32_t dfdb_table_shard_range(const dfdb_table *t, int64_t *block_lo, 
 DFDB_API int32_t dfdb_table_load(dfdb_table *t, const int64_t *col_ids, int32_t n, int32_t mode);
 DFDB_API int32_t dfdb_table_drop_decoded(dfdb_table *t);    /* forget cached decoded bodies (mode DFDB_LOAD_DECODED) */
 
+/* ---- block index + zone maps (no reference counterpart: the format has no index -- skip_block walks
+ *      the headers, src/io/BlockStreams.jl:74-78 -- and no per-block statistics).  dfdb_table_build_zonemaps decodes the columns
+ *      on the device, reduces every block to (min, max, null count) of its non-missing values and writes the optional sidecar
+ *      <table>/<id>.zmap beside the untouched column file, together with the block index {file offset, rows, origin,
+ *      compressed}.  dfdb_table_open uses a sidecar whose recorded size / mtime still match the column file: the index
+ *      replaces the header walk, and predicate stages made of `column <cmp> constant` terms skip (never copy, never decode)
+ *      every block whose range rules the predicate out.  Unsharded tables only; fixed-width numeric columns. ------------- */
+typedef struct dfdb_zone {
+    int64_t rows, null_count;
+    int64_t min_i64, max_i64;     /* integer / Bool / Date columns (unsigned columns: the same bits)                 */
+    double min_f64, max_f64;      /* Float32 / Float64 columns, NaN excluded                                          */
+    int32_t has_value, has_nan;
+} dfdb_zone;
+DFDB_API int32_t dfdb_table_build_zonemaps(dfdb_table *t, const int64_t *col_ids, int32_t n);   /* n == 0: every eligible column */
+DFDB_API int32_t dfdb_table_zonemap(const dfdb_table *t, int64_t col_id, int64_t block, dfdb_zone *out);   /* DFDB_ERR_STATE without a zone map */
+/* blocks the zone maps ruled out in the scan's last run, and blocks of the shard */
+DFDB_API int32_t dfdb_scan_pruned(const dfdb_scan *s, int64_t *pruned, int64_t *blocks);
+
 /* ---- scan: BlocksIterator(v::DFView) (src/io/blocksiterator.jl:20-66) built from the view's
  *      SelectionQueue (src/tables/selection.jl:4-10) and Projection (src/tables/projection.jl:1-9);
  *      plan wire format in dataframedbs.jl_b200/plan.py ----------------------------------------- */

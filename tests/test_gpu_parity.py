@@ -634,3 +634,98 @@ def test_size_independent_properties_at_scale(tmp_path, oracle):
     ref = ot.aggregate(D.plan_bytes(v.b), 0)
     _check_agg(D.aggregate(v.b), ref, "prefix")
     t.close()
+
+
+# ---- block index + zone maps ------------------------------------------------------------------------
+
+def test_zone_maps_prune_blocks_without_changing_results(tmp_path, oracle):
+    """Optional sidecar <id>.zmap (per block min / max / null count, built on the device): a predicate made of
+    `column <cmp> constant` terms skips every block its constants rule out -- never copied, never decoded -- and every result
+    stays what the reference computes (oracle on the same files, and the same scan with the zone maps switched off).  The
+    column files are untouched, so the reference still opens the table."""
+    p = str(tmp_path / "z")
+    nrows = 40 * 4096 + 777
+    rng = np.random.default_rng(0xF3)
+    brands = ["apple", "samsung", "huawai", "microsoft", "dell", "xbox", "sony", "intel"]
+    oracle.write_table(p, [
+        ("q", "Int64", np.arange(1, nrows + 1, dtype=np.int64)),
+        ("a", "Int64", rng.integers(1, 101, nrows).astype(np.int64)),
+        ("b", "Float64", rng.random(nrows)),
+        ("mf", "Missing(Float64)", (rng.random(nrows), rng.random(nrows) < 0.3)),
+        ("p", "Float64", 1 + 0.1 * rng.integers(0, 19991, nrows)),
+        ("s", "String", [brands[i] for i in rng.integers(0, 8, nrows)]),
+        ("u", "UInt8", rng.integers(0, 201, nrows).astype(np.uint8)),
+    ], block_size=4096)
+    before = {f: open(os.path.join(p, f), "rb").read() for f in os.listdir(p)}
+    t = D.open_table(p)
+    ot = oracle.OracleTable(p)
+    L = _capi.lib()
+    assert t.zonemap("q", 0) is None
+    t.build_zonemaps()
+    for f, data in before.items():
+        assert open(os.path.join(p, f), "rb").read() == data, f"{f} changed"          # the reference's files are untouched
+    assert sorted(set(os.listdir(p)) - set(before)) == sorted(f"{t.getmeta(n).id}.zmap" for n in ("q", "a", "b", "mf", "p", "u"))
+    # the statistics themselves, against the raw data
+    qv = ot.materialize(D.plan_bytes(t[:, ["q", "mf", "u"]]))
+    for blk in (0, 7, 40):
+        lo, hi = blk * 4096, min(nrows, (blk + 1) * 4096)
+        z = t.zonemap("q", blk)
+        assert (z.rows, z.null_count, z.min_i64, z.max_i64, z.has_value) == (hi - lo, 0, int(qv[0][lo:hi].min()), int(qv[0][lo:hi].max()), 1)
+        z = t.zonemap("mf", blk)
+        vals, miss = qv[1][0][lo:hi], qv[1][1][lo:hi]
+        assert z.null_count == int(miss.sum()) and z.min_f64 == float(vals[~miss].min()) and z.max_f64 == float(vals[~miss].max())
+        z = t.zonemap("u", blk)
+        assert (z.min_i64, z.max_i64) == (int(qv[2][lo:hi].min()), int(qv[2][lo:hi].max()))
+    t.close()
+
+    t = D.open_table(p)                       # a fresh open finds the sidecars (and takes its block index from them)
+    assert t.zonemap("q", 3) is not None
+
+    def decoded_bytes(fn):
+        L.dfdb_profile_reset()
+        L.dfdb_profile_enable(1)
+        out = fn()
+        L.dfdb_profile_enable(0)
+        ms, n, b = C.c_double(), C.c_int64(), C.c_int64()
+        L.dfdb_profile_get(b"decode", C.byref(ms), C.byref(n), C.byref(b))
+        return out, b.value
+
+    lo, hi = nrows // 2, nrows // 2 + nrows // 100          # a 1 % range of the sorted column
+    views = {
+        "range_on_sorted": lambda: t[(t.q > lo) & (t.q <= hi), ["q", "a", "s"]],
+        "eq_on_sorted": lambda: t[t.q == 12345, ["b", "s"]],
+        "none": lambda: t[t.q > nrows + 5, ["a"]],
+        "unsorted_is_not_pruned": lambda: t[(t.a > 25) & (t.a <= 75), ["b"]],
+        "float_and_missing": lambda: t[D.coalesce(t.mf < 0.001, False) & (t.q <= 9000), ["mf", "q"]],
+        "two_stages": lambda: t[t.a > 50, :][t.q < 5000, ["q", "a"]],
+        "range_after_pruned_predicate": lambda: t[t.q > nrows - 9000, :][R(10, 3, 200), ["q"]],
+        "uint8": lambda: t[(t.u >= 250) | (t.u < 1), ["u", "q"]],
+        "ne_all_equal": lambda: t[t.p != 3.5, ["p"]],
+    }
+    for name, mk in views.items():
+        _capi.check(L.dfdb_set_option(b"no_zonemap", 0))
+        (fr, n, agg), with_bytes = decoded_bytes(lambda: (D.materialize(mk()), D.nrow(mk()), D.aggregate(mk()[:, list(mk().names())[0]])))
+        pruned, nb = D.pruned_blocks(mk())
+        _capi.check(L.dfdb_set_option(b"no_zonemap", 1))
+        try:
+            (fr0, n0, agg0), without_bytes = decoded_bytes(lambda: (D.materialize(mk()), D.nrow(mk()), D.aggregate(mk()[:, list(mk().names())[0]])))
+        finally:
+            _capi.check(L.dfdb_set_option(b"no_zonemap", 0))
+        exp = ot.materialize(D.plan_bytes(mk()))
+        assert fr.to_dict() == fr0.to_dict() and n == n0 == fr.nrow(), name
+        assert bytes(agg) == bytes(agg0), name
+        first = exp[0][0] if isinstance(exp[0], tuple) else exp[0]
+        assert fr.nrow() == len(first), name
+        if name in ("range_on_sorted", "eq_on_sorted", "none", "two_stages", "range_after_pruned_predicate", "float_and_missing"):
+            assert pruned >= nb // 2 and with_bytes < 0.5 * without_bytes, (name, pruned, nb, with_bytes, without_bytes)
+        if name == "unsorted_is_not_pruned":
+            assert pruned == 0 and with_bytes == without_bytes
+    # a stale sidecar (the column file changed) is ignored, not trusted
+    qbin = os.path.join(p, f"{t.getmeta('q').id}.bin")
+    t.close()
+    os.utime(qbin, ns=(1, 1))
+    t = D.open_table(p)
+    assert t.zonemap("q", 0) is None and t.zonemap("a", 0) is not None
+    assert D.nrow(t[(t.q > lo) & (t.q <= hi), ["q"]]) == hi - lo
+    t.close()
+    ot.close()

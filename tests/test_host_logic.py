@@ -192,3 +192,47 @@ def test_bench_plan_constants_match_the_plan_encoder(tmp_path, oracle):
     golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "queries.json")))
     assert bytes.fromhex(next(q["plan"] for q in golden if q["name"] == "range_predicate_aggregate")) == bench.BENCH_PLAN
     t.close()
+
+
+def test_zone_map_sidecar_is_optional_and_validated(tmp_path, oracle):
+    """<id>.zmap (block index + zone maps) is only trusted while it matches the column file; any mismatch falls back to the
+    header walk of the reference (skip_block, BlockStreams.jl:74-78).  Host side only: the sidecars here are hand-made."""
+    import struct as st
+    p = str(tmp_path / "t")
+    oracle.gen_table(p, "q:Int64:iseq;b:Float64:funiform", 5 * 256 + 10, 256, 3, 1)
+    t = D.open_table(p)
+    L = _capi.lib()
+    qid = t.getmeta("q").id
+    nb = t.nblocks()
+    assert nb == 6 and t.zonemap("q", 0) is None
+    t.close()
+    # write a sidecar by hand from the header walk of the oracle-side format description
+    binp = os.path.join(p, f"{qid}.bin")
+    raw = open(binp, "rb").read()
+    pos = 8 + 4 + len("Int64")
+    entries = []
+    blk = 0
+    while pos < len(raw):
+        rows, origin, comp = st.unpack_from("<iqq", raw, pos)
+        lo = blk * 256 + 1
+        entries.append(st.pack("<qiiqqqQQ", pos + 20, rows, 1, origin, comp, 0, lo, lo + rows - 1))
+        pos += 20 + comp
+        blk += 1
+    stt = os.stat(binp)
+    head = b"DFDBZM01" + st.pack("<qqqqqiiii", 256, len(entries), qid, stt.st_size, stt.st_mtime_ns, 4, 0, 8, 1)
+    zm = os.path.join(p, f"{qid}.zmap")
+    open(zm, "wb").write(head + b"".join(entries))
+    t = D.open_table(p)
+    z = t.zonemap("q", 2)
+    assert z is not None and (z.rows, z.min_i64, z.max_i64, z.has_value) == (256, 513, 768, 1)
+    assert t.total_rows() == 5 * 256 + 10 and t.nblocks() == 6
+    t.close()
+    # wrong size recorded, truncated file, wrong magic, an index that does not tile the file: all ignored
+    for bad in (head[:40] + st.pack("<q", stt.st_size + 1) + head[48:] + b"".join(entries),
+                head + b"".join(entries)[:-8],
+                b"DFDBZM99" + head[8:] + b"".join(entries),
+                head + b"".join(entries[:2] + [st.pack("<qiiqqqQQ", 5, 256, 1, 2048, 10, 0, 1, 2)] + entries[3:])):
+        open(zm, "wb").write(bad)
+        t = D.open_table(p)
+        assert t.zonemap("q", 0) is None and t.total_rows() == 5 * 256 + 10
+        t.close()
