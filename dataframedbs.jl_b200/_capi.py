@@ -51,6 +51,7 @@ SYMBOLS = {
     "dfdb_set_stream": (C.c_int32, [C.c_void_p]),
     "dfdb_synchronize": (C.c_int32, []),
     "dfdb_kernel_launches": (C.c_int64, []),
+    "dfdb_numa_node": (C.c_int32, []),
     "dfdb_set_option": (C.c_int32, [C.c_char_p, C.c_int64]),
     "dfdb_profile_enable": (C.c_int32, [C.c_int32]),
     "dfdb_profile_reset": (C.c_int32, []),
@@ -72,6 +73,8 @@ SYMBOLS = {
     "dfdb_table_build_zonemaps": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "dfdb_table_zonemap": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Zone)]),
     "dfdb_scan_pruned": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "dfdb_scan_groupreduce": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int64)]),
+    "dfdb_scan_group_results": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfdb_host_alloc": (C.c_int32, [C.c_int64, C.POINTER(C.c_void_p)]),
     "dfdb_host_free": (C.c_int32, [C.c_void_p]),
     "dfdb_scan_prepare": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int64, C.POINTER(C.c_void_p)]),
@@ -96,6 +99,10 @@ SYMBOLS = {
     "dfdb_scan_count_all": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
     "dfdb_scan_resolve_exchange": (C.c_int32, [C.c_void_p]),
     "dfdb_scan_row_offset_all": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "dfdb_write_column_file": (C.c_int32, [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "dfdb_write_table_meta": (C.c_int32, [C.c_char_p, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]),
+    "dfdb_lz4_compress_blocks": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfdb_lz4_decode_blocks": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
 }
 

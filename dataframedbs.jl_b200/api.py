@@ -21,6 +21,7 @@ Every scan runs on the GPU through the C ABI (dfdb_b200.h); there is no CPU path
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 
 import numpy as np
@@ -204,6 +205,29 @@ class DFTable:
     def drop_decoded(self):
         _capi.check(_capi.lib().dfdb_table_drop_decoded(self._h))
 
+    # ---- add_column! (table.jl:96-124): the new column file is written by the device write path ----
+    def add_column(self, name: str, data, typestring: str | None = None):
+        """`data`: array / masked array / strings (see create_table) or a DFColumn / computed column of THIS table
+        (`t.add_column("c", t.a * t.b)`), which is materialized on the device first."""
+        if name in [m.name for m in self.meta]:
+            raise ArgumentError(f"Column :{name} already exists")
+        if isinstance(data, DFColumn):
+            fr = materialize(data.view)
+            data = fr.columns[0]
+        ts, nrows, vals, miss, sizes, chars = _column_buffers(data, typestring)
+        total = self.total_rows()
+        if total != 0 and total != nrows:
+            raise ArgumentError("Column and table have different sizes")
+        new_id = 1 + max([m.id for m in self.meta], default=0)
+        cols = [(m.id, m.name, m.typestring) for m in self.meta] + [(new_id, name, ts)]
+        write_column_file(self.path, new_id, ts, self.block_size, nrows, vals, miss, sizes, chars, self._device)
+        _write_meta(self.path, self.block_size, cols)
+        # the handle describes the old meta: reopen
+        mode, rank, world, dev = self.mode, self.rank, self.world, self._device
+        self.close()
+        self.__init__(self.path, mode=mode, rank=rank, world=world, device=dev)
+        return self
+
     # ---- block index + zone maps (optional sidecar <id>.zmap; no reference counterpart, SURVEY.md 8f) ----
     def build_zonemaps(self, columns=None):
         """Per-block (min, max, null count) of the given fixed-width numeric columns (default: all of them), computed on the
@@ -289,6 +313,90 @@ class DFTable:
 def open_table(path: str, mode: int = _capi.LOAD_HBM, rank: int = 0, world: int = 1, device: int | None = None) -> DFTable:
     """creators.jl:7-16"""
     return DFTable(path, mode=mode, rank=rank, world=world, device=device)
+
+
+# ---- write path: create_table / add_column! on the device (creators.jl:81-89, table.jl:96-124, columns.jl:65-84) --------------------
+_TYPESTR_OF = {np.dtype(v): k for k, v in _NP.items() if k not in ("Char", "Date", "DateTime", "Time")}
+
+
+def _column_buffers(data, typestring=None):
+    """(typestring, nrows, values, missing, sizes, chars) of a column given as a numpy array (fixed width), a numpy masked array
+    (Union{T,Missing}), a (values, missing) pair, a FlatStringsVector, or a sequence of str / None."""
+    if isinstance(data, FlatStringsVector):
+        sizes = np.ascontiguousarray(data.sizes, dtype=np.int32)
+        chars = np.frombuffer(bytes(data.data), dtype=np.uint8) if not isinstance(data.data, np.ndarray) else np.ascontiguousarray(data.data, dtype=np.uint8)
+        ts = typestring or ("Missing(String)" if (sizes < 0).any() else "String")
+        return ts, len(sizes), None, None, sizes, chars
+    if isinstance(data, np.ma.MaskedArray):
+        data = (np.ma.getdata(data), np.ma.getmaskarray(data))
+    if isinstance(data, tuple) and len(data) == 2 and isinstance(data[0], np.ndarray):
+        vals, miss = np.ascontiguousarray(data[0]), np.ascontiguousarray(data[1], dtype=np.uint8)
+        base = _TYPESTR_OF.get(vals.dtype)
+        if base is None:
+            raise ArgumentError(f"{vals.dtype} is not available as stored column type")
+        vals = np.where(miss.astype(bool), np.zeros((), dtype=vals.dtype), vals)       # bytes under a missing flag are unspecified: write zeros
+        return typestring or f"Missing({base})", len(vals), np.ascontiguousarray(vals), miss, None, None
+    if isinstance(data, np.ndarray) and data.dtype.kind != "O" and data.dtype.kind not in "US":
+        base = _TYPESTR_OF.get(data.dtype)
+        if base is None:
+            raise ArgumentError(f"{data.dtype} is not available as stored column type")
+        return typestring or base, len(data), np.ascontiguousarray(data), None, None, None
+    items = list(data)
+    if all(x is None or isinstance(x, str) for x in items):
+        enc = [None if x is None else x.encode("utf-8") for x in items]
+        sizes = np.array([-1 if b is None else len(b) for b in enc], dtype=np.int32)
+        chars = np.frombuffer(b"".join(b for b in enc if b), dtype=np.uint8)
+        ts = typestring or ("Missing(String)" if any(b is None for b in enc) else "String")
+        return ts, len(items), None, None, sizes, chars
+    if any(x is None for x in items):
+        miss = np.array([x is None for x in items], dtype=np.uint8)
+        vals = np.array([0 if x is None else x for x in items])
+        return _column_buffers((vals, miss), typestring)
+    return _column_buffers(np.array(items), typestring)
+
+
+def write_column_file(path: str, col_id: int, typestring: str, block_size: int, nrows: int, vals, miss, sizes, chars, device=None):
+    """dfdb_write_column_file: bodies assembled, LZ4-compressed and compacted on the device, framed on the host."""
+    _capi.init(device)
+    comp, unc = C.c_int64(), C.c_int64()
+    ptr = lambda a: a.ctypes.data if a is not None and a.size else None      # noqa: E731
+    try:
+        _capi.check(_capi.lib().dfdb_write_column_file(path.encode(), col_id, typestring.encode(), block_size, nrows, ptr(vals), ptr(miss), ptr(sizes),
+                                                       ptr(chars), 0 if chars is None else chars.size, C.byref(comp), C.byref(unc)))
+    except DfdbError as e:
+        if e.code == _capi.ERR_IO:
+            raise RuntimeError(str(e)) from None
+        _raise(e)
+    return comp.value, unc.value
+
+
+def _write_meta(path: str, block_size: int, cols):
+    n = len(cols)
+    ids = (C.c_int64 * max(n, 1))(*[c[0] for c in cols])
+    names = (C.c_char_p * max(n, 1))(*[c[1].encode() for c in cols])
+    types = (C.c_char_p * max(n, 1))(*[c[2].encode() for c in cols])
+    try:
+        _capi.check(_capi.lib().dfdb_write_table_meta(path.encode(), block_size, n, ids, names, types))
+    except DfdbError as e:
+        if e.code == _capi.ERR_IO:
+            raise RuntimeError(str(e)) from None
+        _raise(e)
+
+
+def create_table(path: str, columns, block_size: int = 65536, mode: int = _capi.LOAD_HBM, device=None) -> DFTable:
+    """create_table(path; from = df, block_size) (creators.jl:81-89): `columns` is a dict name -> data or a list of
+    (name, data) / (name, typestring, data); all columns must have the same number of rows.  The column files are written by
+    the device write path (same on-disk format: the reference opens the table)."""
+    if os.path.isdir(path):
+        raise RuntimeError(f"Table {path} already exists")                     # filesystem.jl:36
+    items = [(k, None, v) for k, v in columns.items()] if isinstance(columns, dict) else [(c[0], None, c[1]) if len(c) == 2 else tuple(c) for c in columns]
+    bufs = [(name,) + _column_buffers(data, ts) for name, ts, data in items]
+    if len({b[2] for b in bufs}) > 1:
+        raise ArgumentError("Column and table have different sizes")
+    _write_meta(path, block_size, [(i + 1, b[0], b[1]) for i, b in enumerate(bufs)])
+    for i, (name, ts, nrows, vals, miss, sizes, chars) in enumerate(bufs):
+        write_column_file(path, i + 1, ts, block_size, nrows, vals, miss, sizes, chars, device)
+    return DFTable(path, mode=mode, device=device)
 
 
 def _full_table_projection(table: DFTable) -> Projection:
@@ -757,6 +865,61 @@ def nrow_all(v) -> int:
     except DfdbError as e:
         _raise(e)
     return n.value
+
+
+def groupreduce(view, by, **cols):
+    """groupreduce(view, by; cols...) -- finishes the reference's stub (src/tables/aggregate.jl:1-36): groups of the view's
+    selected rows by the tuple of `by` columns, numbered in order of first appearance like the stub's RobinDict, and per group
+    the reductions of the value columns.  `cols`: result name = source column name.  Returns a dict: every `by` column -> list
+    of key values (None = missing), "count" -> rows per group, and per result name a dict of lists count / nmissing / sum /
+    min / max / mean (None where the group has no non-missing value)."""
+    if isinstance(view, DFTable):
+        view = DFView(view)
+    by = [by] if isinstance(by, str) else list(by)
+    vals = list(cols.values())
+    v = view[:, by + vals]
+    h = _scan_handle(v)
+    L = _capi.lib()
+    ng = C.c_int64()
+    kp = (C.c_int32 * len(by))(*range(len(by)))
+    vp = (C.c_int32 * max(len(vals), 1))(*range(len(by), len(by) + len(vals)))
+    try:
+        _capi.check(L.dfdb_scan_groupreduce(h, kp, len(by), vp, len(vals), C.byref(ng)))
+    except DfdbError as e:
+        _raise(e)
+    n = ng.value
+    first = np.zeros(max(n, 1), dtype=np.int64)
+    aggs = (_capi.Agg * max(n * len(vals), 1))()
+    _capi.check(L.dfdb_scan_group_results(h, first.ctypes.data, aggs))
+    first = first[:n]
+    out = {}
+    # key values: the key columns at the rows where the groups first appear (an index-vector selection of the TABLE)
+    if n:
+        keys = materialize(DFView(view.table)[first.tolist(), by]).to_dict()
+    else:
+        keys = {k: [] for k in by}
+    out.update(keys)
+    out["first_row"] = first.tolist()
+    for j, (name, src) in enumerate(cols.items()):
+        rec = {"count": [], "nmissing": [], "sum": [], "min": [], "max": [], "mean": []}
+        isf = view.table.getmeta(src).type.is_float if hasattr(view.table.getmeta(src).type, "is_float") else view.table.getmeta(src).typestring.replace("Missing(", "").startswith("Float")
+        for g in range(n):
+            a = aggs[g * len(vals) + j]
+            nv = a.count - a.nmissing
+            rec["count"].append(a.count)
+            rec["nmissing"].append(a.nmissing)
+            if a.value_class == 0:
+                rec["sum"].append(0.0 if isf else 0); rec["min"].append(None); rec["max"].append(None); rec["mean"].append(None)
+                continue
+            sm = a.sum_f64 if isf else (a.sum_i64 & ((1 << 64) - 1) if a.value_class == 2 else a.sum_i64)
+            rec["sum"].append(sm)
+            rec["min"].append(a.min_f64 if isf else (a.min_i64 & ((1 << 64) - 1) if a.value_class == 2 else a.min_i64))
+            rec["max"].append(a.max_f64 if isf else (a.max_i64 & ((1 << 64) - 1) if a.value_class == 2 else a.max_i64))
+            rec["mean"].append(sm / nv if nv else None)
+        out[name] = rec
+    if not cols:
+        out["ngroups"] = n
+    return out
 
 
 def pruned_blocks(v):

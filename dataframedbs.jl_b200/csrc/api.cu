@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <fcntl.h>
+#include <sys/syscall.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -32,6 +33,7 @@ struct Runtime {
     bool inited = false;
     int device = 0;
     int sm_count = 148;
+    int numa_node = -1;       // node this process's memory policy prefers (the GPU's), -1 = untouched
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaStream_t decode_stream = nullptr, decode_stream2 = nullptr;   // above the scan stream's priority: the full rounds and the last round of a
                                                                       // decode that the scan of the earlier rounds runs beside (ensure_decoded)
@@ -1148,6 +1150,11 @@ int run_aggregate(dfdb_scan *s, int32_t proj_idx, bool count_only, AggPartial *h
 
 }  // namespace
 
+namespace dfdb {
+RuntimeView runtime_view() { return RuntimeView{rt.stream, rt.d_counter + 8, rt.sm_count, rt.inited}; }
+void runtime_count_launch() { rt.launches++; }
+}  // namespace dfdb
+
 // =================================================================================================
 // C ABI
 // =================================================================================================
@@ -1171,6 +1178,28 @@ int32_t dfdb_init(int32_t device)
     if (prop.major < 10) return fail(DFDB_ERR_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
     rt.device = device;
     rt.sm_count = prop.multiProcessorCount;
+    // One process per GPU: keep this process's host memory -- above all the pinned staging of the transfer-inclusive mode -- on
+    // the NUMA node the GPU hangs off, so that H2D copies do not cross the socket interconnect (measured at 4 and 8 ranks per
+    // box: the per-GPU H2D rate halves when every rank's staging sits on one node).  MPOL_PREFERRED: falls back to other nodes
+    // when the local one is full.  DFDB_NO_NUMA=1 turns it off.
+    rt.numa_node = -1;
+    if (!getenv("DFDB_NO_NUMA")) {
+        char bus[32] = {0};
+        if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) == cudaSuccess) {
+            for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+            const std::string f = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+            if (FILE *fp = fopen(f.c_str(), "r")) {
+                int node = -1;
+                if (fscanf(fp, "%d", &node) == 1 && node >= 0 && node < 64) {
+                    unsigned long mask = 1ul << node;
+#ifdef SYS_set_mempolicy
+                    if (syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 65ul) == 0) rt.numa_node = node;
+#endif
+                }
+                fclose(fp);
+            }
+        }
+    }
     CUDA_TRY(cudaStreamCreateWithFlags(&rt.own_stream, cudaStreamNonBlocking));
     rt.stream = rt.own_stream;
     CUDA_TRY(cudaStreamCreateWithFlags(&rt.copy_stream, cudaStreamNonBlocking));
@@ -1224,6 +1253,7 @@ int32_t dfdb_synchronize(void)
 }
 
 int64_t dfdb_kernel_launches(void) { return rt.launches.load(); }
+int32_t dfdb_numa_node(void) { return rt.numa_node; }
 
 int32_t dfdb_set_option(const char *name, int64_t value)
 {
@@ -2084,7 +2114,7 @@ int32_t dfdb_scan_resolve_exchange(dfdb_scan *s)
     int rc = need_init();
     if (rc) return rc;
     if (!s) return fail(DFDB_ERR_ARGUMENT, "null argument");
-    if (s->tbl->world <= 1) return DFDB_OK;
+    if (s->tbl->world <= 1 && !nccl.comm) return DFDB_OK;
     if (!nccl.comm || nccl.world != s->tbl->world || nccl.rank != s->tbl->rank)
         return fail(DFDB_ERR_STATE, "the table is shard %d of %d but the communicator is rank %d of %d", s->tbl->rank, s->tbl->world, nccl.rank, nccl.world);
     for (int stage = 0; stage < 64; stage++) {
@@ -2116,7 +2146,7 @@ int32_t dfdb_scan_aggregate_all(dfdb_scan *s, int32_t proj_idx, dfdb_agg *out)
     int rc = need_init();
     if (rc) return rc;
     if (!s || !out) return fail(DFDB_ERR_ARGUMENT, "null argument");
-    if (s->tbl->world <= 1) return dfdb_scan_aggregate(s, proj_idx, out);
+    if (s->tbl->world <= 1 && !nccl.comm) return dfdb_scan_aggregate(s, proj_idx, out);     // unsharded, no communicator: the local result is the result
     rc = dfdb_scan_resolve_exchange(s);
     if (rc) return rc;
     dfdb_agg mine;
@@ -2142,7 +2172,8 @@ int32_t dfdb_scan_row_offset_all(dfdb_scan *s, int64_t *local, int64_t *row_offs
     rc = dfdb_scan_count(s, &n);
     if (rc) return rc;
     int64_t lower = 0, all = n;
-    if (s->tbl->world > 1) {
+    if (s->tbl->world > 1 || nccl.comm) {
+        if (!nccl.comm || nccl.world != s->tbl->world) return fail(DFDB_ERR_STATE, "the table is shard %d of %d but the communicator has %d ranks", s->tbl->rank, s->tbl->world, nccl.comm ? nccl.world : 0);
         rc = comm_allgather(&n, sizeof n);
         if (rc) return rc;
         all = 0;
@@ -2163,6 +2194,139 @@ int32_t dfdb_scan_count_all(dfdb_scan *s, int64_t *n)
 {
     if (!n) return fail(DFDB_ERR_ARGUMENT, "null argument");
     return dfdb_scan_row_offset_all(s, nullptr, nullptr, n);
+}
+
+// ---- group-by reduce ------------------------------------------------------------------------------------
+int32_t dfdb_scan_groupreduce(dfdb_scan *s, const int32_t *key_proj, int32_t nkeys, const int32_t *val_proj, int32_t nvals, int64_t *ngroups)
+{
+    int rc = need_init();
+    if (rc) return rc;
+    if (!s || !key_proj || !ngroups) return fail(DFDB_ERR_ARGUMENT, "null argument");
+    if (nkeys < 1 || nkeys > GROUP_MAX_KEYS || nvals < 0 || nvals > GROUP_MAX_VALS) return fail(DFDB_ERR_UNSUPPORTED, "group-by takes 1..%d key and 0..%d value columns", GROUP_MAX_KEYS, GROUP_MAX_VALS);
+    dfdb_table *t = s->tbl;
+    if (t->world != 1) return fail(DFDB_ERR_UNSUPPORTED, "group-by runs on the unsharded table");
+    std::vector<int64_t> need;
+    auto col_of = [&](int32_t pi, bool value, Column **out) -> int {
+        if (pi < 0 || (size_t)pi >= s->projs.size()) return fail(DFDB_ERR_ARGUMENT, "projection index out of range");
+        const Proj &p = s->projs[(size_t)pi];
+        if (p.kind != PJ_COL) return fail(DFDB_ERR_UNSUPPORTED, "group-by keys and values are stored columns (materialize a computed column with add_column first)");
+        Column *c = t->find(p.col);
+        const int cls = value_class(c->type.kind);
+        if (cls == VC_NONE || c->type.elsize > 8) return fail(DFDB_ERR_UNSUPPORTED, "column %s of type %s cannot be grouped", c->name.c_str(), c->typestr.c_str());
+        if (value && cls == VC_STR) return fail(DFDB_ERR_UNSUPPORTED, "aggregate over column %s of type %s", c->name.c_str(), c->typestr.c_str());
+        need.push_back(p.col);
+        *out = c;
+        return DFDB_OK;
+    };
+    Column *kc[GROUP_MAX_KEYS] = {nullptr, nullptr}, *vc[GROUP_MAX_VALS] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < nkeys; i++) if ((rc = col_of(key_proj[i], false, &kc[i]))) return rc;
+    for (int i = 0; i < nvals; i++) if ((rc = col_of(val_proj[i], true, &vc[i]))) return rc;
+    invalidate_decoded(t);
+    BlockWindow win(s);
+    rc = run_selection(s);
+    if (rc) return rc;
+    int64_t total = 0;
+    rc = count_mask(s, &total);
+    if (rc) return rc;
+    s->group_first.clear();
+    s->group_aggs.clear();
+    *ngroups = 0;
+    if (total == 0) return DFDB_OK;
+    {
+        LiveBlocks live(s);
+        rc = ensure_decoded(t, need);
+        if (rc) return rc;
+    }
+    const Geometry g = make_geometry(t);
+    const int nv = std::max(nvals, 1);
+    for (uint64_t cap = 1u << 16; cap <= (1ull << 28); cap <<= 2) {
+        if (cap < (uint64_t)std::min<int64_t>(total, 1 << 26) / 64) continue;       // (start near the size the data suggests)
+        long long *d_rep = nullptr, *d_first = nullptr;
+        GroupAcc *d_acc = nullptr;
+        int *d_flag = nullptr;
+        auto cleanup = [&]() { cudaFree(d_rep); cudaFree(d_first); cudaFree(d_acc); cudaFree(d_flag); };
+        if (cudaMalloc(reinterpret_cast<void **>(&d_rep), cap * 8) != cudaSuccess || cudaMalloc(reinterpret_cast<void **>(&d_first), cap * 8) != cudaSuccess ||
+            cudaMalloc(reinterpret_cast<void **>(&d_acc), cap * nv * sizeof(GroupAcc)) != cudaSuccess || cudaMalloc(reinterpret_cast<void **>(&d_flag), 16) != cudaSuccess) {
+            cleanup();
+            cudaGetLastError();
+            return fail(DFDB_ERR_NOMEM, "out of device memory for a group table of %llu slots", (unsigned long long)cap);
+        }
+        cudaMemsetAsync(d_rep, 0xff, cap * 8, rt.stream);
+        cudaMemsetAsync(d_first, 0x7f, cap * 8, rt.stream);
+        cudaMemsetAsync(d_flag, 0, 16, rt.stream);
+        {
+            std::vector<GroupAcc> init(1);
+            memset(&init[0], 0, sizeof(GroupAcc));
+            cudaMemsetAsync(d_acc, 0, cap * nv * sizeof(GroupAcc), rt.stream);
+        }
+        GroupArgs a;
+        memset(&a, 0, sizeof a);
+        a.g = g; a.mask = s->d_mask; a.nkeys = nkeys; a.nvals = nvals;
+        for (int i = 0; i < nkeys; i++) a.key[i] = make_view(*kc[i]);
+        for (int i = 0; i < nvals; i++) a.val[i] = make_view(*vc[i]);
+        a.rep = d_rep; a.first = d_first; a.acc = d_acc; a.cap_mask = cap - 1; a.overflow = d_flag;
+        a.ngroups = reinterpret_cast<unsigned long long *>(d_flag + 2);
+        // min / max start at the identities of their order
+        {
+            std::vector<GroupAcc> h((size_t)std::min<uint64_t>(cap * nv, 1u << 16));
+            for (size_t i = 0; i < h.size(); i++) {
+                memset(&h[i], 0, sizeof(GroupAcc));
+                const int cls = nvals ? value_class(vc[i % (size_t)nv]->type.kind) : VC_INT;
+                if (cls == VC_UINT || cls == VC_BOOL) { h[i].min_k = -1ll; h[i].max_k = 0; }
+                else { h[i].min_k = INT64_MAX; h[i].max_k = INT64_MIN; }
+            }
+            for (uint64_t off = 0; off < cap * nv; off += h.size())
+                cudaMemcpyAsync(d_acc + off, h.data(), std::min<uint64_t>(h.size(), cap * nv - off) * sizeof(GroupAcc), cudaMemcpyHostToDevice, rt.stream);
+        }
+        if (launch_group_reduce(a, rt.sm_count, rt.stream) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "group-by launch failed"); }
+        rt.launches++;
+        int flag[4] = {0, 0, 0, 0};
+        cudaMemcpyAsync(flag, d_flag, 16, cudaMemcpyDeviceToHost, rt.stream);
+        if (cudaStreamSynchronize(rt.stream) != cudaSuccess) { cleanup(); return fail(DFDB_ERR_CUDA, "group-by kernel failed: %s", cudaGetErrorString(cudaGetLastError())); }
+        unsigned long long ng;
+        memcpy(&ng, flag + 2, 8);
+        if (flag[0] || ng * 2 > cap) { cleanup(); continue; }                        // too full: a table four times the size
+        // ---- results to the host, groups in order of first appearance ----
+        std::vector<long long> first((size_t)cap);
+        std::vector<GroupAcc> acc((size_t)(cap * nv));
+        cudaMemcpyAsync(first.data(), d_first, cap * 8, cudaMemcpyDeviceToHost, rt.stream);
+        cudaMemcpyAsync(acc.data(), d_acc, cap * nv * sizeof(GroupAcc), cudaMemcpyDeviceToHost, rt.stream);
+        cudaError_t e = cudaStreamSynchronize(rt.stream);
+        cleanup();
+        if (e != cudaSuccess) return fail(DFDB_ERR_CUDA, "group-by results: %s", cudaGetErrorString(e));
+        std::vector<std::pair<long long, size_t>> order;
+        for (size_t sl = 0; sl < (size_t)cap; sl++) if (first[sl] != 0x7f7f7f7f7f7f7f7fll) order.emplace_back(first[sl], sl);
+        std::sort(order.begin(), order.end());
+        s->group_first.resize(order.size());
+        s->group_aggs.assign(order.size() * (size_t)nvals, dfdb_agg());
+        for (size_t gi = 0; gi < order.size(); gi++) {
+            s->group_first[gi] = t->blk_lo * t->block_size + order[gi].first + 1;
+            for (int v = 0; v < nvals; v++) {
+                const GroupAcc &ga = acc[order[gi].second * (size_t)nv + (size_t)v];
+                dfdb_agg &o = s->group_aggs[gi * (size_t)nvals + (size_t)v];
+                memset(&o, 0, sizeof o);
+                const int cls = value_class(vc[v]->type.kind);
+                o.count = (int64_t)ga.count; o.nmissing = (int64_t)ga.nmissing; o.sum_i64 = ga.sum_i; o.sum_f64 = ga.sum_f; o.has_nan = (ga.flags >> 1) & 1;
+                if (cls == VC_FLT) {
+                    auto undo = [](long long k) { const long long b = k < 0 ? (long long)(0x8000000000000000ull - (unsigned long long)k) : k; double d; memcpy(&d, &b, 8); return d; };
+                    if (ga.flags & 1) { o.min_f64 = undo(ga.min_k); o.max_f64 = undo(ga.max_k); }
+                    if (ga.flags & 2) { o.min_f64 = o.max_f64 = NAN; }              // NaN propagates through Julia's min / max
+                } else if (ga.flags & 1) { o.min_i64 = ga.min_k; o.max_i64 = ga.max_k; }
+                o.value_class = (ga.flags & 3) ? (cls == VC_FLT ? 3 : cls == VC_UINT ? 2 : cls == VC_BOOL ? 4 : 1) : 0;
+            }
+        }
+        *ngroups = (int64_t)order.size();
+        return DFDB_OK;
+    }
+    return fail(DFDB_ERR_NOMEM, "more groups than the largest group table holds");
+}
+
+int32_t dfdb_scan_group_results(dfdb_scan *s, int64_t *first_rows, dfdb_agg *aggs)
+{
+    if (!s) return fail(DFDB_ERR_ARGUMENT, "null argument");
+    if (first_rows && !s->group_first.empty()) memcpy(first_rows, s->group_first.data(), s->group_first.size() * 8);
+    if (aggs && !s->group_aggs.empty()) memcpy(aggs, s->group_aggs.data(), s->group_aggs.size() * sizeof(dfdb_agg));
+    return DFDB_OK;
 }
 
 // ---- result arena ------------------------------------------------------------------------------------

@@ -103,6 +103,10 @@ struct dfdb_table {
 namespace dfdb {
 
 int table_open_host(const char *path, dfdb_table **out);   // format.cpp
+// runtime of api.cu for the other translation units that launch kernels (write_path.cu)
+struct RuntimeView { void *stream; unsigned int *counter; int sm_count; bool inited; };
+RuntimeView runtime_view();
+void runtime_count_launch();
 int zonemap_write(const dfdb_table *t, const Column &c);    // format.cpp: <table>/<id>.zmap from c.blocks + c.zones
 
 // ------------------------------------------------------------------------------------------------
@@ -229,6 +233,8 @@ struct dfdb_scan {
     std::vector<uint8_t> zone_dead;    // per local block: 1 = the zone maps rule out every row for some predicate stage (never decoded)
     uint8_t *d_zone_dead = nullptr;
     int64_t zone_pruned = 0;           // blocks ruled out by the zone maps in the last run
+    std::vector<int64_t> group_first;  // group-by: 1-based table row of each group's first appearance, ascending
+    std::vector<dfdb_agg> group_aggs;  // ngroups x nvals
     std::vector<int64_t> rank_offsets;
     int64_t exchange_count = -1;       // this shard's count at the first stage whose offset is missing
 };

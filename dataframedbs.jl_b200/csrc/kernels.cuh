@@ -165,6 +165,32 @@ int launch_str_offsets(const Geometry &g, const ColView &col, int32_t *str_off, 
 struct ZoneOut { unsigned long long min_bits, max_bits; long long null_count; int flags, pad; };
 int launch_zone_map(const Geometry &g, const ColView &col, ZoneOut *out, cudaStream_t stream);
 
+// ---- group-by reduce (the stub at src/tables/aggregate.jl:1-36): hash aggregation of the selected rows -----
+constexpr int GROUP_MAX_KEYS = 2;
+constexpr int GROUP_MAX_VALS = 4;
+struct GroupAcc {                    // per (group, value column)
+    unsigned long long count;        // selected rows of the group (missing included)
+    unsigned long long nmissing;
+    long long sum_i;                 // wrapping integer sum
+    double sum_f;
+    long long min_k, max_k;          // integers: the values; floats: their order-preserving integer encoding (NaN excluded)
+    int flags, pad;                  // 1 = has a non-missing, non-NaN value, 2 = has NaN
+};
+struct GroupArgs {
+    Geometry g;
+    const uint32_t *mask;
+    int nkeys, nvals;
+    ColView key[GROUP_MAX_KEYS];
+    ColView val[GROUP_MAX_VALS];
+    long long *rep;                  // cap slots: a row of the group (0-based shard row), -1 = empty
+    long long *first;                // cap slots: lowest row of the group
+    GroupAcc *acc;                   // cap x nvals
+    unsigned long long cap_mask;     // cap - 1 (cap is a power of two)
+    int *overflow;                   // set when the table filled up: the host doubles it and runs again
+    unsigned long long *ngroups;
+};
+int launch_group_reduce(const GroupArgs &a, int sm_count, cudaStream_t stream);
+
 // ---- K5/K6: stream compaction / gathers ---------------------------------------------------------------
 struct GatherArgs {
     Geometry g;

@@ -859,6 +859,129 @@ __global__ void __launch_bounds__(SCAN_THREADS) zone_map_kernel(const Geometry g
     }
 }
 
+// ---- group-by reduce -----------------------------------------------------------------------------------------------
+// One thread per selected row.  A group is identified by a slot of an open-addressing table that stores a ROW of the group
+// (`rep`), not the key: keys are compared by reading the key columns of that row again, which works for any number and
+// type of key columns (strings included) without a key store.  Equality is Julia's isequal, the relation RobinDict uses in
+// the reference's stub (aggregate.jl:7-27): missing equals missing, NaN equals NaN, -0.0 differs from 0.0.
+// Counts, integer sums, minima and maxima are exact and order-independent (atomics on integers); Float64 sums are atomic
+// adds in arrival order: reproducible to rounding, not bit for bit (stated in DESIGN.md).
+__device__ __forceinline__ unsigned long long gmix(unsigned long long x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ unsigned long long canon_bits(const ColView &c, unsigned long long v)
+{
+    if (c.cls == VC_FLT) {
+        const double x = __longlong_as_double((long long)v);
+        if (x != x) return 0x7ff8000000000000ull;               // one NaN
+    }
+    return v;
+}
+__device__ unsigned long long group_key_hash(const GroupArgs &A, int lb, int64_t rows_b, int64_t r)
+{
+    unsigned long long h = 0x243F6A8885A308D3ull;
+    for (int k = 0; k < A.nkeys; k++) {
+        const ColView &c = A.key[k];
+        if (c.cls == VC_STR) {
+            const uint8_t *body = col_body(c, lb);
+            const int sz = reinterpret_cast<const int32_t *>(body + 4)[r];
+            const uint8_t *p = body + 4 + 4 * rows_b + c.str_off[(int64_t)lb * A.g.block_size + r];
+            unsigned long long f = 0xCBF29CE484222325ull;
+            for (int i = 0; i < sz; i++) f = (f ^ p[i]) * 0x100000001B3ull;
+            h = gmix(h ^ f ^ ((unsigned long long)(unsigned)sz << 32));
+        } else if (col_missing(c, lb, r)) {
+            h = gmix(h ^ 0xA5A5A5A5A5A5A5A5ull);
+        } else {
+            h = gmix(h ^ canon_bits(c, load_widen(col_values(c, lb, rows_b) + r * c.elsize, c.kind)));
+        }
+    }
+    return h;
+}
+__device__ bool group_keys_equal(const GroupArgs &A, int lb1, int64_t r1, int lb2, int64_t r2)
+{
+    const int64_t rows1 = block_rows(A.g, lb1), rows2 = block_rows(A.g, lb2);
+    for (int k = 0; k < A.nkeys; k++) {
+        const ColView &c = A.key[k];
+        if (c.cls == VC_STR) {
+            const uint8_t *b1 = col_body(c, lb1), *b2 = col_body(c, lb2);
+            const int s1 = reinterpret_cast<const int32_t *>(b1 + 4)[r1], s2 = reinterpret_cast<const int32_t *>(b2 + 4)[r2];
+            if (s1 != s2) return false;
+            const uint8_t *p1 = b1 + 4 + 4 * rows1 + c.str_off[(int64_t)lb1 * A.g.block_size + r1];
+            const uint8_t *p2 = b2 + 4 + 4 * rows2 + c.str_off[(int64_t)lb2 * A.g.block_size + r2];
+            for (int i = 0; i < s1; i++) if (p1[i] != p2[i]) return false;
+        } else {
+            const bool m1 = col_missing(c, lb1, r1), m2 = col_missing(c, lb2, r2);
+            if (m1 != m2) return false;
+            if (!m1 && canon_bits(c, load_widen(col_values(c, lb1, rows1) + r1 * c.elsize, c.kind)) !=
+                           canon_bits(c, load_widen(col_values(c, lb2, rows2) + r2 * c.elsize, c.kind))) return false;
+        }
+    }
+    return true;
+}
+// order-preserving integer image of a double (NaN never gets here)
+__device__ __forceinline__ long long dbl_order_key(double x)
+{
+    const long long b = __double_as_longlong(x);
+    return b < 0 ? (long long)(0x8000000000000000ull - (unsigned long long)b) : b;      // -0.0 -> 0 - ... below +0.0
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) group_reduce_kernel(const GroupArgs A)
+{
+    const Geometry g = A.g;
+    const int64_t total_words = (int64_t)g.nblocks * g.wpb;
+    for (int64_t w = (int64_t)blockIdx.x * (SCAN_THREADS / 32) + warp_id(); w < total_words; w += (int64_t)gridDim.x * (SCAN_THREADS / 32)) {
+        const int lb = (int)(w / g.wpb);
+        const int64_t r = (w - (int64_t)lb * g.wpb) * 32 + lane_id();
+        const int64_t rows_b = block_rows(g, lb);
+        if (r >= rows_b || !((A.mask[w] >> lane_id()) & 1u)) continue;
+        const long long row = (long long)lb * g.block_size + r;                 // shard row
+        unsigned long long slot = group_key_hash(A, lb, rows_b, r) & A.cap_mask;
+        bool placed = false;
+        for (unsigned long long probe = 0; probe <= A.cap_mask; probe++, slot = (slot + 1) & A.cap_mask) {
+            long long cur = atomicAdd(reinterpret_cast<unsigned long long *>(&A.rep[slot]), 0ull);   // (atomic read)
+            if (cur == -1) {
+                const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&A.rep[slot]), (unsigned long long)-1ll, (unsigned long long)row);
+                if (old == (unsigned long long)-1ll) { atomicAdd(A.ngroups, 1ull); cur = row; }
+                else cur = (long long)old;
+            }
+            if (cur == row || group_keys_equal(A, lb, r, (int)(cur / g.block_size), cur % g.block_size)) { placed = true; break; }
+            if (probe > 4096) break;                                            // hopelessly full: grow
+        }
+        if (!placed) { atomicExch(A.overflow, 1); continue; }
+        atomicMin(reinterpret_cast<long long *>(&A.first[slot]), row);
+        for (int v = 0; v < A.nvals; v++) {
+            const ColView &c = A.val[v];
+            GroupAcc *acc = A.acc + slot * A.nvals + v;
+            atomicAdd(&acc->count, 1ull);
+            if (col_missing(c, lb, r)) { atomicAdd(&acc->nmissing, 1ull); continue; }
+            const unsigned long long bits = load_widen(col_values(c, lb, rows_b) + r * c.elsize, c.kind);
+            if (c.cls == VC_FLT) {
+                const double x = __longlong_as_double((long long)bits);
+                atomicAdd(&acc->sum_f, x);
+                if (x != x) { atomicOr(&acc->flags, 2); continue; }
+                const long long k = dbl_order_key(x);
+                atomicMin(&acc->min_k, k);
+                atomicMax(&acc->max_k, k);
+                atomicOr(&acc->flags, 1);
+            } else {
+                atomicAdd(reinterpret_cast<unsigned long long *>(&acc->sum_i), bits);
+                if (c.cls == VC_UINT || c.cls == VC_BOOL) {
+                    atomicMin(reinterpret_cast<unsigned long long *>(&acc->min_k), bits);
+                    atomicMax(reinterpret_cast<unsigned long long *>(&acc->max_k), bits);
+                } else {
+                    atomicMin(&acc->min_k, (long long)bits);
+                    atomicMax(&acc->max_k, (long long)bits);
+                }
+                atomicOr(&acc->flags, 1);
+            }
+        }
+    }
+}
+
 // ---- K5/K6: warp-aggregated compaction --------------------------------------------------------------------
 // Work unit = (block, warp range of mask words).  Each CTA takes one block at a time; its 8 warps own
 // contiguous word ranges; a first pass counts, a second pass walks the words in order so every selected
@@ -1260,6 +1383,14 @@ int launch_str_offsets(const Geometry &g, const ColView &col, int32_t *str_off, 
     if (lo < 0) lo = 0;
     if (hi <= lo) return 0;
     str_offsets_kernel<<<grid_for((hi - lo + 7) / 8, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(g, col, str_off, status, origin, lo, hi, dead);
+    return CHECK_LAUNCH();
+}
+
+int launch_group_reduce(const GroupArgs &a, int sm_count, cudaStream_t stream)
+{
+    const int64_t words = (int64_t)a.g.nblocks * a.g.wpb;
+    if (words <= 0) return 0;
+    group_reduce_kernel<<<grid_for((words + 7) / 8, sm_count, 8), SCAN_THREADS, 0, stream>>>(a);
     return CHECK_LAUNCH();
 }
 

@@ -88,6 +88,7 @@ DFDB_API const char *dfdb_last_error(void);
 DFDB_API int32_t dfdb_set_stream(void *cuda_stream);        /* run on the caller's cudaStream_t (NULL = library stream)     */
 DFDB_API int32_t dfdb_synchronize(void);
 DFDB_API int64_t dfdb_kernel_launches(void);                /* number of kernels this library has launched so far           */
+DFDB_API int32_t dfdb_numa_node(void);                      /* NUMA node dfdb_init bound this process's host memory to (-1: none) */
 DFDB_API int32_t dfdb_set_option(const char *name, int64_t value);
 /* per-phase device timing (CUDA events on the scan stream): phases "h2d","decode","unpack","select","consume","d2h" */
 DFDB_API int32_t dfdb_profile_enable(int32_t on);
@@ -154,6 +155,19 @@ DFDB_API int32_t dfdb_scan_indices(dfdb_scan *s, int64_t *idx, int64_t cap, int6
 DFDB_API int32_t dfdb_scan_materialize_sizes(dfdb_scan *s, int64_t *nrows, int64_t *str_bytes_per_col);
 DFDB_API int32_t dfdb_scan_materialize(dfdb_scan *s, dfdb_outcol *cols, int32_t ncols);
 
+/* ---- group-by reduce: finishes what the reference stubs in src/tables/aggregate.jl:1-36
+ *      (groupreduce(view, by; cols...): a RobinDict from the tuple of key values to a group number in order of first
+ *      appearance, "Future plans" docs/src/index.md:597).  Hash aggregation on the device over the selected rows: keys = 1..2
+ *      projected columns (any stored type, String included; missing is a key value of its own, equality is isequal), values =
+ *      up to 4 projected numeric columns, each reduced to a dfdb_agg (count / nmissing / sum / min / max) per group.
+ *      dfdb_scan_groupreduce runs it and returns the number of groups; dfdb_scan_group_results copies out, in order of
+ *      first appearance, the 1-based table row where each group first appears (materialize the key columns at those rows
+ *      to get the key values) and ngroups x nvals aggregates (row-major).  Unsharded tables.  Counts, integer sums, minima
+ *      and maxima are exact; Float64 sums are accumulated in arrival order (reproducible to rounding). ------------------- */
+DFDB_API int32_t dfdb_scan_groupreduce(dfdb_scan *s, const int32_t *key_proj, int32_t nkeys, const int32_t *val_proj, int32_t nvals,
+                                       int64_t *ngroups);
+DFDB_API int32_t dfdb_scan_group_results(dfdb_scan *s, int64_t *first_rows, dfdb_agg *aggs);
+
 /* ---- multi-GPU: one process per GPU; each rank scans its shard, the tiny partials are exchanged by
  *      the host (NCCL all-gather) and folded in rank order on every rank ------------------------- */
 DFDB_API int32_t dfdb_agg_fold(const dfdb_agg *partials, int32_t n, dfdb_agg *out);
@@ -200,6 +214,26 @@ DFDB_API int32_t dfdb_scan_row_offset_all(dfdb_scan *s, int64_t *local, int64_t 
  *      false) and a finalizer that calls dfdb_host_free. --------------------------------------------------------- */
 DFDB_API int32_t dfdb_host_alloc(int64_t bytes, void **ptr);
 DFDB_API int32_t dfdb_host_free(void *ptr);
+
+/* ---- write path: LZ4 block compression and block framing on the device.
+ *      dfdb_write_column_file = make_column_file (src/io/filesystem.jl:22-31) + write_column (src/io/columns.jl:65-84,
+ *      one commit_block_write! per block, src/io/BlockStreams.jl:36-60): <table>/<id>.bin = Int64 block_size | typestring |
+ *      { Int32 rows | Int64 origin | Int64 compressed | one raw LZ4 block }*, the body of every block laid out as
+ *      src/io/blocks.jl:2-33 writes it (bits T; Union{T,Missing}: BitArray chunks + values; String: Int32 datasize | Int32
+ *      sizes, -1 = missing | chars).  The bodies are assembled and compressed on the device (lz4_compress.cu), the host only
+ *      frames them.  HOST input buffers: `values` nrows * elsize bytes (fixed width), `missing` nrows bytes (1 = missing,
+ *      nullable types, else NULL), `str_sizes` / `str_chars` for String columns.  The file must not exist.  The compressed
+ *      bytes are not liblz4's (never compared); any LZ4_decompress_safe decodes them to the same body.
+ *      dfdb_write_table_meta = write_table_meta (src/io/table_io.jl:9-19): creates the directory when needed. ----------- */
+DFDB_API int32_t dfdb_write_column_file(const char *table_path, int64_t col_id, const char *typestring, int64_t block_size, int64_t nrows,
+                                        const void *values, const uint8_t *missing, const int32_t *str_sizes, const uint8_t *str_chars,
+                                        int64_t nchars, int64_t *compressed_total, int64_t *uncompressed_total);
+DFDB_API int32_t dfdb_write_table_meta(const char *table_path, int64_t block_size, int32_t ncols, const int64_t *ids,
+                                       const char *const *names, const char *const *typestrings);
+/* codec hook of the write path: LZ4_compress_fast (src/io/BlockStreams.jl:42-48) for n independent HOST bodies; out slots
+ * must hold LZ4_compressBound(len) = len + len / 255 + 16 bytes; comp_len[i] = compressed size */
+DFDB_API int32_t dfdb_lz4_compress_blocks(const uint8_t *bodies, const int64_t *body_off, const int64_t *body_len, int32_t n,
+                                          uint8_t *out, const int64_t *out_off, int64_t *comp_len);
 
 /* ---- codec hook: read_block (src/io/BlockStreams.jl:101-119) for n independent raw LZ4 blocks.
  *      comp/out are HOST buffers; status[i] = 0 or DFDB_ERR_CORRUPT ------------------------------ */
