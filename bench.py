@@ -460,16 +460,45 @@ def main():
         scan_only["frac"] = scan_only["achieved"] / peak
     t.close()
 
+    # ---- what the box gives: pinned host -> device with every rank copying at once (the roofline of the transfer-inclusive mode) ----
+    def h2d_ceiling():
+        nb = 1 << 30
+        host = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+        host.fill_(1)
+        devb = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(4):
+            devb.copy_(host, non_blocking=True)
+        b.record(stream)
+        torch.cuda.synchronize()
+        mine = torch.tensor([4 * nb / 1e9 / (a.elapsed_time(b) / 1e3)], dtype=torch.float64, device="cuda")
+        rates = [mine]
+        if world > 1:
+            rates = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(rates, mine)
+        del host, devb
+        return [round(float(r.item()), 2) for r in rates]
+
     # ---- end to end: compressed blocks in pinned host memory, H2D inside every step ----
     e2e = None
     if not args.no_e2e:
+        ceiling = h2d_ceiling()
         t, v = open_view(D.LOAD_HOST)
         k = max(3, min(args.steps, 5))
         res_e, ms_e, _, _ = timed(v, k, 1, profile=True)
         h2d_ms, _, h2d_bytes = phase("h2d")
         e2e = {"value": total_rows * k / (ms_e / 1e3), "unit": "rows/s", "h2d_bytes_per_step": shard_comp, "d2h_bytes_per_step": C.sizeof(_capi.Agg) + 8,
                "steps": k, "ms_per_step": ms_e / k, "h2d_gbs": (h2d_bytes / 1e9) / (h2d_ms / 1e3) if h2d_ms > 0 else None,
-               "same_result": (res_e.count, res_e.sum_f64, res_e.sum_f64_lo) == (hbm_result.count, hbm_result.sum_f64, hbm_result.sum_f64_lo)}
+               "same_result": (res_e.count, res_e.sum_f64, res_e.sum_f64_lo) == (hbm_result.count, hbm_result.sum_f64, hbm_result.sum_f64_lo),
+               "h2d_ceiling_gbs_per_rank": ceiling, "h2d_ceiling_gbs_aggregate": round(sum(ceiling), 2),
+               "h2d_ceiling_note": "pinned host -> device, 1 GiB x 4, every rank copying at once, measured in this run; a step ends when the "
+                                   "slowest rank ends, so the roofline of the whole job is world x the slowest rank's ceiling"}
+        # roofline of the transfer-inclusive mode: bytes every rank must move / the slowest rank's measured H2D ceiling
+        e2e["h2d_frac_of_node_ceiling"] = (shard_comp / 1e9 / (ms_e / k / 1e3)) / min(ceiling) if ms_e > 0 else None
         t.close()
 
     # ---- the other BASELINE.json configurations and the compressible-b variant of this one, N = 1 only ----

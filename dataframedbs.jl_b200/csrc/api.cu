@@ -2115,6 +2115,13 @@ int32_t dfdb_scan_resolve_exchange(dfdb_scan *s)
     if (rc) return rc;
     if (!s) return fail(DFDB_ERR_ARGUMENT, "null argument");
     if (s->tbl->world <= 1 && !nccl.comm) return DFDB_OK;
+    {
+        // only a range / index-vector stage that follows another stage ranks rows among ALL survivors; every other plan is
+        // shard-local and must not pay a selection pass here
+        size_t ranked = 0;
+        for (size_t i = 1; i < s->stages.size(); i++) ranked += s->stages[i].kind != ST_PRED;
+        if (ranked <= s->rank_offsets.size()) return DFDB_OK;
+    }
     if (!nccl.comm || nccl.world != s->tbl->world || nccl.rank != s->tbl->rank)
         return fail(DFDB_ERR_STATE, "the table is shard %d of %d but the communicator is rank %d of %d", s->tbl->rank, s->tbl->world, nccl.rank, nccl.world);
     for (int stage = 0; stage < 64; stage++) {
