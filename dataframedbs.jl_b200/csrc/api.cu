@@ -51,9 +51,10 @@ struct Runtime {
     int64_t no_wide = 0;
     int64_t no_fused = 0;
     int64_t no_tma = 0;
-    int64_t lz4_flavour = 0;  // K1 flavour: 0 = per column from a token sample at load, 1 = word-regular decoder (v2), 2 = general decoder (v3), 3 = lane-per-block decoder
+    int64_t lz4_flavour = 0;  // K1 flavour: 0 = per column from a token sample at load, 1 = word-regular decoder (v2), 2 = general decoder (v3), 3 = lane-per-block decoder, 4 = warp-per-block decoder with verified token runs (spec)
     int64_t no_overlap = 0;   // do not run the scan of the decoded part of a shard beside the decode of its last part
     int64_t no_alias = 0;     // copy stored (incompressible) blocks like any other block instead of referencing them in place
+    int64_t spec_tail_pct = 25; // spec decoder: share of the blocks decoded beside the scan of the others (A/B)
     int64_t no_zonemap = 0;   // ignore zone maps (A/B: results must not change)
     int64_t no_validate = 0;  // skip the acceptance pass of dfdb_table_load (A/B, load-time measurements)
     int64_t lane_hot = -1;    // lane decoder: -1 = hot-step schedule per column from the token sample, 0 / 1 = force off / on (A/B, tests)
@@ -287,20 +288,21 @@ bool wide_ok(const dfdb_table *t, const Column &c)
 }
 
 // ---- decode ---------------------------------------------------------------------------------------------
-int launch_decode(const DecodeArgs &a, bool general, cudaStream_t stream = nullptr, int cta_limit = 0, int counter_slot = 0)
+int launch_decode(const DecodeArgs &a, int general, cudaStream_t stream = nullptr, int cta_limit = 0, int counter_slot = 0)
 {
     if (!stream) stream = rt.stream;
     unsigned int *counter = rt.d_counter + 4 * counter_slot;   // launches that may run at the same time need their own job counter
     if (rt.lz4_simple || rt.lz4_v1) return launch_lz4_decode(a, counter, rt.sm_count, (int)rt.lz4_simple, stream);
     if (rt.lz4_flavour == 3) {
         DecodeArgs la = a;
-        la.hot = general ? 0 : 1;      // word-regular columns (the token sample at load) run the hot-step schedule
+        la.hot = general == 1 ? 0 : 1;   // word-regular columns (the token sample at load) run the hot-step schedule
         if (rt.lane_hot >= 0) la.hot = (int)rt.lane_hot;
         return launch_lz4_decode_lane(la, nullptr, counter, rt.sm_count, stream, cta_limit);
     }
-    if (rt.lz4_flavour == 1) general = false;
-    if (rt.lz4_flavour == 2) general = true;
-    return general ? launch_lz4_decode_v3(a, counter, rt.sm_count, stream, cta_limit) : launch_lz4_decode_v2(a, counter, rt.sm_count, stream, cta_limit);
+    if (rt.lz4_flavour == 4 || (rt.lz4_flavour == 0 && general == 2)) return launch_lz4_decode_spec(a, counter, rt.sm_count, stream, cta_limit);
+    if (rt.lz4_flavour == 1) general = 0;
+    if (rt.lz4_flavour == 2) general = 1;
+    return general == 1 ? launch_lz4_decode_v3(a, counter, rt.sm_count, stream, cta_limit) : launch_lz4_decode_v2(a, counter, rt.sm_count, stream, cta_limit);
 }
 
 // Which K1 flavour suits a column: walk the token stream of one compressed block on the host (done once, at load).
@@ -309,7 +311,7 @@ int launch_decode(const DecodeArgs &a, bool general, cudaStream_t stream = nullp
 // the few words right before it (chains serialise v2's dependency waves).  Returns -1 when the block gives no verdict.
 int sample_flavour(const uint8_t *src, int64_t n, int64_t origin)
 {
-    int64_t ip = 0, op = 0, nseq = 0, regular = 0, chained = 0;
+    int64_t ip = 0, op = 0, nseq = 0, regular = 0, chained = 0, wordform = 0;
     while (ip < n && nseq < 20000) {
         const uint32_t t = src[ip++];
         int64_t L = t >> 4;
@@ -334,10 +336,14 @@ int sample_flavour(const uint8_t *src, int64_t n, int64_t origin)
             regular++;
             if (off <= 64) chained++;
         }
+        // what the spec decoder turns into whole output words without walking: <= 4 literal bytes + match = 8 bytes (or a plain
+        // match of 16), offset a multiple of 8, at an aligned output position
+        if (plain && L <= 4 && ((off | (op - L)) & 7) == 0 && (L + M == 8 || (L == 0 && M == 16))) wordform++;
         op += M;
         if (op > origin) return -1;
     }
     if (nseq < 64) return -1;
+    if (wordform * 100 >= nseq * 97) return 2;
     return (regular * 100 >= nseq * 98 && chained * 2 <= nseq) ? 0 : 1;
 }
 
@@ -436,8 +442,17 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
     // ---- decode / scan overlap (compressed blocks resident, one flavour, more than one round of blocks) ----
     bool parted = false;
     if (on_part && host_bytes == 0 && !rt.no_overlap && !rt.lz4_simple && !rt.lz4_v1 && rt.lz4_flavour != 3 && todo.size() <= (size_t)DECODE_MAX_COLS) {
+        // (columns whose blocks are all skipped -- stored bodies read in place -- have no say)
         bool one_flavour = true;
-        for (Column *c : todo) one_flavour = one_flavour && c->lz4_general == todo[0]->lz4_general;
+        int flavour0 = -1;
+        for (Column *c : todo) {
+            bool work = false;
+            for (int b = wlo; b < whi && !work; b++) work = !h_skip_of(c)[(size_t)b];
+            if (!work) continue;
+            if (flavour0 < 0) flavour0 = c->lz4_general;
+            one_flavour = one_flavour && c->lz4_general == flavour0;
+        }
+        if (flavour0 < 0) flavour0 = 0;
         const int64_t wave = (int64_t)rt.sm_count * LZ4_SLOTS_PER_SM;
         int64_t real = 0;
         for (Column *c : todo) for (int b = wlo; b < whi; b++) real += h_skip_of(c)[(size_t)b] ? 0 : 1;
@@ -450,8 +465,25 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
                 split = b + 1;
             }
         }
-        const int last_ctas = (int)((last_real + LZ4_SLOTS_PER_SM - 1) / LZ4_SLOTS_PER_SM);
-        if (split > wlo && split < whi && rt.sm_count - last_ctas >= 8) {
+        int last_ctas = (int)((last_real + LZ4_SLOTS_PER_SM - 1) / LZ4_SLOTS_PER_SM);
+        int scan_sms = rt.sm_count - last_ctas;
+        // The warp-per-block decoder (spec) has no rounds: every block is an independent warp-sized job.  Its last part (about a
+        // quarter of the blocks) is launched with 2 CTAs per SM instead of the 4 that fit, so that the scan of everything before
+        // it finds registers and shared memory on every SM and runs beside it.
+        const bool spec = one_flavour && (rt.lz4_flavour == 4 || (rt.lz4_flavour == 0 && flavour0 == 2));
+        if (spec) {
+            split = 0;
+            acc = 0;
+            const int64_t head = real - real / (rt.spec_tail_pct > 0 ? 100 / rt.spec_tail_pct : 4);
+            if (real >= 4096)
+                for (int b = wlo; b < whi && acc < head; b++) {
+                    for (Column *c : todo) acc += h_skip_of(c)[(size_t)b] ? 0 : 1;
+                    split = b + 1;
+                }
+            last_ctas = 2 * rt.sm_count;      // (the spec launcher takes this as a CTA count)
+            scan_sms = rt.sm_count;
+        }
+        if (split > wlo && split < whi && (spec || rt.sm_count - last_ctas >= 8)) {
             // The full rounds go to one launch (its slots pick up blocks as they finish: no barrier between rounds); the last
             // round is a launch of its own on a second stream, so that its CTAs move in as the first launch's CTAs run out
             // of blocks -- again no barrier -- and it is limited to the SMs it can fill.
@@ -468,7 +500,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
                     for (int64_t b = b0; b < b1; b++)
                         if (!h_skip_of(c)[(size_t)b]) bytes += c->blocks[(size_t)(t->blk_lo + b)].compressed + c->blocks[(size_t)(t->blk_lo + b)].origin;
                 }
-                LAUNCH(launch_decode(a, todo[0]->lz4_general, stream, cta_limit, counter_slot));
+                LAUNCH(launch_decode(a, flavour0, stream, cta_limit, counter_slot));
                 return DFDB_OK;
             };
             // one decode phase record for both launches: from the start of the first to the end of the second
@@ -488,7 +520,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
             if (!rc) {
                 CUDA_TRY(cudaEventRecord(e2, rt.decode_stream2));
                 CUDA_TRY(cudaStreamWaitEvent(rt.stream, e1, 0));
-                rc = (*on_part)(wlo, split, rt.sm_count - last_ctas);
+                rc = (*on_part)(wlo, split, scan_sms);
             }
             if (!rc) {
                 CUDA_TRY(cudaStreamWaitEvent(rt.stream, e2, 0));
@@ -507,9 +539,9 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
         }
         if (b1 <= b0) continue;
         // columns of one flavour share a launch
-        for (int general = 0; general < 2; general++) {
+        for (int general = 0; general < 3; general++) {
           std::vector<Column *> grp;
-          for (Column *c : todo) if ((int)c->lz4_general == general) grp.push_back(c);
+          for (Column *c : todo) if (c->lz4_general == general) grp.push_back(c);
           for (size_t i = 0; i < grp.size(); i += DECODE_MAX_COLS) {
             DecodeArgs a;
             memset(&a, 0, sizeof a);
@@ -525,7 +557,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
                     if (!h_skip_of(c)[(size_t)b]) bytes += c->blocks[(size_t)(t->blk_lo + b)].compressed + c->blocks[(size_t)(t->blk_lo + b)].origin;
             }
             PhaseScope ps(PH_DECODE, bytes);
-            LAUNCH(launch_decode(a, general != 0));
+            LAUNCH(launch_decode(a, general));
           }
         }
     }
@@ -1213,6 +1245,7 @@ int32_t dfdb_init(int32_t device)
     CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&rt.d_error), 64));
     CUDA_TRY(cudaMemset(rt.d_error, 0, 64));
     if (const char *fl = getenv("DFDB_LZ4_FLAVOUR")) rt.lz4_flavour = atoll(fl);
+    if (const char *tp = getenv("DFDB_SPEC_TAIL_PCT")) rt.spec_tail_pct = atoll(tp);
     if (const char *ov = getenv("DFDB_NO_OVERLAP")) rt.no_overlap = atoll(ov);       // A/B: decode / scan overlap off   // A/B: force one K1 flavour (see dfdb_set_option "lz4_flavour")
     rt.inited = true;
     return DFDB_OK;
@@ -1269,6 +1302,7 @@ int32_t dfdb_set_option(const char *name, int64_t value)
     else if (n == "lane_hot") rt.lane_hot = value;
     else if (n == "no_validate") rt.no_validate = value;
     else if (n == "no_zonemap") rt.no_zonemap = value;
+    else if (n == "spec_tail_pct") rt.spec_tail_pct = value;
     else if (n == "host_arena_cap_mb") { std::lock_guard<std::mutex> lk(arena.mu); arena.cap_bytes = (size_t)std::max<int64_t>(value, 0) << 20; arena.trim(arena.cap_bytes); }
     else return fail(DFDB_ERR_ARGUMENT, "unknown option %s", n.c_str());
     return DFDB_OK;
@@ -1460,7 +1494,7 @@ int32_t dfdb_table_load(dfdb_table *t, const int64_t *col_ids, int32_t n, int32_
         if (cpos > prev_end) memset(c->h_comp + prev_end, 0, (size_t)(cpos - prev_end));
         // K1 flavour of the column: first, middle and last block vote (stored blocks are never decoded and abstain)
         {
-            int votes[2] = {0, 0};
+            int votes[3] = {0, 0, 0};
             const int64_t cand[3] = {0, nb / 2, nb - 1};
             for (int k = 0; k < 3 && nb > 0; k++) {
                 const int64_t b = cand[k];
@@ -1468,7 +1502,10 @@ int32_t dfdb_table_load(dfdb_table *t, const int64_t *col_ids, int32_t n, int32_
                 const int v = sample_flavour(c->h_comp + comp_off[(size_t)b], comp_len[(size_t)b], origin[(size_t)b]);
                 if (v >= 0) votes[v]++;
             }
-            c->lz4_general = votes[1] > votes[0];
+            c->lz4_general = votes[2] > votes[0] + votes[1] ? 2 : (votes[1] > votes[0] ? 1 : 0);
+            // (a Union{T,Missing} body starts with its incompressible bitmap -- a long literal run the verified-run decoder takes one
+            //  sequence at a time; measured slower than the walker flavour there)
+            if (c->lz4_general == 2 && c->type.nullable) c->lz4_general = votes[1] > votes[0] ? 1 : 0;
         }
         CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&c->d_comp), c->comp_bytes));
         if ((rc = dev_upload(&c->d_comp_off, comp_off))) return rc;
@@ -1497,7 +1534,7 @@ int32_t dfdb_table_load(dfdb_table *t, const int64_t *col_ids, int32_t n, int32_
             memset(&va, 0, sizeof va);
             va.ncols = 1;
             va.nblocks = (int)nb;
-            va.hot = c->lz4_general ? 0 : 1;
+            va.hot = c->lz4_general == 1 ? 0 : 1;
             va.col[0] = DecodeCol{c->d_comp, c->d_comp_off, c->d_comp_len, c->d_dec_off, c->d_origin, c->d_decoded, c->d_status, c->d_skip};
             LAUNCH(launch_lz4_decode_lane(va, nullptr, rt.d_counter, rt.sm_count, rt.stream));
             c->h_corrupt.assign((size_t)nb, 0);

@@ -1,0 +1,205 @@
+// lz4_decode_spec.cu -- K1 for word-regular columns: one warp per column block, token positions VERIFIED instead of walked.
+//
+// Replaces read_block's LZ4_decompress_safe call (/root/reference/src/io/BlockStreams.jl:101-119) for the column kind that
+// dominates the benchmark: 8-byte values whose LZ4 stream is almost entirely "plain" sequences -- token 0x04 / 0x0C (no
+// literals, match of 8 or 16 bytes), a two-byte offset that is a multiple of 8.  Such a sequence is exactly 3 stream bytes, so
+// inside a run of them token k sits at p0 + 3k: nobody has to walk the chain.  Every lane reads the three bytes at its assumed
+// position and checks that they ARE a plain sequence; by induction from lane 0 (whose position is known) the first lane that
+// fails the check ends the run, and every lane before it is a real sequence.  Lane = sequence = output word.  A source word
+// before the batch is final in global memory (L2); a source word inside the batch is another lane's word, and chains of those
+// collapse by pointer jumping over warp shuffles.  The run may be closed by one sequence of the "word form" -- up to 5 literal
+// bytes followed by a match, 8 or 16 bytes in all ((1, 7), (2, 6), (0, 16) ...) -- which its own lane expands.  One coalesced
+// store per batch; the next batch's stream bytes are requested before this batch's sources are waited for.  Anything else --
+// length extensions, unaligned offsets, the last sequences of the block -- is decoded one sequence at a time by the whole
+// warp (decode_one_sequence, lz4_common.cuh).
+//
+// Against the walker / consumer kernel (lz4_decode_v2.cu, ~350 warp instructions per 32 tokens: ring entries, polls, dependency
+// waves) a batch here is ~50 instructions for ~12-32 tokens, at full occupancy (64 warps per SM).  The kernel is memory-safe
+// on any input (every access is bounds-checked, errors set a per-block status); the accept / reject verdict of damaged streams
+// is the lane decoder's, taken at load (api.cu).
+//
+// Algorithmic bytes per block (roofline): compressed bytes read + origin bytes written.
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+#include "lz4_common.cuh"
+
+namespace dfdb {
+namespace {
+
+using namespace lz4;
+
+constexpr int SPEC_WARPS = 8;
+constexpr uint32_t SPEC_RING = 512;      // per warp: the last output words of its block, in shared memory (match sources are nearly always recent)
+constexpr uint32_t SPEC_NEAR = SPEC_RING - 64;   // a source at most this many words back is read from the ring (the margin keeps this batch's stores off it)
+
+__device__ __forceinline__ uint32_t ldg_u32(const uint8_t *p) { return __ldg(reinterpret_cast<const unsigned int *>(p)); }
+
+// the 8 stream bytes at ip + stride * lane (three aligned words; payload buffers carry slack behind the last block, so reading a
+// few words past this block's payload is safe -- such bytes are never USED: the fast path checks the positions first)
+__device__ __forceinline__ uint64_t load_stream(const uint8_t *__restrict__ src, uint32_t ip, uint32_t lane, uint32_t stride)
+{
+    const uint32_t tp = ip + stride * lane;
+    const uint8_t *a = src + (tp & ~3u);
+    const uint32_t sh = (tp & 3u) * 8u;
+    const uint32_t w0 = ldg_u32(a), w1 = ldg_u32(a + 4), w2 = ldg_u32(a + 8);
+    return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+}
+
+// one block, whole warp; returns E_*.  (Positions are 32-bit in the batch loop: column blocks are far below 4 GB; the kernel
+// is instruction-bound -- IPC 2.9 per SM in the first profile -- so the loop is kept lean.)
+__device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_len, uint8_t *dst, uint32_t origin, unsigned long long *ring)
+{
+    const uint32_t lane = lane_id();
+    uint32_t ip = 0, op = 0;
+    bool done = false;
+    unsigned long long *out64 = reinterpret_cast<unsigned long long *>(dst);
+    // A run is a stretch of sequences of ONE shape: L0 literal bytes (0..4) + a match of 8 - L0 bytes, offset a multiple of 8,
+    // at an aligned output position -- 3 + L0 stream bytes and one output word each.  rand(1:100) Int64 columns are runs of
+    // L0 = 0 (token 0x04), sorted Int64 columns runs of L0 = 2 (token 0x22).  The stride of the last run is assumed for the next
+    // batch (its bytes are requested early); two sequences of another shape in a row switch the run's shape.
+    uint32_t L0 = 0, pendL = 0xffu;
+    uint32_t ring_from = 0;            // output words >= this one (and within SPEC_RING of the position) are in the ring
+    // a match never writes the block's last 12 bytes in the fast path (the end-of-block rules stay with the one-sequence path):
+    // an output word w may be written when w < lim_w; and the fast path needs 7 * 32 + 16 stream bytes ahead
+    const uint32_t lim_w = origin >= 12u ? (origin - 12u) >> 3 : 0u;
+    const uint32_t ip_lim = comp_len >= 7u * 32u + 16u ? comp_len - (7u * 32u + 16u) : 0u;
+    const bool fast_possible = comp_len >= 7u * 32u + 16u;
+    // a source word: from the ring when it is recent, else from global memory (final there: L2)
+    auto source = [&](uint32_t sw, uint32_t opw) -> unsigned long long {
+        if (sw >= ring_from && opw - sw <= SPEC_NEAR) return ring[sw & (SPEC_RING - 1)];
+        return __ldcg(out64 + sw);
+    };
+    uint64_t x = load_stream(src, 0, lane, 3);
+    while (!done) {
+        if (fast_possible && (op & 7u) == 0 && ip <= ip_lim) {
+            const uint32_t opw = op >> 3, myw = opw + lane;
+            const uint32_t tok = (uint32_t)x & 0xffu;
+            const uint32_t off = (uint32_t)(x >> ((8u + 8u * L0) & 63u)) & 0xffffu, offw = off >> 3;
+            const bool okp = tok == ((L0 << 4) | (4u - L0)) && (off & 7u) == 0 && off != 0 && offw <= myw && myw < lim_w;
+            const uint32_t badp = ~__ballot_sync(FULL, okp);
+            const uint32_t n = badp ? (uint32_t)__ffs(badp) - 1u : 32u;
+            // the sequence that ends the run, analysed by its own lane: any "word form" -- L <= 5 literal bytes + match, 8 or 16 bytes in all
+            const uint32_t L = tok >> 4, LM = L + (tok & 15u) + 4u;
+            const uint32_t off_s = (uint32_t)(x >> ((8u + 8u * L) & 63u)) & 0xffffu, offw_s = off_s >> 3;
+            const uint32_t W = LM >> 3;
+            const bool sp = lane == n && L <= 5u && (tok & 15u) != 15u && (LM & 7u) == 0 && (off_s & 7u) == 0 && off_s != 0 &&
+                            offw_s <= myw && offw_s >= lane + W &&                         // sources inside the output and final (before the batch)
+                            myw + W <= lim_w;
+            const uint32_t spb = __ballot_sync(FULL, sp);
+            uint32_t hdr_s = 0, W_s = 0;
+            if (spb) {
+                const uint32_t pk = __shfl_sync(FULL, (L << 8) | W, n & 31u);
+                hdr_s = 3u + (pk >> 8);
+                W_s = pk & 0xffu;
+            }
+            const uint32_t adv_words = n + W_s;
+            if (adv_words > 0) {
+                // a sequence of another one-word shape alone at the head of a batch is just the closing sequence of an empty run;
+                // two of the same shape in a row are a new run: switch (the bytes requested next use the new stride)
+                const uint32_t nip = ip + (3u + L0) * n + hdr_s;
+                if (n == 0 && W_s == 1u) {
+                    const uint32_t Lh = hdr_s - 3u;
+                    if (Lh == pendL && Lh <= 4u) L0 = Lh;
+                    pendL = Lh;
+                } else {
+                    pendL = 0xffu;
+                }
+                const uint64_t nx = load_stream(src, nip, lane, 3u + L0);      // the next batch's bytes travel while this one's sources do
+                // ... and the stream a few batches ahead is pulled from HBM into L2 now: the compressed bytes are read exactly once,
+                // so without this every batch waits a DRAM round trip for its own bytes (one batch of lead covers an L2 hit, not DRAM)
+                if (lane < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ((nip + 512u + 128u * lane) & ~127u)));
+                // sources: before the batch -> the ring (or global memory); inside the batch -> another lane's word.  Only the bytes
+                // behind the literal bytes come from the source, so a chain of in-batch sources ends in the word of its far root.
+                const bool mine = lane < n;
+                const bool far = mine && offw > lane;
+                unsigned long long v = 0;
+                if (far) v = source(myw - offw, opw);
+                bool res = far || !mine;
+                uint32_t sl = (mine && !far) ? lane - offw : lane;
+                while (__any_sync(FULL, !res)) {                                // chains collapse by pointer jumping: <= 5 rounds
+                    const unsigned long long v_s = __shfl_sync(FULL, v, sl);
+                    const uint32_t pk = __shfl_sync(FULL, (sl << 1) | (res ? 1u : 0u), sl);
+                    if (!res) { if (pk & 1u) { v = v_s; res = true; } else sl = pk >> 1; }
+                }
+                const unsigned long long lits = (unsigned long long)(x >> 8);
+                if (sp) {
+                    const unsigned long long keep = ~0ull << (8u * L);          // (L == 0: everything comes from the source word)
+                    const unsigned long long w0 = (source(myw - offw_s, opw) & keep) | (lits & ~keep);
+                    out64[myw] = w0;
+                    ring[myw & (SPEC_RING - 1)] = w0;
+                    if (W == 2u) {
+                        const unsigned long long w1 = source(myw + 1u - offw_s, opw);
+                        out64[myw + 1u] = w1;
+                        ring[(myw + 1u) & (SPEC_RING - 1)] = w1;
+                    }
+                }
+                if (mine) {
+                    const unsigned long long keep = ~0ull << (8u * L0);
+                    const unsigned long long w = (v & keep) | (lits & ~keep);
+                    out64[myw] = w;
+                    ring[myw & (SPEC_RING - 1)] = w;
+                }
+                __syncwarp();                                                   // the batch's words are visible to the whole warp
+                ip = nip;
+                op += 8u * adv_words;
+                x = nx;
+                continue;
+            }
+        }
+        // ---- anything else: one sequence, whole warp ----
+        int64_t ip64 = ip, op64 = op;
+        const int e = decode_one_sequence(src, comp_len, dst, origin, ip64, op64, done);
+        if (e) return e;
+        ip = (uint32_t)ip64;
+        op = (uint32_t)op64;
+        ring_from = (op + 7u) >> 3;                                             // (what this path wrote is in global memory only)
+        x = load_stream(src, ip, lane, 3u + L0);
+    }
+    return (op == origin && ip == comp_len) ? E_OK : E_SIZE;
+}
+
+__global__ void __launch_bounds__(SPEC_WARPS * 32, 4) lz4_decode_spec_kernel(const __grid_constant__ DecodeArgs args, unsigned int *counter)
+{
+    __shared__ unsigned long long rings[SPEC_WARPS][SPEC_RING];
+    unsigned long long *ring = rings[threadIdx.x >> 5];
+    const uint32_t lane = lane_id();
+    const long long njobs = (long long)args.ncols * args.nblocks;
+    for (;;) {
+        unsigned int job = 0;
+        if (lane == 0) job = atomicAdd(counter, 1u);
+        job = __shfl_sync(FULL, job, 0);
+        if ((long long)job >= njobs) return;
+        const int c = (int)(job % args.ncols);
+        const int b = args.blk0 + (int)(job / args.ncols);
+        const DecodeCol &col = args.col[c];
+        if (col.skip && col.skip[b]) continue;
+        const uint8_t *src = col.comp + col.comp_off[b];
+        uint8_t *dst = col.out + col.dec_off[b];
+        const uint32_t comp_len = (uint32_t)col.comp_len[b], origin = (uint32_t)col.origin[b];
+        int e;
+        if (origin == 0) e = (comp_len == 1 && src[0] == 0) ? E_OK : E_SIZE;
+        else if (comp_len == 0) e = E_TRUNCATED;
+        else if (((uintptr_t)src & 3u) || ((uintptr_t)dst & 7u)) e = decode_simple(src, comp_len, dst, origin);
+        else e = decode_block_spec(src, comp_len, dst, origin, ring);
+        if (lane == 0) col.status[b] = e;
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+int launch_lz4_decode_spec(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit)
+{
+    const long long njobs = (long long)args.ncols * args.nblocks;
+    if (njobs <= 0) return 0;
+    cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream);
+    long long ctas = (njobs + SPEC_WARPS - 1) / SPEC_WARPS;
+    long long max_ctas = cta_limit > 0 ? cta_limit : (long long)sm_count * 4;      // 4 CTAs of 8 warps fit an SM (64 registers per thread); persistent over the job queue
+    if (ctas > max_ctas) ctas = max_ctas;
+    if (ctas < 1) ctas = 1;
+    lz4_decode_spec_kernel<<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, d_counter);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace dfdb

@@ -265,6 +265,45 @@ end
 minimum(c::DFColumn) = _extreme(c, a -> a.min_i64, a -> a.min_f64)
 maximum(c::DFColumn) = _extreme(c, a -> a.max_i64, a -> a.max_f64)
 
+# ---- the rows beyond the scan path (SURVEY.md 8f): zone maps, write path, group-by ----------------------------------------
+"""
+    B200.build_zonemaps!(t::DFTable)
+
+Per-block (min, max, null count) of every fixed-width numeric column, computed on the device and written beside the column
+files as the optional sidecar `<id>.zmap` (the reference ignores it).  Predicates of `column <cmp> constant` terms then skip
+the blocks their constants rule out; `open_table` + `enable!` pick the sidecars up again later.
+"""
+build_zonemaps!(t::DFTable) = (check(ccall((:dfdb_table_build_zonemaps, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}, Int32), handle(t), C_NULL, Int32(0))); t)
+
+# write_column (columns.jl:65-84) for a Vector of a stored bits type: bodies assembled, LZ4-compressed and compacted on the
+# device, framed on the host (make_column_file + commit_block_write!).  add_column! (table.jl:96-124) calls it instead of
+# write_column_from_iterator when B200 is enabled; meta.bin is still written by the reference's own write_table_meta.
+function write_column_file(t::DFTable, id::Integer, data::Vector{T}) where {T}
+    start()
+    isbitstype(T) || throw(ArgumentError("$(T) is not written by the device path"))
+    comp = Ref{Int64}(0); unc = Ref{Int64}(0)
+    GC.@preserve data check(ccall((:dfdb_write_column_file, LIB), Int32,
+        (Cstring, Int64, Cstring, Int64, Int64, Ptr{Cvoid}, Ptr{UInt8}, Ptr{Int32}, Ptr{UInt8}, Int64, Ref{Int64}, Ref{Int64}),
+        t.path, Int64(id), DataFrameDBs.ColumnTypes.typestring(T), Int64(DataFrameDBs.blocksize(t)), Int64(length(data)),
+        pointer(data), C_NULL, C_NULL, C_NULL, Int64(0), comp, unc))
+    (compressed = comp[], uncompressed = unc[])
+end
+
+# groupreduce(view, by; cols...) -- finishes the stub in src/tables/aggregate.jl:1-36.  Returns the 1-based table rows where the
+# groups first appear (materialize the key columns there for the key values) and one Agg per (group, value column).
+function groupreduce(v::DFView, by::Tuple{Vararg{Symbol}}, vals::Tuple{Vararg{Symbol}})
+    gv = v[:, [by..., vals...]]
+    with_scan(gv) do s
+        ng = Ref{Int64}(0)
+        kp = Int32.(0:length(by)-1); vp = Int32.(length(by):length(by)+length(vals)-1)
+        check(ccall((:dfdb_scan_groupreduce, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Int32, Ptr{Int32}, Int32, Ref{Int64}),
+                    s, kp, Int32(length(kp)), vp, Int32(length(vp)), ng))
+        first = Vector{Int64}(undef, ng[]); aggs = Vector{Agg}(undef, ng[] * length(vals))
+        check(ccall((:dfdb_scan_group_results, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Agg}), s, first, aggs))
+        (first_rows = first, aggs = reshape(aggs, length(vals), :))
+    end
+end
+
 end # module B200
 
 # ---- the hooks: methods of the package's own generic functions (this file is part of the package) --------------------------

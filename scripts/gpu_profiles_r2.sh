@@ -5,6 +5,10 @@ mkdir -p $OUT
 cap() {  # cap <name> <kernel regex> <skip> <workload> [rows]
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -o $OUT/$1 python scripts/prof_workloads.py $4 $5 > $OUT/$1.log 2>&1
   tail -1 $OUT/$1.log
+  # gpurun brings back at most 64 MiB: keep the text pages, drop the report
+  ncu -i $OUT/$1.ncu-rep --page details > $OUT/$1.details.txt 2>/dev/null
+  ncu -i $OUT/$1.ncu-rep --page raw --csv > $OUT/$1.raw.csv 2>/dev/null
+  rm -f $OUT/$1.ncu-rep
 }
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_bench.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-variants --no-verify > $OUT/launches_bench.log 2>&1
 cap lz4_decode_v2_1B lz4_decode_v2 2 walker 1000000000
