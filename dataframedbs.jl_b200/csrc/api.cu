@@ -50,6 +50,7 @@ struct Runtime {
     int64_t lz4_v1 = 0;       // first-generation warp-per-block decoder instead of the walker/consumer kernel
     int64_t no_wide = 0;
     int64_t no_fused = 0;
+    int64_t no_decode_fused = 1;                                    // 0: fold predicate + aggregate into the decode kernel (measured: no faster than decode + scan, see lz4_decode_spec.cu)
     int64_t no_tma = 0;
     int64_t lz4_flavour = 0;  // K1 flavour: 0 = per column from a token sample at load, 1 = word-regular decoder (v2), 2 = general decoder (v3), 3 = lane-per-block decoder, 4 = warp-per-block decoder with verified token runs (spec)
     int64_t no_overlap = 0;   // do not run the scan of the decoded part of a shard beside the decode of its last part
@@ -288,7 +289,9 @@ bool wide_ok(const dfdb_table *t, const Column &c)
 }
 
 // ---- decode ---------------------------------------------------------------------------------------------
-int launch_decode(const DecodeArgs &a, int general, cudaStream_t stream = nullptr, int cta_limit = 0, int counter_slot = 0)
+bool spec_flavour(int general) { return !rt.lz4_simple && !rt.lz4_v1 && (rt.lz4_flavour == 4 || (rt.lz4_flavour == 0 && general == 2)); }
+
+int launch_decode(const DecodeArgs &a, int general, cudaStream_t stream = nullptr, int cta_limit = 0, int counter_slot = 0, const LaneFused *fuse = nullptr)
 {
     if (!stream) stream = rt.stream;
     unsigned int *counter = rt.d_counter + 4 * counter_slot;   // launches that may run at the same time need their own job counter
@@ -299,7 +302,8 @@ int launch_decode(const DecodeArgs &a, int general, cudaStream_t stream = nullpt
         if (rt.lane_hot >= 0) la.hot = (int)rt.lane_hot;
         return launch_lz4_decode_lane(la, nullptr, counter, rt.sm_count, stream, cta_limit);
     }
-    if (rt.lz4_flavour == 4 || (rt.lz4_flavour == 0 && general == 2)) return launch_lz4_decode_spec(a, counter, rt.sm_count, stream, cta_limit);
+    if (rt.lz4_flavour == 4 || (rt.lz4_flavour == 0 && general == 2)) return launch_lz4_decode_spec(a, counter, rt.sm_count, stream, cta_limit, fuse);
+    if (fuse) return 1;
     if (rt.lz4_flavour == 1) general = 0;
     if (rt.lz4_flavour == 2) general = 1;
     return general == 1 ? launch_lz4_decode_v3(a, counter, rt.sm_count, stream, cta_limit) : launch_lz4_decode_v2(a, counter, rt.sm_count, stream, cta_limit);
@@ -355,8 +359,13 @@ int sample_flavour(const uint8_t *src, int64_t n, int64_t origin)
 // on the others.  Never called when nothing had to be decoded.
 using PartFn = std::function<int(int, int, int)>;
 
-int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const PartFn *on_part = nullptr)
+//
+// fuse / fused_out: optional.  When the one column to decode is a spec-flavour column whose compressed blocks are resident,
+// its decode launch also evaluates the predicate and folds the aggregate described by *fuse (per-block partials), and
+// *fused_out is set; otherwise nothing of *fuse is used and the caller scans as usual.
+int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const PartFn *on_part = nullptr, const LaneFused *fuse = nullptr, bool *fused_out = nullptr)
 {
+    if (fused_out) *fused_out = false;
     // Only the blocks inside the scan's window are decoded (skip_block / skipblocks in the reference,
     // src/io/blocksiterator.jl:69-78, src/tables/selection.jl:177-184: blocks that a leading range stage rules out are
     // seeked over, not decompressed).  A column remembers which block range of it is currently decoded.
@@ -531,6 +540,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
             parted = true;
         }
     }
+    const bool fusing = fuse && fused_out && todo.size() == 1 && host_bytes == 0 && nchunks == 1 && !parted && spec_flavour(todo[0]->lz4_general);
     for (int k = 0; k < nchunks && !parted; k++) {
         const int b0 = wlo + (int)((int64_t)(whi - wlo) * k / nchunks), b1 = wlo + (int)((int64_t)(whi - wlo) * (k + 1) / nchunks);
         if (!copied.empty()) {
@@ -557,7 +567,14 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
                     if (!h_skip_of(c)[(size_t)b]) bytes += c->blocks[(size_t)(t->blk_lo + b)].compressed + c->blocks[(size_t)(t->blk_lo + b)].origin;
             }
             PhaseScope ps(PH_DECODE, bytes);
-            LAUNCH(launch_decode(a, general));
+            if (fusing) {
+                LaneFused lf = *fuse;
+                lf.pred_col = 0;
+                LAUNCH(launch_decode(a, general, nullptr, 0, 0, &lf));
+                *fused_out = true;
+            } else {
+                LAUNCH(launch_decode(a, general));
+            }
           }
         }
     }
@@ -1110,7 +1127,7 @@ int run_aggregate(dfdb_scan *s, int32_t proj_idx, bool count_only, AggPartial *h
     int64_t scan_bytes = 0;
     TmaScanArgs ta;
     memset(&ta, 0, sizeof ta);
-    bool use_tma = false, scanned = false;
+    bool use_tma = false, scanned = false, fused_done = false;
     // the TMA scan of local blocks [b0, b1) on `sms` SMs (partials are per work unit, so parts compose)
     auto scan_part = [&](int b0, int b1, int sms) -> int {
         if (!use_tma || b1 <= b0) return DFDB_OK;
@@ -1150,8 +1167,28 @@ int run_aggregate(dfdb_scan *s, int32_t proj_idx, bool count_only, AggPartial *h
             ta.g = g;
             ta.agg_cls = cls;
         }
-        rc = ensure_decoded(t, need, use_tma ? &part_fn : nullptr);
-        if (rc) return rc;
+        // Decode + predicate + aggregate in ONE kernel: a single interval test on a spec-flavour column that still has to be
+        // decoded, the aggregated column (if any) being another, readable column.  The decoded words are tested while they are
+        // in registers; the scan kernel and its read of the decoded column fall away.
+        Column *pc = (!s->stages.empty() && s->stages[0].e.col_ids.size() == 1) ? t->find(s->stages[0].e.col_ids[0]) : nullptr;
+        if (use_tma && !rt.no_decode_fused && pc && pc != ac && ta.ntests == 1 && pc->mode != DFDB_LOAD_HOST && spec_flavour(pc->lz4_general)) {
+            if (ac) { rc = ensure_decoded(t, {ac->id}); if (rc) return rc; }
+            LaneFused lf;
+            memset(&lf, 0, sizeof lf);
+            lf.test = ta.test[0];
+            if (ac) lf.agg = make_view(*ac);
+            lf.agg_kind = agg;
+            lf.agg_cls = cls;
+            lf.partials = static_cast<AggPartial *>(s->d_partials);
+            lf.part_blk0 = 0;
+            lf.segs_per_block = g.segs_per_block;
+            CUDA_TRY(cudaMemsetAsync(s->d_partials, 0, (size_t)std::max(nunits, 1) * sizeof(AggPartial), rt.stream));
+            rc = ensure_decoded(t, {pc->id}, nullptr, &lf, &fused_done);
+            if (rc) return rc;
+        } else {
+            rc = ensure_decoded(t, need, use_tma ? &part_fn : nullptr);
+            if (rc) return rc;
+        }
     } else {
         rc = run_selection(s);
         if (rc) return rc;
@@ -1163,7 +1200,9 @@ int run_aggregate(dfdb_scan *s, int32_t proj_idx, bool count_only, AggPartial *h
     }
     if (ac) { a.agg_col = make_view(*ac); a.agg_cls = cls; }
     {
-        if (use_tma) {
+        if (fused_done) {
+            // (the decode kernel left one partial per block)
+        } else if (use_tma) {
             if (!scanned) { rc = scan_part(0, g.nblocks, rt.sm_count); if (rc) return rc; }   // everything was decoded already
         } else if (nunits > 0) {
             PhaseScope ps(PH_CONSUME, scan_bytes);
@@ -1246,6 +1285,7 @@ int32_t dfdb_init(int32_t device)
     CUDA_TRY(cudaMemset(rt.d_error, 0, 64));
     if (const char *fl = getenv("DFDB_LZ4_FLAVOUR")) rt.lz4_flavour = atoll(fl);
     if (const char *tp = getenv("DFDB_SPEC_TAIL_PCT")) rt.spec_tail_pct = atoll(tp);
+    if (const char *nf = getenv("DFDB_NO_DECODE_FUSED")) rt.no_decode_fused = atoll(nf);   // A/B: decode, then scan
     if (const char *ov = getenv("DFDB_NO_OVERLAP")) rt.no_overlap = atoll(ov);       // A/B: decode / scan overlap off   // A/B: force one K1 flavour (see dfdb_set_option "lz4_flavour")
     rt.inited = true;
     return DFDB_OK;
@@ -1295,6 +1335,7 @@ int32_t dfdb_set_option(const char *name, int64_t value)
     else if (n == "lz4_v1") rt.lz4_v1 = value;
     else if (n == "no_wide") rt.no_wide = value;
     else if (n == "no_fused") rt.no_fused = value;
+    else if (n == "no_decode_fused") rt.no_decode_fused = value;
     else if (n == "no_tma") rt.no_tma = value;
     else if (n == "lz4_flavour") rt.lz4_flavour = value;
     else if (n == "no_overlap") rt.no_overlap = value;

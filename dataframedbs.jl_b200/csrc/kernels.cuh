@@ -30,7 +30,9 @@ int launch_lz4_decode(const DecodeArgs &args, unsigned int *d_counter, int sm_co
 constexpr int LZ4_SLOTS_PER_SM = 60;   // column blocks one decoder CTA keeps in flight (NSLOT of both walker/consumer flavours)
 int launch_lz4_decode_v2(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit = 0);                     // v2: walker / consumer warps, word-regular columns
 int launch_lz4_decode_v3(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit = 0);
-int launch_lz4_decode_spec(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit = 0);                   // warp per block, plain token runs verified in parallel (word-regular columns)                     // v3: same organisation, general columns (strings, literal-heavy, chains)
+struct LaneFused;
+int launch_lz4_decode_spec(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit = 0,
+                           const LaneFused *fused = nullptr);   // warp per block, plain token runs verified in parallel (word-regular columns); optionally with K3 + K7 fused in                     // v3: same organisation, general columns (strings, literal-heavy, chains)
 
 // ---- write path: raw LZ4 block compression (lz4_compress.cu), one warp per body ---------------------------------------
 struct CompressArgs {

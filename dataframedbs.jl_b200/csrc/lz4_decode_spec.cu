@@ -23,11 +23,13 @@
 
 #include "kernels.cuh"
 #include "lz4_common.cuh"
+#include "lz4_fused.cuh"
 
 namespace dfdb {
 namespace {
 
 using namespace lz4;
+using fused::LaneAcc;
 
 constexpr int SPEC_WARPS = 8;
 constexpr uint32_t SPEC_RING = 512;      // per warp: the last output words of its block, in shared memory (match sources are nearly always recent)
@@ -48,8 +50,104 @@ __device__ __forceinline__ uint64_t load_stream(const uint8_t *__restrict__ src,
 
 // one block, whole warp; returns E_*.  (Positions are 32-bit in the batch loop: column blocks are far below 4 GB; the kernel
 // is instruction-bound -- IPC 2.9 per SM in the first profile -- so the loop is kept lean.)
-__device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_len, uint8_t *dst, uint32_t origin, unsigned long long *ring)
+//
+// FUSED (1 = count, 2 = integer aggregate, 3 = Float64 aggregate): the block belongs to the predicate column of a
+// filter + aggregate query.  Every FOLD_ROWS decoded rows the warp stops decoding and folds them: the words it has just
+// written are read back from L2 (32 rows per load, all lanes busy, no divergence worth the name), tested against the plan's
+// interval, and the matching rows of the aggregated column `bvals` (resident, same rows) go into per-lane accumulators that
+// live in shared memory between folds -- the decode loop itself carries no extra registers.  The decoded column is not read
+// from HBM again.  (Folding inside the batch loop instead -- each lane its own word while it is in a register -- was measured
+// first: 354 instead of 211 instructions per batch, spills at 64 registers, 18.5 ms instead of 9.4 for 1e9 rows: the kernel is
+// instruction-bound, and a fold at 24 of 32 lanes with half of them masked off is the expensive way to issue it.)
+constexpr uint32_t FOLD_SHIFT = 11, FOLD_ROWS = 1u << (FOLD_SHIFT - 3);   // every 256 rows (2 KB of output)
+
+template <int AGG>
+__device__ __forceinline__ void acc_load(LaneAcc &a, const unsigned long long *s)
 {
+    const unsigned long long cf = s[4 * SPEC_WARPS * 32];
+    a.count = (int)(uint32_t)cf; a.flags = (int)(cf >> 32);
+    if (AGG == 2) {
+        a.sum_hi = __longlong_as_double((long long)s[0]); a.sum_lo = __longlong_as_double((long long)s[SPEC_WARPS * 32]);
+        a.min_f = __longlong_as_double((long long)s[2 * SPEC_WARPS * 32]); a.max_f = __longlong_as_double((long long)s[3 * SPEC_WARPS * 32]);
+    } else if (AGG == 1) {
+        a.sum_i = (long long)s[0]; a.min_i = (long long)s[2 * SPEC_WARPS * 32]; a.max_i = (long long)s[3 * SPEC_WARPS * 32];
+    }
+}
+template <int AGG>
+__device__ __forceinline__ void acc_store(const LaneAcc &a, unsigned long long *s)
+{
+    s[4 * SPEC_WARPS * 32] = (unsigned long long)(uint32_t)a.count | ((unsigned long long)(uint32_t)a.flags << 32);
+    if (AGG == 2) {
+        s[0] = (unsigned long long)__double_as_longlong(a.sum_hi); s[SPEC_WARPS * 32] = (unsigned long long)__double_as_longlong(a.sum_lo);
+        s[2 * SPEC_WARPS * 32] = (unsigned long long)__double_as_longlong(a.min_f); s[3 * SPEC_WARPS * 32] = (unsigned long long)__double_as_longlong(a.max_f);
+    } else if (AGG == 1) {
+        s[0] = (unsigned long long)a.sum_i; s[2 * SPEC_WARPS * 32] = (unsigned long long)a.min_i; s[3 * SPEC_WARPS * 32] = (unsigned long long)a.max_i;
+    }
+}
+// Folds the complete FOLD_ROWS-row windows below row `upto` that have not been folded yet (all remaining rows when `last`).
+// Where the previous fold stopped and the block's rows of the aggregated column are kept, like the accumulators, in shared
+// memory: nothing of this is live in the decode loop.  Windows are fixed (row r always goes to lane r % 32), and each fold
+// asks L2 for the next window of the aggregated column, so that window's loads find it there ~20 000 cycles later.
+constexpr int ACC_WORDS = 5 * SPEC_WARPS * 32;          // then per warp: rows folded so far, the block's rows of the aggregated column
+template <int AGG>
+__device__ __noinline__ void fold_rows(const LaneFused &F, const unsigned long long *out64, uint32_t upto, unsigned long long *accs)
+{
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned long long *acc_s = accs + threadIdx.x;
+    uint32_t from = (uint32_t)accs[ACC_WORDS + warp];
+    const bool last = upto == (uint32_t)(accs[ACC_WORDS + warp] >> 32);      // (the block's row count rides in the upper half)
+    const unsigned long long *__restrict__ bvals = AGG ? reinterpret_cast<const unsigned long long *>(accs[ACC_WORDS + SPEC_WARPS + warp]) : nullptr;
+    const bool uns = F.agg_cls == VC_UINT || F.agg_cls == VC_BOOL;
+    LaneAcc acc;
+    acc_load<AGG>(acc, acc_s);
+    while (from + FOLD_ROWS <= upto) {
+        if (AGG && lane < FOLD_ROWS / 16u) asm volatile("prefetch.global.L2 [%0];" ::"l"(bvals + from + FOLD_ROWS + 16u * lane));   // (past the block's end: the next block's rows, or the 128-byte slack behind the column)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            unsigned long long a[4], bb[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                a[k] = __ldcg(out64 + from + lane + 32u * (4 * h + k));
+                bb[k] = AGG ? __ldcs(bvals + from + lane + 32u * (4 * h + k)) : 0ull;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (fused::lane_test(F, a[k])) fused::acc_add<AGG>(acc, bb[k], uns);
+        }
+        from += FOLD_ROWS;
+    }
+    if (last) {
+        for (uint32_t r = from + lane; r < upto; r += 32u)
+            if (fused::lane_test(F, __ldcg(out64 + r))) fused::acc_add<AGG>(acc, AGG ? __ldcs(bvals + r) : 0ull, uns);
+        from = upto;
+    }
+    acc_store<AGG>(acc, acc_s);
+    __syncwarp();
+    if (lane == 0) reinterpret_cast<uint32_t *>(accs + ACC_WORDS + warp)[0] = from;
+    __syncwarp();
+}
+
+template <int AGG>
+__device__ __noinline__ void fold_begin(const LaneFused &F, int b, uint32_t rows, unsigned long long *accs)
+{
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    LaneAcc z;
+    fused::acc_reset(z, F.agg_cls == VC_UINT || F.agg_cls == VC_BOOL);
+    acc_store<AGG>(z, accs + threadIdx.x);
+    const uint8_t *bv = AGG ? F.agg.base + F.agg.blk_off[b] : nullptr;
+    if (lane == 0) {
+        accs[ACC_WORDS + warp] = (unsigned long long)rows << 32;
+        accs[ACC_WORDS + SPEC_WARPS + warp] = (unsigned long long)bv;
+    }
+    if (AGG && lane < FOLD_ROWS / 16u) asm volatile("prefetch.global.L2 [%0];" ::"l"(bv + 128u * lane));
+    __syncwarp();
+}
+
+template <int FUSED>
+__device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_len, uint8_t *dst, uint32_t origin, unsigned long long *ring,
+                                 const LaneFused &F, unsigned long long *accs)
+{
+    constexpr int AGG = FUSED == 3 ? 2 : FUSED == 2 ? 1 : 0;
     const uint32_t lane = lane_id();
     uint32_t ip = 0, op = 0;
     bool done = false;
@@ -72,6 +170,8 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
     };
     uint64_t x = load_stream(src, 0, lane, 3);
     while (!done) {
+        bool batch = false;
+        const uint32_t op_was = op;
         if (fast_possible && (op & 7u) == 0 && ip <= ip_lim) {
             const uint32_t opw = op >> 3, myw = opw + lane;
             const uint32_t tok = (uint32_t)x & 0xffu;
@@ -144,26 +244,37 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
                 ip = nip;
                 op += 8u * adv_words;
                 x = nx;
-                continue;
+                batch = true;
             }
         }
-        // ---- anything else: one sequence, whole warp ----
-        int64_t ip64 = ip, op64 = op;
-        const int e = decode_one_sequence(src, comp_len, dst, origin, ip64, op64, done);
-        if (e) return e;
-        ip = (uint32_t)ip64;
-        op = (uint32_t)op64;
-        ring_from = (op + 7u) >> 3;                                             // (what this path wrote is in global memory only)
-        x = load_stream(src, ip, lane, 3u + L0);
+        if (!batch) {
+            // ---- anything else: one sequence, whole warp ----
+            int64_t ip64 = ip, op64 = op;
+            const int e = decode_one_sequence(src, comp_len, dst, origin, ip64, op64, done);
+            if (e) return e;
+            ip = (uint32_t)ip64;
+            op = (uint32_t)op64;
+            ring_from = (op + 7u) >> 3;                                         // (what this path wrote is in global memory only)
+            x = load_stream(src, ip, lane, 3u + L0);
+        }
+        if (FUSED && (((op ^ op_was) >> FOLD_SHIFT) != 0 || done)) {             // the output crossed a FOLD_ROWS boundary
+            __syncwarp();
+            fold_rows<AGG>(F, out64, op >> 3, accs);
+        }
     }
     return (op == origin && ip == comp_len) ? E_OK : E_SIZE;
 }
 
-__global__ void __launch_bounds__(SPEC_WARPS * 32, 4) lz4_decode_spec_kernel(const __grid_constant__ DecodeArgs args, unsigned int *counter)
+template <int FUSED>
+__global__ void __launch_bounds__(SPEC_WARPS * 32, 4) lz4_decode_spec_kernel(const __grid_constant__ DecodeArgs args, const __grid_constant__ LaneFused F,
+                                                                                          unsigned int *counter)
 {
     __shared__ unsigned long long rings[SPEC_WARPS][SPEC_RING];
+    __shared__ unsigned long long accs[FUSED ? ACC_WORDS + 2 * SPEC_WARPS : 1];   // per-lane accumulators, field-major; then the per-warp fold state
     unsigned long long *ring = rings[threadIdx.x >> 5];
+    unsigned long long *acc_s = accs + (FUSED ? threadIdx.x : 0);
     const uint32_t lane = lane_id();
+    constexpr int AGG = FUSED == 3 ? 2 : FUSED == 2 ? 1 : 0;
     const long long njobs = (long long)args.ncols * args.nblocks;
     for (;;) {
         unsigned int job = 0;
@@ -177,19 +288,31 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, 4) lz4_decode_spec_kernel(con
         const uint8_t *src = col.comp + col.comp_off[b];
         uint8_t *dst = col.out + col.dec_off[b];
         const uint32_t comp_len = (uint32_t)col.comp_len[b], origin = (uint32_t)col.origin[b];
+        constexpr bool pred = FUSED != 0;                       // a fused launch holds the predicate column alone (see the launcher)
         int e;
+        if (FUSED) fold_begin<AGG>(F, b, origin >> 3, accs);
         if (origin == 0) e = (comp_len == 1 && src[0] == 0) ? E_OK : E_SIZE;
         else if (comp_len == 0) e = E_TRUNCATED;
-        else if (((uintptr_t)src & 3u) || ((uintptr_t)dst & 7u)) e = decode_simple(src, comp_len, dst, origin);
-        else e = decode_block_spec(src, comp_len, dst, origin, ring);
+        else if (((uintptr_t)src & 3u) || ((uintptr_t)dst & 7u)) e = pred ? E_INTERNAL : decode_simple(src, comp_len, dst, origin);
+        else e = decode_block_spec<FUSED>(src, comp_len, dst, origin, ring, F, accs);
         if (lane == 0) col.status[b] = e;
+        if (pred) {
+            // the block's partial: the 32 lanes' accumulators folded in a fixed order
+            const bool uns = F.agg_cls == VC_UINT || F.agg_cls == VC_BOOL;
+            LaneAcc acc;
+            fused::acc_reset(acc, uns);                          // (the fields this aggregate does not use)
+            acc_load<AGG>(acc, acc_s);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) fused::acc_merge_xor<AGG>(acc, d, uns, (lane & d) != 0);
+            if (lane == 0) F.partials[(int64_t)(b - F.part_blk0) * F.segs_per_block] = fused::acc_to_partial<AGG>(acc);
+        }
         __syncwarp();
     }
 }
 
 }  // namespace
 
-int launch_lz4_decode_spec(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit)
+int launch_lz4_decode_spec(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit, const LaneFused *fused_args)
 {
     const long long njobs = (long long)args.ncols * args.nblocks;
     if (njobs <= 0) return 0;
@@ -198,7 +321,17 @@ int launch_lz4_decode_spec(const DecodeArgs &args, unsigned int *d_counter, int 
     long long max_ctas = cta_limit > 0 ? cta_limit : (long long)sm_count * 4;      // 4 CTAs of 8 warps fit an SM (64 registers per thread); persistent over the job queue
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
-    lz4_decode_spec_kernel<<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, d_counter);
+    LaneFused f;
+    memset(&f, 0, sizeof f);
+    if (fused_args && args.ncols != 1) return 1;
+    const int variant = fused_args ? (fused_args->agg_kind == 0 ? 1 : fused_args->agg_kind == 1 ? 2 : 3) : 0;
+    if (fused_args) f = *fused_args;
+    switch (variant) {
+    case 0: lz4_decode_spec_kernel<0><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter); break;
+    case 1: lz4_decode_spec_kernel<1><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter); break;
+    case 2: lz4_decode_spec_kernel<2><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter); break;
+    default: lz4_decode_spec_kernel<3><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter); break;
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
