@@ -64,6 +64,7 @@ struct Runtime {
     std::vector<PhaseRec> recs;
     double acc_ms[PH_COUNT] = {0};
     int64_t acc_launches[PH_COUNT] = {0}, acc_bytes[PH_COUNT] = {0};
+    int64_t k1_launches[5] = {0};   // decode launches per K1 kernel (v1, v2, v3, lane, spec): dfdb_profile_get("k1_<name>")
 } rt;
 
 #define CUDA_TRY(expr)                                                                                         \
@@ -295,17 +296,19 @@ int launch_decode(const DecodeArgs &a, int general, cudaStream_t stream = nullpt
 {
     if (!stream) stream = rt.stream;
     unsigned int *counter = rt.d_counter + 4 * counter_slot;   // launches that may run at the same time need their own job counter
-    if (rt.lz4_simple || rt.lz4_v1) return launch_lz4_decode(a, counter, rt.sm_count, (int)rt.lz4_simple, stream);
+    if (rt.lz4_simple || rt.lz4_v1) { rt.k1_launches[0]++; return launch_lz4_decode(a, counter, rt.sm_count, (int)rt.lz4_simple, stream); }
     if (rt.lz4_flavour == 3) {
+        rt.k1_launches[3]++;
         DecodeArgs la = a;
         la.hot = general == 1 ? 0 : 1;   // word-regular columns (the token sample at load) run the hot-step schedule
         if (rt.lane_hot >= 0) la.hot = (int)rt.lane_hot;
         return launch_lz4_decode_lane(la, nullptr, counter, rt.sm_count, stream, cta_limit);
     }
-    if (rt.lz4_flavour == 4 || (rt.lz4_flavour == 0 && general == 2)) return launch_lz4_decode_spec(a, counter, rt.sm_count, stream, cta_limit, fuse);
+    if (rt.lz4_flavour == 4 || (rt.lz4_flavour == 0 && general == 2)) { rt.k1_launches[4]++; return launch_lz4_decode_spec(a, counter, rt.sm_count, stream, cta_limit, fuse); }
     if (fuse) return 1;
     if (rt.lz4_flavour == 1) general = 0;
     if (rt.lz4_flavour == 2) general = 1;
+    rt.k1_launches[general == 1 ? 2 : 1]++;
     return general == 1 ? launch_lz4_decode_v3(a, counter, rt.sm_count, stream, cta_limit) : launch_lz4_decode_v2(a, counter, rt.sm_count, stream, cta_limit);
 }
 
@@ -1354,6 +1357,7 @@ int32_t dfdb_profile_reset(void)
 {
     if (rt.inited) { cudaStreamSynchronize(rt.stream); profile_collect(); }
     for (int i = 0; i < PH_COUNT; i++) { rt.acc_ms[i] = 0; rt.acc_launches[i] = 0; rt.acc_bytes[i] = 0; }
+    for (int64_t &n : rt.k1_launches) n = 0;
     return DFDB_OK;
 }
 int32_t dfdb_profile_get(const char *phase, double *total_ms, int64_t *launches, int64_t *bytes)
@@ -1364,6 +1368,15 @@ int32_t dfdb_profile_get(const char *phase, double *total_ms, int64_t *launches,
             if (total_ms) *total_ms = rt.acc_ms[i];
             if (launches) *launches = rt.acc_launches[i];
             if (bytes) *bytes = rt.acc_bytes[i];
+            return DFDB_OK;
+        }
+    // "k1_v1" / "k1_v2" / "k1_v3" / "k1_lane" / "k1_spec": decode launches per K1 kernel since the last reset (launches only)
+    static const char *k1_names[5] = {"k1_v1", "k1_v2", "k1_v3", "k1_lane", "k1_spec"};
+    for (int i = 0; i < 5; i++)
+        if (strcmp(phase, k1_names[i]) == 0) {
+            if (total_ms) *total_ms = 0;
+            if (launches) *launches = rt.k1_launches[i];
+            if (bytes) *bytes = 0;
             return DFDB_OK;
         }
     return fail(DFDB_ERR_ARGUMENT, "unknown phase %s", phase);

@@ -157,6 +157,8 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
     // L0 = 0 (token 0x04), sorted Int64 columns runs of L0 = 2 (token 0x22).  The stride of the last run is assumed for the next
     // batch (its bytes are requested early); two sequences of another shape in a row switch the run's shape.
     uint32_t L0 = 0, pendL = 0xffu;
+    uint32_t tok0 = 0x04u, sh0 = 8u;       // the run's token, where its offset sits in the lane's stream bytes, the bytes a word takes from its source
+    unsigned long long kp0 = ~0ull;
     uint32_t ring_from = 0;            // output words >= this one (and within SPEC_RING of the position) are in the ring
     // a match never writes the block's last 12 bytes in the fast path (the end-of-block rules stay with the one-sequence path):
     // an output word w may be written when w < lim_w; and the fast path needs 7 * 32 + 16 stream bytes ahead
@@ -168,6 +170,9 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
         if (sw >= ring_from && opw - sw <= SPEC_NEAR) return ring[sw & (SPEC_RING - 1)];
         return __ldcg(out64 + sw);
     };
+    // the compressed bytes are read exactly once, so each batch would wait a DRAM round trip for its own bytes: the stream is
+    // pulled from HBM into L2 eight 128-byte lines ahead of the position, one request per line (here: the first nine lines)
+    if (lane < 9u) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 128u * lane));
     uint64_t x = load_stream(src, 0, lane, 3);
     while (!done) {
         bool batch = false;
@@ -175,70 +180,74 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
         if (fast_possible && (op & 7u) == 0 && ip <= ip_lim) {
             const uint32_t opw = op >> 3, myw = opw + lane;
             const uint32_t tok = (uint32_t)x & 0xffu;
-            const uint32_t off = (uint32_t)(x >> ((8u + 8u * L0) & 63u)) & 0xffffu, offw = off >> 3;
-            const bool okp = tok == ((L0 << 4) | (4u - L0)) && (off & 7u) == 0 && off != 0 && offw <= myw && myw < lim_w;
+            const uint32_t off = (uint32_t)(x >> sh0) & 0xffffu;
+            // offset a multiple of 8, not zero, inside the output: rotate the low three bits to the top -- any of them set, or a
+            // zero offset (minus one wraps), fails the one comparison; for the lanes that pass, offr is the offset in words
+            const uint32_t offr = __funnelshift_r(off, off, 3);
+            const bool okp = tok == tok0 && offr - 1u < myw && myw < lim_w;
             const uint32_t badp = ~__ballot_sync(FULL, okp);
-            const uint32_t n = badp ? (uint32_t)__ffs(badp) - 1u : 32u;
-            // the sequence that ends the run, analysed by its own lane: any "word form" -- L <= 5 literal bytes + match, 8 or 16 bytes in all
-            const uint32_t L = tok >> 4, LM = L + (tok & 15u) + 4u;
-            const uint32_t off_s = (uint32_t)(x >> ((8u + 8u * L) & 63u)) & 0xffffu, offw_s = off_s >> 3;
-            const uint32_t W = LM >> 3;
-            const bool sp = lane == n && L <= 5u && (tok & 15u) != 15u && (LM & 7u) == 0 && (off_s & 7u) == 0 && off_s != 0 &&
-                            offw_s <= myw && offw_s >= lane + W &&                         // sources inside the output and final (before the batch)
-                            myw + W <= lim_w;
-            const uint32_t spb = __ballot_sync(FULL, sp);
-            uint32_t hdr_s = 0, W_s = 0;
-            if (spb) {
-                const uint32_t pk = __shfl_sync(FULL, (L << 8) | W, n & 31u);
-                hdr_s = 3u + (pk >> 8);
-                W_s = pk & 0xffu;
-            }
-            const uint32_t adv_words = n + W_s;
-            if (adv_words > 0) {
+            uint32_t n = 32u, W_s = 0, hdr_s = 0, srcw = offr;
+            unsigned long long kp = kp0;                                        // the bytes that come from the source word (the others are literals)
+            bool sp = false;
+            const uint32_t stride_was = 3u + L0;
+            if (!badp) {
+                pendL = 0xffu;
+            } else {
+                n = (uint32_t)__ffs(badp) - 1u;
+                // the sequence that ends the run, analysed by its own lane: any "word form" -- L <= 5 literal bytes + match, 8 or 16 bytes in all
+                const uint32_t L = tok >> 4, LM = L + (tok & 15u) + 4u;
+                const uint32_t off_s = (uint32_t)(x >> ((8u + 8u * L) & 63u)) & 0xffffu, offw_s = off_s >> 3;
+                const uint32_t W = LM >> 3;
+                sp = lane == n && L <= 5u && (tok & 15u) != 15u && (LM & 7u) == 0 && (off_s & 7u) == 0 && off_s != 0 &&
+                     offw_s <= myw && offw_s >= lane + W &&                                // sources inside the output and final (before the batch)
+                     myw + W <= lim_w;
+                if (__ballot_sync(FULL, sp)) {
+                    const uint32_t pk = __shfl_sync(FULL, (L << 8) | W, n);
+                    hdr_s = 3u + (pk >> 8);
+                    W_s = pk & 0xffu;
+                }
+                if (sp) { srcw = offw_s; kp = ~0ull << (8u * L); }
                 // a sequence of another one-word shape alone at the head of a batch is just the closing sequence of an empty run;
                 // two of the same shape in a row are a new run: switch (the bytes requested next use the new stride)
-                const uint32_t nip = ip + (3u + L0) * n + hdr_s;
                 if (n == 0 && W_s == 1u) {
                     const uint32_t Lh = hdr_s - 3u;
-                    if (Lh == pendL && Lh <= 4u) L0 = Lh;
+                    if (Lh == pendL && Lh <= 4u) {
+                        L0 = Lh;
+                        tok0 = (L0 << 4) | (4u - L0); sh0 = 8u + 8u * L0; kp0 = ~0ull << (8u * L0);
+                    }
                     pendL = Lh;
                 } else {
                     pendL = 0xffu;
                 }
+            }
+            const uint32_t adv_words = n + W_s;
+            if (adv_words > 0) {
+                const uint32_t nip = ip + stride_was * n + hdr_s;
                 const uint64_t nx = load_stream(src, nip, lane, 3u + L0);      // the next batch's bytes travel while this one's sources do
-                // ... and the stream a few batches ahead is pulled from HBM into L2 now: the compressed bytes are read exactly once,
-                // so without this every batch waits a DRAM round trip for its own bytes (one batch of lead covers an L2 hit, not DRAM)
-                if (lane < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ((nip + 512u + 128u * lane) & ~127u)));
-                // sources: before the batch -> the ring (or global memory); inside the batch -> another lane's word.  Only the bytes
-                // behind the literal bytes come from the source, so a chain of in-batch sources ends in the word of its far root.
+                const uint32_t crossed = (nip >> 7) - (ip >> 7);               // (0, 1 or 2 lines entered)
+                if (lane < crossed) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (((nip >> 7) + 8u - lane) << 7)));
+                // Sources.  Lane = sequence = output word; its source word is `s`.  A source inside the batch is another lane's word,
+                // and only the bytes behind the literal bytes come from it, so a chain of in-batch sources ends in the word of its
+                // far root: the chains collapse by pointer jumping over the word INDEX (<= 5 rounds, one shuffle each), and every
+                // lane then fetches its root itself -- from the ring when it is recent, else from global memory (final there: L2).
                 const bool mine = lane < n;
-                const bool far = mine && offw > lane;
-                unsigned long long v = 0;
-                if (far) v = source(myw - offw, opw);
-                bool res = far || !mine;
-                uint32_t sl = (mine && !far) ? lane - offw : lane;
-                while (__any_sync(FULL, !res)) {                                // chains collapse by pointer jumping: <= 5 rounds
-                    const unsigned long long v_s = __shfl_sync(FULL, v, sl);
-                    const uint32_t pk = __shfl_sync(FULL, (sl << 1) | (res ? 1u : 0u), sl);
-                    if (!res) { if (pk & 1u) { v = v_s; res = true; } else sl = pk >> 1; }
+                uint32_t s = myw - srcw;
+                bool inb = mine && s >= opw;
+                while (__any_sync(FULL, inb)) {
+                    const uint32_t t = __shfl_sync(FULL, s, s - opw);
+                    if (inb) { s = t; inb = s >= opw; }
                 }
-                const unsigned long long lits = (unsigned long long)(x >> 8);
-                if (sp) {
-                    const unsigned long long keep = ~0ull << (8u * L);          // (L == 0: everything comes from the source word)
-                    const unsigned long long w0 = (source(myw - offw_s, opw) & keep) | (lits & ~keep);
-                    out64[myw] = w0;
-                    ring[myw & (SPEC_RING - 1)] = w0;
-                    if (W == 2u) {
-                        const unsigned long long w1 = source(myw + 1u - offw_s, opw);
-                        out64[myw + 1u] = w1;
-                        ring[(myw + 1u) & (SPEC_RING - 1)] = w1;
-                    }
-                }
-                if (mine) {
-                    const unsigned long long keep = ~0ull << (8u * L0);
-                    const unsigned long long w = (v & keep) | (lits & ~keep);
+                const bool act = mine || sp;
+                if (act) {
+                    const unsigned long long v = source(s, opw);
+                    const unsigned long long w = (v & kp) | ((unsigned long long)(x >> 8) & ~kp);
                     out64[myw] = w;
                     ring[myw & (SPEC_RING - 1)] = w;
+                }
+                if (W_s == 2u && sp) {                                          // a closing sequence of two words
+                    const unsigned long long w1 = source(s + 1u, opw);
+                    out64[myw + 1u] = w1;
+                    ring[(myw + 1u) & (SPEC_RING - 1)] = w1;
                 }
                 __syncwarp();                                                   // the batch's words are visible to the whole warp
                 ip = nip;
