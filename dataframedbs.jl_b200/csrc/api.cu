@@ -554,7 +554,13 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
         // columns of one flavour share a launch
         for (int general = 0; general < 3; general++) {
           std::vector<Column *> grp;
-          for (Column *c : todo) if (c->lz4_general == general) grp.push_back(c);
+          for (Column *c : todo) {
+              if (c->lz4_general != general) continue;
+              // (a column whose blocks in this range are all skipped -- stored bodies read in place, blocks without selected rows -- needs no launch)
+              bool work = false;
+              for (int b = b0; b < b1 && !work; b++) work = !h_skip_of(c)[(size_t)b];
+              if (work) grp.push_back(c);
+          }
           for (size_t i = 0; i < grp.size(); i += DECODE_MAX_COLS) {
             DecodeArgs a;
             memset(&a, 0, sizeof a);
@@ -1288,6 +1294,7 @@ int32_t dfdb_init(int32_t device)
     CUDA_TRY(cudaMemset(rt.d_error, 0, 64));
     if (const char *fl = getenv("DFDB_LZ4_FLAVOUR")) rt.lz4_flavour = atoll(fl);
     if (const char *tp = getenv("DFDB_SPEC_TAIL_PCT")) rt.spec_tail_pct = atoll(tp);
+    if (const char *sc = getenv("DFDB_SPEC_CTAS")) g_spec_ctas = atoi(sc);
     if (const char *nf = getenv("DFDB_NO_DECODE_FUSED")) rt.no_decode_fused = atoll(nf);   // A/B: decode, then scan
     if (const char *ov = getenv("DFDB_NO_OVERLAP")) rt.no_overlap = atoll(ov);       // A/B: decode / scan overlap off   // A/B: force one K1 flavour (see dfdb_set_option "lz4_flavour")
     rt.inited = true;
@@ -1347,6 +1354,7 @@ int32_t dfdb_set_option(const char *name, int64_t value)
     else if (n == "no_validate") rt.no_validate = value;
     else if (n == "no_zonemap") rt.no_zonemap = value;
     else if (n == "spec_tail_pct") rt.spec_tail_pct = value;
+    else if (n == "spec_ctas") g_spec_ctas = (int)value;
     else if (n == "host_arena_cap_mb") { std::lock_guard<std::mutex> lk(arena.mu); arena.cap_bytes = (size_t)std::max<int64_t>(value, 0) << 20; arena.trim(arena.cap_bytes); }
     else return fail(DFDB_ERR_ARGUMENT, "unknown option %s", n.c_str());
     return DFDB_OK;

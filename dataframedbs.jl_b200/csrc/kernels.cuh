@@ -31,6 +31,7 @@ constexpr int LZ4_SLOTS_PER_SM = 60;   // column blocks one decoder CTA keeps in
 int launch_lz4_decode_v2(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit = 0);                     // v2: walker / consumer warps, word-regular columns
 int launch_lz4_decode_v3(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit = 0);
 struct LaneFused;
+extern int g_spec_ctas;   // resident CTAs per SM of the spec decoder (4..6; option "spec_ctas")
 int launch_lz4_decode_spec(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit = 0,
                            const LaneFused *fused = nullptr);   // warp per block, plain token runs verified in parallel (word-regular columns); optionally with K3 + K7 fused in                     // v3: same organisation, general columns (strings, literal-heavy, chains)
 

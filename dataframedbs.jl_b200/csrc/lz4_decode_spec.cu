@@ -21,6 +21,8 @@
 // Algorithmic bytes per block (roofline): compressed bytes read + origin bytes written.
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "kernels.cuh"
 #include "lz4_common.cuh"
 #include "lz4_fused.cuh"
@@ -37,13 +39,12 @@ constexpr uint32_t SPEC_NEAR = SPEC_RING - 64;   // a source at most this many w
 
 __device__ __forceinline__ uint32_t ldg_u32(const uint8_t *p) { return __ldg(reinterpret_cast<const unsigned int *>(p)); }
 
-// the 8 stream bytes at ip + stride * lane (three aligned words; payload buffers carry slack behind the last block, so reading a
+// the 8 stream bytes at tp = ip + stride * lane (three aligned words; payload buffers carry slack behind the last block, so reading a
 // few words past this block's payload is safe -- such bytes are never USED: the fast path checks the positions first)
-__device__ __forceinline__ uint64_t load_stream(const uint8_t *__restrict__ src, uint32_t ip, uint32_t lane, uint32_t stride)
+__device__ __forceinline__ uint64_t load_stream_at(const uint8_t *__restrict__ src, uint32_t tp)
 {
-    const uint32_t tp = ip + stride * lane;
     const uint8_t *a = src + (tp & ~3u);
-    const uint32_t sh = (tp & 3u) * 8u;
+    const uint32_t sh = tp * 8u;             // (the funnel shift takes it modulo 32)
     const uint32_t w0 = ldg_u32(a), w1 = ldg_u32(a + 4), w2 = ldg_u32(a + 8);
     return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
 }
@@ -165,15 +166,59 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
     const uint32_t lim_w = origin >= 12u ? (origin - 12u) >> 3 : 0u;
     const uint32_t ip_lim = comp_len >= 7u * 32u + 16u ? comp_len - (7u * 32u + 16u) : 0u;
     const bool fast_possible = comp_len >= 7u * 32u + 16u;
-    // a source word: from the ring when it is recent, else from global memory (final there: L2)
+    // a source word: from the ring when it is recent, else from global memory (final there: L2).  The ring is 4 KB aligned in
+    // the shared window, so a word's slot is one LOP3 away from its index.
+    const uint32_t ring_s = smem_addr(ring);
+    if (ring_s & (SPEC_RING * 8u - 1u)) return E_INTERNAL;
+    auto ring_slot = [&](uint32_t w) -> uint32_t { return ((w << 3) & ((SPEC_RING - 1u) << 3)) | ring_s; };
     auto source = [&](uint32_t sw, uint32_t opw) -> unsigned long long {
-        if (sw >= ring_from && opw - sw <= SPEC_NEAR) return ring[sw & (SPEC_RING - 1)];
-        return __ldcg(out64 + sw);
+        unsigned long long v;
+        if (sw >= ring_from && opw - sw <= SPEC_NEAR) asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(ring_slot(sw)));
+        else v = __ldcg(out64 + sw);
+        return v;
+    };
+    auto put = [&](uint32_t w, unsigned long long v) {
+        out64[w] = v;
+        asm volatile("st.shared.u64 [%0], %1;" ::"r"(ring_slot(w)), "l"(v) : "memory");
     };
     // the compressed bytes are read exactly once, so each batch would wait a DRAM round trip for its own bytes: the stream is
-    // pulled from HBM into L2 eight 128-byte lines ahead of the position, one request per line (here: the first nine lines)
-    if (lane < 9u) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 128u * lane));
-    uint64_t x = load_stream(src, 0, lane, 3);
+    // pulled from HBM into L2 two to three 512-byte groups ahead of the position, one request per 128-byte line
+    if (lane < 12u) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 128u * lane));
+    uint32_t tp = 3u * lane;                 // where this lane's sequence starts in the stream: ip + stride * lane
+    uint64_t x = load_stream_at(src, tp);
+    // The batch proper, once the run (n sequences, one per lane) and its closing sequence are known.  FB: a full batch of 32
+    // plain sequences -- by far the most frequent case, compiled without the closing sequence's selects.
+    auto do_batch = [&](auto full, uint32_t opw, uint32_t n, uint32_t W_s, uint32_t hdr_s, uint32_t srcw, unsigned long long kp, bool sp, uint32_t stride) {
+        constexpr bool FB = decltype(full)::value;
+        const uint32_t myw = opw + lane;
+        const uint32_t adv = FB ? 32u * stride : stride * n + hdr_s;
+        const uint32_t nip = ip + adv;
+        tp = (!FB && stride != 3u + L0) ? nip + (3u + L0) * lane : tp + adv;     // (the run's shape -- the stride -- may just have changed)
+        const uint64_t nx = load_stream_at(src, tp);                             // the next batch's bytes travel while this one's sources do
+        if ((nip ^ ip) >> 9) {                                                   // entered a new 512-byte group of the stream: request the group after the next
+            if (lane < 4u) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ((((nip >> 9) + 2u) << 9) + 128u * lane)));
+        }
+        // Sources.  Lane = sequence = output word; its source word is `s`.  A source inside the batch is another lane's word,
+        // and only the bytes behind the literal bytes come from it, so a chain of in-batch sources ends in the word of its
+        // far root: the chains collapse by pointer jumping over the word INDEX (<= 5 rounds, one shuffle each), and every
+        // lane then fetches its root itself.
+        const bool mine = FB || lane < n;
+        uint32_t s = myw - srcw;
+        bool inb = mine && s >= opw;
+        while (__any_sync(FULL, inb)) {
+            const uint32_t t = __shfl_sync(FULL, s, s - opw);
+            if (inb) { s = t; inb = s >= opw; }
+        }
+        if (FB || mine || sp) {
+            const unsigned long long v = source(s, opw);
+            put(myw, (v & kp) | ((unsigned long long)(x >> 8) & ~kp));
+        }
+        if (!FB && W_s == 2u && sp) put(myw + 1u, source(s + 1u, opw));         // a closing sequence of two words
+        __syncwarp();                                                           // the batch's words are visible to the whole warp
+        ip = nip;
+        op += 8u * (FB ? 32u : n + W_s);
+        x = nx;
+    };
     while (!done) {
         bool batch = false;
         const uint32_t op_was = op;
@@ -186,74 +231,42 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
             const uint32_t offr = __funnelshift_r(off, off, 3);
             const bool okp = tok == tok0 && offr - 1u < myw && myw < lim_w;
             const uint32_t badp = ~__ballot_sync(FULL, okp);
-            uint32_t n = 32u, W_s = 0, hdr_s = 0, srcw = offr;
-            unsigned long long kp = kp0;                                        // the bytes that come from the source word (the others are literals)
-            bool sp = false;
-            const uint32_t stride_was = 3u + L0;
             if (!badp) {
                 pendL = 0xffu;
+                do_batch(std::true_type{}, opw, 32u, 0u, 0u, offr, kp0, false, 3u + L0);
+                batch = true;
             } else {
-                n = (uint32_t)__ffs(badp) - 1u;
+                const uint32_t n = (uint32_t)__ffs(badp) - 1u;
                 // the sequence that ends the run, analysed by its own lane: any "word form" -- L <= 5 literal bytes + match, 8 or 16 bytes in all
                 const uint32_t L = tok >> 4, LM = L + (tok & 15u) + 4u;
                 const uint32_t off_s = (uint32_t)(x >> ((8u + 8u * L) & 63u)) & 0xffffu, offw_s = off_s >> 3;
                 const uint32_t W = LM >> 3;
-                sp = lane == n && L <= 5u && (tok & 15u) != 15u && (LM & 7u) == 0 && (off_s & 7u) == 0 && off_s != 0 &&
-                     offw_s <= myw && offw_s >= lane + W &&                                // sources inside the output and final (before the batch)
-                     myw + W <= lim_w;
+                const bool sp = lane == n && L <= 5u && (tok & 15u) != 15u && (LM & 7u) == 0 && (off_s & 7u) == 0 && off_s != 0 &&
+                                offw_s <= myw && offw_s >= lane + W &&                     // sources inside the output and final (before the batch)
+                                myw + W <= lim_w;
+                uint32_t hdr_s = 0, W_s = 0;
                 if (__ballot_sync(FULL, sp)) {
                     const uint32_t pk = __shfl_sync(FULL, (L << 8) | W, n);
                     hdr_s = 3u + (pk >> 8);
                     W_s = pk & 0xffu;
                 }
-                if (sp) { srcw = offw_s; kp = ~0ull << (8u * L); }
-                // a sequence of another one-word shape alone at the head of a batch is just the closing sequence of an empty run;
-                // two of the same shape in a row are a new run: switch (the bytes requested next use the new stride)
-                if (n == 0 && W_s == 1u) {
-                    const uint32_t Lh = hdr_s - 3u;
-                    if (Lh == pendL && Lh <= 4u) {
-                        L0 = Lh;
-                        tok0 = (L0 << 4) | (4u - L0); sh0 = 8u + 8u * L0; kp0 = ~0ull << (8u * L0);
+                if (n + W_s > 0) {
+                    const uint32_t stride = 3u + L0;
+                    // a sequence of another one-word shape alone at the head of a batch is just the closing sequence of an empty run;
+                    // two of the same shape in a row are a new run: switch (the bytes requested next use the new stride)
+                    if (n == 0 && W_s == 1u) {
+                        const uint32_t Lh = hdr_s - 3u;
+                        if (Lh == pendL && Lh <= 4u) {
+                            L0 = Lh;
+                            tok0 = (L0 << 4) | (4u - L0); sh0 = 8u + 8u * L0; kp0 = ~0ull << (8u * L0);
+                        }
+                        pendL = Lh;
+                    } else {
+                        pendL = 0xffu;
                     }
-                    pendL = Lh;
-                } else {
-                    pendL = 0xffu;
+                    do_batch(std::false_type{}, opw, n, W_s, hdr_s, sp ? offw_s : offr, sp ? ~0ull << (8u * L) : kp0, sp, stride);
+                    batch = true;
                 }
-            }
-            const uint32_t adv_words = n + W_s;
-            if (adv_words > 0) {
-                const uint32_t nip = ip + stride_was * n + hdr_s;
-                const uint64_t nx = load_stream(src, nip, lane, 3u + L0);      // the next batch's bytes travel while this one's sources do
-                const uint32_t crossed = (nip >> 7) - (ip >> 7);               // (0, 1 or 2 lines entered)
-                if (lane < crossed) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (((nip >> 7) + 8u - lane) << 7)));
-                // Sources.  Lane = sequence = output word; its source word is `s`.  A source inside the batch is another lane's word,
-                // and only the bytes behind the literal bytes come from it, so a chain of in-batch sources ends in the word of its
-                // far root: the chains collapse by pointer jumping over the word INDEX (<= 5 rounds, one shuffle each), and every
-                // lane then fetches its root itself -- from the ring when it is recent, else from global memory (final there: L2).
-                const bool mine = lane < n;
-                uint32_t s = myw - srcw;
-                bool inb = mine && s >= opw;
-                while (__any_sync(FULL, inb)) {
-                    const uint32_t t = __shfl_sync(FULL, s, s - opw);
-                    if (inb) { s = t; inb = s >= opw; }
-                }
-                const bool act = mine || sp;
-                if (act) {
-                    const unsigned long long v = source(s, opw);
-                    const unsigned long long w = (v & kp) | ((unsigned long long)(x >> 8) & ~kp);
-                    out64[myw] = w;
-                    ring[myw & (SPEC_RING - 1)] = w;
-                }
-                if (W_s == 2u && sp) {                                          // a closing sequence of two words
-                    const unsigned long long w1 = source(s + 1u, opw);
-                    out64[myw + 1u] = w1;
-                    ring[(myw + 1u) & (SPEC_RING - 1)] = w1;
-                }
-                __syncwarp();                                                   // the batch's words are visible to the whole warp
-                ip = nip;
-                op += 8u * adv_words;
-                x = nx;
-                batch = true;
             }
         }
         if (!batch) {
@@ -264,7 +277,8 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
             ip = (uint32_t)ip64;
             op = (uint32_t)op64;
             ring_from = (op + 7u) >> 3;                                         // (what this path wrote is in global memory only)
-            x = load_stream(src, ip, lane, 3u + L0);
+            tp = ip + (3u + L0) * lane;
+            x = load_stream_at(src, tp);
         }
         if (FUSED && (((op ^ op_was) >> FOLD_SHIFT) != 0 || done)) {             // the output crossed a FOLD_ROWS boundary
             __syncwarp();
@@ -274,11 +288,12 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
     return (op == origin && ip == comp_len) ? E_OK : E_SIZE;
 }
 
-template <int FUSED>
-__global__ void __launch_bounds__(SPEC_WARPS * 32, 4) lz4_decode_spec_kernel(const __grid_constant__ DecodeArgs args, const __grid_constant__ LaneFused F,
+// CTAS: resident CTAs per SM the kernel is compiled for (4: 64 registers per thread, 5: 48, 6: 40) -- an A/B axis, option "spec_ctas"
+template <int FUSED, int CTAS>
+__global__ void __launch_bounds__(SPEC_WARPS * 32, CTAS) lz4_decode_spec_kernel(const __grid_constant__ DecodeArgs args, const __grid_constant__ LaneFused F,
                                                                                           unsigned int *counter)
 {
-    __shared__ unsigned long long rings[SPEC_WARPS][SPEC_RING];
+    __shared__ __align__(4096) unsigned long long rings[SPEC_WARPS][SPEC_RING];
     __shared__ unsigned long long accs[FUSED ? ACC_WORDS + 2 * SPEC_WARPS : 1];   // per-lane accumulators, field-major; then the per-warp fold state
     unsigned long long *ring = rings[threadIdx.x >> 5];
     unsigned long long *acc_s = accs + (FUSED ? threadIdx.x : 0);
@@ -321,13 +336,16 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, 4) lz4_decode_spec_kernel(con
 
 }  // namespace
 
+int g_spec_ctas = 4;
+
 int launch_lz4_decode_spec(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit, const LaneFused *fused_args)
 {
     const long long njobs = (long long)args.ncols * args.nblocks;
     if (njobs <= 0) return 0;
     cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream);
     long long ctas = (njobs + SPEC_WARPS - 1) / SPEC_WARPS;
-    long long max_ctas = cta_limit > 0 ? cta_limit : (long long)sm_count * 4;      // 4 CTAs of 8 warps fit an SM (64 registers per thread); persistent over the job queue
+    int per_sm = fused_args ? 4 : (g_spec_ctas >= 4 && g_spec_ctas <= 6 ? g_spec_ctas : 4);
+    long long max_ctas = cta_limit > 0 ? cta_limit : (long long)sm_count * per_sm;   // persistent over the job queue
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
     LaneFused f;
@@ -336,10 +354,14 @@ int launch_lz4_decode_spec(const DecodeArgs &args, unsigned int *d_counter, int 
     const int variant = fused_args ? (fused_args->agg_kind == 0 ? 1 : fused_args->agg_kind == 1 ? 2 : 3) : 0;
     if (fused_args) f = *fused_args;
     switch (variant) {
-    case 0: lz4_decode_spec_kernel<0><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter); break;
-    case 1: lz4_decode_spec_kernel<1><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter); break;
-    case 2: lz4_decode_spec_kernel<2><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter); break;
-    default: lz4_decode_spec_kernel<3><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter); break;
+    case 0:
+        if (per_sm == 6) lz4_decode_spec_kernel<0, 6><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter);
+        else if (per_sm == 5) lz4_decode_spec_kernel<0, 5><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter);
+        else lz4_decode_spec_kernel<0, 4><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter);
+        break;
+    case 1: lz4_decode_spec_kernel<1, 4><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter); break;
+    case 2: lz4_decode_spec_kernel<2, 4><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter); break;
+    default: lz4_decode_spec_kernel<3, 4><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter); break;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -7,7 +7,7 @@ mkdir -p $OUT
 tail -3 $OUT/pytest.log
 if grep -q "failed\|error\|Timeout" $OUT/pytest.log; then echo "SPEC TESTS FAILED"; grep -E "Error|assert" $OUT/pytest.log | head; exit 1; fi
 for V in "DFDB_NO_OVERLAP=1" "DFDB_SPEC_TAIL_PCT=25" $EXTRA_VARIANTS; do
-( env $V timeout 900 python bench.py --steps 10 --warmup 3 --no-e2e --no-variants ) > $OUT/bench_$V.json 2> $OUT/bench_$V.err
+( env ${V//,/ } timeout 900 python bench.py --steps 10 --warmup 3 --no-e2e --no-variants ) > $OUT/bench_$V.json 2> $OUT/bench_$V.err
 python - <<PY
 import json
 b=json.loads(open("$OUT/bench_$V.json").read().strip().splitlines()[-1])
