@@ -35,6 +35,7 @@ using fused::LaneAcc;
 
 constexpr int SPEC_WARPS = 8;
 constexpr uint32_t SPEC_RING = 512;      // per warp: the last output words of its block, in shared memory (match sources are nearly always recent)
+constexpr uint32_t SPEC_SMEM = (SPEC_WARPS + 1) * SPEC_RING * 8;   // dynamic shared memory per CTA: the rings + alignment slack
 constexpr uint32_t SPEC_NEAR = SPEC_RING - 64;   // a source at most this many words back is read from the ring (the margin keeps this batch's stores off it)
 
 __device__ __forceinline__ uint32_t ldg_u32(const uint8_t *p) { return __ldg(reinterpret_cast<const unsigned int *>(p)); }
@@ -145,7 +146,7 @@ __device__ __noinline__ void fold_begin(const LaneFused &F, int b, uint32_t rows
 }
 
 template <int FUSED>
-__device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_len, uint8_t *dst, uint32_t origin, unsigned long long *ring,
+__device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_len, uint8_t *dst, uint32_t origin, uint32_t ring_s,
                                  const LaneFused &F, unsigned long long *accs)
 {
     constexpr int AGG = FUSED == 3 ? 2 : FUSED == 2 ? 1 : 0;
@@ -166,14 +167,13 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
     const uint32_t lim_w = origin >= 12u ? (origin - 12u) >> 3 : 0u;
     const uint32_t ip_lim = comp_len >= 7u * 32u + 16u ? comp_len - (7u * 32u + 16u) : 0u;
     const bool fast_possible = comp_len >= 7u * 32u + 16u;
-    // a source word: from the ring when it is recent, else from global memory (final there: L2).  The ring is 4 KB aligned in
-    // the shared window, so a word's slot is one LOP3 away from its index.
-    const uint32_t ring_s = smem_addr(ring);
-    if (ring_s & (SPEC_RING * 8u - 1u)) return E_INTERNAL;
+    // a source word: from the ring when it is recent, else from global memory (final there: L2).  ring_s, the ring's address in
+    // the shared window, is a multiple of the ring's 4 KB (the kernel aligns it at run time), so a word's slot is one LOP3 away
+    // from its index.
     auto ring_slot = [&](uint32_t w) -> uint32_t { return ((w << 3) & ((SPEC_RING - 1u) << 3)) | ring_s; };
     auto source = [&](uint32_t sw, uint32_t opw) -> unsigned long long {
         unsigned long long v;
-        if (sw >= ring_from && opw - sw <= SPEC_NEAR) asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(ring_slot(sw)));
+        if (sw >= ring_from && opw - sw <= SPEC_NEAR) asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(ring_slot(sw)) : "memory");
         else v = __ldcg(out64 + sw);
         return v;
     };
@@ -293,9 +293,11 @@ template <int FUSED, int CTAS>
 __global__ void __launch_bounds__(SPEC_WARPS * 32, CTAS) lz4_decode_spec_kernel(const __grid_constant__ DecodeArgs args, const __grid_constant__ LaneFused F,
                                                                                           unsigned int *counter)
 {
-    __shared__ __align__(4096) unsigned long long rings[SPEC_WARPS][SPEC_RING];
+    // the rings: dynamic shared memory, aligned HERE to the ring size (the shared window starts behind the 1 KB the system
+    // reserves, so a declared alignment does not give an aligned address; the launcher adds one ring of slack)
+    extern __shared__ unsigned char spec_dyn[];
+    const uint32_t ring_s = ((smem_addr(spec_dyn) + SPEC_RING * 8u - 1u) & ~(SPEC_RING * 8u - 1u)) + (threadIdx.x >> 5) * (SPEC_RING * 8u);
     __shared__ unsigned long long accs[FUSED ? ACC_WORDS + 2 * SPEC_WARPS : 1];   // per-lane accumulators, field-major; then the per-warp fold state
-    unsigned long long *ring = rings[threadIdx.x >> 5];
     unsigned long long *acc_s = accs + (FUSED ? threadIdx.x : 0);
     const uint32_t lane = lane_id();
     constexpr int AGG = FUSED == 3 ? 2 : FUSED == 2 ? 1 : 0;
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, CTAS) lz4_decode_spec_kernel(
         if (origin == 0) e = (comp_len == 1 && src[0] == 0) ? E_OK : E_SIZE;
         else if (comp_len == 0) e = E_TRUNCATED;
         else if (((uintptr_t)src & 3u) || ((uintptr_t)dst & 7u)) e = pred ? E_INTERNAL : decode_simple(src, comp_len, dst, origin);
-        else e = decode_block_spec<FUSED>(src, comp_len, dst, origin, ring, F, accs);
+        else e = decode_block_spec<FUSED>(src, comp_len, dst, origin, ring_s, F, accs);
         if (lane == 0) col.status[b] = e;
         if (pred) {
             // the block's partial: the 32 lanes' accumulators folded in a fixed order
@@ -355,13 +357,13 @@ int launch_lz4_decode_spec(const DecodeArgs &args, unsigned int *d_counter, int 
     if (fused_args) f = *fused_args;
     switch (variant) {
     case 0:
-        if (per_sm == 6) lz4_decode_spec_kernel<0, 6><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter);
-        else if (per_sm == 5) lz4_decode_spec_kernel<0, 5><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter);
-        else lz4_decode_spec_kernel<0, 4><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter);
+        if (per_sm == 6) lz4_decode_spec_kernel<0, 6><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, f, d_counter);
+        else if (per_sm == 5) lz4_decode_spec_kernel<0, 5><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, f, d_counter);
+        else lz4_decode_spec_kernel<0, 4><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, f, d_counter);
         break;
-    case 1: lz4_decode_spec_kernel<1, 4><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter); break;
-    case 2: lz4_decode_spec_kernel<2, 4><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter); break;
-    default: lz4_decode_spec_kernel<3, 4><<<(unsigned int)ctas, SPEC_WARPS * 32, 0, stream>>>(args, f, d_counter); break;
+    case 1: lz4_decode_spec_kernel<1, 4><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, f, d_counter); break;
+    case 2: lz4_decode_spec_kernel<2, 4><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, f, d_counter); break;
+    default: lz4_decode_spec_kernel<3, 4><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, f, d_counter); break;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
