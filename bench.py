@@ -408,11 +408,11 @@ def main():
     achieved = (dec_bytes / max(dec_n, 1)) / (dec_launch_ms / 1e3) / 1e9 if dec_ms > 0 else 0.0
     st_blocks, st_bytes = C.c_int64(), C.c_int64()
     L.dfdb_table_column_stored(t._h, t.getmeta("b").id, C.byref(st_blocks), C.byref(st_bytes))
-    # which K1 kernel decoded (the library picks a flavour per column from a token sample at load): the one with the launches
+    # which K1 kernel decoded (the library picks a flavour per column from a token sample at load): the one that decoded the most bytes
     k1 = {}
     for nm, kern in (("k1_v1", "lz4_decode_kernel"), ("k1_v2", "lz4_decode_v2_kernel"), ("k1_v3", "lz4_decode_v3_kernel"),
                      ("k1_lane", "lz4_decode_lane_kernel"), ("k1_spec", "lz4_decode_spec_kernel")):
-        k1[kern] = phase(nm)[1]
+        k1[kern] = phase(nm)[2]            # algorithmic bytes this kernel decoded
     k1_kernel = max(k1, key=k1.get)
     roofline = {"bound": "hbm", "kernel": k1_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (lambda tr: int(tr / max(dec_n / max(args.steps, 1), 1)) if tr else tr)(ncu_traffic(k1_kernel, shard_rows)),

@@ -64,7 +64,7 @@ struct Runtime {
     std::vector<PhaseRec> recs;
     double acc_ms[PH_COUNT] = {0};
     int64_t acc_launches[PH_COUNT] = {0}, acc_bytes[PH_COUNT] = {0};
-    int64_t k1_launches[5] = {0};   // decode launches per K1 kernel (v1, v2, v3, lane, spec): dfdb_profile_get("k1_<name>")
+    int64_t k1_launches[5] = {0}, k1_bytes[5] = {0};   // decode launches / algorithmic bytes per K1 kernel (v1, v2, v3, lane, spec): dfdb_profile_get("k1_<name>")
 } rt;
 
 #define CUDA_TRY(expr)                                                                                         \
@@ -292,23 +292,24 @@ bool wide_ok(const dfdb_table *t, const Column &c)
 // ---- decode ---------------------------------------------------------------------------------------------
 bool spec_flavour(int general) { return !rt.lz4_simple && !rt.lz4_v1 && (rt.lz4_flavour == 4 || (rt.lz4_flavour == 0 && general == 2)); }
 
-int launch_decode(const DecodeArgs &a, int general, cudaStream_t stream = nullptr, int cta_limit = 0, int counter_slot = 0, const LaneFused *fuse = nullptr)
+int launch_decode(const DecodeArgs &a, int general, cudaStream_t stream = nullptr, int cta_limit = 0, int counter_slot = 0, const LaneFused *fuse = nullptr, int64_t bytes = 0)
 {
+    auto count = [&](int k) { rt.k1_launches[k]++; rt.k1_bytes[k] += bytes; };
     if (!stream) stream = rt.stream;
     unsigned int *counter = rt.d_counter + 4 * counter_slot;   // launches that may run at the same time need their own job counter
-    if (rt.lz4_simple || rt.lz4_v1) { rt.k1_launches[0]++; return launch_lz4_decode(a, counter, rt.sm_count, (int)rt.lz4_simple, stream); }
+    if (rt.lz4_simple || rt.lz4_v1) { count(0); return launch_lz4_decode(a, counter, rt.sm_count, (int)rt.lz4_simple, stream); }
     if (rt.lz4_flavour == 3) {
-        rt.k1_launches[3]++;
+        count(3);
         DecodeArgs la = a;
         la.hot = general == 1 ? 0 : 1;   // word-regular columns (the token sample at load) run the hot-step schedule
         if (rt.lane_hot >= 0) la.hot = (int)rt.lane_hot;
         return launch_lz4_decode_lane(la, nullptr, counter, rt.sm_count, stream, cta_limit);
     }
-    if (rt.lz4_flavour == 4 || (rt.lz4_flavour == 0 && general == 2)) { rt.k1_launches[4]++; return launch_lz4_decode_spec(a, counter, rt.sm_count, stream, cta_limit, fuse); }
+    if (rt.lz4_flavour == 4 || (rt.lz4_flavour == 0 && general == 2)) { count(4); return launch_lz4_decode_spec(a, counter, rt.sm_count, stream, cta_limit, fuse); }
     if (fuse) return 1;
     if (rt.lz4_flavour == 1) general = 0;
     if (rt.lz4_flavour == 2) general = 1;
-    rt.k1_launches[general == 1 ? 2 : 1]++;
+    count(general == 1 ? 2 : 1);
     return general == 1 ? launch_lz4_decode_v3(a, counter, rt.sm_count, stream, cta_limit) : launch_lz4_decode_v2(a, counter, rt.sm_count, stream, cta_limit);
 }
 
@@ -451,6 +452,24 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
             copied.push_back(e);
         }
     }
+    // The K1 flavour each column is decoded with in THIS call.  Every decoder decodes every stream; the flavours differ in what
+    // they are fast at.  A column with only a handful of blocks to decode (an incompressible column is stored blocks read in
+    // place, plus the odd block LZ4 did shave a few bytes off) is not worth a launch of its own, nor should it keep the
+    // others from the decode / scan overlap: it rides in the launch of the column that has the most work.
+    std::vector<int> eff((size_t)todo.size());
+    {
+        std::vector<int64_t> work((size_t)todo.size(), 0);
+        size_t main_i = 0;
+        for (size_t i = 0; i < todo.size(); i++) {
+            for (int b = wlo; b < whi; b++) work[i] += h_skip_of(todo[i])[(size_t)b] ? 0 : 1;
+            if (work[i] > work[main_i]) main_i = i;
+        }
+        for (size_t i = 0; i < todo.size(); i++) {
+            eff[i] = todo[i]->lz4_general;
+            if (rt.lz4_flavour == 0 && work[i] * 64 <= work[main_i]) eff[i] = todo[main_i]->lz4_general;
+        }
+    }
+    auto eff_of = [&](Column *c) -> int { for (size_t i = 0; i < todo.size(); i++) if (todo[i] == c) return eff[i]; return c->lz4_general; };
     // ---- decode / scan overlap (compressed blocks resident, one flavour, more than one round of blocks) ----
     bool parted = false;
     if (on_part && host_bytes == 0 && !rt.no_overlap && !rt.lz4_simple && !rt.lz4_v1 && rt.lz4_flavour != 3 && todo.size() <= (size_t)DECODE_MAX_COLS) {
@@ -461,8 +480,8 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
             bool work = false;
             for (int b = wlo; b < whi && !work; b++) work = !h_skip_of(c)[(size_t)b];
             if (!work) continue;
-            if (flavour0 < 0) flavour0 = c->lz4_general;
-            one_flavour = one_flavour && c->lz4_general == flavour0;
+            if (flavour0 < 0) flavour0 = eff_of(c);
+            one_flavour = one_flavour && eff_of(c) == flavour0;
         }
         if (flavour0 < 0) flavour0 = 0;
         const int64_t wave = (int64_t)rt.sm_count * LZ4_SLOTS_PER_SM;
@@ -492,8 +511,12 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
                     for (Column *c : todo) acc += h_skip_of(c)[(size_t)b] ? 0 : 1;
                     split = b + 1;
                 }
-            last_ctas = 2 * rt.sm_count;      // (the spec launcher takes this as a CTA count)
-            scan_sms = rt.sm_count;
+            // (the spec launcher takes this as a CTA count.)  Registers decide what fits beside one scan CTA of 256 threads x ~90
+            // registers: three CTAs of the 48-register build, two of the 64-register build; the scan gets ONE CTA per SM -- its work
+            // units are dealt out by CTA index, so a second CTA that cannot become resident would sit on its half of the work
+            // until the decode is over
+            last_ctas = (g_spec_ctas == 5 ? 3 : 2) * rt.sm_count;
+            scan_sms = rt.sm_count / 2;
         }
         if (split > wlo && split < whi && (spec || rt.sm_count - last_ctas >= 8)) {
             // The full rounds go to one launch (its slots pick up blocks as they finish: no barrier between rounds); the last
@@ -505,6 +528,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
                 memset(&a, 0, sizeof a);
                 a.nblocks = b1 - b0;
                 a.blk0 = b0;
+                const int64_t bytes_before = bytes;
                 for (Column *c : todo) {
                     DecodeCol &d = a.col[a.ncols++];
                     d.comp = c->d_comp; d.comp_off = c->d_comp_off; d.comp_len = c->d_comp_len; d.dec_off = c->d_dec_off;
@@ -512,7 +536,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
                     for (int64_t b = b0; b < b1; b++)
                         if (!h_skip_of(c)[(size_t)b]) bytes += c->blocks[(size_t)(t->blk_lo + b)].compressed + c->blocks[(size_t)(t->blk_lo + b)].origin;
                 }
-                LAUNCH(launch_decode(a, flavour0, stream, cta_limit, counter_slot));
+                LAUNCH(launch_decode(a, flavour0, stream, cta_limit, counter_slot, nullptr, bytes - bytes_before));
                 return DFDB_OK;
             };
             // one decode phase record for both launches: from the start of the first to the end of the second
@@ -543,7 +567,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
             parted = true;
         }
     }
-    const bool fusing = fuse && fused_out && todo.size() == 1 && host_bytes == 0 && nchunks == 1 && !parted && spec_flavour(todo[0]->lz4_general);
+    const bool fusing = fuse && fused_out && todo.size() == 1 && host_bytes == 0 && nchunks == 1 && !parted && spec_flavour(eff[0]);
     for (int k = 0; k < nchunks && !parted; k++) {
         const int b0 = wlo + (int)((int64_t)(whi - wlo) * k / nchunks), b1 = wlo + (int)((int64_t)(whi - wlo) * (k + 1) / nchunks);
         if (!copied.empty()) {
@@ -555,7 +579,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
         for (int general = 0; general < 3; general++) {
           std::vector<Column *> grp;
           for (Column *c : todo) {
-              if (c->lz4_general != general) continue;
+              if (eff_of(c) != general) continue;
               // (a column whose blocks in this range are all skipped -- stored bodies read in place, blocks without selected rows -- needs no launch)
               bool work = false;
               for (int b = b0; b < b1 && !work; b++) work = !h_skip_of(c)[(size_t)b];
@@ -579,10 +603,10 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
             if (fusing) {
                 LaneFused lf = *fuse;
                 lf.pred_col = 0;
-                LAUNCH(launch_decode(a, general, nullptr, 0, 0, &lf));
+                LAUNCH(launch_decode(a, general, nullptr, 0, 0, &lf, bytes));
                 *fused_out = true;
             } else {
-                LAUNCH(launch_decode(a, general));
+                LAUNCH(launch_decode(a, general, nullptr, 0, 0, nullptr, bytes));
             }
           }
         }
@@ -1366,6 +1390,7 @@ int32_t dfdb_profile_reset(void)
     if (rt.inited) { cudaStreamSynchronize(rt.stream); profile_collect(); }
     for (int i = 0; i < PH_COUNT; i++) { rt.acc_ms[i] = 0; rt.acc_launches[i] = 0; rt.acc_bytes[i] = 0; }
     for (int64_t &n : rt.k1_launches) n = 0;
+    for (int64_t &n : rt.k1_bytes) n = 0;
     return DFDB_OK;
 }
 int32_t dfdb_profile_get(const char *phase, double *total_ms, int64_t *launches, int64_t *bytes)
@@ -1384,7 +1409,7 @@ int32_t dfdb_profile_get(const char *phase, double *total_ms, int64_t *launches,
         if (strcmp(phase, k1_names[i]) == 0) {
             if (total_ms) *total_ms = 0;
             if (launches) *launches = rt.k1_launches[i];
-            if (bytes) *bytes = 0;
+            if (bytes) *bytes = rt.k1_bytes[i];
             return DFDB_OK;
         }
     return fail(DFDB_ERR_ARGUMENT, "unknown phase %s", phase);

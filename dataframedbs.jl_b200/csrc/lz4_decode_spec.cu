@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, CTAS) lz4_decode_spec_kernel(
 
 }  // namespace
 
-int g_spec_ctas = 4;
+int g_spec_ctas = 5;
 
 int launch_lz4_decode_spec(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit, const LaneFused *fused_args)
 {
@@ -346,7 +346,7 @@ int launch_lz4_decode_spec(const DecodeArgs &args, unsigned int *d_counter, int 
     if (njobs <= 0) return 0;
     cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream);
     long long ctas = (njobs + SPEC_WARPS - 1) / SPEC_WARPS;
-    int per_sm = fused_args ? 4 : (g_spec_ctas >= 4 && g_spec_ctas <= 6 ? g_spec_ctas : 4);
+    int per_sm = fused_args ? 4 : (g_spec_ctas >= 4 && g_spec_ctas <= 6 ? g_spec_ctas : 5);
     long long max_ctas = cta_limit > 0 ? cta_limit : (long long)sm_count * per_sm;   // persistent over the job queue
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
