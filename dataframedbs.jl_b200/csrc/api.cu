@@ -55,7 +55,7 @@ struct Runtime {
     int64_t lz4_flavour = 0;  // K1 flavour: 0 = per column from a token sample at load, 1 = word-regular decoder (v2), 2 = general decoder (v3), 3 = lane-per-block decoder, 4 = warp-per-block decoder with verified token runs (spec)
     int64_t no_overlap = 0;   // do not run the scan of the decoded part of a shard beside the decode of its last part
     int64_t no_alias = 0;     // copy stored (incompressible) blocks like any other block instead of referencing them in place
-    int64_t spec_tail_pct = 25; // spec decoder: share of the blocks decoded beside the scan of the others (A/B)
+    int64_t spec_tail_pct = 0;  // spec decoder: share of the blocks decoded beside the scan of the others; 0 = plain sequence (measured: the overlap loses, 10.1 vs 8.5 ms per step at 1e9 rows -- the tail decodes at reduced occupancy and one scan CTA per SM is slow)
     int64_t no_zonemap = 0;   // ignore zone maps (A/B: results must not change)
     int64_t no_validate = 0;  // skip the acceptance pass of dfdb_table_load (A/B, load-time measurements)
     int64_t lane_hot = -1;    // lane decoder: -1 = hot-step schedule per column from the token sample, 0 / 1 = force off / on (A/B, tests)
@@ -506,7 +506,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
             split = 0;
             acc = 0;
             const int64_t head = real - real / (rt.spec_tail_pct > 0 ? 100 / rt.spec_tail_pct : 4);
-            if (real >= 4096)
+            if (real >= 4096 && rt.spec_tail_pct > 0)
                 for (int b = wlo; b < whi && acc < head; b++) {
                     for (Column *c : todo) acc += h_skip_of(c)[(size_t)b] ? 0 : 1;
                     split = b + 1;

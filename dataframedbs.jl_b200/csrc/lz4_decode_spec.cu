@@ -50,6 +50,14 @@ __device__ __forceinline__ uint64_t load_stream_at(const uint8_t *__restrict__ s
     return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
 }
 
+// Requests one 512-byte group of the stream (four 128-byte lines) from HBM into L2.  A real call on purpose: inlined, the
+// few instructions are predicated and cost their issue slots in every batch; as a call they cost a branch that is taken once
+// in about five batches.
+static __device__ __noinline__ void prefetch_group(const uint8_t *group, uint32_t lane)
+{
+    if (lane < 4u) asm volatile("prefetch.global.L2 [%0];" ::"l"(group + 128u * lane));
+}
+
 // one block, whole warp; returns E_*.  (Positions are 32-bit in the batch loop: column blocks are far below 4 GB; the kernel
 // is instruction-bound -- IPC 2.9 per SM in the first profile -- so the loop is kept lean.)
 //
@@ -165,8 +173,8 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
     // a match never writes the block's last 12 bytes in the fast path (the end-of-block rules stay with the one-sequence path):
     // an output word w may be written when w < lim_w; and the fast path needs 7 * 32 + 16 stream bytes ahead
     const uint32_t lim_w = origin >= 12u ? (origin - 12u) >> 3 : 0u;
-    const uint32_t ip_lim = comp_len >= 7u * 32u + 16u ? comp_len - (7u * 32u + 16u) : 0u;
-    const bool fast_possible = comp_len >= 7u * 32u + 16u;
+    int32_t ip_lim = comp_len >= 7u * 32u + 16u ? (int32_t)(comp_len - (7u * 32u + 16u)) : -1;     // (-1: the block is too short for the fast path)
+    asm volatile("" : "+r"(ip_lim));         // (kept in a register: ptxas otherwise recomputes it in every batch)
     // a source word: from the ring when it is recent, else from global memory (final there: L2).  ring_s, the ring's address in
     // the shared window, is a multiple of the ring's 4 KB (the kernel aligns it at run time), so a word's slot is one LOP3 away
     // from its index.
@@ -186,75 +194,89 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
     if (lane < 12u) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 128u * lane));
     uint32_t tp = 3u * lane;                 // where this lane's sequence starts in the stream: ip + stride * lane
     uint64_t x = load_stream_at(src, tp);
-    // The batch proper, once the run (n sequences, one per lane) and its closing sequence are known.  FB: a full batch of 32
-    // plain sequences -- by far the most frequent case, compiled without the closing sequence's selects.
-    auto do_batch = [&](auto full, uint32_t opw, uint32_t n, uint32_t W_s, uint32_t hdr_s, uint32_t srcw, unsigned long long kp, bool sp, uint32_t stride) {
-        constexpr bool FB = decltype(full)::value;
-        const uint32_t myw = opw + lane;
-        const uint32_t adv = FB ? 32u * stride : stride * n + hdr_s;
+    // What every batch does once it knows its shape: ask for the next batch's stream bytes (they travel while this batch's
+    // sources do) and, on entering a new 512-byte group of the stream, for the group after the next.
+    auto advance_stream = [&](uint32_t adv, bool restride) -> uint64_t {
         const uint32_t nip = ip + adv;
-        tp = (!FB && stride != 3u + L0) ? nip + (3u + L0) * lane : tp + adv;     // (the run's shape -- the stride -- may just have changed)
-        const uint64_t nx = load_stream_at(src, tp);                             // the next batch's bytes travel while this one's sources do
-        if ((nip ^ ip) >> 9) {                                                   // entered a new 512-byte group of the stream: request the group after the next
-            if (lane < 4u) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ((((nip >> 9) + 2u) << 9) + 128u * lane)));
-        }
-        // Sources.  Lane = sequence = output word; its source word is `s`.  A source inside the batch is another lane's word,
-        // and only the bytes behind the literal bytes come from it, so a chain of in-batch sources ends in the word of its
-        // far root: the chains collapse by pointer jumping over the word INDEX (<= 5 rounds, one shuffle each), and every
-        // lane then fetches its root itself.
-        const bool mine = FB || lane < n;
-        uint32_t s = myw - srcw;
-        bool inb = mine && s >= opw;
-        while (__any_sync(FULL, inb)) {
-            const uint32_t t = __shfl_sync(FULL, s, s - opw);
-            if (inb) { s = t; inb = s >= opw; }
-        }
-        if (FB || mine || sp) {
-            const unsigned long long v = source(s, opw);
-            put(myw, (v & kp) | ((unsigned long long)(x >> 8) & ~kp));
-        }
-        if (!FB && W_s == 2u && sp) put(myw + 1u, source(s + 1u, opw));         // a closing sequence of two words
-        __syncwarp();                                                           // the batch's words are visible to the whole warp
+        tp = restride ? nip + (3u + L0) * lane : tp + adv;
+        const uint64_t nx = load_stream_at(src, tp);
+        if ((nip ^ ip) >> 9) prefetch_group(src + (((nip >> 9) + 2u) << 9), lane);
         ip = nip;
-        op += 8u * (FB ? 32u : n + W_s);
-        x = nx;
+        return nx;
     };
+    const uint32_t lt = (1u << lane) - 1u;
     while (!done) {
         bool batch = false;
         const uint32_t op_was = op;
-        if (fast_possible && (op & 7u) == 0 && ip <= ip_lim) {
-            const uint32_t opw = op >> 3, myw = opw + lane;
+        if ((op & 7u) == 0 && (int32_t)ip <= ip_lim) {
+            const uint32_t opw = op >> 3;
             const uint32_t tok = (uint32_t)x & 0xffu;
             const uint32_t off = (uint32_t)(x >> sh0) & 0xffffu;
             // offset a multiple of 8, not zero, inside the output: rotate the low three bits to the top -- any of them set, or a
             // zero offset (minus one wraps), fails the one comparison; for the lanes that pass, offr is the offset in words
             const uint32_t offr = __funnelshift_r(off, off, 3);
-            const bool okp = tok == tok0 && offr - 1u < myw && myw < lim_w;
-            const uint32_t badp = ~__ballot_sync(FULL, okp);
-            if (!badp) {
+            const bool okp = tok == tok0 && offr - 1u < opw + lane && opw + lane < lim_w;
+            if (__all_sync(FULL, okp)) {
+                // ---- a full batch of 32 one-word sequences: lane = sequence = output word ----
                 pendL = 0xffu;
-                do_batch(std::true_type{}, opw, 32u, 0u, 0u, offr, kp0, false, 3u + L0);
+                const uint64_t nx = advance_stream(32u * (3u + L0), false);
+                // Sources.  A source inside the batch is another lane's word, and only the bytes behind the literal bytes come
+                // from it, so a chain of in-batch sources ends in the word of its far root: the chains collapse by pointer jumping
+                // over the word INDEX (<= 5 rounds, one shuffle each), and every lane then fetches its root itself.
+                const uint32_t myw = opw + lane;
+                uint32_t s = myw - offr;
+                bool inb = s >= opw;
+                while (__any_sync(FULL, inb)) {
+                    const uint32_t t = __shfl_sync(FULL, s, s - opw);
+                    if (inb) { s = t; inb = s >= opw; }
+                }
+                const unsigned long long v = source(s, opw);
+                put(myw, (v & kp0) | ((unsigned long long)(x >> 8) & ~kp0));
+                __syncwarp();                                                   // the batch's words are visible to the whole warp
+                op += 256u;
+                x = nx;
                 batch = true;
             } else {
-                const uint32_t n = (uint32_t)__ffs(badp) - 1u;
-                // the sequence that ends the run, analysed by its own lane: any "word form" -- L <= 5 literal bytes + match, 8 or 16 bytes in all
-                const uint32_t L = tok >> 4, LM = L + (tok & 15u) + 4u;
-                const uint32_t off_s = (uint32_t)(x >> ((8u + 8u * L) & 63u)) & 0xffffu, offw_s = off_s >> 3;
-                const uint32_t W = LM >> 3;
-                const bool sp = lane == n && L <= 5u && (tok & 15u) != 15u && (LM & 7u) == 0 && (off_s & 7u) == 0 && off_s != 0 &&
-                                offw_s <= myw && offw_s >= lane + W &&                     // sources inside the output and final (before the batch)
-                                myw + W <= lim_w;
-                uint32_t hdr_s = 0, W_s = 0;
-                if (__ballot_sync(FULL, sp)) {
-                    const uint32_t pk = __shfl_sync(FULL, (L << 8) | W, n);
-                    hdr_s = 3u + (pk >> 8);
-                    W_s = pk & 0xffu;
+                // ---- a general batch: up to 32 output words of the run -- sequences of its shape with a match of 8 - L0 bytes (one
+                // word) or 16 - L0 bytes (two words: the same 3 + L0 stream bytes, so the positions stay regular) -- and then maybe
+                // one closing sequence of another word form.  Lane = sequence; its first word is lane + (two-word lanes below it).
+                // A two-word sequence must have both sources before the batch (else it ends the batch and opens the next one).
+                const uint32_t d = tok - tok0;
+                const bool is2 = d == 8u;
+                const uint32_t m2 = __ballot_sync(FULL, is2);
+                const uint32_t r = lane + __popc(m2 & lt);
+                const uint32_t W = is2 ? 2u : 1u;
+                const uint32_t myw = opw + r;
+                const bool oknf = (d & ~8u) == 0 && offr - 1u < myw && myw + W <= lim_w && (!is2 || offr >= r + 2u);
+                const uint32_t vnf = __ballot_sync(FULL, oknf);
+                const uint32_t bad = ~__ballot_sync(FULL, oknf && r + W <= 32u);
+                const uint32_t n = bad ? (uint32_t)__ffs(bad) - 1u : 32u;
+                const uint32_t m2n = m2 & (n >= 32u ? FULL : (1u << n) - 1u);
+                const bool trunc = n >= 32u || ((vnf >> n) & 1u) != 0;           // lane n is a fine sequence of the run: the batch is just full
+                uint32_t hdr_s = 0, W_s = 0, srcw = offr;
+                unsigned long long kp = kp0;                                    // the bytes a word takes from its source (the others are literals)
+                bool sp = false;
+                if (!trunc) {
+                    // the sequence that ends the run, analysed by its own lane: any "word form" -- L <= 5 literal bytes + match, 8 or 16 bytes in all
+                    const uint32_t L = tok >> 4, LM = L + (tok & 15u) + 4u;
+                    const uint32_t off_s = (uint32_t)(x >> ((8u + 8u * L) & 63u)) & 0xffffu, offw_s = off_s >> 3;
+                    const uint32_t Wc = LM >> 3;
+                    sp = lane == n && L <= 5u && (tok & 15u) != 15u && (LM & 7u) == 0 && (off_s & 7u) == 0 && off_s != 0 &&
+                         offw_s <= myw && offw_s >= r + Wc &&                              // sources inside the output and final (before the batch)
+                         myw + Wc <= lim_w;
+                    if (__ballot_sync(FULL, sp)) {
+                        const uint32_t pk = __shfl_sync(FULL, (L << 8) | Wc, n);
+                        hdr_s = 3u + (pk >> 8);
+                        W_s = pk & 0xffu;
+                    }
+                    if (sp) { srcw = offw_s; kp = ~0ull << (8u * L); }
                 }
-                if (n + W_s > 0) {
+                const uint32_t words = n + (uint32_t)__popc(m2n) + W_s;
+                if (words > 0) {
                     const uint32_t stride = 3u + L0;
                     // a sequence of another one-word shape alone at the head of a batch is just the closing sequence of an empty run;
                     // two of the same shape in a row are a new run: switch (the bytes requested next use the new stride)
-                    if (n == 0 && W_s == 1u) {
+                    if (!trunc && n == 0 && W_s == 1u) {
                         const uint32_t Lh = hdr_s - 3u;
                         if (Lh == pendL && Lh <= 4u) {
                             L0 = Lh;
@@ -264,7 +286,35 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
                     } else {
                         pendL = 0xffu;
                     }
-                    do_batch(std::false_type{}, opw, n, W_s, hdr_s, sp ? offw_s : offr, sp ? ~0ull << (8u * L) : kp0, sp, stride);
+                    const uint64_t nx = advance_stream(stride * n + hdr_s, stride != 3u + L0);
+                    const bool mine = lane < n;
+                    uint32_t s = myw - srcw;
+                    bool inb = mine && s >= opw;                                // (never a two-word lane)
+                    if (m2n == 0) {
+                        while (__any_sync(FULL, inb)) {
+                            const uint32_t t = __shfl_sync(FULL, s, s - opw);
+                            if (inb) { s = t; inb = s >= opw; }
+                        }
+                    } else {
+                        // the lane that owns word q of the batch: first[] has a bit for the first word of every lane
+                        const uint32_t first = __reduce_or_sync(FULL, mine ? 1u << r : 0u);
+                        while (__any_sync(FULL, inb)) {
+                            const uint32_t q = (s - opw) & 31u;
+                            const uint32_t owner = (uint32_t)__popc(first & (0xffffffffu >> (31u - q))) - 1u;
+                            const uint32_t t = __shfl_sync(FULL, s, owner);
+                            if (inb) { s = t + (((first >> q) & 1u) ^ 1u); inb = s >= opw; }   // (the second word of a two-word lane: its source is the next word)
+                        }
+                    }
+                    if (mine || sp) {
+                        const unsigned long long v = source(s, opw);
+                        put(myw, (v & kp) | ((unsigned long long)(x >> 8) & ~kp));
+                    }
+                    if (m2n != 0 || W_s == 2u) {
+                        if ((mine && is2) || (sp && W_s == 2u)) put(myw + 1u, source(s + 1u, opw));
+                    }
+                    __syncwarp();                                               // the batch's words are visible to the whole warp
+                    op += 8u * words;
+                    x = nx;
                     batch = true;
                 }
             }
