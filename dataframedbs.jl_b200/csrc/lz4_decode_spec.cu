@@ -158,7 +158,8 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
                                  const LaneFused &F, unsigned long long *accs)
 {
     constexpr int AGG = FUSED == 3 ? 2 : FUSED == 2 ? 1 : 0;
-    const uint32_t lane = lane_id();
+    uint32_t lane = lane_id();
+    asm volatile("" : "+r"(lane));           // (kept in a register instead of an S2R in every batch)
     uint32_t ip = 0, op = 0;
     bool done = false;
     unsigned long long *out64 = reinterpret_cast<unsigned long long *>(dst);
@@ -172,12 +173,14 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
     uint32_t ring_from = 0;            // output words >= this one (and within SPEC_RING of the position) are in the ring
     // a match never writes the block's last 12 bytes in the fast path (the end-of-block rules stay with the one-sequence path):
     // an output word w may be written when w < lim_w; and the fast path needs 7 * 32 + 16 stream bytes ahead
-    const uint32_t lim_w = origin >= 12u ? (origin - 12u) >> 3 : 0u;
+    uint32_t lim_w = origin >= 12u ? (origin - 12u) >> 3 : 0u;
+    asm volatile("" : "+r"(lim_w));          // (kept in a register: ptxas otherwise recomputes it -- and ring_s, 11 instructions -- in every batch)
     int32_t ip_lim = comp_len >= 7u * 32u + 16u ? (int32_t)(comp_len - (7u * 32u + 16u)) : -1;     // (-1: the block is too short for the fast path)
     asm volatile("" : "+r"(ip_lim));         // (kept in a register: ptxas otherwise recomputes it in every batch)
     // a source word: from the ring when it is recent, else from global memory (final there: L2).  ring_s, the ring's address in
     // the shared window, is a multiple of the ring's 4 KB (the kernel aligns it at run time), so a word's slot is one LOP3 away
     // from its index.
+    asm volatile("" : "+r"(ring_s));
     auto ring_slot = [&](uint32_t w) -> uint32_t { return ((w << 3) & ((SPEC_RING - 1u) << 3)) | ring_s; };
     auto source = [&](uint32_t sw, uint32_t opw) -> unsigned long long {
         unsigned long long v;
@@ -204,7 +207,6 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
         ip = nip;
         return nx;
     };
-    const uint32_t lt = (1u << lane) - 1u;
     while (!done) {
         bool batch = false;
         const uint32_t op_was = op;
@@ -237,46 +239,32 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
                 x = nx;
                 batch = true;
             } else {
-                // ---- a general batch: up to 32 output words of the run -- sequences of its shape with a match of 8 - L0 bytes (one
-                // word) or 16 - L0 bytes (two words: the same 3 + L0 stream bytes, so the positions stay regular) -- and then maybe
-                // one closing sequence of another word form.  Lane = sequence; its first word is lane + (two-word lanes below it).
-                // A two-word sequence must have both sources before the batch (else it ends the batch and opens the next one).
-                const uint32_t d = tok - tok0;
-                const bool is2 = d == 8u;
-                const uint32_t m2 = __ballot_sync(FULL, is2);
-                const uint32_t r = lane + __popc(m2 & lt);
-                const uint32_t W = is2 ? 2u : 1u;
-                const uint32_t myw = opw + r;
-                const bool oknf = (d & ~8u) == 0 && offr - 1u < myw && myw + W <= lim_w && (!is2 || offr >= r + 2u);
-                const uint32_t vnf = __ballot_sync(FULL, oknf);
-                const uint32_t bad = ~__ballot_sync(FULL, oknf && r + W <= 32u);
-                const uint32_t n = bad ? (uint32_t)__ffs(bad) - 1u : 32u;
-                const uint32_t m2n = m2 & (n >= 32u ? FULL : (1u << n) - 1u);
-                const bool trunc = n >= 32u || ((vnf >> n) & 1u) != 0;           // lane n is a fine sequence of the run: the batch is just full
-                uint32_t hdr_s = 0, W_s = 0, srcw = offr;
-                unsigned long long kp = kp0;                                    // the bytes a word takes from its source (the others are literals)
-                bool sp = false;
-                if (!trunc) {
-                    // the sequence that ends the run, analysed by its own lane: any "word form" -- L <= 5 literal bytes + match, 8 or 16 bytes in all
-                    const uint32_t L = tok >> 4, LM = L + (tok & 15u) + 4u;
-                    const uint32_t off_s = (uint32_t)(x >> ((8u + 8u * L) & 63u)) & 0xffffu, offw_s = off_s >> 3;
-                    const uint32_t Wc = LM >> 3;
-                    sp = lane == n && L <= 5u && (tok & 15u) != 15u && (LM & 7u) == 0 && (off_s & 7u) == 0 && off_s != 0 &&
-                         offw_s <= myw && offw_s >= r + Wc &&                              // sources inside the output and final (before the batch)
-                         myw + Wc <= lim_w;
-                    if (__ballot_sync(FULL, sp)) {
-                        const uint32_t pk = __shfl_sync(FULL, (L << 8) | Wc, n);
-                        hdr_s = 3u + (pk >> 8);
-                        W_s = pk & 0xffu;
-                    }
-                    if (sp) { srcw = offw_s; kp = ~0ull << (8u * L); }
+                // ---- the run ends inside the batch: n one-word sequences, then maybe one closing sequence of another word form ----
+                // (Keeping sequences of 16 - L0 match bytes -- two words, same stream stride -- inside the run was built and
+                // measured: 13 % fewer batches, but the bookkeeping (first-word masks, owner lookup, truncation at 32 words) made
+                // every such batch dearer; 5.6 G instead of 4.9 G warp instructions per 1e9 rows.  They close the run like any
+                // other shape.)
+                const uint32_t n = (uint32_t)__ffs(~__ballot_sync(FULL, okp)) - 1u;
+                const uint32_t myw = opw + lane;
+                // the sequence that ends the run, analysed by its own lane: any "word form" -- L <= 5 literal bytes + match, 8 or 16 bytes in all
+                const uint32_t L = tok >> 4, LM = L + (tok & 15u) + 4u;
+                const uint32_t off_s = (uint32_t)(x >> ((8u + 8u * L) & 63u)) & 0xffffu, offw_s = off_s >> 3;
+                const uint32_t Wc = LM >> 3;
+                const bool sp = lane == n && L <= 5u && (LM == 8u || LM == 16u) && (off_s & 7u) == 0 && off_s != 0 &&
+                                offw_s <= myw && offw_s >= lane + Wc &&                    // sources inside the output and final (before the batch)
+                                myw + Wc <= lim_w;
+                uint32_t hdr_s = 0, W_s = 0;
+                if (__ballot_sync(FULL, sp)) {
+                    const uint32_t pk = __shfl_sync(FULL, (L << 8) | Wc, n);
+                    hdr_s = 3u + (pk >> 8);
+                    W_s = pk & 0xffu;
                 }
-                const uint32_t words = n + (uint32_t)__popc(m2n) + W_s;
-                if (words > 0) {
+                if (n + W_s > 0) {
                     const uint32_t stride = 3u + L0;
+                    const unsigned long long kp = sp ? ~0ull << (8u * L) : kp0;   // the bytes a word takes from its source (the others are literals)
                     // a sequence of another one-word shape alone at the head of a batch is just the closing sequence of an empty run;
                     // two of the same shape in a row are a new run: switch (the bytes requested next use the new stride)
-                    if (!trunc && n == 0 && W_s == 1u) {
+                    if (n == 0 && W_s == 1u) {
                         const uint32_t Lh = hdr_s - 3u;
                         if (Lh == pendL && Lh <= 4u) {
                             L0 = Lh;
@@ -288,32 +276,19 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
                     }
                     const uint64_t nx = advance_stream(stride * n + hdr_s, stride != 3u + L0);
                     const bool mine = lane < n;
-                    uint32_t s = myw - srcw;
-                    bool inb = mine && s >= opw;                                // (never a two-word lane)
-                    if (m2n == 0) {
-                        while (__any_sync(FULL, inb)) {
-                            const uint32_t t = __shfl_sync(FULL, s, s - opw);
-                            if (inb) { s = t; inb = s >= opw; }
-                        }
-                    } else {
-                        // the lane that owns word q of the batch: first[] has a bit for the first word of every lane
-                        const uint32_t first = __reduce_or_sync(FULL, mine ? 1u << r : 0u);
-                        while (__any_sync(FULL, inb)) {
-                            const uint32_t q = (s - opw) & 31u;
-                            const uint32_t owner = (uint32_t)__popc(first & (0xffffffffu >> (31u - q))) - 1u;
-                            const uint32_t t = __shfl_sync(FULL, s, owner);
-                            if (inb) { s = t + (((first >> q) & 1u) ^ 1u); inb = s >= opw; }   // (the second word of a two-word lane: its source is the next word)
-                        }
+                    uint32_t s = myw - (sp ? offw_s : offr);
+                    bool inb = mine && s >= opw;
+                    while (__any_sync(FULL, inb)) {
+                        const uint32_t t = __shfl_sync(FULL, s, s - opw);
+                        if (inb) { s = t; inb = s >= opw; }
                     }
                     if (mine || sp) {
                         const unsigned long long v = source(s, opw);
                         put(myw, (v & kp) | ((unsigned long long)(x >> 8) & ~kp));
                     }
-                    if (m2n != 0 || W_s == 2u) {
-                        if ((mine && is2) || (sp && W_s == 2u)) put(myw + 1u, source(s + 1u, opw));
-                    }
+                    if (W_s == 2u && sp) put(myw + 1u, source(s + 1u, opw));    // a closing sequence of two words
                     __syncwarp();                                               // the batch's words are visible to the whole warp
-                    op += 8u * words;
+                    op += 8u * (n + W_s);
                     x = nx;
                     batch = true;
                 }
