@@ -248,7 +248,8 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
                 const uint32_t myw = opw + lane;
                 // the sequence that ends the run, analysed by its own lane: any "word form" -- L <= 5 literal bytes + match, 8 or 16 bytes in all
                 const uint32_t L = tok >> 4, LM = L + (tok & 15u) + 4u;
-                const uint32_t off_s = (uint32_t)(x >> ((8u + 8u * L) & 63u)) & 0xffffu, offw_s = off_s >> 3;
+                // (its offset: stream bytes L + 1 and L + 2 of the lane's eight, picked by one PRMT -- a 64-bit variable shift is a dozen instructions)
+                const uint32_t off_s = __byte_perm((uint32_t)x, (uint32_t)(x >> 32), 0x4421u + 0x11u * L) & 0xffffu, offw_s = off_s >> 3;
                 const uint32_t Wc = LM >> 3;
                 const bool sp = lane == n && L <= 5u && (LM == 8u || LM == 16u) && (off_s & 7u) == 0 && off_s != 0 &&
                                 offw_s <= myw && offw_s >= lane + Wc &&                    // sources inside the output and final (before the batch)
