@@ -77,7 +77,7 @@ struct Column {
     std::vector<uint8_t> h_skip;
     std::vector<int32_t> h_corrupt;  // per local block: LZ4_decompress_safe's verdict (0 = accepted), decided once at load by the lane-per-block decoder
     int64_t stored_blocks = 0;
-    int lz4_general = 0;             // K1 flavour, decided at load from a token sample: 0 = word-regular walker (v2), 1 = general walker (v3),
+    int lz4_general = 1;             // K1 flavour, decided at load from a token sample: 1 = walker / consumer decoder (v3),
                                      // 2 = warp per block with verified runs (spec: nearly every sequence is one aligned word)
     int32_t *d_str_off = nullptr;    // String columns: per-row char offset inside the block's char area
     bool str_off_valid = false;

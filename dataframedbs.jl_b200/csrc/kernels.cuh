@@ -23,14 +23,14 @@ struct DecodeArgs {
     int ncols;
     int nblocks;   // blocks per column in this launch
     int blk0;      // first local block of the launch (chunked, copy-overlapped decode)
-    unsigned long long *stats;   // optional diagnostics counters (null = off), see lz4_decode_v2.cu
+    unsigned long long *stats;   // optional diagnostics counters (null = off), see lz4_decode_v3.cu
     int hot;       // lane decoder: the columns are word-regular (nearly every token is 0x04 with an offset that is a multiple of 8): hot-step schedule
 };
 int launch_lz4_decode(const DecodeArgs &args, unsigned int *d_counter, int sm_count, int simple_mode, cudaStream_t stream);      // v1: warp per block
-constexpr int LZ4_SLOTS_PER_SM = 60;   // column blocks one decoder CTA keeps in flight (NSLOT of both walker/consumer flavours)
-int launch_lz4_decode_v2(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit = 0);                     // v2: walker / consumer warps, word-regular columns
+constexpr int LZ4_SLOTS_PER_SM = 60;   // column blocks one decoder CTA keeps in flight (NSLOT of the walker / consumer decoder)
 int launch_lz4_decode_v3(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit = 0);
 struct LaneFused;
+extern int g_spec_prefetch;   // spec decoder: how far the stream is prefetched (0: L2, 1: + next group into L1, 2: L1)
 extern int g_spec_ctas;   // resident CTAs per SM of the spec decoder (4..6; option "spec_ctas")
 int launch_lz4_decode_spec(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit = 0,
                            const LaneFused *fused = nullptr);   // warp per block, plain token runs verified in parallel (word-regular columns); optionally with K3 + K7 fused in                     // v3: same organisation, general columns (strings, literal-heavy, chains)

@@ -1,4 +1,4 @@
-// lz4_common.cuh -- device helpers shared by the two LZ4 block decoders (lz4_decode.cu, lz4_decode_v2.cu).
+// lz4_common.cuh -- device helpers shared by the LZ4 block decoders (lz4_decode.cu, lz4_decode_v3.cu, lz4_decode_spec.cu).
 //
 // Everything here follows the raw LZ4 block format decoded by LZ4_decompress_safe, the call the reference
 // makes in read_block (/root/reference/src/io/BlockStreams.jl:110-112): never read outside the compressed

@@ -6,7 +6,7 @@
 // per-block status instead of the reference's `@assert size == sizes.origin "decompression error"`.
 //
 // Why this shape.  The serial part of an LZ4 block is its token chain; the walker / consumer kernels
-// (lz4_decode_v2.cu, lz4_decode_v3.cu) spend ~350 warp instructions per 256 output bytes on handing the chain's
+// (lz4_decode_v3.cu) spend ~350 warp instructions per 256 output bytes on handing the chain's
 // result from one warp to another (ring entries, polls, per-batch prefix work).  Here nothing is handed over:
 // every lane runs the whole decoder of its own block as a two-stage software pipeline in registers
 // (parse -> DEPTH-deep piece queue -> emit, lz4_lane_core.cuh), one piece of at most 8 output bytes per lane

@@ -13,7 +13,7 @@
 // length extensions, unaligned offsets, the last sequences of the block -- is decoded one sequence at a time by the whole
 // warp (decode_one_sequence, lz4_common.cuh).
 //
-// Against the walker / consumer kernel (lz4_decode_v2.cu, ~350 warp instructions per 32 tokens: ring entries, polls, dependency
+// Against the walker / consumer kernel (lz4_decode_v3.cu, ~350 warp instructions per 32 tokens: ring entries, polls, dependency
 // waves) a batch here is ~50 instructions for ~12-32 tokens, at full occupancy (64 warps per SM).  The kernel is memory-safe
 // on any input (every access is bounds-checked, errors set a per-block status); the accept / reject verdict of damaged streams
 // is the lane decoder's, taken at load (api.cu).
@@ -50,12 +50,20 @@ __device__ __forceinline__ uint64_t load_stream_at(const uint8_t *__restrict__ s
     return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
 }
 
-// Requests one 512-byte group of the stream (four 128-byte lines) from HBM into L2.  A real call on purpose: inlined, the
-// few instructions are predicated and cost their issue slots in every batch; as a call they cost a branch that is taken once
-// in about five batches.
-static __device__ __noinline__ void prefetch_group(const uint8_t *group, uint32_t lane)
+// Requests 512-byte groups of the stream (four 128-byte lines each) ahead of the position: group g + 2 from HBM into L2 and,
+// by mode, into L1 as well (mode 2), or group g + 1 -- which the previous call brought into L2 -- into L1 (mode 1); the stream
+// loads are ld.global.nc and allocate in L1, nothing else of this kernel does.  A real call on purpose: inlined, the few
+// instructions are predicated and cost their issue slots in every batch; as a call they cost a branch that is taken once in
+// about five batches.
+static __device__ __noinline__ void prefetch_group(const uint8_t *src, uint32_t g, uint32_t lane, int mode)
 {
-    if (lane < 4u) asm volatile("prefetch.global.L2 [%0];" ::"l"(group + 128u * lane));
+    const uint8_t *far = src + ((g + 2u) << 9) + 128u * (lane & 3u);
+    if (mode == 2) {
+        if (lane < 4u) asm volatile("prefetch.global.L1 [%0];" ::"l"(far));
+    } else {
+        if (lane < 4u) asm volatile("prefetch.global.L2 [%0];" ::"l"(far));
+        else if (mode == 1 && lane < 8u) asm volatile("prefetch.global.L1 [%0];" ::"l"(far - 512));
+    }
 }
 
 // one block, whole warp; returns E_*.  (Positions are 32-bit in the batch loop: column blocks are far below 4 GB; the kernel
@@ -154,7 +162,7 @@ __device__ __noinline__ void fold_begin(const LaneFused &F, int b, uint32_t rows
 }
 
 template <int FUSED>
-__device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_len, uint8_t *dst, uint32_t origin, uint32_t ring_s,
+__device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_len, uint8_t *dst, uint32_t origin, uint32_t ring_s, int pf_mode,
                                  const LaneFused &F, unsigned long long *accs)
 {
     constexpr int AGG = FUSED == 3 ? 2 : FUSED == 2 ? 1 : 0;
@@ -195,6 +203,7 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
     // the compressed bytes are read exactly once, so each batch would wait a DRAM round trip for its own bytes: the stream is
     // pulled from HBM into L2 two to three 512-byte groups ahead of the position, one request per 128-byte line
     if (lane < 12u) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 128u * lane));
+    if (pf_mode != 0 && lane < (pf_mode == 2 ? 12u : 8u)) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + 128u * lane));
     uint32_t tp = 3u * lane;                 // where this lane's sequence starts in the stream: ip + stride * lane
     uint64_t x = load_stream_at(src, tp);
     // What every batch does once it knows its shape: ask for the next batch's stream bytes (they travel while this batch's
@@ -203,7 +212,7 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
         const uint32_t nip = ip + adv;
         tp = restride ? nip + (3u + L0) * lane : tp + adv;
         const uint64_t nx = load_stream_at(src, tp);
-        if ((nip ^ ip) >> 9) prefetch_group(src + (((nip >> 9) + 2u) << 9), lane);
+        if ((nip ^ ip) >> 9) prefetch_group(src, nip >> 9, lane, pf_mode);
         ip = nip;
         return nx;
     };
@@ -346,7 +355,7 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, CTAS) lz4_decode_spec_kernel(
         if (origin == 0) e = (comp_len == 1 && src[0] == 0) ? E_OK : E_SIZE;
         else if (comp_len == 0) e = E_TRUNCATED;
         else if (((uintptr_t)src & 3u) || ((uintptr_t)dst & 7u)) e = pred ? E_INTERNAL : decode_simple(src, comp_len, dst, origin);
-        else e = decode_block_spec<FUSED>(src, comp_len, dst, origin, ring_s, F, accs);
+        else e = decode_block_spec<FUSED>(src, comp_len, dst, origin, ring_s, args.hot, F, accs);
         if (lane == 0) col.status[b] = e;
         if (pred) {
             // the block's partial: the 32 lanes' accumulators folded in a fixed order
@@ -365,6 +374,7 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, CTAS) lz4_decode_spec_kernel(
 }  // namespace
 
 int g_spec_ctas = 5;
+int g_spec_prefetch = 0;   // 0: stream groups into L2, 1: + the next group into L1, 2: into L1 directly (option "spec_prefetch")
 
 int launch_lz4_decode_spec(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit, const LaneFused *fused_args)
 {

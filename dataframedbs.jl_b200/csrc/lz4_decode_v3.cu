@@ -1,15 +1,25 @@
-// lz4_decode_v3.cu -- K1, general flavour: raw LZ4 block decode on sm_100a for columns whose token stream is not
-// word-regular (strings, literal-heavy bodies such as Union{Float64,Missing}, sorted integers, shifted Float64 grids).
+// lz4_decode_v3.cu -- K1, walker / consumer flavour: raw LZ4 block decode on sm_100a for every column the warp-per-block decoder
+// (lz4_decode_spec.cu) is not made for: strings, literal-heavy bodies such as Union{Float64,Missing}, shifted Float64 grids,
+// nullable integer columns.
 //
 // Replaces read_block's LZ4_decompress_safe call (/root/reference/src/io/BlockStreams.jl:101-119, liblz4 via
 // CodecLz4) for whole batches of independent column blocks, with the same safety contract: never reads
 // outside the compressed payload, never writes outside `origin`, per-block status instead of the
 // reference's `@assert size == sizes.origin "decompression error"`.
 //
-// Same organisation as lz4_decode_v2.cu (read that header first): one persistent CTA per SM, NWALK walker warps whose
-// LANES walk the token chains of NSLOT blocks through shared-memory windows of their compressed streams and emit one
-// 4-byte ring entry (the token's stream position) per sequence, NCONS consumer warps with SPC block slots each that
-// take 32 entries at a time.  What is different here:
+// Why this shape.  The only inherently serial part of an LZ4 block is finding where each token starts (token k+1 starts
+// 3 + literal_length(k) bytes after token k).  The first-generation kernel (lz4_decode.cu) let a whole warp walk that chain
+// (3 instructions, ~35 cycles of latency per token, 1 useful lane of 32).  Here one persistent CTA per SM keeps NSLOT column
+// blocks in flight at once: NWALK walker warps whose LANES walk the token chains of NSLOT blocks through shared-memory
+// windows of their compressed streams and emit one 4-byte ring entry (the token's stream position) per sequence -- 32 chains
+// per warp advance in the latency of one --, and NCONS consumer warps with SPC block slots each that take 32 entries at a
+// time and materialise them lane-parallel.  "Word-regular" runs (8-byte aligned output, offset and length multiples of 8)
+// are expanded to one output word per lane (far sources: one 8-byte load; in-batch sources: warp shuffles); everything else
+// goes through the generic batches below.  Ring validity comes from the walker's release store of its entry count; the
+// window fill level and restart commands are published with release stores.  (Until round 2 a second copy of this kernel,
+// lz4_decode_v2.cu, tuned for word-regular columns only, sat beside it; the warp-per-block decoder took over those columns
+// and the copy was removed -- on the one kind it still served, Union{Int64,Missing}, this kernel is the faster one.)
+// Beyond that organisation:
 //   * the walker gets past tokens with length extensions on its own when the extension bytes are in the window
 //     (walker_resolve); the entry stays in the ring, the consumer recognises it by its nibbles.  Only the last
 //     sequence of a block and extensions that reach beyond the window still park the lane until the consumer posts a

@@ -21,9 +21,9 @@ cap agg_vm_200M agg_vm 1 arith 200000000
 cap group_reduce_200M group_reduce 1 group 200000000
 cap zone_map_200M zone_map 0 zone 200000000
 cap lz4_compress_50M lz4_compress 1 write 50000000
-# racecheck over the GPU parity tests of the scan / gather / aggregate / write kernels; the two walker decoders hand data between
-# warps through shared-memory rings with release / acquire flags, which racecheck reports by design: they are excluded by name
-( timeout 900 compute-sanitizer --tool racecheck --kernel-name-exclude kns=lz4_decode_v2 --kernel-name-exclude kns=lz4_decode_v3 \
+# racecheck over the GPU parity tests of the scan / gather / aggregate / write kernels; the walker / consumer decoder hands data between
+# warps through shared-memory rings with release / acquire flags, which racecheck reports by design: it is excluded by name
+( timeout 900 compute-sanitizer --tool racecheck --kernel-name-exclude kns=lz4_decode_v3 \
     python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "plans_match_oracle or aggregates_match or groupreduce or zone_maps_prune or flat_strings or missings or write_path or selection_stages" ) > $OUT/racecheck.txt 2>&1
 tail -5 $OUT/racecheck.txt
 ls -la $OUT | head -40

@@ -15,7 +15,7 @@ cat $OUT/bench_ref.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-verify > $OUT/launches_bench.log 2>&1
 # full capture of the two hot kernels of the headline bench at 1B rows
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:lz4_decode_v2 -s 1 -c 1 -o $OUT/prof_lz4 -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:lz4_decode_spec -s 1 -c 1 -o $OUT/prof_lz4 -f \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-verify > $OUT/prof_lz4.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fused_scan -s 1 -c 1 -o $OUT/prof_scan -f \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-verify > $OUT/prof_scan.log 2>&1
