@@ -929,9 +929,30 @@ __device__ __forceinline__ long long dbl_order_key(double x)
     return b < 0 ? (long long)(0x8000000000000000ull - (unsigned long long)b) : b;      // -0.0 -> 0 - ... below +0.0
 }
 
+// The accumulators of a group are hit by every one of its rows: with a handful of groups (the usual GROUP BY) that is a hundred
+// million atomics on a few dozen addresses, and they serialise in L2 (first version: 84 ms for 100M selected rows in 8 groups,
+// IPC 0.22).  Every CTA therefore keeps a small direct-mapped cache of groups in shared memory -- entry = table slot mod
+// GROUP_CACHE, claimed by the first group that maps to it -- accumulates there with shared-memory atomics, and merges its
+// entries into the table once, at the end.  A group whose entry is taken by another group goes to the table directly, as
+// before, so a query with millions of groups loses nothing but the tag test.
+constexpr int GROUP_CACHE = 64;
+
+__device__ __forceinline__ void group_acc_neutral(GroupAcc &a, int cls)
+{
+    a.count = 0; a.nmissing = 0; a.sum_i = 0; a.sum_f = 0.0; a.flags = 0; a.pad = 0;
+    if (cls == VC_UINT || cls == VC_BOOL) { a.min_k = -1ll; a.max_k = 0; }
+    else { a.min_k = INT64_MAX; a.max_k = INT64_MIN; }
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS) group_reduce_kernel(const GroupArgs A)
 {
+    __shared__ unsigned long long ctag[GROUP_CACHE];                    // table slot + 1 of the group the entry holds, 0 = free
+    __shared__ long long cfirst[GROUP_CACHE];
+    __shared__ GroupAcc cacc[GROUP_CACHE * GROUP_MAX_VALS];
     const Geometry g = A.g;
+    for (int i = threadIdx.x; i < GROUP_CACHE; i += SCAN_THREADS) { ctag[i] = 0; cfirst[i] = INT64_MAX; }
+    for (int i = threadIdx.x; i < GROUP_CACHE * A.nvals; i += SCAN_THREADS) group_acc_neutral(cacc[i], A.val[i % A.nvals].cls);
+    __syncthreads();
     const int64_t total_words = (int64_t)g.nblocks * g.wpb;
     for (int64_t w = (int64_t)blockIdx.x * (SCAN_THREADS / 32) + warp_id(); w < total_words; w += (int64_t)gridDim.x * (SCAN_THREADS / 32)) {
         const int lb = (int)(w / g.wpb);
@@ -942,7 +963,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) group_reduce_kernel(const GroupA
         unsigned long long slot = group_key_hash(A, lb, rows_b, r) & A.cap_mask;
         bool placed = false;
         for (unsigned long long probe = 0; probe <= A.cap_mask; probe++, slot = (slot + 1) & A.cap_mask) {
-            long long cur = atomicAdd(reinterpret_cast<unsigned long long *>(&A.rep[slot]), 0ull);   // (atomic read)
+            // (a slot changes once, from -1 to its group's row: a plain L2 read is enough, a stale -1 only costs the CAS below)
+            long long cur = __ldcg(&A.rep[slot]);
             if (cur == -1) {
                 const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&A.rep[slot]), (unsigned long long)-1ll, (unsigned long long)row);
                 if (old == (unsigned long long)-1ll) { atomicAdd(A.ngroups, 1ull); cur = row; }
@@ -952,10 +974,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) group_reduce_kernel(const GroupA
             if (probe > 4096) break;                                            // hopelessly full: grow
         }
         if (!placed) { atomicExch(A.overflow, 1); continue; }
-        atomicMin(reinterpret_cast<long long *>(&A.first[slot]), row);
+        // the CTA's cache entry for this group, if it has (or can claim) one
+        const int e = (int)(slot & (GROUP_CACHE - 1));
+        unsigned long long tag = *reinterpret_cast<volatile unsigned long long *>(&ctag[e]);
+        if (tag == 0) {
+            const unsigned long long old = atomicCAS(&ctag[e], 0ull, slot + 1);
+            tag = old == 0 ? slot + 1 : old;
+        }
+        const bool cached = tag == slot + 1;
+        atomicMin(cached ? &cfirst[e] : reinterpret_cast<long long *>(&A.first[slot]), row);
         for (int v = 0; v < A.nvals; v++) {
             const ColView &c = A.val[v];
-            GroupAcc *acc = A.acc + slot * A.nvals + v;
+            GroupAcc *acc = cached ? &cacc[e * A.nvals + v] : A.acc + slot * A.nvals + v;
             atomicAdd(&acc->count, 1ull);
             if (col_missing(c, lb, r)) { atomicAdd(&acc->nmissing, 1ull); continue; }
             const unsigned long long bits = load_widen(col_values(c, lb, rows_b) + r * c.elsize, c.kind);
@@ -979,6 +1009,35 @@ __global__ void __launch_bounds__(SCAN_THREADS) group_reduce_kernel(const GroupA
                 atomicOr(&acc->flags, 1);
             }
         }
+    }
+    // merge the cache into the table: one thread per (entry, value column)
+    __syncthreads();
+    for (int i = threadIdx.x; i < GROUP_CACHE * A.nvals; i += SCAN_THREADS) {
+        const int e = i / A.nvals, v = i - e * A.nvals;
+        if (ctag[e] == 0) continue;
+        const unsigned long long slot = ctag[e] - 1;
+        if (v == 0 && cfirst[e] != INT64_MAX) atomicMin(reinterpret_cast<long long *>(&A.first[slot]), cfirst[e]);
+        const GroupAcc &ca = cacc[i];
+        if (ca.count == 0) continue;
+        GroupAcc *acc = A.acc + slot * A.nvals + v;
+        atomicAdd(&acc->count, ca.count);
+        if (ca.nmissing) atomicAdd(&acc->nmissing, ca.nmissing);
+        const int cls = A.val[v].cls;
+        if (cls == VC_FLT) {
+            if (ca.count != ca.nmissing) atomicAdd(&acc->sum_f, ca.sum_f);
+        } else if (ca.sum_i) {
+            atomicAdd(reinterpret_cast<unsigned long long *>(&acc->sum_i), (unsigned long long)ca.sum_i);
+        }
+        if (ca.flags & 1) {
+            if (cls == VC_UINT || cls == VC_BOOL) {
+                atomicMin(reinterpret_cast<unsigned long long *>(&acc->min_k), (unsigned long long)ca.min_k);
+                atomicMax(reinterpret_cast<unsigned long long *>(&acc->max_k), (unsigned long long)ca.max_k);
+            } else {
+                atomicMin(&acc->min_k, ca.min_k);
+                atomicMax(&acc->max_k, ca.max_k);
+            }
+        }
+        if (ca.flags) atomicOr(&acc->flags, ca.flags);
     }
 }
 
