@@ -930,18 +930,42 @@ __device__ __forceinline__ long long dbl_order_key(double x)
 }
 
 // The accumulators of a group are hit by every one of its rows: with a handful of groups (the usual GROUP BY) that is a hundred
-// million atomics on a few dozen addresses, and they serialise in L2 (first version: 84 ms for 100M selected rows in 8 groups,
-// IPC 0.22).  Every CTA therefore keeps a small direct-mapped cache of groups in shared memory -- entry = table slot mod
-// GROUP_CACHE, claimed by the first group that maps to it -- accumulates there with shared-memory atomics, and merges its
-// entries into the table once, at the end.  A group whose entry is taken by another group goes to the table directly, as
-// before, so a query with millions of groups loses nothing but the tag test.
+// million atomics on a few dozen addresses, and they serialise -- in L2, and just the same in shared memory (first version:
+// 84 ms for 100M selected rows in 8 groups, IPC 0.22; a per-CTA shared-memory copy of the accumulators alone: 83 ms).  So a
+// warp first sorts its 32 rows by group (MATCH.ANY on the table slot) and, when they fall into at most GROUP_WARP_MAX groups,
+// reduces every group's rows in registers -- shuffle trees over the member lanes -- and its leader lane issues ONE set of
+// atomics; those go to a small direct-mapped cache of groups in the CTA's shared memory (entry = table slot mod GROUP_CACHE,
+// claimed by the first group that maps to it), which is merged into the table once, at the end.  Warps whose rows are spread
+// over many groups (a query with millions of groups) take the direct path: one set of atomics per row on the table itself,
+// where they do not collide.
 constexpr int GROUP_CACHE = 64;
+constexpr int GROUP_WARP_MAX = 12;
 
 __device__ __forceinline__ void group_acc_neutral(GroupAcc &a, int cls)
 {
     a.count = 0; a.nmissing = 0; a.sum_i = 0; a.sum_f = 0.0; a.flags = 0; a.pad = 0;
     if (cls == VC_UINT || cls == VC_BOOL) { a.min_k = -1ll; a.max_k = 0; }
     else { a.min_k = INT64_MAX; a.max_k = INT64_MIN; }
+}
+// one row's (or one pre-reduced group's) contribution to an accumulator
+__device__ __forceinline__ void group_acc_add(GroupAcc *acc, int cls, unsigned long long count, unsigned long long nmissing, long long sum_i, double sum_f,
+                                              long long min_k, long long max_k, int flags)
+{
+    atomicAdd(&acc->count, count);
+    if (nmissing) atomicAdd(&acc->nmissing, nmissing);
+    if (count == nmissing) return;
+    if (cls == VC_FLT) atomicAdd(&acc->sum_f, sum_f);
+    else atomicAdd(reinterpret_cast<unsigned long long *>(&acc->sum_i), (unsigned long long)sum_i);
+    if (flags & 1) {
+        if (cls == VC_UINT || cls == VC_BOOL) {
+            atomicMin(reinterpret_cast<unsigned long long *>(&acc->min_k), (unsigned long long)min_k);
+            atomicMax(reinterpret_cast<unsigned long long *>(&acc->max_k), (unsigned long long)max_k);
+        } else {
+            atomicMin(&acc->min_k, min_k);
+            atomicMax(&acc->max_k, max_k);
+        }
+    }
+    if (flags) atomicOr(&acc->flags, flags);
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) group_reduce_kernel(const GroupArgs A)
@@ -950,94 +974,130 @@ __global__ void __launch_bounds__(SCAN_THREADS) group_reduce_kernel(const GroupA
     __shared__ long long cfirst[GROUP_CACHE];
     __shared__ GroupAcc cacc[GROUP_CACHE * GROUP_MAX_VALS];
     const Geometry g = A.g;
+    const unsigned lane = lane_id();
     for (int i = threadIdx.x; i < GROUP_CACHE; i += SCAN_THREADS) { ctag[i] = 0; cfirst[i] = INT64_MAX; }
     for (int i = threadIdx.x; i < GROUP_CACHE * A.nvals; i += SCAN_THREADS) group_acc_neutral(cacc[i], A.val[i % A.nvals].cls);
     __syncthreads();
     const int64_t total_words = (int64_t)g.nblocks * g.wpb;
     for (int64_t w = (int64_t)blockIdx.x * (SCAN_THREADS / 32) + warp_id(); w < total_words; w += (int64_t)gridDim.x * (SCAN_THREADS / 32)) {
         const int lb = (int)(w / g.wpb);
-        const int64_t r = (w - (int64_t)lb * g.wpb) * 32 + lane_id();
+        const int64_t r = (w - (int64_t)lb * g.wpb) * 32 + lane;
         const int64_t rows_b = block_rows(g, lb);
-        if (r >= rows_b || !((A.mask[w] >> lane_id()) & 1u)) continue;
+        const bool active = r < rows_b && ((A.mask[w] >> lane) & 1u);
         const long long row = (long long)lb * g.block_size + r;                 // shard row
-        unsigned long long slot = group_key_hash(A, lb, rows_b, r) & A.cap_mask;
+        unsigned long long slot = 0;
         bool placed = false;
-        for (unsigned long long probe = 0; probe <= A.cap_mask; probe++, slot = (slot + 1) & A.cap_mask) {
-            // (a slot changes once, from -1 to its group's row: a plain L2 read is enough, a stale -1 only costs the CAS below)
-            long long cur = __ldcg(&A.rep[slot]);
-            if (cur == -1) {
-                const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&A.rep[slot]), (unsigned long long)-1ll, (unsigned long long)row);
-                if (old == (unsigned long long)-1ll) { atomicAdd(A.ngroups, 1ull); cur = row; }
-                else cur = (long long)old;
+        if (active) {
+            slot = group_key_hash(A, lb, rows_b, r) & A.cap_mask;
+            for (unsigned long long probe = 0; probe <= A.cap_mask; probe++, slot = (slot + 1) & A.cap_mask) {
+                // (a slot changes once, from -1 to its group's row: a plain L2 read is enough, a stale -1 only costs the CAS below)
+                long long cur = __ldcg(&A.rep[slot]);
+                if (cur == -1) {
+                    const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&A.rep[slot]), (unsigned long long)-1ll, (unsigned long long)row);
+                    if (old == (unsigned long long)-1ll) { atomicAdd(A.ngroups, 1ull); cur = row; }
+                    else cur = (long long)old;
+                }
+                if (cur == row || group_keys_equal(A, lb, r, (int)(cur / g.block_size), cur % g.block_size)) { placed = true; break; }
+                if (probe > 4096) break;                                        // hopelessly full: grow
             }
-            if (cur == row || group_keys_equal(A, lb, r, (int)(cur / g.block_size), cur % g.block_size)) { placed = true; break; }
-            if (probe > 4096) break;                                            // hopelessly full: grow
+            if (!placed) atomicExch(A.overflow, 1);
         }
-        if (!placed) { atomicExch(A.overflow, 1); continue; }
-        // the CTA's cache entry for this group, if it has (or can claim) one
-        const int e = (int)(slot & (GROUP_CACHE - 1));
-        unsigned long long tag = *reinterpret_cast<volatile unsigned long long *>(&ctag[e]);
-        if (tag == 0) {
-            const unsigned long long old = atomicCAS(&ctag[e], 0ull, slot + 1);
-            tag = old == 0 ? slot + 1 : old;
+        __syncwarp();
+        const unsigned am = __ballot_sync(FULL, placed);
+        if (am == 0) continue;
+        unsigned peers = 0;
+        if (placed) peers = __match_any_sync(am, slot);                         // the lanes whose rows belong to my group
+        const bool leader = placed && (unsigned)(__ffs(peers) - 1) == lane;     // (lowest lane = lowest row of the group in this word)
+        const unsigned leaders = __ballot_sync(FULL, leader);
+        if (__popc(leaders) > GROUP_WARP_MAX) {
+            // ---- many groups in this word: every row goes to the table on its own ----
+            if (placed) {
+                atomicMin(reinterpret_cast<long long *>(&A.first[slot]), row);
+                for (int v = 0; v < A.nvals; v++) {
+                    const ColView &c = A.val[v];
+                    GroupAcc *acc = A.acc + slot * A.nvals + v;
+                    if (col_missing(c, lb, r)) { group_acc_add(acc, c.cls, 1, 1, 0, 0.0, 0, 0, 0); continue; }
+                    const unsigned long long bits = load_widen(col_values(c, lb, rows_b) + r * c.elsize, c.kind);
+                    if (c.cls == VC_FLT) {
+                        const double x = __longlong_as_double((long long)bits);
+                        const long long k = x != x ? 0 : dbl_order_key(x);
+                        group_acc_add(acc, c.cls, 1, 0, 0, x, k, k, x != x ? 2 : 1);
+                    } else {
+                        group_acc_add(acc, c.cls, 1, 0, (long long)bits, 0.0, (long long)bits, (long long)bits, 1);
+                    }
+                }
+            }
+            continue;
         }
-        const bool cached = tag == slot + 1;
-        atomicMin(cached ? &cfirst[e] : reinterpret_cast<long long *>(&A.first[slot]), row);
+        // ---- few groups: reduce each group's rows in registers, its leader lane adds the result to the CTA's cache ----
+        GroupAcc *dst = nullptr;          // leader: where this group's accumulators are (cache entry or table)
+        if (leader) {
+            const int e = (int)(slot & (GROUP_CACHE - 1));
+            unsigned long long tag = *reinterpret_cast<volatile unsigned long long *>(&ctag[e]);
+            if (tag == 0) {
+                const unsigned long long old = atomicCAS(&ctag[e], 0ull, slot + 1);
+                tag = old == 0 ? slot + 1 : old;
+            }
+            const bool cached = tag == slot + 1;
+            atomicMin(cached ? &cfirst[e] : reinterpret_cast<long long *>(&A.first[slot]), row);
+            dst = cached ? &cacc[e * A.nvals] : A.acc + slot * A.nvals;
+        }
         for (int v = 0; v < A.nvals; v++) {
             const ColView &c = A.val[v];
-            GroupAcc *acc = cached ? &cacc[e * A.nvals + v] : A.acc + slot * A.nvals + v;
-            atomicAdd(&acc->count, 1ull);
-            if (col_missing(c, lb, r)) { atomicAdd(&acc->nmissing, 1ull); continue; }
-            const unsigned long long bits = load_widen(col_values(c, lb, rows_b) + r * c.elsize, c.kind);
+            const bool uns = c.cls == VC_UINT || c.cls == VC_BOOL;
+            bool missing = false, isnan = false;
+            unsigned long long bits = 0;
+            if (placed) {
+                missing = col_missing(c, lb, r);
+                if (!missing) bits = load_widen(col_values(c, lb, rows_b) + r * c.elsize, c.kind);
+            }
+            double x = 0.0;
+            long long key = (long long)bits;
             if (c.cls == VC_FLT) {
-                const double x = __longlong_as_double((long long)bits);
-                atomicAdd(&acc->sum_f, x);
-                if (x != x) { atomicOr(&acc->flags, 2); continue; }
-                const long long k = dbl_order_key(x);
-                atomicMin(&acc->min_k, k);
-                atomicMax(&acc->max_k, k);
-                atomicOr(&acc->flags, 1);
-            } else {
-                atomicAdd(reinterpret_cast<unsigned long long *>(&acc->sum_i), bits);
-                if (c.cls == VC_UINT || c.cls == VC_BOOL) {
-                    atomicMin(reinterpret_cast<unsigned long long *>(&acc->min_k), bits);
-                    atomicMax(reinterpret_cast<unsigned long long *>(&acc->max_k), bits);
-                } else {
-                    atomicMin(&acc->min_k, (long long)bits);
-                    atomicMax(&acc->max_k, (long long)bits);
+                x = __longlong_as_double((long long)bits);
+                isnan = placed && !missing && x != x;
+                key = isnan ? 0 : dbl_order_key(x);
+            }
+            const bool has = placed && !missing;            // contributes to the sum
+            const bool ord = has && !isnan;                 // contributes to min / max
+            for (unsigned rest = leaders; rest; rest &= rest - 1) {             // (uniform: one round per group of the word)
+                const int l = __ffs(rest) - 1;
+                const unsigned mem = __shfl_sync(FULL, peers, l);
+                const bool in = (mem >> lane) & 1u;
+                const unsigned nmiss = __popc(__ballot_sync(FULL, in && missing));
+                const unsigned nnan = __popc(__ballot_sync(FULL, in && isnan));
+                const unsigned nord = __popc(__ballot_sync(FULL, in && ord));
+                double sf = (in && has) ? x : 0.0;
+                unsigned long long si = (in && has) ? bits : 0ull;
+                long long mn = (in && ord) ? key : (uns ? -1ll : INT64_MAX), mx = (in && ord) ? key : (uns ? 0ll : INT64_MIN);
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    if (c.cls == VC_FLT) sf += __shfl_xor_sync(FULL, sf, d);
+                    else si += __shfl_xor_sync(FULL, si, d);
+                    const long long omn = __shfl_xor_sync(FULL, mn, d), omx = __shfl_xor_sync(FULL, mx, d);
+                    if (uns) {
+                        if ((unsigned long long)omn < (unsigned long long)mn) mn = omn;
+                        if ((unsigned long long)omx > (unsigned long long)mx) mx = omx;
+                    } else {
+                        if (omn < mn) mn = omn;
+                        if (omx > mx) mx = omx;
+                    }
                 }
-                atomicOr(&acc->flags, 1);
+                if ((int)lane == l)
+                    group_acc_add(dst + v, c.cls, (unsigned long long)__popc(mem), nmiss, (long long)si, sf, mn, mx, (nord ? 1 : 0) | (nnan ? 2 : 0));
             }
         }
     }
-    // merge the cache into the table: one thread per (entry, value column)
+    // merge the cache into the table
     __syncthreads();
+    for (int e = threadIdx.x; e < GROUP_CACHE; e += SCAN_THREADS)
+        if (ctag[e] != 0 && cfirst[e] != INT64_MAX) atomicMin(reinterpret_cast<long long *>(&A.first[ctag[e] - 1]), cfirst[e]);
     for (int i = threadIdx.x; i < GROUP_CACHE * A.nvals; i += SCAN_THREADS) {
         const int e = i / A.nvals, v = i - e * A.nvals;
         if (ctag[e] == 0) continue;
-        const unsigned long long slot = ctag[e] - 1;
-        if (v == 0 && cfirst[e] != INT64_MAX) atomicMin(reinterpret_cast<long long *>(&A.first[slot]), cfirst[e]);
         const GroupAcc &ca = cacc[i];
         if (ca.count == 0) continue;
-        GroupAcc *acc = A.acc + slot * A.nvals + v;
-        atomicAdd(&acc->count, ca.count);
-        if (ca.nmissing) atomicAdd(&acc->nmissing, ca.nmissing);
-        const int cls = A.val[v].cls;
-        if (cls == VC_FLT) {
-            if (ca.count != ca.nmissing) atomicAdd(&acc->sum_f, ca.sum_f);
-        } else if (ca.sum_i) {
-            atomicAdd(reinterpret_cast<unsigned long long *>(&acc->sum_i), (unsigned long long)ca.sum_i);
-        }
-        if (ca.flags & 1) {
-            if (cls == VC_UINT || cls == VC_BOOL) {
-                atomicMin(reinterpret_cast<unsigned long long *>(&acc->min_k), (unsigned long long)ca.min_k);
-                atomicMax(reinterpret_cast<unsigned long long *>(&acc->max_k), (unsigned long long)ca.max_k);
-            } else {
-                atomicMin(&acc->min_k, ca.min_k);
-                atomicMax(&acc->max_k, ca.max_k);
-            }
-        }
-        if (ca.flags) atomicOr(&acc->flags, ca.flags);
+        group_acc_add(A.acc + (ctag[e] - 1) * A.nvals + v, A.val[v].cls, ca.count, ca.nmissing, ca.sum_i, ca.sum_f, ca.min_k, ca.max_k, ca.flags);
     }
 }
 
