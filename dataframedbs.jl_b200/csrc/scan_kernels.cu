@@ -990,8 +990,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) group_reduce_kernel(const GroupA
         if (active) {
             slot = group_key_hash(A, lb, rows_b, r) & A.cap_mask;
             for (unsigned long long probe = 0; probe <= A.cap_mask; probe++, slot = (slot + 1) & A.cap_mask) {
-                // (a slot changes once, from -1 to its group's row: a plain L2 read is enough, a stale -1 only costs the CAS below)
-                long long cur = __ldcg(&A.rep[slot]);
+                // (a slot changes once, from -1 to its group's row, so a read through L1 is enough: a stale -1 only costs the CAS
+                //  below, and there is no other stale value.  An L2 read -- or the atomic read of the first version -- makes the few
+                //  slots of a query with few groups a hot spot that every row of the table queues up at: 84 ms for 100M rows.)
+                long long cur = __ldca(&A.rep[slot]);
                 if (cur == -1) {
                     const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&A.rep[slot]), (unsigned long long)-1ll, (unsigned long long)row);
                     if (old == (unsigned long long)-1ll) { atomicAdd(A.ngroups, 1ull); cur = row; }
