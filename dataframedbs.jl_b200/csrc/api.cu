@@ -2385,11 +2385,6 @@ int32_t dfdb_scan_groupreduce(dfdb_scan *s, const int32_t *key_proj, int32_t nke
         cudaMemsetAsync(d_rep, 0xff, cap * 8, rt.stream);
         cudaMemsetAsync(d_first, 0x7f, cap * 8, rt.stream);
         cudaMemsetAsync(d_flag, 0, 16, rt.stream);
-        {
-            std::vector<GroupAcc> init(1);
-            memset(&init[0], 0, sizeof(GroupAcc));
-            cudaMemsetAsync(d_acc, 0, cap * nv * sizeof(GroupAcc), rt.stream);
-        }
         GroupArgs a;
         memset(&a, 0, sizeof a);
         a.g = g; a.mask = s->d_mask; a.nkeys = nkeys; a.nvals = nvals;
@@ -2399,15 +2394,10 @@ int32_t dfdb_scan_groupreduce(dfdb_scan *s, const int32_t *key_proj, int32_t nke
         a.ngroups = reinterpret_cast<unsigned long long *>(d_flag + 2);
         // min / max start at the identities of their order
         {
-            std::vector<GroupAcc> h((size_t)std::min<uint64_t>(cap * nv, 1u << 16));
-            for (size_t i = 0; i < h.size(); i++) {
-                memset(&h[i], 0, sizeof(GroupAcc));
-                const int cls = nvals ? value_class(vc[i % (size_t)nv]->type.kind) : VC_INT;
-                if (cls == VC_UINT || cls == VC_BOOL) { h[i].min_k = -1ll; h[i].max_k = 0; }
-                else { h[i].min_k = INT64_MAX; h[i].max_k = INT64_MIN; }
-            }
-            for (uint64_t off = 0; off < cap * nv; off += h.size())
-                cudaMemcpyAsync(d_acc + off, h.data(), std::min<uint64_t>(h.size(), cap * nv - off) * sizeof(GroupAcc), cudaMemcpyHostToDevice, rt.stream);
+            int cls4[4] = {VC_INT, VC_INT, VC_INT, VC_INT};
+            for (int i = 0; i < nvals; i++) cls4[i] = value_class(vc[i]->type.kind);
+            if (launch_group_init(d_acc, (long long)(cap * nv), nv, cls4, rt.stream) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "group-by launch failed"); }
+            rt.launches++;
         }
         if (launch_group_reduce(a, rt.sm_count, rt.stream) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "group-by launch failed"); }
         rt.launches++;
@@ -2417,16 +2407,31 @@ int32_t dfdb_scan_groupreduce(dfdb_scan *s, const int32_t *key_proj, int32_t nke
         unsigned long long ng;
         memcpy(&ng, flag + 2, 8);
         if (flag[0] || ng * 2 > cap) { cleanup(); continue; }                        // too full: a table four times the size
-        // ---- results to the host, groups in order of first appearance ----
-        std::vector<long long> first((size_t)cap);
-        std::vector<GroupAcc> acc((size_t)(cap * nv));
-        cudaMemcpyAsync(first.data(), d_first, cap * 8, cudaMemcpyDeviceToHost, rt.stream);
-        cudaMemcpyAsync(acc.data(), d_acc, cap * nv * sizeof(GroupAcc), cudaMemcpyDeviceToHost, rt.stream);
+        // ---- results to the host, groups in order of first appearance: the used slots are packed on the device first ----
+        long long *d_pfirst = nullptr;
+        GroupAcc *d_pacc = nullptr;
+        const size_t ngz = (size_t)std::max<unsigned long long>(ng, 1);
+        if (cudaMalloc(reinterpret_cast<void **>(&d_pfirst), ngz * 8) != cudaSuccess || cudaMalloc(reinterpret_cast<void **>(&d_pacc), ngz * nv * sizeof(GroupAcc)) != cudaSuccess) {
+            cudaFree(d_pfirst); cleanup();
+            cudaGetLastError();
+            return fail(DFDB_ERR_NOMEM, "out of device memory for %llu group results", ng);
+        }
+        cudaMemsetAsync(d_flag + 2, 0, 8, rt.stream);                              // (the group counter is the pack cursor now)
+        if (launch_group_compact(d_first, d_acc, (long long)cap, nv, 0x7f7f7f7f7f7f7f7fll, reinterpret_cast<unsigned long long *>(d_flag + 2), d_pfirst, d_pacc, rt.stream) != 0) {
+            cudaFree(d_pfirst); cudaFree(d_pacc); cleanup();
+            return fail(DFDB_ERR_CUDA, "group-by launch failed");
+        }
+        rt.launches++;
+        std::vector<long long> first(ngz);
+        std::vector<GroupAcc> acc(ngz * (size_t)nv);
+        cudaMemcpyAsync(first.data(), d_pfirst, (size_t)ng * 8, cudaMemcpyDeviceToHost, rt.stream);
+        cudaMemcpyAsync(acc.data(), d_pacc, (size_t)ng * nv * sizeof(GroupAcc), cudaMemcpyDeviceToHost, rt.stream);
         cudaError_t e = cudaStreamSynchronize(rt.stream);
+        cudaFree(d_pfirst); cudaFree(d_pacc);
         cleanup();
         if (e != cudaSuccess) return fail(DFDB_ERR_CUDA, "group-by results: %s", cudaGetErrorString(e));
         std::vector<std::pair<long long, size_t>> order;
-        for (size_t sl = 0; sl < (size_t)cap; sl++) if (first[sl] != 0x7f7f7f7f7f7f7f7fll) order.emplace_back(first[sl], sl);
+        for (size_t sl = 0; sl < (size_t)ng; sl++) order.emplace_back(first[sl], sl);
         std::sort(order.begin(), order.end());
         s->group_first.resize(order.size());
         s->group_aggs.assign(order.size() * (size_t)nvals, dfdb_agg());

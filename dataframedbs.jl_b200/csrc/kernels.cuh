@@ -194,6 +194,9 @@ struct GroupArgs {
     unsigned long long *ngroups;
 };
 int launch_group_reduce(const GroupArgs &a, int sm_count, cudaStream_t stream);
+int launch_group_init(GroupAcc *acc, long long n, int nvals, const int *cls, cudaStream_t stream);     // accumulators at the identities of their order
+int launch_group_compact(const long long *first, const GroupAcc *acc, long long cap, int nv, long long sentinel, unsigned long long *counter,
+                         long long *out_first, GroupAcc *out_acc, cudaStream_t stream);                // used slots, packed
 
 // ---- K5/K6: stream compaction / gathers ---------------------------------------------------------------
 struct GatherArgs {

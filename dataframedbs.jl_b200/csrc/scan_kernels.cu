@@ -971,38 +971,73 @@ __device__ __forceinline__ void group_acc_add(GroupAcc *acc, int cls, unsigned l
 __global__ void __launch_bounds__(SCAN_THREADS) group_reduce_kernel(const GroupArgs A)
 {
     __shared__ unsigned long long ctag[GROUP_CACHE];                    // table slot + 1 of the group the entry holds, 0 = free
+    __shared__ unsigned long long chash[GROUP_CACHE];                   // ... the hash of its key
+    __shared__ long long crep[GROUP_CACHE];                             // ... a row of the group (the table's representative)
+    __shared__ int cready[GROUP_CACHE];                                 // hash and row are published
     __shared__ long long cfirst[GROUP_CACHE];
     __shared__ GroupAcc cacc[GROUP_CACHE * GROUP_MAX_VALS];
     const Geometry g = A.g;
     const unsigned lane = lane_id();
-    for (int i = threadIdx.x; i < GROUP_CACHE; i += SCAN_THREADS) { ctag[i] = 0; cfirst[i] = INT64_MAX; }
+    for (int i = threadIdx.x; i < GROUP_CACHE; i += SCAN_THREADS) { ctag[i] = 0; cready[i] = 0; cfirst[i] = INT64_MAX; }
     for (int i = threadIdx.x; i < GROUP_CACHE * A.nvals; i += SCAN_THREADS) group_acc_neutral(cacc[i], A.val[i % A.nvals].cls);
     __syncthreads();
     const int64_t total_words = (int64_t)g.nblocks * g.wpb;
     for (int64_t w = (int64_t)blockIdx.x * (SCAN_THREADS / 32) + warp_id(); w < total_words; w += (int64_t)gridDim.x * (SCAN_THREADS / 32)) {
+        if (*reinterpret_cast<volatile int *>(A.overflow)) break;              // the table is full: the host runs again with a larger one
         const int lb = (int)(w / g.wpb);
         const int64_t r = (w - (int64_t)lb * g.wpb) * 32 + lane;
         const int64_t rows_b = block_rows(g, lb);
         const bool active = r < rows_b && ((A.mask[w] >> lane) & 1u);
         const long long row = (long long)lb * g.block_size + r;                 // shard row
         unsigned long long slot = 0;
-        bool placed = false;
+        bool placed = false, cached = false;
+        int e = 0;
         if (active) {
-            slot = group_key_hash(A, lb, rows_b, r) & A.cap_mask;
-            for (unsigned long long probe = 0; probe <= A.cap_mask; probe++, slot = (slot + 1) & A.cap_mask) {
-                // (a slot changes once, from -1 to its group's row, so a read through L1 is enough: a stale -1 only costs the CAS
-                //  below, and there is no other stale value.  An L2 read -- or the atomic read of the first version -- makes the few
-                //  slots of a query with few groups a hot spot that every row of the table queues up at: 84 ms for 100M rows.)
-                long long cur = __ldca(&A.rep[slot]);
-                if (cur == -1) {
-                    const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&A.rep[slot]), (unsigned long long)-1ll, (unsigned long long)row);
-                    if (old == (unsigned long long)-1ll) { atomicAdd(A.ngroups, 1ull); cur = row; }
-                    else cur = (long long)old;
+            // The CTA's cache first: entry = hash mod GROUP_CACHE.  A hit is verified against the group's representative row (its key
+            // bytes are immutable and come through L1), so the table -- where the few slots of a query with few groups are a hot
+            // spot every row of the column would queue up at, in L2 -- is only consulted by the first rows of a group in this CTA.
+            const unsigned long long h = group_key_hash(A, lb, rows_b, r);
+            e = (int)((h >> 20) & (GROUP_CACHE - 1));
+            if (*reinterpret_cast<volatile int *>(&cready[e]) && chash[e] == h) {
+                const long long rep = crep[e];
+                if (rep == row || group_keys_equal(A, lb, r, (int)(rep / g.block_size), rep % g.block_size)) {
+                    slot = ctag[e] - 1;
+                    placed = cached = true;
                 }
-                if (cur == row || group_keys_equal(A, lb, r, (int)(cur / g.block_size), cur % g.block_size)) { placed = true; break; }
-                if (probe > 4096) break;                                        // hopelessly full: grow
             }
-            if (!placed) atomicExch(A.overflow, 1);
+            if (!placed) {
+                long long cur = -1;
+                slot = h & A.cap_mask;
+                for (unsigned long long probe = 0; probe <= A.cap_mask; probe++, slot = (slot + 1) & A.cap_mask) {
+                    cur = __ldcg(&A.rep[slot]);                                 // (a slot changes once, from -1 to its group's row)
+                    if (cur == -1) {
+                        const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&A.rep[slot]), (unsigned long long)-1ll, (unsigned long long)row);
+                        if (old == (unsigned long long)-1ll) { atomicAdd(A.ngroups, 1ull); cur = row; }
+                        else cur = (long long)old;
+                    }
+                    if (cur == row || group_keys_equal(A, lb, r, (int)(cur / g.block_size), cur % g.block_size)) { placed = true; break; }
+                    if (probe > 4096) break;                                    // hopelessly full: grow
+                }
+                if (!placed) {
+                    atomicExch(A.overflow, 1);
+                } else {
+                    // claim the cache entry for this group if it is free
+                    unsigned long long tag = *reinterpret_cast<volatile unsigned long long *>(&ctag[e]);
+                    if (tag == 0) {
+                        const unsigned long long old = atomicCAS(&ctag[e], 0ull, slot + 1);
+                        if (old == 0) {
+                            chash[e] = h;
+                            crep[e] = cur;
+                            __threadfence_block();
+                            *reinterpret_cast<volatile int *>(&cready[e]) = 1;
+                            tag = slot + 1;
+                        } else {
+                            tag = old;
+                        }
+                    }
+                    cached = tag == slot + 1;
+                }
+            }
         }
         __syncwarp();
         const unsigned am = __ballot_sync(FULL, placed);
@@ -1034,13 +1069,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) group_reduce_kernel(const GroupA
         // ---- few groups: reduce each group's rows in registers, its leader lane adds the result to the CTA's cache ----
         GroupAcc *dst = nullptr;          // leader: where this group's accumulators are (cache entry or table)
         if (leader) {
-            const int e = (int)(slot & (GROUP_CACHE - 1));
-            unsigned long long tag = *reinterpret_cast<volatile unsigned long long *>(&ctag[e]);
-            if (tag == 0) {
-                const unsigned long long old = atomicCAS(&ctag[e], 0ull, slot + 1);
-                tag = old == 0 ? slot + 1 : old;
-            }
-            const bool cached = tag == slot + 1;
             atomicMin(cached ? &cfirst[e] : reinterpret_cast<long long *>(&A.first[slot]), row);
             dst = cached ? &cacc[e * A.nvals] : A.acc + slot * A.nvals;
         }
@@ -1504,6 +1532,36 @@ int launch_str_offsets(const Geometry &g, const ColView &col, int32_t *str_off, 
     if (lo < 0) lo = 0;
     if (hi <= lo) return 0;
     str_offsets_kernel<<<grid_for((hi - lo + 7) / 8, g_sm_count, 8), SCAN_THREADS, 0, stream>>>(g, col, str_off, status, origin, lo, hi, dead);
+    return CHECK_LAUNCH();
+}
+
+__global__ void group_init_kernel(GroupAcc *acc, long long n, int nvals, int c0, int c1, int c2, int c3)
+{
+    const int cls[4] = {c0, c1, c2, c3};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) group_acc_neutral(acc[i], cls[i % nvals]);
+}
+// the used slots of the table, packed: (first row, accumulators) per group, in no particular order
+__global__ void group_compact_kernel(const long long *first, const GroupAcc *acc, long long cap, int nv, long long sentinel, unsigned long long *counter,
+                                     long long *out_first, GroupAcc *out_acc)
+{
+    for (long long sl = (long long)blockIdx.x * blockDim.x + threadIdx.x; sl < cap; sl += (long long)gridDim.x * blockDim.x) {
+        const long long f = first[sl];
+        if (f == sentinel) continue;
+        const unsigned long long i = atomicAdd(counter, 1ull);
+        out_first[i] = f;
+        for (int v = 0; v < nv; v++) out_acc[i * nv + v] = acc[sl * nv + v];
+    }
+}
+int launch_group_init(GroupAcc *acc, long long n, int nvals, const int *cls, cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    group_init_kernel<<<grid_for((n + 255) / 256, g_sm_count, 8), 256, 0, stream>>>(acc, n, nvals > 0 ? nvals : 1, cls[0], cls[1], cls[2], cls[3]);
+    return CHECK_LAUNCH();
+}
+int launch_group_compact(const long long *first, const GroupAcc *acc, long long cap, int nv, long long sentinel, unsigned long long *counter,
+                         long long *out_first, GroupAcc *out_acc, cudaStream_t stream)
+{
+    group_compact_kernel<<<grid_for((cap + 255) / 256, g_sm_count, 8), 256, 0, stream>>>(first, acc, cap, nv, sentinel, counter, out_first, out_acc);
     return CHECK_LAUNCH();
 }
 
