@@ -2399,8 +2399,11 @@ int32_t dfdb_scan_groupreduce(dfdb_scan *s, const int32_t *key_proj, int32_t nke
             if (launch_group_init(d_acc, (long long)(cap * nv), nv, cls4, rt.stream) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "group-by launch failed"); }
             rt.launches++;
         }
-        if (launch_group_reduce(a, rt.sm_count, rt.stream) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "group-by launch failed"); }
-        rt.launches++;
+        {
+            PhaseScope ps(PH_CONSUME, 0);
+            if (launch_group_reduce(a, rt.sm_count, rt.stream) != 0) { cleanup(); return fail(DFDB_ERR_CUDA, "group-by launch failed"); }
+            rt.launches++;
+        }
         int flag[4] = {0, 0, 0, 0};
         cudaMemcpyAsync(flag, d_flag, 16, cudaMemcpyDeviceToHost, rt.stream);
         if (cudaStreamSynchronize(rt.stream) != cudaSuccess) { cleanup(); return fail(DFDB_ERR_CUDA, "group-by kernel failed: %s", cudaGetErrorString(cudaGetLastError())); }

@@ -983,7 +983,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) group_reduce_kernel(const GroupA
     __syncthreads();
     const int64_t total_words = (int64_t)g.nblocks * g.wpb;
     for (int64_t w = (int64_t)blockIdx.x * (SCAN_THREADS / 32) + warp_id(); w < total_words; w += (int64_t)gridDim.x * (SCAN_THREADS / 32)) {
-        if (*reinterpret_cast<volatile int *>(A.overflow)) break;              // the table is full: the host runs again with a larger one
+        // (the table is full: the host runs again with a larger one.  Looked at once in 64 words: the flag is one address for every warp of the grid)
+        if (((w / ((int64_t)gridDim.x * (SCAN_THREADS / 32))) & 63) == 0 && *reinterpret_cast<volatile int *>(A.overflow)) break;
         const int lb = (int)(w / g.wpb);
         const int64_t r = (w - (int64_t)lb * g.wpb) * 32 + lane;
         const int64_t rows_b = block_rows(g, lb);

@@ -21,11 +21,21 @@ def main():
                      ("1e6 groups (Int64 key), all rows, 1 value column", lambda: D.groupreduce(t2[:, :], ["k"], total="b"))):
         fn()
         torch.cuda.synchronize()
+        L = _capi.lib()
+        L.dfdb_profile_reset(); L.dfdb_profile_enable(1)
         t0 = time.time()
         for _ in range(3):
             r = fn()
         torch.cuda.synchronize()
         dt = (time.time() - t0) / 3
+        L.dfdb_profile_enable(0)
+        import ctypes as C
+        ph = {}
+        for nm in ("decode", "select", "consume", "d2h"):
+            ms, n, b = C.c_double(), C.c_int64(), C.c_int64()
+            L.dfdb_profile_get(nm.encode(), C.byref(ms), C.byref(n), C.byref(b))
+            ph[nm] = round(ms.value / 3, 2)
+        print("   device phases (ms per call):", ph)
         ng = len(next(iter(r.values()))) if isinstance(r, dict) else -1
         print(f"{name}: {dt * 1e3:.1f} ms per call (wall, decoded columns cached), groups {ng}", flush=True)
 
