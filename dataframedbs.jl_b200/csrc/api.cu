@@ -55,6 +55,7 @@ struct Runtime {
     int64_t lz4_flavour = 0;  // K1 flavour: 0 = per column from a token sample at load, 2 (and 1, a removed kernel's number) = walker / consumer decoder (v3), 3 = lane-per-block decoder, 4 = warp-per-block decoder with verified token runs (spec)
     int64_t no_overlap = 0;   // do not run the scan of the decoded part of a shard beside the decode of its last part
     int64_t no_alias = 0;     // copy stored (incompressible) blocks like any other block instead of referencing them in place
+    int64_t no_decode_split = 0;   // 1: columns of the walker / consumer flavour always share a launch (A/B)
     int64_t spec_tail_pct = 0;  // spec decoder: share of the blocks decoded beside the scan of the others; 0 = plain sequence (measured: the overlap loses, 10.1 vs 8.5 ms per step at 1e9 rows -- the tail decodes at reduced occupancy and one scan CTA per SM is slow)
     int64_t no_zonemap = 0;   // ignore zone maps (A/B: results must not change)
     int64_t no_validate = 0;  // skip the acceptance pass of dfdb_table_load (A/B, load-time measurements)
@@ -583,13 +584,23 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
               for (int b = b0; b < b1 && !work; b++) work = !h_skip_of(c)[(size_t)b];
               if (work) grp.push_back(c);
           }
-          for (size_t i = 0; i < grp.size(); i += DECODE_MAX_COLS) {
+          // The walker / consumer decoder works in rounds of sm_count x LZ4_SLOTS_PER_SM blocks, and a block takes about as long
+          // whether the round is full or not.  Columns that fit a round each but not together are better off in launches of their
+          // own (config 4: Union{Int64,Missing} + Union{Float64,Missing}, 7 630 blocks each: one mixed launch is two rounds in
+          // which the slow column's blocks set the pace).  The warp-per-block decoder has no rounds: its columns share a launch.
+          size_t per_launch = DECODE_MAX_COLS;
+          if (general != 2 && grp.size() > 1 && !rt.no_decode_split) {
+              int64_t jobs = 0;
+              for (Column *c : grp) for (int b = b0; b < b1; b++) jobs += h_skip_of(c)[(size_t)b] ? 0 : 1;
+              if (jobs > (int64_t)rt.sm_count * LZ4_SLOTS_PER_SM) per_launch = 1;
+          }
+          for (size_t i = 0; i < grp.size(); i += per_launch) {
             DecodeArgs a;
             memset(&a, 0, sizeof a);
             a.nblocks = b1 - b0;
             a.blk0 = b0;
             int64_t bytes = 0;
-            for (size_t q = i; q < grp.size() && q < i + DECODE_MAX_COLS; q++) {
+            for (size_t q = i; q < grp.size() && q < i + per_launch; q++) {
                 Column *c = grp[q];
                 DecodeCol &d = a.col[a.ncols++];
                 d.comp = c->d_comp; d.comp_off = c->d_comp_off; d.comp_len = c->d_comp_len; d.dec_off = c->d_dec_off;
@@ -1317,6 +1328,7 @@ int32_t dfdb_init(int32_t device)
     if (const char *fl = getenv("DFDB_LZ4_FLAVOUR")) rt.lz4_flavour = atoll(fl);
     if (const char *tp = getenv("DFDB_SPEC_TAIL_PCT")) rt.spec_tail_pct = atoll(tp);
     if (const char *sc = getenv("DFDB_SPEC_CTAS")) g_spec_ctas = atoi(sc);
+    if (const char *ns = getenv("DFDB_NO_DECODE_SPLIT")) rt.no_decode_split = atoll(ns);
     if (const char *sp = getenv("DFDB_SPEC_PREFETCH")) g_spec_prefetch = atoi(sp);
     if (const char *nf = getenv("DFDB_NO_DECODE_FUSED")) rt.no_decode_fused = atoll(nf);   // A/B: decode, then scan
     if (const char *ov = getenv("DFDB_NO_OVERLAP")) rt.no_overlap = atoll(ov);       // A/B: decode / scan overlap off   // A/B: force one K1 flavour (see dfdb_set_option "lz4_flavour")
@@ -1378,6 +1390,7 @@ int32_t dfdb_set_option(const char *name, int64_t value)
     else if (n == "no_zonemap") rt.no_zonemap = value;
     else if (n == "spec_tail_pct") rt.spec_tail_pct = value;
     else if (n == "spec_ctas") g_spec_ctas = (int)value;
+    else if (n == "no_decode_split") rt.no_decode_split = value;
     else if (n == "spec_prefetch") g_spec_prefetch = (int)value;
     else if (n == "host_arena_cap_mb") { std::lock_guard<std::mutex> lk(arena.mu); arena.cap_bytes = (size_t)std::max<int64_t>(value, 0) << 20; arena.trim(arena.cap_bytes); }
     else return fail(DFDB_ERR_ARGUMENT, "unknown option %s", n.c_str());
