@@ -52,7 +52,7 @@ struct Runtime {
     int64_t no_fused = 0;
     int64_t no_decode_fused = 1;                                    // 0: fold predicate + aggregate into the decode kernel (measured: no faster than decode + scan, see lz4_decode_spec.cu)
     int64_t no_tma = 0;
-    int64_t lz4_flavour = 0;  // K1 flavour: 0 = per column from a token sample at load, 2 (and 1, a removed kernel's number) = walker / consumer decoder (v3), 3 = lane-per-block decoder, 4 = warp-per-block decoder with verified token runs (spec)
+    int64_t lz4_flavour = 0;  // K1 flavour: 0 = per column from a token sample at load, 2 (and 1, a removed kernel's number) = walker / consumer decoder (v3), 3 = lane-per-block decoder, 4 = warp-per-block decoder with verified token runs (spec), 5 = warp-per-block decoder for long sequences
     int64_t no_overlap = 0;   // do not run the scan of the decoded part of a shard beside the decode of its last part
     int64_t no_alias = 0;     // copy stored (incompressible) blocks like any other block instead of referencing them in place
     int64_t no_decode_split = 0;   // 1: columns of the walker / consumer flavour always share a launch (A/B)
@@ -302,7 +302,7 @@ int launch_decode(const DecodeArgs &a, int general, cudaStream_t stream = nullpt
     if (rt.lz4_flavour == 3) {
         count(3);
         DecodeArgs la = a;
-        la.hot = general == 1 ? 0 : 1;   // word-regular columns (the token sample at load) run the hot-step schedule
+        la.hot = general == 2 ? 1 : 0;   // word-regular columns (the token sample at load) run the hot-step schedule
         if (rt.lane_hot >= 0) la.hot = (int)rt.lane_hot;
         return launch_lz4_decode_lane(la, nullptr, counter, rt.sm_count, stream, cta_limit);
     }
@@ -313,13 +313,15 @@ int launch_decode(const DecodeArgs &a, int general, cudaStream_t stream = nullpt
         return launch_lz4_decode_spec(sa, counter, rt.sm_count, stream, cta_limit, fuse);
     }
     if (fuse) return 1;
+    if (rt.lz4_flavour == 5 || (rt.lz4_flavour == 0 && general == 3)) { count(1); return launch_lz4_decode_long(a, counter, rt.sm_count, stream, cta_limit); }
     count(2);     // (lz4_flavour 1 used to select a second walker / consumer kernel tuned for word-regular columns; it is an alias of 2 now)
     return launch_lz4_decode_v3(a, counter, rt.sm_count, stream, cta_limit);
 }
 
 // Which K1 flavour suits a column: walk the token stream of one compressed block on the host (done once, at load).
 // 2 = the warp-per-block decoder with verified runs (nearly every sequence is plain -- no length extensions -- and makes
-// whole aligned output words), 1 = the walker / consumer decoder (everything else).  Returns -1 when the block gives no verdict.
+// whole aligned output words), 3 = the warp-per-block decoder for long sequences (Union{Float64,Missing} bodies, decimal
+// strings), 1 = the walker / consumer decoder (everything else).  Returns -1 when the block gives no verdict.
 int sample_flavour(const uint8_t *src, int64_t n, int64_t origin)
 {
     int64_t ip = 0, op = 0, nseq = 0, wordform = 0;
@@ -349,8 +351,9 @@ int sample_flavour(const uint8_t *src, int64_t n, int64_t origin)
         op += M;
         if (op > origin) return -1;
     }
-    if (nseq < 64) return -1;
+    if (nseq < 64) return op >= 64 * 24 ? 3 : -1;               // (a few very long sequences: a verdict all the same)
     if (wordform * 100 >= nseq * 97) return 2;
+    if (op >= nseq * 24) return 3;                               // long sequences (>= 24 output bytes on average): the one-sequence-at-a-time decoder with its stream window
     return 1;
 }
 
@@ -489,7 +492,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
         // the last round: what is left after the full rounds
         int split = 0;
         int64_t last_real = real % wave, acc = 0;
-        if (one_flavour && real > wave && last_real > 0) {
+        if (one_flavour && flavour0 <= 1 && rt.lz4_flavour <= 2 && real > wave && last_real > 0) {
             for (int b = wlo; b < whi && acc < real - last_real; b++) {
                 for (Column *c : todo) acc += h_skip_of(c)[(size_t)b] ? 0 : 1;
                 split = b + 1;
@@ -575,7 +578,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
         }
         if (b1 <= b0) continue;
         // columns of one flavour share a launch
-        for (int general = 0; general < 3; general++) {
+        for (int general = 0; general < 4; general++) {
           std::vector<Column *> grp;
           for (Column *c : todo) {
               if (eff_of(c) != general) continue;
@@ -589,7 +592,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
           // own (config 4: Union{Int64,Missing} + Union{Float64,Missing}, 7 630 blocks each: one mixed launch is two rounds in
           // which the slow column's blocks set the pace).  The warp-per-block decoder has no rounds: its columns share a launch.
           size_t per_launch = DECODE_MAX_COLS;
-          if (general != 2 && grp.size() > 1 && !rt.no_decode_split) {
+          if (general <= 1 && grp.size() > 1 && !rt.no_decode_split) {
               int64_t jobs = 0;
               for (Column *c : grp) for (int b = b0; b < b1; b++) jobs += h_skip_of(c)[(size_t)b] ? 0 : 1;
               if (jobs > (int64_t)rt.sm_count * LZ4_SLOTS_PER_SM) per_launch = 1;
@@ -1416,8 +1419,8 @@ int32_t dfdb_profile_get(const char *phase, double *total_ms, int64_t *launches,
             if (bytes) *bytes = rt.acc_bytes[i];
             return DFDB_OK;
         }
-    // "k1_v1" / "k1_v3" / "k1_lane" / "k1_spec": decode launches and bytes per K1 kernel since the last reset ("k1_v2": a removed kernel, always 0)
-    static const char *k1_names[5] = {"k1_v1", "k1_v2", "k1_v3", "k1_lane", "k1_spec"};
+    // "k1_v1" / "k1_long" / "k1_v3" / "k1_lane" / "k1_spec": decode launches and bytes per K1 kernel since the last reset
+    static const char *k1_names[5] = {"k1_v1", "k1_long", "k1_v3", "k1_lane", "k1_spec"};   // (slot 1 was a removed kernel's)
     for (int i = 0; i < 5; i++)
         if (strcmp(phase, k1_names[i]) == 0) {
             if (total_ms) *total_ms = 0;
@@ -1594,7 +1597,7 @@ int32_t dfdb_table_load(dfdb_table *t, const int64_t *col_ids, int32_t n, int32_
         if (cpos > prev_end) memset(c->h_comp + prev_end, 0, (size_t)(cpos - prev_end));
         // K1 flavour of the column: first, middle and last block vote (stored blocks are never decoded and abstain)
         {
-            int votes[3] = {0, 0, 0};
+            int votes[4] = {0, 0, 0, 0};
             const int64_t cand[3] = {0, nb / 2, nb - 1};
             for (int k = 0; k < 3 && nb > 0; k++) {
                 const int64_t b = cand[k];
@@ -1602,7 +1605,7 @@ int32_t dfdb_table_load(dfdb_table *t, const int64_t *col_ids, int32_t n, int32_
                 const int v = sample_flavour(c->h_comp + comp_off[(size_t)b], comp_len[(size_t)b], origin[(size_t)b]);
                 if (v >= 0) votes[v]++;
             }
-            c->lz4_general = votes[2] > votes[0] + votes[1] ? 2 : 1;
+            c->lz4_general = votes[2] > votes[0] + votes[1] + votes[3] ? 2 : (votes[3] > votes[0] + votes[1] + votes[2] ? 3 : 1);
             // (a Union{T,Missing} body starts with its incompressible bitmap -- a long literal run the verified-run decoder takes one
             //  sequence at a time; measured slower than the walker / consumer decoder there: 6.7 against 5.3 ms for 200M Union{Int64,Missing} rows)
             if (c->lz4_general == 2 && c->type.nullable) c->lz4_general = 1;
@@ -1634,7 +1637,7 @@ int32_t dfdb_table_load(dfdb_table *t, const int64_t *col_ids, int32_t n, int32_
             memset(&va, 0, sizeof va);
             va.ncols = 1;
             va.nblocks = (int)nb;
-            va.hot = c->lz4_general == 1 ? 0 : 1;
+            va.hot = c->lz4_general == 2 ? 1 : 0;
             va.col[0] = DecodeCol{c->d_comp, c->d_comp_off, c->d_comp_len, c->d_dec_off, c->d_origin, c->d_decoded, c->d_status, c->d_skip};
             LAUNCH(launch_lz4_decode_lane(va, nullptr, rt.d_counter, rt.sm_count, rt.stream));
             c->h_corrupt.assign((size_t)nb, 0);

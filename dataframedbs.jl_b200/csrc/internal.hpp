@@ -78,7 +78,8 @@ struct Column {
     std::vector<int32_t> h_corrupt;  // per local block: LZ4_decompress_safe's verdict (0 = accepted), decided once at load by the lane-per-block decoder
     int64_t stored_blocks = 0;
     int lz4_general = 1;             // K1 flavour, decided at load from a token sample: 1 = walker / consumer decoder (v3),
-                                     // 2 = warp per block with verified runs (spec: nearly every sequence is one aligned word)
+                                     // 2 = warp per block with verified runs (spec: nearly every sequence is one aligned word),
+                                     // 3 = warp per block, one sequence at a time through a stream window (long sequences)
     int32_t *d_str_off = nullptr;    // String columns: per-row char offset inside the block's char area
     bool str_off_valid = false;
     std::vector<int64_t> h_dec_off, h_comp_off;

@@ -323,6 +323,109 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
     return (op == origin && ip == comp_len) ? E_OK : E_SIZE;
 }
 
+// ---- long-sequence columns: one sequence at a time, the stream parsed out of shared memory -------------------------------------
+// Union{Float64,Missing} bodies, decimal strings, anything whose sequences are long (tens of bytes: a literal run with a length
+// extension, a match): there are few tokens per output byte, so the token chain is not the problem -- the LATENCY of reading it is.
+// decode_one_sequence fetches token, extension bytes and offset from global memory, three dependent round trips to L2 per
+// sequence (~2 000 cycles); the walker / consumer kernel parks its walker lane at every length extension.  Here the warp keeps a
+// 4 KB circular window of the stream in shared memory (the spec decoder's ring, unused in this mode), filled 512 bytes at a time
+// with cp.async two kilobytes ahead of the position, and parses the headers out of it: a sequence costs a few shared-memory
+// reads plus its copies, which are fire-and-forget (literals: stream -> output, the lines are in L2 because the window fetched
+// them; match: output -> output through L2, ordered by __syncwarp).  Same safety contract as every decoder here.
+constexpr uint32_t LW = SPEC_RING * 8u;      // window bytes (4 KB), a power of two
+constexpr uint32_t LW_CHUNK = 512u;          // one warp-wide cp.async: 32 lanes x 16 bytes
+constexpr uint32_t LW_AHEAD = 2048u;         // how far ahead of the position the window is requested
+
+__device__ int decode_block_long(const uint8_t *__restrict__ src, uint32_t comp_len, uint8_t *dst, uint32_t origin, uint32_t win_s)
+{
+    const uint32_t lane = lane_id();
+    uint32_t ip = 0, op = 0;
+    uint32_t issued = 0;                     // stream bytes [.., issued) are in the window or on their way (multiple of LW_CHUNK)
+    uint32_t ready = 0;                      // stream bytes [.., ready) are in the window for sure
+    auto request = [&](uint32_t upto) {      // ask for chunks until `upto` is covered (the payload slot is padded, the buffer has slack behind it)
+        while (issued < upto) {
+            const uint32_t pos = issued + 16u * lane;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(win_s + (pos & (LW - 1u))), "l"(src + pos) : "memory");
+            issued += LW_CHUNK;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto need = [&](uint32_t upto) {         // make sure bytes [ip, upto) can be read from the window
+        if (upto > ready) {
+            if (upto > issued) request((upto + LW_CHUNK - 1u) & ~(LW_CHUNK - 1u));
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            ready = issued;
+        }
+    };
+    auto wbyte = [&](uint32_t pos) -> uint32_t {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(win_s + (pos & (LW - 1u))) : "memory");
+        return v;
+    };
+    // length extension bytes (add bytes while they are 255), 32 at a time out of the window
+    auto length_ext = [&](uint32_t &len) -> bool {
+        for (;;) {
+            need(ip + 32u);
+            const uint32_t p = ip + lane;
+            const uint32_t b = p < comp_len ? wbyte(p) : 0u;          // past the end reads as a terminator and is caught below
+            const uint32_t stop = __ballot_sync(FULL, b != 255u);
+            if (stop == 0) { len += 255u * 32u; ip += 32u; if (ip >= comp_len || len > 0x7f000000u) return false; continue; }
+            const uint32_t f = (uint32_t)__ffs(stop) - 1u;
+            const uint32_t last = __shfl_sync(FULL, b, f);
+            if (ip + f >= comp_len) return false;
+            len += 255u * f + last;
+            ip += f + 1u;
+            return true;
+        }
+    };
+    request(LW_AHEAD);
+    for (;;) {
+        // keep the window LW_AHEAD ahead; never request past what the window can hold beyond the position
+        if (issued < ip + LW_AHEAD && issued + LW_CHUNK <= (ip & ~(LW_CHUNK - 1u)) + LW) request(issued + LW_CHUNK);
+        if (ip >= comp_len) return E_TRUNCATED;
+        need(ip + 4u);
+        const uint32_t token = wbyte(ip);
+        ip += 1u;
+        uint32_t L = token >> 4;
+        if (L == 15u && !length_ext(L)) return E_TRUNCATED;
+        if (L > comp_len - ip) return E_TRUNCATED;
+        if (L > origin - op) return E_OVERFLOW;
+        if (L > 0) warp_copy(dst + op, src + ip, (int64_t)L);
+        ip += L;
+        op += L;
+        if (ip == comp_len) break;                                     // last sequence: literals only
+        if (ip + 2u > comp_len) return E_TRUNCATED;
+        if (ip >= issued) {                                            // a long literal run left the window behind: restart it at the position
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            issued = ready = ip & ~(LW_CHUNK - 1u);
+        }
+        need(ip + 3u);
+        const uint32_t off = wbyte(ip) | (wbyte(ip + 1u) << 8);
+        ip += 2u;
+        uint32_t M = token & 15u;
+        if (M == 15u && !length_ext(M)) return E_TRUNCATED;
+        M += 4u;
+        if (off == 0 || off > op) return E_OFFSET;
+        if (M > origin - op) return E_OVERFLOW;
+        __syncwarp();                                                  // literal bytes visible to the whole warp
+        // every source byte is < op, i.e. already final: the copy is fully parallel even when it overlaps
+        uint8_t *m_dst = dst + op;
+        const uint8_t *m_src = dst + op - off;
+        if (off >= M) {
+            if (M <= 32u) { if (lane < M) m_dst[lane] = __ldcg(m_src + lane); }
+            else for (uint32_t i = lane; i < M; i += 32u) m_dst[i] = __ldcg(m_src + i);
+        } else {
+            for (uint32_t i = lane; i < M; i += 32u) m_dst[i] = __ldcg(m_src + (i % off));
+        }
+        op += M;
+        __syncwarp();
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    return (op == origin && ip == comp_len) ? E_OK : E_SIZE;
+}
+
 // CTAS: resident CTAs per SM the kernel is compiled for (4: 64 registers per thread, 5: 48, 6: 40) -- an A/B axis, option "spec_ctas"
 template <int FUSED, int CTAS>
 __global__ void __launch_bounds__(SPEC_WARPS * 32, CTAS) lz4_decode_spec_kernel(const __grid_constant__ DecodeArgs args, const __grid_constant__ LaneFused F,
@@ -372,6 +475,51 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, CTAS) lz4_decode_spec_kernel(
 }
 
 }  // namespace
+
+namespace {
+// the long-sequence decoder as a kernel of its own (inside the spec kernel its registers spilled the batch loop): same job queue,
+// one warp per block, 8 warps per CTA, the 4 KB window per warp in dynamic shared memory
+__global__ void __launch_bounds__(SPEC_WARPS * 32, 4) lz4_decode_long_kernel(const __grid_constant__ DecodeArgs args, unsigned int *counter)
+{
+    extern __shared__ unsigned char spec_dyn[];
+    const uint32_t win_s = ((smem_addr(spec_dyn) + LW - 1u) & ~(LW - 1u)) + (threadIdx.x >> 5) * LW;
+    const uint32_t lane = lane_id();
+    const long long njobs = (long long)args.ncols * args.nblocks;
+    for (;;) {
+        unsigned int job = 0;
+        if (lane == 0) job = atomicAdd(counter, 1u);
+        job = __shfl_sync(FULL, job, 0);
+        if ((long long)job >= njobs) return;
+        const int c = (int)(job % args.ncols);
+        const int b = args.blk0 + (int)(job / args.ncols);
+        const DecodeCol &col = args.col[c];
+        if (col.skip && col.skip[b]) continue;
+        const uint8_t *src = col.comp + col.comp_off[b];
+        uint8_t *dst = col.out + col.dec_off[b];
+        const uint32_t comp_len = (uint32_t)col.comp_len[b], origin = (uint32_t)col.origin[b];
+        int e;
+        if (origin == 0) e = (comp_len == 1 && src[0] == 0) ? E_OK : E_SIZE;
+        else if (comp_len == 0) e = E_TRUNCATED;
+        else if ((uintptr_t)src & 15u) e = decode_simple(src, comp_len, dst, origin);
+        else e = decode_block_long(src, comp_len, dst, origin, win_s);
+        if (lane == 0) col.status[b] = e;
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+int launch_lz4_decode_long(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit)
+{
+    const long long njobs = (long long)args.ncols * args.nblocks;
+    if (njobs <= 0) return 0;
+    cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream);
+    long long ctas = (njobs + SPEC_WARPS - 1) / SPEC_WARPS;
+    const long long max_ctas = cta_limit > 0 ? cta_limit : (long long)sm_count * 4;
+    if (ctas > max_ctas) ctas = max_ctas;
+    lz4_decode_long_kernel<<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, d_counter);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
 
 int g_spec_ctas = 5;
 int g_spec_prefetch = 0;   // 0: stream groups into L2, 1: + the next group into L1, 2: into L1 directly (option "spec_prefetch")
