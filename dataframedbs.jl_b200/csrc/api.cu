@@ -351,9 +351,9 @@ int sample_flavour(const uint8_t *src, int64_t n, int64_t origin)
         op += M;
         if (op > origin) return -1;
     }
-    if (nseq < 64) return op >= 64 * 24 ? 3 : -1;               // (a few very long sequences: a verdict all the same)
+    if (nseq < 64) return op >= 64 * 48 ? 3 : -1;               // (a few very long sequences: a verdict all the same)
     if (wordform * 100 >= nseq * 97) return 2;
-    if (op >= nseq * 24) return 3;                               // long sequences (>= 24 output bytes on average): the one-sequence-at-a-time decoder with its stream window
+    if (op >= nseq * 48) return 3;                               // long sequences (>= 48 output bytes on average): the one-sequence-at-a-time decoder with its stream window
     return 1;
 }
 

@@ -379,6 +379,18 @@ __device__ int decode_block_long(const uint8_t *__restrict__ src, uint32_t comp_
             return true;
         }
     };
+    // A short match (<= 32 bytes: one byte per lane) is loaded when it is parsed and STORED one sequence later, after the next header
+    // has been parsed: the L2 round trip of its source runs under that parse instead of stalling the warp.  Nothing can observe
+    // the delay: the store is issued before the next sequence writes or loads anything.
+    uint8_t *pend_dst = nullptr;
+    uint32_t pend_len = 0, pend_val = 0;
+    auto flush_pending = [&]() {
+        if (pend_len) {
+            if (lane < pend_len) pend_dst[lane] = (uint8_t)pend_val;
+            pend_len = 0;
+            __syncwarp();
+        }
+    };
     request(LW_AHEAD);
     for (;;) {
         // keep the window LW_AHEAD ahead; never request past what the window can hold beyond the position
@@ -391,7 +403,16 @@ __device__ int decode_block_long(const uint8_t *__restrict__ src, uint32_t comp_
         if (L == 15u && !length_ext(L)) return E_TRUNCATED;
         if (L > comp_len - ip) return E_TRUNCATED;
         if (L > origin - op) return E_OVERFLOW;
-        if (L > 0) warp_copy(dst + op, src + ip, (int64_t)L);
+        flush_pending();
+        if (L > 0) {
+            if (L <= 1024u) {
+                // literals out of the window (they are stream bytes): no round trip to L2
+                need(ip + L);
+                for (uint32_t i = lane; i < L; i += 32u) dst[op + i] = (uint8_t)wbyte(ip + i);
+            } else {
+                warp_copy(dst + op, src + ip, (int64_t)L);
+            }
+        }
         ip += L;
         op += L;
         if (ip == comp_len) break;                                     // last sequence: literals only
@@ -413,15 +434,20 @@ __device__ int decode_block_long(const uint8_t *__restrict__ src, uint32_t comp_
         // every source byte is < op, i.e. already final: the copy is fully parallel even when it overlaps
         uint8_t *m_dst = dst + op;
         const uint8_t *m_src = dst + op - off;
-        if (off >= M) {
-            if (M <= 32u) { if (lane < M) m_dst[lane] = __ldcg(m_src + lane); }
-            else for (uint32_t i = lane; i < M; i += 32u) m_dst[i] = __ldcg(m_src + i);
+        if (M <= 32u) {
+            if (lane < M) pend_val = __ldcg(m_src + (off >= M ? lane : lane % off));
+            pend_dst = m_dst;
+            pend_len = M;
+        } else if (off >= M) {
+            for (uint32_t i = lane; i < M; i += 32u) m_dst[i] = __ldcg(m_src + i);
+            __syncwarp();
         } else {
             for (uint32_t i = lane; i < M; i += 32u) m_dst[i] = __ldcg(m_src + (i % off));
+            __syncwarp();
         }
         op += M;
-        __syncwarp();
     }
+    flush_pending();
     asm volatile("cp.async.wait_all;" ::: "memory");
     return (op == origin && ip == comp_len) ? E_OK : E_SIZE;
 }
