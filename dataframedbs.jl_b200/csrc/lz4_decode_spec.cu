@@ -346,16 +346,20 @@ __device__ int decode_block_long(const uint8_t *__restrict__ src, uint32_t comp_
         while (issued < upto) {
             const uint32_t pos = issued + 16u * lane;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(win_s + (pos & (LW - 1u))), "l"(src + pos) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");        // one group per chunk: chunks complete in order
             issued += LW_CHUNK;
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
     };
     auto need = [&](uint32_t upto) {         // make sure bytes [ip, upto) can be read from the window
         if (upto > ready) {
             if (upto > issued) request((upto + LW_CHUNK - 1u) & ~(LW_CHUNK - 1u));
-            asm volatile("cp.async.wait_all;" ::: "memory");
+            // wait for no more than the chunks that are needed: the youngest ones (requested LW_AHEAD ahead) stay in flight
+            const uint32_t young = (issued - upto) / LW_CHUNK;          // whole chunks behind `upto` that may remain pending
+            if (young >= 3u) { asm volatile("cp.async.wait_group 3;" ::: "memory"); ready = issued - 3u * LW_CHUNK; }
+            else if (young == 2u) { asm volatile("cp.async.wait_group 2;" ::: "memory"); ready = issued - 2u * LW_CHUNK; }
+            else if (young == 1u) { asm volatile("cp.async.wait_group 1;" ::: "memory"); ready = issued - LW_CHUNK; }
+            else { asm volatile("cp.async.wait_group 0;" ::: "memory"); ready = issued; }
             __syncwarp();
-            ready = issued;
         }
     };
     auto wbyte = [&](uint32_t pos) -> uint32_t {
@@ -382,15 +386,19 @@ __device__ int decode_block_long(const uint8_t *__restrict__ src, uint32_t comp_
     // A short match (<= 32 bytes: one byte per lane) is loaded when it is parsed and STORED one sequence later, after the next header
     // has been parsed: the L2 round trip of its source runs under that parse instead of stalling the warp.  Nothing can observe
     // the delay: the store is issued before the next sequence writes or loads anything.
-    uint8_t *pend_dst = nullptr;
-    uint32_t pend_len = 0, pend_val = 0;
-    auto flush_pending = [&]() {
-        if (pend_len) {
-            if (lane < pend_len) pend_dst[lane] = (uint8_t)pend_val;
-            pend_len = 0;
+    // (Two of them are kept: the older one is stored after the next header has been parsed, so a source has two parses and a
+    // literal copy to arrive in.  A match that reads what a pending match has yet to write flushes both first.)
+    uint32_t p0_pos = 0, p0_len = 0, p0_val = 0;       // older pending match: output position, length, this lane's byte
+    uint32_t p1_pos = 0, p1_len = 0, p1_val = 0;       // younger one
+    auto store_older = [&]() {
+        if (p0_len) {
+            if (lane < p0_len) dst[p0_pos + lane] = (uint8_t)p0_val;
             __syncwarp();
         }
+        p0_pos = p1_pos; p0_len = p1_len; p0_val = p1_val;
+        p1_len = 0;
     };
+    auto flush_pending = [&]() { store_older(); store_older(); };
     request(LW_AHEAD);
     for (;;) {
         // keep the window LW_AHEAD ahead; never request past what the window can hold beyond the position
@@ -403,7 +411,7 @@ __device__ int decode_block_long(const uint8_t *__restrict__ src, uint32_t comp_
         if (L == 15u && !length_ext(L)) return E_TRUNCATED;
         if (L > comp_len - ip) return E_TRUNCATED;
         if (L > origin - op) return E_OVERFLOW;
-        flush_pending();
+        store_older();
         if (L > 0) {
             if (L <= 1024u) {
                 // literals out of the window (they are stream bytes): no round trip to L2
@@ -434,15 +442,16 @@ __device__ int decode_block_long(const uint8_t *__restrict__ src, uint32_t comp_
         // every source byte is < op, i.e. already final: the copy is fully parallel even when it overlaps
         uint8_t *m_dst = dst + op;
         const uint8_t *m_src = dst + op - off;
+        // (a source that a pending match has yet to write: store first.  p1 is free here -- store_older moved it to p0.)
+        if (p0_len && op - off < p0_pos + p0_len && op - off + (off >= M ? M : off) > p0_pos) store_older();
         if (M <= 32u) {
-            if (lane < M) pend_val = __ldcg(m_src + (off >= M ? lane : lane % off));
-            pend_dst = m_dst;
-            pend_len = M;
-        } else if (off >= M) {
-            for (uint32_t i = lane; i < M; i += 32u) m_dst[i] = __ldcg(m_src + i);
-            __syncwarp();
+            if (lane < M) p1_val = __ldcg(m_src + (off >= M ? lane : lane % off));
+            p1_pos = op;
+            p1_len = M;
         } else {
-            for (uint32_t i = lane; i < M; i += 32u) m_dst[i] = __ldcg(m_src + (i % off));
+            flush_pending();
+            if (off >= M) for (uint32_t i = lane; i < M; i += 32u) m_dst[i] = __ldcg(m_src + i);
+            else for (uint32_t i = lane; i < M; i += 32u) m_dst[i] = __ldcg(m_src + (i % off));
             __syncwarp();
         }
         op += M;
