@@ -383,48 +383,59 @@ __device__ int decode_block_long(const uint8_t *__restrict__ src, uint32_t comp_
             return true;
         }
     };
-    // A short match (<= 32 bytes: one byte per lane) is loaded when it is parsed and STORED one sequence later, after the next header
-    // has been parsed: the L2 round trip of its source runs under that parse instead of stalling the warp.  Nothing can observe
-    // the delay: the store is issued before the next sequence writes or loads anything.
-    // (Two of them are kept: the older one is stored after the next header has been parsed, so a source has two parses and a
-    // literal copy to arrive in.  A match that reads what a pending match has yet to write flushes both first.)
-    uint32_t p0_pos = 0, p0_len = 0, p0_val = 0;       // older pending match: output position, length, this lane's byte
-    uint32_t p1_pos = 0, p1_len = 0, p1_val = 0;       // younger one
-    auto store_older = [&]() {
-        if (p0_len) {
-            if (lane < p0_len) dst[p0_pos + lane] = (uint8_t)p0_val;
+    // four stream bytes at any position of the window (two aligned words, funnel shift)
+    auto wword = [&](uint32_t pos) -> uint32_t {
+        uint32_t w0, w1;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(win_s + (pos & (LW - 4u))) : "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(win_s + ((pos + 4u) & (LW - 4u))) : "memory");
+        return __funnelshift_r(w0, w1, pos * 8u);
+    };
+    // A short match (<= 32 bytes: one byte per lane) is loaded when it is parsed and STORED two sequences later, after the headers
+    // of the next two have been parsed: the L2 round trip of its source runs under those parses instead of stalling the warp.
+    // Nothing can observe the delay: a pending match is stored before anything reads what it writes (the check below), and
+    // stores of different sequences never overlap.  Two slots that swap roles from one sequence to the next (the loop body is
+    // instantiated twice) -- moving a pending value from a "younger" to an "older" register would wait for its load.
+    struct Pend { uint32_t pos = 0, len = 0, val = 0; };
+    Pend pa, pb;
+    auto store = [&](Pend &p) {
+        if (p.len) {
+            if (lane < p.len) dst[p.pos + lane] = (uint8_t)p.val;
+            p.len = 0;
             __syncwarp();
         }
-        p0_pos = p1_pos; p0_len = p1_len; p0_val = p1_val;
-        p1_len = 0;
     };
-    auto flush_pending = [&]() { store_older(); store_older(); };
-    request(LW_AHEAD);
-    for (;;) {
+    // one sequence; `mine` holds the match of two sequences ago (stored here, then reused), `other` the previous one's.
+    // returns 0: go on, 1: the block's last sequence is done, < 0: -E_*
+    auto step = [&](Pend &mine, Pend &other) -> int {
         // keep the window LW_AHEAD ahead; never request past what the window can hold beyond the position
         if (issued < ip + LW_AHEAD && issued + LW_CHUNK <= (ip & ~(LW_CHUNK - 1u)) + LW) request(issued + LW_CHUNK);
-        if (ip >= comp_len) return E_TRUNCATED;
+        if (ip >= comp_len) return -E_TRUNCATED;
         need(ip + 4u);
         const uint32_t token = wbyte(ip);
         ip += 1u;
         uint32_t L = token >> 4;
-        if (L == 15u && !length_ext(L)) return E_TRUNCATED;
-        if (L > comp_len - ip) return E_TRUNCATED;
-        if (L > origin - op) return E_OVERFLOW;
-        store_older();
+        if (L == 15u && !length_ext(L)) return -E_TRUNCATED;
+        if (L > comp_len - ip) return -E_TRUNCATED;
+        if (L > origin - op) return -E_OVERFLOW;
+        store(mine);
         if (L > 0) {
             if (L <= 1024u) {
-                // literals out of the window (they are stream bytes): no round trip to L2
+                // literals out of the window (they are stream bytes, no round trip to L2): bytes up to the output's next 4-byte
+                // boundary, whole words, the bytes behind the last whole word
                 need(ip + L);
-                for (uint32_t i = lane; i < L; i += 32u) dst[op + i] = (uint8_t)wbyte(ip + i);
+                uint8_t *d = dst + op;
+                const uint32_t head = min((uint32_t)(-(intptr_t)d) & 3u, L), words = (L - head) >> 2, tail0 = head + 4u * words;
+                if (lane < head) d[lane] = (uint8_t)wbyte(ip + lane);
+                for (uint32_t i = lane; i < words; i += 32u) reinterpret_cast<uint32_t *>(d + head)[i] = wword(ip + head + 4u * i);
+                if (lane < L - tail0) d[tail0 + lane] = (uint8_t)wbyte(ip + tail0 + lane);
             } else {
                 warp_copy(dst + op, src + ip, (int64_t)L);
             }
         }
         ip += L;
         op += L;
-        if (ip == comp_len) break;                                     // last sequence: literals only
-        if (ip + 2u > comp_len) return E_TRUNCATED;
+        if (ip == comp_len) return 1;                                  // last sequence: literals only
+        if (ip + 2u > comp_len) return -E_TRUNCATED;
         if (ip >= issued) {                                            // a long literal run left the window behind: restart it at the position
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();
@@ -434,29 +445,40 @@ __device__ int decode_block_long(const uint8_t *__restrict__ src, uint32_t comp_
         const uint32_t off = wbyte(ip) | (wbyte(ip + 1u) << 8);
         ip += 2u;
         uint32_t M = token & 15u;
-        if (M == 15u && !length_ext(M)) return E_TRUNCATED;
+        if (M == 15u && !length_ext(M)) return -E_TRUNCATED;
         M += 4u;
-        if (off == 0 || off > op) return E_OFFSET;
-        if (M > origin - op) return E_OVERFLOW;
-        __syncwarp();                                                  // literal bytes visible to the whole warp
-        // every source byte is < op, i.e. already final: the copy is fully parallel even when it overlaps
-        uint8_t *m_dst = dst + op;
+        if (off == 0 || off > op) return -E_OFFSET;
+        if (M > origin - op) return -E_OVERFLOW;
+        // a source that the previous sequence's pending match has yet to write: store that one first
+        // (source = [op - off, op - off + min(M, off)), pending = [other.pos, other.pos + other.len))
+        if (other.len && off > op - (other.pos + other.len) && off - min(M, off) < op - other.pos) store(other);
+        __syncwarp();                                                  // literal bytes (and stored matches) visible to the whole warp
+        // every source byte is < op, i.e. already final or just stored: the copy is fully parallel even when it overlaps
         const uint8_t *m_src = dst + op - off;
-        // (a source that a pending match has yet to write: store first.  p1 is free here -- store_older moved it to p0.)
-        if (p0_len && op - off < p0_pos + p0_len && op - off + (off >= M ? M : off) > p0_pos) store_older();
         if (M <= 32u) {
-            if (lane < M) p1_val = __ldcg(m_src + (off >= M ? lane : lane % off));
-            p1_pos = op;
-            p1_len = M;
+            if (off >= M) { if (lane < M) mine.val = __ldcg(m_src + lane); }
+            else if (lane < M) mine.val = __ldcg(m_src + lane % off);
+            mine.pos = op;
+            mine.len = M;
         } else {
-            flush_pending();
+            store(other);
+            uint8_t *m_dst = dst + op;
             if (off >= M) for (uint32_t i = lane; i < M; i += 32u) m_dst[i] = __ldcg(m_src + i);
             else for (uint32_t i = lane; i < M; i += 32u) m_dst[i] = __ldcg(m_src + (i % off));
             __syncwarp();
         }
         op += M;
+        return 0;
+    };
+    request(LW_AHEAD);
+    for (;;) {
+        int r = step(pa, pb);
+        if (r == 0) r = step(pb, pa);
+        if (r < 0) return -r;
+        if (r > 0) break;
     }
-    flush_pending();
+    store(pa);
+    store(pb);
     asm volatile("cp.async.wait_all;" ::: "memory");
     return (op == origin && ip == comp_len) ? E_OK : E_SIZE;
 }
