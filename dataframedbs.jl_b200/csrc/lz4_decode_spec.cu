@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, CTAS) lz4_decode_spec_kernel(
 namespace {
 // the long-sequence decoder as a kernel of its own (inside the spec kernel its registers spilled the batch loop): same job queue,
 // one warp per block, 8 warps per CTA, the 4 KB window per warp in dynamic shared memory
-__global__ void __launch_bounds__(SPEC_WARPS * 32, 4) lz4_decode_long_kernel(const __grid_constant__ DecodeArgs args, unsigned int *counter)
+__global__ void __launch_bounds__(SPEC_WARPS * 32, 3) lz4_decode_long_kernel(const __grid_constant__ DecodeArgs args, unsigned int *counter)
 {
     extern __shared__ unsigned char spec_dyn[];
     const uint32_t win_s = ((smem_addr(spec_dyn) + LW - 1u) & ~(LW - 1u)) + (threadIdx.x >> 5) * LW;
@@ -572,7 +572,7 @@ int launch_lz4_decode_long(const DecodeArgs &args, unsigned int *d_counter, int 
     if (njobs <= 0) return 0;
     cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream);
     long long ctas = (njobs + SPEC_WARPS - 1) / SPEC_WARPS;
-    const long long max_ctas = cta_limit > 0 ? cta_limit : (long long)sm_count * 4;
+    const long long max_ctas = cta_limit > 0 ? cta_limit : (long long)sm_count * 3;
     if (ctas > max_ctas) ctas = max_ctas;
     lz4_decode_long_kernel<<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, d_counter);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
