@@ -410,7 +410,7 @@ def main():
     L.dfdb_table_column_stored(t._h, t.getmeta("b").id, C.byref(st_blocks), C.byref(st_bytes))
     # which K1 kernel decoded (the library picks a flavour per column from a token sample at load): the one that decoded the most bytes
     k1 = {}
-    for nm, kern in (("k1_v1", "lz4_decode_kernel"), ("k1_v3", "lz4_decode_v3_kernel"),
+    for nm, kern in (("k1_v1", "lz4_decode_kernel"), ("k1_v3", "lz4_decode_v3_kernel"), ("k1_long", "lz4_decode_long_kernel"),
                      ("k1_lane", "lz4_decode_lane_kernel"), ("k1_spec", "lz4_decode_spec_kernel")):
         k1[kern] = phase(nm)[2]            # algorithmic bytes this kernel decoded
     k1_kernel = max(k1, key=k1.get)
@@ -419,9 +419,8 @@ def main():
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": dec_bytes // max(dec_n, 1), "launches_per_step": dec_n / max(args.steps, 1),
                 "avg_launch_ms": dec_launch_ms, "share_of_step": dec_ms / ms if ms else None,
                 "note": "algorithmic bytes = compressed read + decoded written of the blocks the kernel decodes (column a); "
-                        "the decode is two launches per step (the first part at full width, then the last part on half the resident CTAs "
-                        "while the scan of the first part runs beside it): achieved = bytes of "
-                        "both / time from the start of the first to the end of the second; "
+                        "achieved = those bytes / the decode phase's device time (CUDA events around the launch; when a decode is split in "
+                        "two launches, from the start of the first to the end of the second); "
                         f"column b is {st_blocks.value} stored (incompressible) blocks = {st_bytes.value} bytes that the scan reads in place, no copy"}
     scan_achieved = (con_bytes / max(args.steps, 1)) / ((con_ms / max(args.steps, 1)) / 1e3) / 1e9 if con_ms > 0 else 0.0
     hbm_result = res
