@@ -426,6 +426,7 @@ __device__ int decode_block_long(const uint8_t *__restrict__ src, uint32_t comp_
                 uint8_t *d = dst + op;
                 const uint32_t head = min((uint32_t)(-(intptr_t)d) & 3u, L), words = (L - head) >> 2, tail0 = head + 4u * words;
                 if (lane < head) d[lane] = (uint8_t)wbyte(ip + lane);
+#pragma unroll 1
                 for (uint32_t i = lane; i < words; i += 32u) reinterpret_cast<uint32_t *>(d + head)[i] = wword(ip + head + 4u * i);
                 if (lane < L - tail0) d[tail0 + lane] = (uint8_t)wbyte(ip + tail0 + lane);
             } else {
@@ -463,8 +464,13 @@ __device__ int decode_block_long(const uint8_t *__restrict__ src, uint32_t comp_
         } else {
             store(other);
             uint8_t *m_dst = dst + op;
-            if (off >= M) for (uint32_t i = lane; i < M; i += 32u) m_dst[i] = __ldcg(m_src + i);
-            else for (uint32_t i = lane; i < M; i += 32u) m_dst[i] = __ldcg(m_src + (i % off));
+            if (off >= M) {
+#pragma unroll 2
+                for (uint32_t i = lane; i < M; i += 32u) m_dst[i] = __ldcg(m_src + i);
+            } else {
+#pragma unroll 1
+                for (uint32_t i = lane; i < M; i += 32u) m_dst[i] = __ldcg(m_src + (i % off));
+            }
             __syncwarp();
         }
         op += M;
