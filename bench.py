@@ -410,7 +410,7 @@ def main():
     L.dfdb_table_column_stored(t._h, t.getmeta("b").id, C.byref(st_blocks), C.byref(st_bytes))
     # which K1 kernel decoded (the library picks a flavour per column from a token sample at load): the one that decoded the most bytes
     k1 = {}
-    for nm, kern in (("k1_v1", "lz4_decode_kernel"), ("k1_v3", "lz4_decode_v3_kernel"), ("k1_long", "lz4_decode_long_kernel"),
+    for nm, kern in (("k1_v1", "lz4_decode_kernel"), ("k1_v3", "lz4_decode_v3_kernel"), ("k1_long", "lz4_decode_long_kernel"), ("k1_bytes", "lz4_decode_bytes_kernel"),
                      ("k1_lane", "lz4_decode_lane_kernel"), ("k1_spec", "lz4_decode_spec_kernel")):
         k1[kern] = phase(nm)[2]            # algorithmic bytes this kernel decoded
     k1_kernel = max(k1, key=k1.get)

@@ -52,7 +52,7 @@ struct Runtime {
     int64_t no_fused = 0;
     int64_t no_decode_fused = 1;                                    // 0: fold predicate + aggregate into the decode kernel (measured: no faster than decode + scan, see lz4_decode_spec.cu)
     int64_t no_tma = 0;
-    int64_t lz4_flavour = 0;  // K1 flavour: 0 = per column from a token sample at load, 2 (and 1, a removed kernel's number) = walker / consumer decoder (v3), 3 = lane-per-block decoder, 4 = warp-per-block decoder with verified token runs (spec), 5 = warp-per-block decoder for long sequences
+    int64_t lz4_flavour = 0;  // K1 flavour: 0 = per column from a token sample at load, 2 (and 1, a removed kernel's number) = walker / consumer decoder (v3), 3 = lane-per-block decoder, 4 = warp-per-block decoder with verified token runs (spec), 5 = warp-per-block decoder for long sequences, 6 = warp-per-block decoder for bare-match byte streams
     int64_t no_overlap = 0;   // do not run the scan of the decoded part of a shard beside the decode of its last part
     int64_t no_alias = 0;     // copy stored (incompressible) blocks like any other block instead of referencing them in place
     int64_t no_decode_split = 0;   // 1: columns of the walker / consumer flavour always share a launch (A/B)
@@ -65,7 +65,7 @@ struct Runtime {
     std::vector<PhaseRec> recs;
     double acc_ms[PH_COUNT] = {0};
     int64_t acc_launches[PH_COUNT] = {0}, acc_bytes[PH_COUNT] = {0};
-    int64_t k1_launches[5] = {0}, k1_bytes[5] = {0};   // decode launches / algorithmic bytes per K1 kernel (v1, v2, v3, lane, spec): dfdb_profile_get("k1_<name>")
+    int64_t k1_launches[6] = {0}, k1_bytes[6] = {0};   // decode launches / algorithmic bytes per K1 kernel (v1, v2, v3, lane, spec): dfdb_profile_get("k1_<name>")
 } rt;
 
 #define CUDA_TRY(expr)                                                                                         \
@@ -314,6 +314,7 @@ int launch_decode(const DecodeArgs &a, int general, cudaStream_t stream = nullpt
     }
     if (fuse) return 1;
     if (rt.lz4_flavour == 5 || (rt.lz4_flavour == 0 && general == 3)) { count(1); return launch_lz4_decode_long(a, counter, rt.sm_count, stream, cta_limit); }
+    if (rt.lz4_flavour == 6 || (rt.lz4_flavour == 0 && general == 4)) { count(5); return launch_lz4_decode_bytes(a, counter, rt.sm_count, stream, cta_limit); }
     count(2);     // (lz4_flavour 1 used to select a second walker / consumer kernel tuned for word-regular columns; it is an alias of 2 now)
     return launch_lz4_decode_v3(a, counter, rt.sm_count, stream, cta_limit);
 }
@@ -321,10 +322,11 @@ int launch_decode(const DecodeArgs &a, int general, cudaStream_t stream = nullpt
 // Which K1 flavour suits a column: walk the token stream of one compressed block on the host (done once, at load).
 // 2 = the warp-per-block decoder with verified runs (nearly every sequence is plain -- no length extensions -- and makes
 // whole aligned output words), 3 = the warp-per-block decoder for long sequences (Union{Float64,Missing} bodies, decimal
-// strings), 1 = the walker / consumer decoder (everything else).  Returns -1 when the block gives no verdict.
+// strings), 4 = the warp-per-block decoder for bare-match byte streams (strings of few distinct values), 1 = the walker /
+// consumer decoder (everything else).  Returns -1 when the block gives no verdict.
 int sample_flavour(const uint8_t *src, int64_t n, int64_t origin)
 {
-    int64_t ip = 0, op = 0, nseq = 0, wordform = 0;
+    int64_t ip = 0, op = 0, nseq = 0, wordform = 0, bare = 0;
     while (ip < n && nseq < 20000) {
         const uint32_t t = src[ip++];
         int64_t L = t >> 4;
@@ -348,11 +350,13 @@ int sample_flavour(const uint8_t *src, int64_t n, int64_t origin)
         // what the spec decoder turns into whole output words without walking: <= 4 literal bytes + match = 8 bytes (or a plain
         // match of 16), offset a multiple of 8, at an aligned output position
         if (plain && L <= 4 && ((off | (op - L)) & 7) == 0 && (L + M == 8 || (L == 0 && M == 16))) wordform++;
+        if (plain && L == 0) bare++;                                // a bare match: 3 stream bytes, what the byte-stream decoder verifies in parallel
         op += M;
         if (op > origin) return -1;
     }
     if (nseq < 64) return op >= 64 * 48 ? 3 : -1;               // (a few very long sequences: a verdict all the same)
     if (wordform * 100 >= nseq * 97) return 2;
+    if (bare * 100 >= nseq * 97) return 4;                       // match-only byte streams (strings of few distinct values)
     if (op >= nseq * 48) return 3;                               // long sequences (>= 48 output bytes on average): the one-sequence-at-a-time decoder with its stream window
     return 1;
 }
@@ -578,7 +582,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
         }
         if (b1 <= b0) continue;
         // columns of one flavour share a launch
-        for (int general = 0; general < 4; general++) {
+        for (int general = 0; general < 5; general++) {
           std::vector<Column *> grp;
           for (Column *c : todo) {
               if (eff_of(c) != general) continue;
@@ -1419,9 +1423,9 @@ int32_t dfdb_profile_get(const char *phase, double *total_ms, int64_t *launches,
             if (bytes) *bytes = rt.acc_bytes[i];
             return DFDB_OK;
         }
-    // "k1_v1" / "k1_long" / "k1_v3" / "k1_lane" / "k1_spec": decode launches and bytes per K1 kernel since the last reset
-    static const char *k1_names[5] = {"k1_v1", "k1_long", "k1_v3", "k1_lane", "k1_spec"};   // (slot 1 was a removed kernel's)
-    for (int i = 0; i < 5; i++)
+    // "k1_v1" / "k1_long" / "k1_v3" / "k1_lane" / "k1_spec" / "k1_bytes": decode launches and bytes per K1 kernel since the last reset
+    static const char *k1_names[6] = {"k1_v1", "k1_long", "k1_v3", "k1_lane", "k1_spec", "k1_bytes"};   // (slot 1 was a removed kernel's)
+    for (int i = 0; i < 6; i++)
         if (strcmp(phase, k1_names[i]) == 0) {
             if (total_ms) *total_ms = 0;
             if (launches) *launches = rt.k1_launches[i];
@@ -1597,7 +1601,7 @@ int32_t dfdb_table_load(dfdb_table *t, const int64_t *col_ids, int32_t n, int32_
         if (cpos > prev_end) memset(c->h_comp + prev_end, 0, (size_t)(cpos - prev_end));
         // K1 flavour of the column: first, middle and last block vote (stored blocks are never decoded and abstain)
         {
-            int votes[4] = {0, 0, 0, 0};
+            int votes[5] = {0, 0, 0, 0, 0};
             const int64_t cand[3] = {0, nb / 2, nb - 1};
             for (int k = 0; k < 3 && nb > 0; k++) {
                 const int64_t b = cand[k];
@@ -1605,7 +1609,8 @@ int32_t dfdb_table_load(dfdb_table *t, const int64_t *col_ids, int32_t n, int32_
                 const int v = sample_flavour(c->h_comp + comp_off[(size_t)b], comp_len[(size_t)b], origin[(size_t)b]);
                 if (v >= 0) votes[v]++;
             }
-            c->lz4_general = votes[2] > votes[0] + votes[1] + votes[3] ? 2 : (votes[3] > votes[0] + votes[1] + votes[2] ? 3 : 1);
+            c->lz4_general = 1;
+            for (int f = 2; f <= 4; f++) if (2 * votes[f] > votes[0] + votes[1] + votes[2] + votes[3] + votes[4]) c->lz4_general = f;
             // (a Union{T,Missing} body starts with its incompressible bitmap -- a long literal run the verified-run decoder takes one
             //  sequence at a time; measured slower than the walker / consumer decoder there: 6.7 against 5.3 ms for 200M Union{Int64,Missing} rows)
             if (c->lz4_general == 2 && c->type.nullable) c->lz4_general = 1;

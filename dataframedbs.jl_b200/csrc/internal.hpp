@@ -79,7 +79,8 @@ struct Column {
     int64_t stored_blocks = 0;
     int lz4_general = 1;             // K1 flavour, decided at load from a token sample: 1 = walker / consumer decoder (v3),
                                      // 2 = warp per block with verified runs (spec: nearly every sequence is one aligned word),
-                                     // 3 = warp per block, one sequence at a time through a stream window (long sequences)
+                                     // 3 = warp per block, one sequence at a time through a stream window (long sequences),
+                                     // 4 = warp per block, bare-match byte streams
     int32_t *d_str_off = nullptr;    // String columns: per-row char offset inside the block's char area
     bool str_off_valid = false;
     std::vector<int64_t> h_dec_off, h_comp_off;

@@ -31,6 +31,7 @@ constexpr int LZ4_SLOTS_PER_SM = 60;   // column blocks one decoder CTA keeps in
 int launch_lz4_decode_v3(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit = 0);
 struct LaneFused;
 int launch_lz4_decode_long(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit = 0);   // warp per block, one sequence at a time, headers parsed out of a shared-memory window of the stream (long-sequence columns)
+int launch_lz4_decode_bytes(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit = 0);  // warp per block, bare-match byte streams: verified token positions, byte copies by pointer jumping (lz4_decode_bytes.cu)
 extern int g_spec_prefetch;   // spec decoder: how far the stream is prefetched (0: L2, 1: + next group into L1, 2: L1)
 extern int g_spec_ctas;   // resident CTAs per SM of the spec decoder (4..6; option "spec_ctas")
 int launch_lz4_decode_spec(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit = 0,

@@ -1,0 +1,188 @@
+// lz4_decode_bytes.cu -- K1 for match-only byte streams (String columns of few distinct values): one warp per column block,
+// token positions VERIFIED instead of walked, byte-granular copies resolved by pointer jumping.
+//
+// Replaces read_block's LZ4_decompress_safe call (/root/reference/src/io/BlockStreams.jl:101-119) for bodies such as the
+// `brand` strings of the reference's docs: after the first few hundred bytes LZ4 emits no literals at all -- 99.9 % of the
+// sequences are a bare match (token 0x0M, two offset bytes), i.e. exactly 3 stream bytes -- so, as in lz4_decode_spec.cu,
+// token k of a run sits at p0 + 3k and every lane can check its own.  What differs from the word decoder: the matches are
+// 4..18 bytes at any offset, mostly a few dozen bytes back, so output positions are a prefix sum over the match lengths and
+// most sources lie INSIDE the batch.  A batch therefore lays out one int per output byte, P[j] = the byte it copies (an
+// earlier byte of the batch, or -distance for a byte before the batch), collapses the chains by pointer jumping in shared
+// memory (P[j] = P[P[j]] until every entry is negative: O(log) rounds, every lane on its own bytes), and then every byte
+// fetches its root from the warp's ring of recent output (shared memory) or, older than that, from global memory (L2).
+// Anything that is not a bare match ends the batch and is decoded by the whole warp (decode_one_sequence).
+//
+// Memory-safe on any input (every access bounds-checked, per-block status); the accept / reject verdict of damaged streams is
+// the lane decoder's, taken at load (api.cu).  Algorithmic bytes per block (roofline): compressed bytes read + origin bytes written.
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+#include "lz4_common.cuh"
+
+namespace dfdb {
+namespace {
+
+using namespace lz4;
+
+constexpr int BY_WARPS = 8;
+constexpr uint32_t BY_RING = 4096;                   // bytes of recent output per warp (a power of two)
+constexpr uint32_t BY_MAXT = 32 * 18;                // output bytes of a batch: 32 matches of at most 18 bytes
+constexpr uint32_t BY_NEAR = BY_RING - BY_MAXT - 64; // a source at most this far back is read from the ring (this batch's writes stay off it)
+constexpr uint32_t BY_WARP_SMEM = BY_RING + 4 * BY_MAXT;     // ring + P
+constexpr uint32_t BY_SMEM = BY_WARPS * BY_WARP_SMEM + BY_RING;   // + alignment slack
+
+__device__ __forceinline__ uint32_t ldg_u32(const uint8_t *p) { return __ldg(reinterpret_cast<const unsigned int *>(p)); }
+// the 4 stream bytes at tp (two aligned words; payload buffers carry slack behind the last block)
+__device__ __forceinline__ uint32_t load_stream4(const uint8_t *__restrict__ src, uint32_t tp)
+{
+    const uint8_t *a = src + (tp & ~3u);
+    return __funnelshift_r(ldg_u32(a), ldg_u32(a + 4), tp * 8u);
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// one block, whole warp; returns E_*.  ring_s: this warp's ring (BY_RING aligned), P behind it.
+__device__ int decode_block_bytes(const uint8_t *__restrict__ src, uint32_t comp_len, uint8_t *dst, uint32_t origin, uint32_t ring_s)
+{
+    uint32_t lane = lane_id();
+    asm volatile("" : "+r"(lane));
+    const uint32_t P_s = ring_s + BY_RING;
+    uint32_t ip = 0, op = 0;
+    bool done = false;
+    uint32_t ring_from = 0;                  // output bytes >= this one (and within the ring's reach) are in the ring
+    // matches of the fast path never write the block's last 12 bytes (the end-of-block rules stay with the one-sequence path),
+    // and the fast path needs 3 * 32 + 8 stream bytes ahead
+    const uint32_t lim_b = origin >= 12u ? origin - 12u : 0u;
+    int32_t ip_lim = comp_len >= 3u * 32u + 8u ? (int32_t)(comp_len - (3u * 32u + 8u)) : -1;
+    asm volatile("" : "+r"(ip_lim));
+    if (lane < 8u) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 128u * lane));
+    uint32_t tp = 3u * lane;
+    uint32_t x = load_stream4(src, tp);
+    while (!done) {
+        bool batch = false;
+        if ((int32_t)ip <= ip_lim) {
+            const uint32_t tok = x & 0xffu, off = (x >> 8) & 0xffffu;
+            const uint32_t M = (tok & 15u) + 4u;
+            const bool shape = (tok & 0xf0u) == 0 && (tok & 15u) != 15u && off != 0;
+            const uint32_t bad0 = ~__ballot_sync(FULL, shape);
+            const uint32_t n0 = bad0 ? (uint32_t)__ffs(bad0) - 1u : 32u;
+            const uint32_t Mk = lane < n0 ? M : 0u;
+            uint32_t inc = Mk;                                          // inclusive prefix sum of the match lengths
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, inc, d);
+                if ((int)lane >= d) inc += t;
+            }
+            const uint32_t o = inc - Mk;                                // where this lane's match starts in the batch
+            const bool ok = lane < n0 && off <= op + o && op + inc <= lim_b;
+            const uint32_t bad = ~__ballot_sync(FULL, ok);
+            const uint32_t n = bad ? (uint32_t)__ffs(bad) - 1u : 32u;
+            if (n > 0) {
+                const uint32_t T = __shfl_sync(FULL, inc, n - 1u);      // output bytes of the batch
+                const uint32_t nip = ip + 3u * n;
+                tp += 3u * n;
+                const uint32_t nx = load_stream4(src, tp);              // the next batch's bytes travel while this one is resolved
+                if ((nip ^ ip) >> 7) { if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (((nip >> 7) + 8u) << 7))); }
+                // ---- lay out the batch: P[j] = index of the batch byte that byte j copies, or -(distance back from the batch start) ----
+                if (lane < n) {
+                    const int rel = (int)o - (int)off;                  // source of the match's first byte, relative to the batch start
+                    const uint32_t a = P_s + 4u * o;
+                    for (uint32_t i = 0; i < M; i++) sts_s32(a + 4u * i, rel + (int)i);
+                }
+                __syncwarp();
+                // ---- collapse the chains: every byte ends up pointing before the batch ----
+                for (;;) {
+                    bool more = false;
+                    for (uint32_t j = lane; j < T; j += 32u) {
+                        const int p = lds_s32(P_s + 4u * j);
+                        if (p >= 0) {
+                            const int q = lds_s32(P_s + 4u * (uint32_t)p);
+                            sts_s32(P_s + 4u * j, q);
+                            more = more || q >= 0;
+                        }
+                    }
+                    __syncwarp();
+                    if (!__any_sync(FULL, more)) break;
+                }
+                // ---- fetch the roots, write the bytes (global memory and the ring) ----
+                for (uint32_t j = lane; j < T; j += 32u) {
+                    const uint32_t back = (uint32_t)(-lds_s32(P_s + 4u * j));     // 1 .. 65535 bytes before the batch start
+                    const uint32_t a = op - back;
+                    uint32_t b;
+                    if (back <= BY_NEAR && a >= ring_from) b = lds_u8(ring_s + (a & (BY_RING - 1u)));
+                    else b = __ldcg(dst + a);
+                    dst[op + j] = (uint8_t)b;
+                    sts_u8(ring_s + ((op + j) & (BY_RING - 1u)), b);
+                }
+                __syncwarp();
+                ip = nip;
+                op += T;
+                x = nx;
+                batch = true;
+            }
+        }
+        if (!batch) {
+            // ---- anything else: one sequence, whole warp ----
+            int64_t ip64 = ip, op64 = op;
+            const int e = decode_one_sequence(src, comp_len, dst, origin, ip64, op64, done);
+            if (e) return e;
+            ip = (uint32_t)ip64;
+            op = (uint32_t)op64;
+            ring_from = op;                                             // (what this path wrote is in global memory only)
+            tp = ip + 3u * lane;
+            x = load_stream4(src, tp);
+        }
+    }
+    return (op == origin && ip == comp_len) ? E_OK : E_SIZE;
+}
+
+__global__ void __launch_bounds__(BY_WARPS * 32, 4) lz4_decode_bytes_kernel(const __grid_constant__ DecodeArgs args, unsigned int *counter)
+{
+    extern __shared__ unsigned char by_dyn[];
+    const uint32_t ring_s = ((smem_addr(by_dyn) + BY_RING - 1u) & ~(BY_RING - 1u)) + (threadIdx.x >> 5) * BY_WARP_SMEM;
+    const uint32_t lane = lane_id();
+    const long long njobs = (long long)args.ncols * args.nblocks;
+    for (;;) {
+        unsigned int job = 0;
+        if (lane == 0) job = atomicAdd(counter, 1u);
+        job = __shfl_sync(FULL, job, 0);
+        if ((long long)job >= njobs) return;
+        const int c = (int)(job % args.ncols);
+        const int b = args.blk0 + (int)(job / args.ncols);
+        const DecodeCol &col = args.col[c];
+        if (col.skip && col.skip[b]) continue;
+        const uint8_t *src = col.comp + col.comp_off[b];
+        uint8_t *dst = col.out + col.dec_off[b];
+        const uint32_t comp_len = (uint32_t)col.comp_len[b], origin = (uint32_t)col.origin[b];
+        int e;
+        if (origin == 0) e = (comp_len == 1 && src[0] == 0) ? E_OK : E_SIZE;
+        else if (comp_len == 0) e = E_TRUNCATED;
+        else if ((uintptr_t)src & 3u) e = decode_simple(src, comp_len, dst, origin);
+        else e = decode_block_bytes(src, comp_len, dst, origin, ring_s);
+        if (lane == 0) col.status[b] = e;
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+int launch_lz4_decode_bytes(const DecodeArgs &args, unsigned int *d_counter, int sm_count, cudaStream_t stream, int cta_limit)
+{
+    const long long njobs = (long long)args.ncols * args.nblocks;
+    if (njobs <= 0) return 0;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(lz4_decode_bytes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BY_SMEM) != cudaSuccess) return 1;
+        configured = true;
+    }
+    cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream);
+    long long ctas = (njobs + BY_WARPS - 1) / BY_WARPS;
+    const long long max_ctas = cta_limit > 0 ? cta_limit : (long long)sm_count * 4;
+    if (ctas > max_ctas) ctas = max_ctas;
+    lz4_decode_bytes_kernel<<<(unsigned int)ctas, BY_WARPS * 32, BY_SMEM, stream>>>(args, d_counter);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace dfdb

@@ -131,7 +131,7 @@ def test_golden_tables_hold_the_raw_data(oracle):
 # ---- GPU: the CUDA path against the same files ----------------------------------------------------------------
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("flavour", [2, 4, 5], ids=["walker_consumer", "verified_runs", "long_sequences"])
+@pytest.mark.parametrize("flavour", [2, 4, 5, 6], ids=["walker_consumer", "verified_runs", "long_sequences", "byte_streams"])
 def test_gpu_codec_decodes_liblz4_streams(flavour):
     _capi.init(0)
     L = _capi.lib()

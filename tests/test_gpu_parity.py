@@ -84,6 +84,8 @@ def _set_variant(variant):
         _capi.check(L.dfdb_set_option(b"lz4_flavour", 3))
     elif variant == "long":           # warp per block, one sequence at a time, headers parsed out of a shared-memory window of the stream
         _capi.check(L.dfdb_set_option(b"lz4_flavour", 5))
+    elif variant == "bytes":          # warp per block, bare-match byte streams: verified positions, byte copies by pointer jumping
+        _capi.check(L.dfdb_set_option(b"lz4_flavour", 6))
     elif variant == "spec":           # warp per block, plain token runs verified in parallel
         _capi.check(L.dfdb_set_option(b"lz4_flavour", 4))
     elif variant == "lane_hot":       # the lane-per-block decoder on the hot-step schedule of word-regular columns
@@ -93,7 +95,7 @@ def _set_variant(variant):
         _capi.check(L.dfdb_set_option(variant.encode(), 1))
 
 
-@pytest.mark.parametrize("variant", ["spec", "long", "lane", "lane_hot", "v3", "lz4_v1", "lz4_simple"], ids=["verified_runs", "long_sequences", "lane_per_block", "lane_hot_steps", "walker_consumer", "warp_per_block", "sequential"])
+@pytest.mark.parametrize("variant", ["spec", "long", "bytes", "lane", "lane_hot", "v3", "lz4_v1", "lz4_simple"], ids=["verified_runs", "long_sequences", "byte_streams", "lane_per_block", "lane_hot_steps", "walker_consumer", "warp_per_block", "sequential"])
 def test_lz4_decode_matches_reference_codec(oracle, variant):
     """read_block BlockStreams.jl:101-119: decoded bytes are determined by the LZ4 block format."""
     bodies = _bodies(oracle)
@@ -110,7 +112,7 @@ def test_lz4_decode_matches_reference_codec(oracle, variant):
         assert got[i] == bodies[k], f"decoded bytes differ for {k} (first diff at {next(j for j in range(len(got[i])) if got[i][j] != bodies[k][j])})"
 
 
-@pytest.mark.parametrize("variant", ["spec", "long", "lane", "lane_hot", "v3"], ids=["verified_runs", "long_sequences", "lane_per_block", "lane_hot_steps", "walker_consumer"])
+@pytest.mark.parametrize("variant", ["spec", "long", "bytes", "lane", "lane_hot", "v3"], ids=["verified_runs", "long_sequences", "byte_streams", "lane_per_block", "lane_hot_steps", "walker_consumer"])
 def test_lz4_decode_many_small_blocks(oracle, variant):
     """More blocks than the persistent decoder has slots (148 SMs x 87), ragged sizes, every body kind: slots are
     reused, rings wrap, windows re-base after long literal / match runs."""
@@ -136,7 +138,7 @@ def test_lz4_decode_many_small_blocks(oracle, variant):
     assert not bad, f"{len(bad)} of {len(idx)} blocks differ, first: block {bad[0]} (pool {idx[bad[0]]}, origin {origins[bad[0]]}, status {status[bad[0]]})"
 
 
-@pytest.mark.parametrize("variant", ["spec", "long", "lane", "lane_hot", "v3"], ids=["verified_runs", "long_sequences", "lane_per_block", "lane_hot_steps", "walker_consumer"])
+@pytest.mark.parametrize("variant", ["spec", "long", "bytes", "lane", "lane_hot", "v3"], ids=["verified_runs", "long_sequences", "byte_streams", "lane_per_block", "lane_hot_steps", "walker_consumer"])
 def test_lz4_decode_rejects_corrupt_blocks(oracle, variant):
     """@assert size == sizes.origin "decompression error" (BlockStreams.jl:112)"""
     body = np.random.default_rng(3).integers(1, 101, 4096).astype(np.int64).tobytes()
@@ -156,7 +158,7 @@ def test_lz4_decode_rejects_corrupt_blocks(oracle, variant):
             oracle.lz4_decompress(blk, org)
 
 
-@pytest.mark.parametrize("variant", ["spec", "long", "lane", "lane_hot", "v3"], ids=["verified_runs", "long_sequences", "lane_per_block", "lane_hot_steps", "walker_consumer"])
+@pytest.mark.parametrize("variant", ["spec", "long", "bytes", "lane", "lane_hot", "v3"], ids=["verified_runs", "long_sequences", "byte_streams", "lane_per_block", "lane_hot_steps", "walker_consumer"])
 def test_lz4_decode_fuzzed_streams(oracle, variant):
     """LZ4_decompress_safe contract on damaged streams (@assert size == sizes.origin, BlockStreams.jl:110-112): no crash, no
     out-of-bounds write, a stream is refused exactly when the CPU codec refuses it, and an accepted one decodes to the same
