@@ -128,9 +128,18 @@ __device__ int decode_block_bytes(const uint8_t *__restrict__ src, uint32_t comp
             int64_t ip64 = ip, op64 = op;
             const int e = decode_one_sequence(src, comp_len, dst, origin, ip64, op64, done);
             if (e) return e;
+            const uint32_t op_was = op;
             ip = (uint32_t)ip64;
             op = (uint32_t)op64;
-            ring_from = op;                                             // (what this path wrote is in global memory only)
+            // what this path wrote is in global memory only: a short sequence (the usual case: a length extension, a literal or two)
+            // is copied into the ring at once -- one round trip to L2 here instead of one per source byte in the batches that
+            // follow --, a long one restarts the ring
+            if (op - op_was <= 128u) {
+                for (uint32_t a = op_was + lane; a < op; a += 32u) sts_u8(ring_s + (a & (BY_RING - 1u)), __ldcg(dst + a));
+                __syncwarp();
+            } else {
+                ring_from = op;
+            }
             tp = ip + 3u * lane;
             x = load_stream4(src, tp);
         }
