@@ -26,7 +26,8 @@ using namespace lz4;
 
 constexpr int BY_WARPS = 8;
 constexpr uint32_t BY_RING = 4096;                   // bytes of recent output per warp (a power of two)
-constexpr uint32_t BY_MAXT = 32 * 18;                // output bytes of a batch: 32 matches of at most 18 bytes
+constexpr uint32_t BY_CLOSE_MAX = 82;                // longest closing match taken inside a batch (19 + one extension byte <= 63)
+constexpr uint32_t BY_MAXT = 31 * 18 + BY_CLOSE_MAX;  // output bytes of a batch: bare matches of at most 18 bytes and one closing match
 constexpr uint32_t BY_NEAR = BY_RING - BY_MAXT - 64; // a source at most this far back is read from the ring (this batch's writes stay off it)
 constexpr uint32_t BY_WARP_SMEM = BY_RING + 4 * BY_MAXT;     // ring + P
 constexpr uint32_t BY_SMEM = BY_WARPS * BY_WARP_SMEM + BY_RING;   // + alignment slack
@@ -55,7 +56,7 @@ __device__ int decode_block_bytes(const uint8_t *__restrict__ src, uint32_t comp
     // matches of the fast path never write the block's last 12 bytes (the end-of-block rules stay with the one-sequence path),
     // and the fast path needs 3 * 32 + 8 stream bytes ahead
     const uint32_t lim_b = origin >= 12u ? origin - 12u : 0u;
-    int32_t ip_lim = comp_len >= 3u * 32u + 8u ? (int32_t)(comp_len - (3u * 32u + 8u)) : -1;
+    int32_t ip_lim = comp_len >= 3u * 32u + 12u ? (int32_t)(comp_len - (3u * 32u + 12u)) : -1;
     asm volatile("" : "+r"(ip_lim));
     if (lane < 8u) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 128u * lane));
     uint32_t tp = 3u * lane;
@@ -68,7 +69,12 @@ __device__ int decode_block_bytes(const uint8_t *__restrict__ src, uint32_t comp
             const bool shape = (tok & 0xf0u) == 0 && (tok & 15u) != 15u && off != 0;
             const uint32_t bad0 = ~__ballot_sync(FULL, shape);
             const uint32_t n0 = bad0 ? (uint32_t)__ffs(bad0) - 1u : 32u;
-            const uint32_t Mk = lane < n0 ? M : 0u;
+            // the sequence that ends the run may still be a match without literals whose length takes ONE extension byte (19 .. 82
+            // bytes: two brand names in a row): 4 stream bytes, and its lane has them.  It closes the batch.
+            const uint32_t ext = x >> 24;
+            const bool closing = lane == n0 && (tok & 0xf0u) == 0 && (tok & 15u) == 15u && off != 0 && ext <= BY_CLOSE_MAX - 19u;
+            const uint32_t ncl = __ballot_sync(FULL, closing) ? 1u : 0u;
+            const uint32_t Mk = lane < n0 ? M : (closing ? 19u + ext : 0u);
             uint32_t inc = Mk;                                          // inclusive prefix sum of the match lengths
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -76,20 +82,21 @@ __device__ int decode_block_bytes(const uint8_t *__restrict__ src, uint32_t comp
                 if ((int)lane >= d) inc += t;
             }
             const uint32_t o = inc - Mk;                                // where this lane's match starts in the batch
-            const bool ok = lane < n0 && off <= op + o && op + inc <= lim_b;
+            const bool ok = lane < n0 + ncl && off <= op + o && op + inc <= lim_b;
             const uint32_t bad = ~__ballot_sync(FULL, ok);
-            const uint32_t n = bad ? (uint32_t)__ffs(bad) - 1u : 32u;
+            const uint32_t n = bad ? (uint32_t)__ffs(bad) - 1u : 32u;   // sequences of the batch (the closing one included)
             if (n > 0) {
                 const uint32_t T = __shfl_sync(FULL, inc, n - 1u);      // output bytes of the batch
-                const uint32_t nip = ip + 3u * n;
-                tp += 3u * n;
+                const uint32_t adv = 3u * n + (n > n0 ? 1u : 0u);       // (the closing sequence is 4 stream bytes)
+                const uint32_t nip = ip + adv;
+                tp += adv;
                 const uint32_t nx = load_stream4(src, tp);              // the next batch's bytes travel while this one is resolved
                 if ((nip ^ ip) >> 7) { if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (((nip >> 7) + 8u) << 7))); }
                 // ---- lay out the batch: P[j] = index of the batch byte that byte j copies, or -(distance back from the batch start) ----
                 if (lane < n) {
                     const int rel = (int)o - (int)off;                  // source of the match's first byte, relative to the batch start
                     const uint32_t a = P_s + 4u * o;
-                    for (uint32_t i = 0; i < M; i++) sts_s32(a + 4u * i, rel + (int)i);
+                    for (uint32_t i = 0; i < Mk; i++) sts_s32(a + 4u * i, rel + (int)i);
                 }
                 __syncwarp();
                 // ---- collapse the chains: every byte ends up pointing before the batch ----
@@ -147,7 +154,7 @@ __device__ int decode_block_bytes(const uint8_t *__restrict__ src, uint32_t comp
     return (op == origin && ip == comp_len) ? E_OK : E_SIZE;
 }
 
-__global__ void __launch_bounds__(BY_WARPS * 32, 4) lz4_decode_bytes_kernel(const __grid_constant__ DecodeArgs args, unsigned int *counter)
+__global__ void __launch_bounds__(BY_WARPS * 32, 3) lz4_decode_bytes_kernel(const __grid_constant__ DecodeArgs args, unsigned int *counter)
 {
     extern __shared__ unsigned char by_dyn[];
     const uint32_t ring_s = ((smem_addr(by_dyn) + BY_RING - 1u) & ~(BY_RING - 1u)) + (threadIdx.x >> 5) * BY_WARP_SMEM;
@@ -188,7 +195,7 @@ int launch_lz4_decode_bytes(const DecodeArgs &args, unsigned int *d_counter, int
     }
     cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream);
     long long ctas = (njobs + BY_WARPS - 1) / BY_WARPS;
-    const long long max_ctas = cta_limit > 0 ? cta_limit : (long long)sm_count * 4;
+    const long long max_ctas = cta_limit > 0 ? cta_limit : (long long)sm_count * 3;
     if (ctas > max_ctas) ctas = max_ctas;
     lz4_decode_bytes_kernel<<<(unsigned int)ctas, BY_WARPS * 32, BY_SMEM, stream>>>(args, d_counter);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
