@@ -99,29 +99,46 @@ __device__ int decode_block_bytes(const uint8_t *__restrict__ src, uint32_t comp
                     for (uint32_t i = 0; i < Mk; i++) sts_s32(a + 4u * i, rel + (int)i);
                 }
                 __syncwarp();
-                // ---- collapse the chains: every byte ends up pointing before the batch ----
-                for (;;) {
-                    bool more = false;
-                    for (uint32_t j = lane; j < T; j += 32u) {
-                        const int p = lds_s32(P_s + 4u * j);
-                        if (p >= 0) {
-                            const int q = lds_s32(P_s + 4u * (uint32_t)p);
-                            sts_s32(P_s + 4u * j, q);
-                            more = more || q >= 0;
-                        }
+                // ---- collapse the chains: every byte ends up pointing before the batch.  A lane owns bytes lane, lane + 32, ... and
+                // keeps a bit per byte that still points into the batch (about half of them never do), so a round touches only those ----
+                uint32_t um = 0;
+                for (uint32_t j = lane, k = 0; j < T; j += 32u, k++)
+                    if (lds_s32(P_s + 4u * j) >= 0) um |= 1u << k;
+                while (__any_sync(FULL, um != 0)) {
+                    for (uint32_t m = um; m; m &= m - 1u) {
+                        const uint32_t k = (uint32_t)__ffs(m) - 1u;
+                        const uint32_t pa = P_s + 4u * (lane + 32u * k);
+                        const int q = lds_s32(P_s + 4u * (uint32_t)lds_s32(pa));
+                        sts_s32(pa, q);
+                        if (q < 0) um &= ~(1u << k);
                     }
                     __syncwarp();
-                    if (!__any_sync(FULL, more)) break;
                 }
-                // ---- fetch the roots, write the bytes (global memory and the ring) ----
-                for (uint32_t j = lane; j < T; j += 32u) {
+                // ---- fetch the roots, write the bytes (global memory and the ring): bytes up to the output's next 4-byte boundary
+                // one per lane, then a word per lane ----
+                auto root_byte = [&](uint32_t j) -> uint32_t {
                     const uint32_t back = (uint32_t)(-lds_s32(P_s + 4u * j));     // 1 .. 65535 bytes before the batch start
                     const uint32_t a = op - back;
-                    uint32_t b;
-                    if (back <= BY_NEAR && a >= ring_from) b = lds_u8(ring_s + (a & (BY_RING - 1u)));
-                    else b = __ldcg(dst + a);
-                    dst[op + j] = (uint8_t)b;
-                    sts_u8(ring_s + ((op + j) & (BY_RING - 1u)), b);
+                    if (back <= BY_NEAR && a >= ring_from) return lds_u8(ring_s + (a & (BY_RING - 1u)));
+                    return __ldcg(dst + a);
+                };
+                const uint32_t head = min((0u - op) & 3u, T);
+                if (lane < head) {
+                    const uint32_t b = root_byte(lane);
+                    dst[op + lane] = (uint8_t)b;
+                    sts_u8(ring_s + ((op + lane) & (BY_RING - 1u)), b);
+                }
+                const uint32_t words = (T - head) >> 2, tail0 = head + 4u * words;
+                for (uint32_t w = lane; w < words; w += 32u) {
+                    const uint32_t j = head + 4u * w;
+                    const uint32_t v = root_byte(j) | (root_byte(j + 1u) << 8) | (root_byte(j + 2u) << 16) | (root_byte(j + 3u) << 24);
+                    *reinterpret_cast<uint32_t *>(dst + op + j) = v;
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(ring_s + ((op + j) & (BY_RING - 1u))), "r"(v) : "memory");
+                }
+                if (lane < T - tail0) {
+                    const uint32_t b = root_byte(tail0 + lane);
+                    dst[op + tail0 + lane] = (uint8_t)b;
+                    sts_u8(ring_s + ((op + tail0 + lane) & (BY_RING - 1u)), b);
                 }
                 __syncwarp();
                 ip = nip;
