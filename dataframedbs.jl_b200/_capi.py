@@ -104,6 +104,7 @@ SYMBOLS = {
     "dfdb_write_table_meta": (C.c_int32, [C.c_char_p, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]),
     "dfdb_lz4_compress_blocks": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfdb_lz4_decode_blocks": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "dfdb_lz4_classify_block": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64]),
 }
 
 _lib = None

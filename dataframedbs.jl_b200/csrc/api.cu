@@ -2540,6 +2540,12 @@ int32_t dfdb_host_free(void *ptr)
     return DFDB_OK;
 }
 
+int32_t dfdb_lz4_classify_block(const uint8_t *comp, int64_t comp_len, int64_t origin)
+{
+    if (!comp || comp_len < 0 || origin < 0) return fail(DFDB_ERR_ARGUMENT, "bad block");
+    return sample_flavour(comp, comp_len, origin);
+}
+
 // ---- codec hook ---------------------------------------------------------------------------------------
 int32_t dfdb_lz4_decode_blocks(const uint8_t *comp, const int64_t *comp_off, const int64_t *comp_len, uint8_t *out,
                                const int64_t *out_off, const int64_t *origin, int32_t n, int32_t *status)

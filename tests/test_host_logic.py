@@ -236,3 +236,31 @@ def test_zone_map_sidecar_is_optional_and_validated(tmp_path, oracle):
         t = D.open_table(p)
         assert t.zonemap("q", 0) is None and t.total_rows() == 5 * 256 + 10
         t.close()
+
+
+def test_k1_flavour_is_chosen_from_the_token_stream():
+    """dfdb_table_load picks a K1 decoder per column from a token sample of its blocks (api.cu: sample_flavour; no device needed):
+    word-regular bodies -> verified word runs (2), match-only byte streams -> byte decoder (4), long sequences -> window decoder (3),
+    everything else -> walker / consumer (1).  Bodies are the kinds of src/io/blocks.jl:2-33, compressed by the oracle's codec."""
+    import numpy as np
+    from dfdb_b200 import _capi
+    from oracle import oracle as O
+    O.build()
+    L = _capi.lib()
+    rng = np.random.default_rng(5)
+    N = 65536
+    brands = ["apple", "samsung", "huawai", "microsoft", "dell", "xbox", "sony", "intel"]
+    bodies = {
+        "rand100": (rng.integers(1, 101, N).astype(np.int64).tobytes(), 2),
+        "sorted": (np.arange(1, N + 1, dtype=np.int64).tobytes(), 2),
+        "brands": (O.block_body("String", [brands[i] for i in rng.integers(0, 8, N)], 0, N), 4),
+        "missing_float": (O.block_body("Missing(Float64)", (rng.random(N), rng.random(N) < 0.1), 0, N), 3),
+        "decimals": (O.block_body("String", [str(int(v)) for v in rng.integers(-2**31, 2**31, N)], 0, N), 1),
+        "price_grid": ((1 + 0.1 * rng.integers(0, 19991, N)).astype(np.float64).tobytes(), 1),
+        "tiny": (b"abc" * 10, -1),
+    }
+    for name, (body, want) in bodies.items():
+        comp = O.compress_block(body)
+        buf = np.frombuffer(comp, dtype=np.uint8)
+        got = L.dfdb_lz4_classify_block(buf.ctypes.data, len(comp), len(body))
+        assert got == want, (name, got, want)
