@@ -615,6 +615,14 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
                 for (int64_t b = b0; b < b1; b++)
                     if (!h_skip_of(c)[(size_t)b]) bytes += c->blocks[(size_t)(t->blk_lo + b)].compressed + c->blocks[(size_t)(t->blk_lo + b)].origin;
             }
+            std::vector<int32_t> pending;             // (alive until the copy below is enqueued: pageable memory, the call returns after the staging copy)
+            if (fusing) {
+                // the scan warps of a fused launch wait for a block's status to leave "pending" (-1); blocks the decoders skip stay at 0
+                Column *c = grp[i];
+                pending.assign((size_t)nblocks, 0);
+                for (int b = b0; b < b1; b++) pending[(size_t)b] = h_skip_of(c)[(size_t)b] ? 0 : -1;
+                CUDA_TRY(cudaMemcpyAsync(c->d_status + b0, pending.data() + b0, (size_t)(b1 - b0) * 4, cudaMemcpyHostToDevice, rt.stream));
+            }
             PhaseScope ps(PH_DECODE, bytes);
             if (fusing) {
                 LaneFused lf = *fuse;

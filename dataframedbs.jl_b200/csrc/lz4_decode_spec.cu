@@ -69,103 +69,49 @@ static __device__ __noinline__ void prefetch_group(const uint8_t *src, uint32_t 
 // one block, whole warp; returns E_*.  (Positions are 32-bit in the batch loop: column blocks are far below 4 GB; the kernel
 // is instruction-bound -- IPC 2.9 per SM in the first profile -- so the loop is kept lean.)
 //
-// FUSED (1 = count, 2 = integer aggregate, 3 = Float64 aggregate): the block belongs to the predicate column of a
-// filter + aggregate query.  Every FOLD_ROWS decoded rows the warp stops decoding and folds them: the words it has just
-// written are read back from L2 (32 rows per load, all lanes busy, no divergence worth the name), tested against the plan's
-// interval, and the matching rows of the aggregated column `bvals` (resident, same rows) go into per-lane accumulators that
-// live in shared memory between folds -- the decode loop itself carries no extra registers.  The decoded column is not read
-// from HBM again.  (Folding inside the batch loop instead -- each lane its own word while it is in a register -- was measured
-// first: 354 instead of 211 instructions per batch, spills at 64 registers, 18.5 ms instead of 9.4 for 1e9 rows: the kernel is
-// instruction-bound, and a fold at 24 of 32 lanes with half of them masked off is the expensive way to issue it.)
-constexpr uint32_t FOLD_SHIFT = 11, FOLD_ROWS = 1u << (FOLD_SHIFT - 3);   // every 256 rows (2 KB of output)
+// FUSED (1 = count, 2 = integer aggregate, 3 = Float64 aggregate): the launch decodes the predicate column of a filter +
+// aggregate query, and the scan runs INSIDE it: the last warp of every CTA does not decode -- it takes blocks in the order the
+// decoders take them, waits for a block's status word to leave its "pending" value (the decoder stores it behind a
+// __threadfence), and scans the block: the decoded words come back from L2, the aggregated column `bvals` (resident, same rows)
+// streams in from HBM, the plan's interval is tested and the matching rows are folded into per-lane accumulators, combined in a
+// fixed order into the block's partial.  The decode is issue-bound and the scan memory-bound, so the two share the SM well; what
+// the scan costs the decoders is one warp slot in eight and ~25 instructions per 32 rows.  (Two earlier forms of the fusion lost
+// to decode + separate scan: folding each word while it is in a decoder lane's register -- 354 instead of 211 instructions per
+// batch, spills --, and the decoding warp itself folding every 256 rows from L2 -- 12.3 against 9.9 + 2.4 ms.)
+constexpr int SPEC_PENDING = -1;             // status of a block that is not decoded yet (set by the host before a fused launch)
 
 template <int AGG>
-__device__ __forceinline__ void acc_load(LaneAcc &a, const unsigned long long *s)
+__device__ __forceinline__ void scan_block(const LaneFused &F, const unsigned long long *__restrict__ a64, const unsigned long long *__restrict__ bvals, uint32_t rows,
+                           AggPartial *out)
 {
-    const unsigned long long cf = s[4 * SPEC_WARPS * 32];
-    a.count = (int)(uint32_t)cf; a.flags = (int)(cf >> 32);
-    if (AGG == 2) {
-        a.sum_hi = __longlong_as_double((long long)s[0]); a.sum_lo = __longlong_as_double((long long)s[SPEC_WARPS * 32]);
-        a.min_f = __longlong_as_double((long long)s[2 * SPEC_WARPS * 32]); a.max_f = __longlong_as_double((long long)s[3 * SPEC_WARPS * 32]);
-    } else if (AGG == 1) {
-        a.sum_i = (long long)s[0]; a.min_i = (long long)s[2 * SPEC_WARPS * 32]; a.max_i = (long long)s[3 * SPEC_WARPS * 32];
-    }
-}
-template <int AGG>
-__device__ __forceinline__ void acc_store(const LaneAcc &a, unsigned long long *s)
-{
-    s[4 * SPEC_WARPS * 32] = (unsigned long long)(uint32_t)a.count | ((unsigned long long)(uint32_t)a.flags << 32);
-    if (AGG == 2) {
-        s[0] = (unsigned long long)__double_as_longlong(a.sum_hi); s[SPEC_WARPS * 32] = (unsigned long long)__double_as_longlong(a.sum_lo);
-        s[2 * SPEC_WARPS * 32] = (unsigned long long)__double_as_longlong(a.min_f); s[3 * SPEC_WARPS * 32] = (unsigned long long)__double_as_longlong(a.max_f);
-    } else if (AGG == 1) {
-        s[0] = (unsigned long long)a.sum_i; s[2 * SPEC_WARPS * 32] = (unsigned long long)a.min_i; s[3 * SPEC_WARPS * 32] = (unsigned long long)a.max_i;
-    }
-}
-// Folds the complete FOLD_ROWS-row windows below row `upto` that have not been folded yet (all remaining rows when `last`).
-// Where the previous fold stopped and the block's rows of the aggregated column are kept, like the accumulators, in shared
-// memory: nothing of this is live in the decode loop.  Windows are fixed (row r always goes to lane r % 32), and each fold
-// asks L2 for the next window of the aggregated column, so that window's loads find it there ~20 000 cycles later.
-constexpr int ACC_WORDS = 5 * SPEC_WARPS * 32;          // then per warp: rows folded so far, the block's rows of the aggregated column
-template <int AGG>
-__device__ __noinline__ void fold_rows(const LaneFused &F, const unsigned long long *out64, uint32_t upto, unsigned long long *accs)
-{
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    unsigned long long *acc_s = accs + threadIdx.x;
-    uint32_t from = (uint32_t)accs[ACC_WORDS + warp];
-    const bool last = upto == (uint32_t)(accs[ACC_WORDS + warp] >> 32);      // (the block's row count rides in the upper half)
-    const unsigned long long *__restrict__ bvals = AGG ? reinterpret_cast<const unsigned long long *>(accs[ACC_WORDS + SPEC_WARPS + warp]) : nullptr;
+    const uint32_t lane = lane_id();
     const bool uns = F.agg_cls == VC_UINT || F.agg_cls == VC_BOOL;
     LaneAcc acc;
-    acc_load<AGG>(acc, acc_s);
-    while (from + FOLD_ROWS <= upto) {
-        if (AGG && lane < FOLD_ROWS / 16u) asm volatile("prefetch.global.L2 [%0];" ::"l"(bvals + from + FOLD_ROWS + 16u * lane));   // (past the block's end: the next block's rows, or the 128-byte slack behind the column)
+    fused::acc_reset(acc, uns);
+    uint32_t r = 0;
+    // 128 rows per step (eight loads in flight per lane): row r + 32 k + lane goes to lane `lane`, in a fixed order
+    for (; r + 128u <= rows; r += 128u) {
+        if (AGG && (r & 255u) == 0 && lane < 16u) asm volatile("prefetch.global.L2 [%0];" ::"l"(bvals + r + 512u + 16u * lane));   // (past the block's end: the next block's rows, or the slack behind the column)
+        unsigned long long a[4], bb[4];
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            unsigned long long a[4], bb[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                a[k] = __ldcg(out64 + from + lane + 32u * (4 * h + k));
-                bb[k] = AGG ? __ldcs(bvals + from + lane + 32u * (4 * h + k)) : 0ull;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (fused::lane_test(F, a[k])) fused::acc_add<AGG>(acc, bb[k], uns);
+        for (int k = 0; k < 4; k++) {
+            a[k] = __ldcg(a64 + r + lane + 32u * k);
+            bb[k] = AGG ? __ldcs(bvals + r + lane + 32u * k) : 0ull;
         }
-        from += FOLD_ROWS;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (fused::lane_test(F, a[k])) fused::acc_add<AGG>(acc, bb[k], uns);
     }
-    if (last) {
-        for (uint32_t r = from + lane; r < upto; r += 32u)
-            if (fused::lane_test(F, __ldcg(out64 + r))) fused::acc_add<AGG>(acc, AGG ? __ldcs(bvals + r) : 0ull, uns);
-        from = upto;
-    }
-    acc_store<AGG>(acc, acc_s);
-    __syncwarp();
-    if (lane == 0) reinterpret_cast<uint32_t *>(accs + ACC_WORDS + warp)[0] = from;
-    __syncwarp();
+    for (uint32_t q = r + lane; q < rows; q += 32u)
+        if (fused::lane_test(F, __ldcg(a64 + q))) fused::acc_add<AGG>(acc, AGG ? __ldcs(bvals + q) : 0ull, uns);
+    // the block's partial: the 32 lanes' accumulators folded in a fixed order
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) fused::acc_merge_xor<AGG>(acc, d, uns, (lane & d) != 0);
+    if (lane == 0) *out = fused::acc_to_partial<AGG>(acc);
 }
 
-template <int AGG>
-__device__ __noinline__ void fold_begin(const LaneFused &F, int b, uint32_t rows, unsigned long long *accs)
+__device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_len, uint8_t *dst, uint32_t origin, uint32_t ring_s, int pf_mode)
 {
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    LaneAcc z;
-    fused::acc_reset(z, F.agg_cls == VC_UINT || F.agg_cls == VC_BOOL);
-    acc_store<AGG>(z, accs + threadIdx.x);
-    const uint8_t *bv = AGG ? F.agg.base + F.agg.blk_off[b] : nullptr;
-    if (lane == 0) {
-        accs[ACC_WORDS + warp] = (unsigned long long)rows << 32;
-        accs[ACC_WORDS + SPEC_WARPS + warp] = (unsigned long long)bv;
-    }
-    if (AGG && lane < FOLD_ROWS / 16u) asm volatile("prefetch.global.L2 [%0];" ::"l"(bv + 128u * lane));
-    __syncwarp();
-}
-
-template <int FUSED>
-__device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_len, uint8_t *dst, uint32_t origin, uint32_t ring_s, int pf_mode,
-                                 const LaneFused &F, unsigned long long *accs)
-{
-    constexpr int AGG = FUSED == 3 ? 2 : FUSED == 2 ? 1 : 0;
     uint32_t lane = lane_id();
     asm volatile("" : "+r"(lane));           // (kept in a register instead of an S2R in every batch)
     uint32_t ip = 0, op = 0;
@@ -218,7 +164,6 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
     };
     while (!done) {
         bool batch = false;
-        const uint32_t op_was = op;
         if ((op & 7u) == 0 && (int32_t)ip <= ip_lim) {
             const uint32_t opw = op >> 3;
             const uint32_t tok = (uint32_t)x & 0xffu;
@@ -314,10 +259,6 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
             ring_from = (op + 7u) >> 3;                                         // (what this path wrote is in global memory only)
             tp = ip + (3u + L0) * lane;
             x = load_stream_at(src, tp);
-        }
-        if (FUSED && (((op ^ op_was) >> FOLD_SHIFT) != 0 || done)) {             // the output crossed a FOLD_ROWS boundary
-            __syncwarp();
-            fold_rows<AGG>(F, out64, op >> 3, accs);
         }
     }
     return (op == origin && ip == comp_len) ? E_OK : E_SIZE;
@@ -489,6 +430,36 @@ __device__ int decode_block_long(const uint8_t *__restrict__ src, uint32_t comp_
     return (op == origin && ip == comp_len) ? E_OK : E_SIZE;
 }
 
+// the CTA's scan warp of a fused launch (the launch holds the predicate column alone: job = block)
+template <int AGG>
+__device__ __noinline__ void scan_warp_main(const DecodeArgs &args, const LaneFused &F, unsigned int *counter)
+{
+    const uint32_t lane = lane_id();
+    const long long njobs = (long long)args.ncols * args.nblocks;
+    const DecodeCol &col = args.col[0];
+    for (;;) {
+        unsigned int job = 0;
+        if (lane == 0) job = atomicAdd(counter + 1, 1u);
+        job = __shfl_sync(FULL, job, 0);
+        if ((long long)job >= njobs) return;
+        const int b = args.blk0 + (int)job;
+        if (col.skip && col.skip[b]) continue;                     // (not decoded: its partial stays empty)
+        if (lane == 0) {
+            int st;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(st) : "l"(col.status + b) : "memory");
+                if (st != SPEC_PENDING) break;
+                __nanosleep(400);
+            }
+        }
+        __syncwarp();
+        const unsigned long long *bvals = AGG ? reinterpret_cast<const unsigned long long *>(F.agg.base + F.agg.blk_off[b]) : nullptr;
+        scan_block<AGG>(F, reinterpret_cast<const unsigned long long *>(col.out + col.dec_off[b]), bvals, (uint32_t)col.origin[b] >> 3,
+                        F.partials + (int64_t)(b - F.part_blk0) * F.segs_per_block);
+        __syncwarp();
+    }
+}
+
 // CTAS: resident CTAs per SM the kernel is compiled for (4: 64 registers per thread, 5: 48, 6: 40) -- an A/B axis, option "spec_ctas"
 template <int FUSED, int CTAS>
 __global__ void __launch_bounds__(SPEC_WARPS * 32, CTAS) lz4_decode_spec_kernel(const __grid_constant__ DecodeArgs args, const __grid_constant__ LaneFused F,
@@ -498,11 +469,13 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, CTAS) lz4_decode_spec_kernel(
     // reserves, so a declared alignment does not give an aligned address; the launcher adds one ring of slack)
     extern __shared__ unsigned char spec_dyn[];
     const uint32_t ring_s = ((smem_addr(spec_dyn) + SPEC_RING * 8u - 1u) & ~(SPEC_RING * 8u - 1u)) + (threadIdx.x >> 5) * (SPEC_RING * 8u);
-    __shared__ unsigned long long accs[FUSED ? ACC_WORDS + 2 * SPEC_WARPS : 1];   // per-lane accumulators, field-major; then the per-warp fold state
-    unsigned long long *acc_s = accs + (FUSED ? threadIdx.x : 0);
     const uint32_t lane = lane_id();
     constexpr int AGG = FUSED == 3 ? 2 : FUSED == 2 ? 1 : 0;
     const long long njobs = (long long)args.ncols * args.nblocks;
+    if (FUSED && (threadIdx.x >> 5) == SPEC_WARPS - 1) {
+        scan_warp_main<AGG>(args, F, counter);                     // (a function of its own: inlined here, its registers spill the decoders' batch loop)
+        return;
+    }
     for (;;) {
         unsigned int job = 0;
         if (lane == 0) job = atomicAdd(counter, 1u);
@@ -511,27 +484,21 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, CTAS) lz4_decode_spec_kernel(
         const int c = (int)(job % args.ncols);
         const int b = args.blk0 + (int)(job / args.ncols);
         const DecodeCol &col = args.col[c];
-        if (col.skip && col.skip[b]) continue;
+        if (col.skip && col.skip[b]) continue;                     // (the host leaves the status of such a block at 0, not pending)
         const uint8_t *src = col.comp + col.comp_off[b];
         uint8_t *dst = col.out + col.dec_off[b];
         const uint32_t comp_len = (uint32_t)col.comp_len[b], origin = (uint32_t)col.origin[b];
-        constexpr bool pred = FUSED != 0;                       // a fused launch holds the predicate column alone (see the launcher)
         int e;
-        if (FUSED) fold_begin<AGG>(F, b, origin >> 3, accs);
         if (origin == 0) e = (comp_len == 1 && src[0] == 0) ? E_OK : E_SIZE;
         else if (comp_len == 0) e = E_TRUNCATED;
-        else if (((uintptr_t)src & 3u) || ((uintptr_t)dst & 7u)) e = pred ? E_INTERNAL : decode_simple(src, comp_len, dst, origin);
-        else e = decode_block_spec<FUSED>(src, comp_len, dst, origin, ring_s, args.hot, F, accs);
-        if (lane == 0) col.status[b] = e;
-        if (pred) {
-            // the block's partial: the 32 lanes' accumulators folded in a fixed order
-            const bool uns = F.agg_cls == VC_UINT || F.agg_cls == VC_BOOL;
-            LaneAcc acc;
-            fused::acc_reset(acc, uns);                          // (the fields this aggregate does not use)
-            acc_load<AGG>(acc, acc_s);
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) fused::acc_merge_xor<AGG>(acc, d, uns, (lane & d) != 0);
-            if (lane == 0) F.partials[(int64_t)(b - F.part_blk0) * F.segs_per_block] = fused::acc_to_partial<AGG>(acc);
+        else if (((uintptr_t)src & 3u) || ((uintptr_t)dst & 7u)) e = decode_simple(src, comp_len, dst, origin);
+        else e = decode_block_spec(src, comp_len, dst, origin, ring_s, args.hot);
+        if (FUSED) {
+            __threadfence();                                       // this lane's words are visible before the status says so
+            __syncwarp();
+            if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(col.status + b), "r"(e) : "memory");
+        } else if (lane == 0) {
+            col.status[b] = e;
         }
         __syncwarp();
     }
@@ -591,9 +558,10 @@ int launch_lz4_decode_spec(const DecodeArgs &args, unsigned int *d_counter, int 
 {
     const long long njobs = (long long)args.ncols * args.nblocks;
     if (njobs <= 0) return 0;
-    cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream);
-    long long ctas = (njobs + SPEC_WARPS - 1) / SPEC_WARPS;
-    int per_sm = fused_args ? 4 : (g_spec_ctas >= 4 && g_spec_ctas <= 6 ? g_spec_ctas : 5);
+    cudaMemsetAsync(d_counter, 0, 2 * sizeof(unsigned int), stream);   // (job counters: decoders, scan warps)
+    const int dec_warps = fused_args ? SPEC_WARPS - 1 : SPEC_WARPS;      // a fused launch gives the last warp of every CTA to the scan
+    long long ctas = (njobs + dec_warps - 1) / dec_warps;
+    int per_sm = fused_args ? 5 : (g_spec_ctas >= 4 && g_spec_ctas <= 6 ? g_spec_ctas : 5);
     long long max_ctas = cta_limit > 0 ? cta_limit : (long long)sm_count * per_sm;   // persistent over the job queue
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
@@ -608,9 +576,9 @@ int launch_lz4_decode_spec(const DecodeArgs &args, unsigned int *d_counter, int 
         else if (per_sm == 5) lz4_decode_spec_kernel<0, 5><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, f, d_counter);
         else lz4_decode_spec_kernel<0, 4><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, f, d_counter);
         break;
-    case 1: lz4_decode_spec_kernel<1, 4><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, f, d_counter); break;
-    case 2: lz4_decode_spec_kernel<2, 4><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, f, d_counter); break;
-    default: lz4_decode_spec_kernel<3, 4><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, f, d_counter); break;
+    case 1: lz4_decode_spec_kernel<1, 5><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, f, d_counter); break;
+    case 2: lz4_decode_spec_kernel<2, 5><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, f, d_counter); break;
+    default: lz4_decode_spec_kernel<3, 5><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, f, d_counter); break;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
