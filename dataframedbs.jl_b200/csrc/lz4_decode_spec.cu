@@ -80,29 +80,50 @@ static __device__ __noinline__ void prefetch_group(const uint8_t *src, uint32_t 
 // batch, spills --, and the decoding warp itself folding every 256 rows from L2 -- 12.3 against 9.9 + 2.4 ms.)
 constexpr int SPEC_PENDING = -1;             // status of a block that is not decoded yet (set by the host before a fused launch)
 
+// One block's scan by one warp.  The two columns stream through shared memory: SCAN_ST stages of SCAN_ROWS rows, filled with
+// cp.async (16 bytes per lane and instruction, 12 KB in flight per warp -- with plain loads a warp keeps 2 KB in flight and 740
+// scan warps reach 0.9 TB/s: the first version of this took 17.5 ms per 1e9 rows), row r of a stage always in lane r % 32.
+constexpr uint32_t SCAN_ROWS = 256, SCAN_ST = 3;
+constexpr uint32_t SCAN_SMEM = SCAN_ST * 2u * SCAN_ROWS * 8u;      // 12 KB: the scan warp's own ring slot + 8 KB the fused launch adds
+
 template <int AGG>
 __device__ __forceinline__ void scan_block(const LaneFused &F, const unsigned long long *__restrict__ a64, const unsigned long long *__restrict__ bvals, uint32_t rows,
-                           AggPartial *out)
+                                           AggPartial *out, uint32_t buf_s)
 {
     const uint32_t lane = lane_id();
     const bool uns = F.agg_cls == VC_UINT || F.agg_cls == VC_BOOL;
     LaneAcc acc;
     fused::acc_reset(acc, uns);
-    uint32_t r = 0;
-    // 128 rows per step (eight loads in flight per lane): row r + 32 k + lane goes to lane `lane`, in a fixed order
-    for (; r + 128u <= rows; r += 128u) {
-        if (AGG && (r & 255u) == 0 && lane < 16u) asm volatile("prefetch.global.L2 [%0];" ::"l"(bvals + r + 512u + 16u * lane));   // (past the block's end: the next block's rows, or the slack behind the column)
-        unsigned long long a[4], bb[4];
+    const uint32_t nfull = rows / SCAN_ROWS;
+    auto issue = [&](uint32_t st) {
+        const uint32_t base = buf_s + (st % SCAN_ST) * (2u * SCAN_ROWS * 8u);
+        const unsigned long long *pa = a64 + (size_t)st * SCAN_ROWS, *pb = bvals + (size_t)st * SCAN_ROWS;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            a[k] = __ldcg(a64 + r + lane + 32u * k);
-            bb[k] = AGG ? __ldcs(bvals + r + lane + 32u * k) : 0ull;
+        for (uint32_t k = 0; k < SCAN_ROWS * 8u / 512u; k++) {
+            const uint32_t c16 = (lane + 32u * k) * 16u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + c16), "l"(reinterpret_cast<const char *>(pa) + c16) : "memory");
+            if (AGG) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + SCAN_ROWS * 8u + c16), "l"(reinterpret_cast<const char *>(pb) + c16) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (uint32_t st = 0; st < SCAN_ST && st < nfull; st++) issue(st);
+    for (uint32_t st = 0; st < nfull; st++) {
+        if (st + 2u < nfull) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (st + 1u < nfull) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        const uint32_t base = buf_s + (st % SCAN_ST) * (2u * SCAN_ROWS * 8u);
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (fused::lane_test(F, a[k])) fused::acc_add<AGG>(acc, bb[k], uns);
+        for (uint32_t k = 0; k < SCAN_ROWS / 32u; k++) {
+            unsigned long long a, bb = 0;
+            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(a) : "r"(base + (lane + 32u * k) * 8u) : "memory");
+            if (AGG) asm volatile("ld.shared.u64 %0, [%1];" : "=l"(bb) : "r"(base + SCAN_ROWS * 8u + (lane + 32u * k) * 8u) : "memory");
+            if (fused::lane_test(F, a)) fused::acc_add<AGG>(acc, bb, uns);
+        }
+        __syncwarp();                                              // every lane is done with the stage before it is filled again
+        if (st + SCAN_ST < nfull) issue(st + SCAN_ST);
     }
-    for (uint32_t q = r + lane; q < rows; q += 32u)
+    for (uint32_t q = nfull * SCAN_ROWS + lane; q < rows; q += 32u)
         if (fused::lane_test(F, __ldcg(a64 + q))) fused::acc_add<AGG>(acc, AGG ? __ldcs(bvals + q) : 0ull, uns);
     // the block's partial: the 32 lanes' accumulators folded in a fixed order
 #pragma unroll
@@ -432,7 +453,7 @@ __device__ int decode_block_long(const uint8_t *__restrict__ src, uint32_t comp_
 
 // the CTA's scan warp of a fused launch (the launch holds the predicate column alone: job = block)
 template <int AGG>
-__device__ __noinline__ void scan_warp_main(const DecodeArgs &args, const LaneFused &F, unsigned int *counter)
+__device__ __noinline__ void scan_warp_main(const DecodeArgs &args, const LaneFused &F, unsigned int *counter, uint32_t buf_s)
 {
     const uint32_t lane = lane_id();
     const long long njobs = (long long)args.ncols * args.nblocks;
@@ -455,7 +476,7 @@ __device__ __noinline__ void scan_warp_main(const DecodeArgs &args, const LaneFu
         __syncwarp();
         const unsigned long long *bvals = AGG ? reinterpret_cast<const unsigned long long *>(F.agg.base + F.agg.blk_off[b]) : nullptr;
         scan_block<AGG>(F, reinterpret_cast<const unsigned long long *>(col.out + col.dec_off[b]), bvals, (uint32_t)col.origin[b] >> 3,
-                        F.partials + (int64_t)(b - F.part_blk0) * F.segs_per_block);
+                        F.partials + (int64_t)(b - F.part_blk0) * F.segs_per_block, buf_s);
         __syncwarp();
     }
 }
@@ -473,7 +494,7 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, CTAS) lz4_decode_spec_kernel(
     constexpr int AGG = FUSED == 3 ? 2 : FUSED == 2 ? 1 : 0;
     const long long njobs = (long long)args.ncols * args.nblocks;
     if (FUSED && (threadIdx.x >> 5) == SPEC_WARPS - 1) {
-        scan_warp_main<AGG>(args, F, counter);                     // (a function of its own: inlined here, its registers spill the decoders' batch loop)
+        scan_warp_main<AGG>(args, F, counter, ring_s);                 // (a function of its own: inlined here, its registers spill the decoders' batch loop)
         return;
     }
     for (;;) {
@@ -576,9 +597,9 @@ int launch_lz4_decode_spec(const DecodeArgs &args, unsigned int *d_counter, int 
         else if (per_sm == 5) lz4_decode_spec_kernel<0, 5><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, f, d_counter);
         else lz4_decode_spec_kernel<0, 4><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, f, d_counter);
         break;
-    case 1: lz4_decode_spec_kernel<1, 5><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, f, d_counter); break;
-    case 2: lz4_decode_spec_kernel<2, 5><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, f, d_counter); break;
-    default: lz4_decode_spec_kernel<3, 5><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM, stream>>>(args, f, d_counter); break;
+    case 1: lz4_decode_spec_kernel<1, 5><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM + SCAN_SMEM - SPEC_RING * 8u, stream>>>(args, f, d_counter); break;
+    case 2: lz4_decode_spec_kernel<2, 5><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM + SCAN_SMEM - SPEC_RING * 8u, stream>>>(args, f, d_counter); break;
+    default: lz4_decode_spec_kernel<3, 5><<<(unsigned int)ctas, SPEC_WARPS * 32, SPEC_SMEM + SCAN_SMEM - SPEC_RING * 8u, stream>>>(args, f, d_counter); break;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
