@@ -50,7 +50,7 @@ struct Runtime {
     int64_t lz4_v1 = 0;       // first-generation warp-per-block decoder instead of the walker/consumer kernel
     int64_t no_wide = 0;
     int64_t no_fused = 0;
-    int64_t no_decode_fused = 1;                                    // 0: fold predicate + aggregate into the decode kernel (measured: no faster than decode + scan, see lz4_decode_spec.cu)
+    int64_t no_decode_fused = 1;                                    // 0: predicate + aggregate inside the decode launch (scan warps; measured: 15.8 against 8.8 ms per step at 1e9 rows, see lz4_decode_spec.cu and DESIGN.md)
     int64_t no_tma = 0;
     int64_t lz4_flavour = 0;  // K1 flavour: 0 = per column from a token sample at load, 2 (and 1, a removed kernel's number) = walker / consumer decoder (v3), 3 = lane-per-block decoder, 4 = warp-per-block decoder with verified token runs (spec), 5 = warp-per-block decoder for long sequences, 6 = warp-per-block decoder for bare-match byte streams
     int64_t no_overlap = 0;   // do not run the scan of the decoded part of a shard beside the decode of its last part

@@ -74,8 +74,9 @@ static __device__ __noinline__ void prefetch_group(const uint8_t *src, uint32_t 
 // decoders take them, waits for a block's status word to leave its "pending" value (the decoder stores it behind a
 // __threadfence), and scans the block: the decoded words come back from L2, the aggregated column `bvals` (resident, same rows)
 // streams in from HBM, the plan's interval is tested and the matching rows are folded into per-lane accumulators, combined in a
-// fixed order into the block's partial.  The decode is issue-bound and the scan memory-bound, so the two share the SM well; what
-// the scan costs the decoders is one warp slot in eight and ~25 instructions per 32 rows.  (Two earlier forms of the fusion lost
+// fixed order into the block's partial.  The decode is issue-bound and the scan memory-bound, so the two ought to share the SM
+// well -- measured, they do not: 15.8 ms per 1e9 rows against 6.1 + 2.4 ms one after the other, because five scan warps per SM
+// cannot issue the scan's instructions in the time the decoders need.  Kept as an option (no_decode_fused = 0).  (Two earlier forms of the fusion lost
 // to decode + separate scan: folding each word while it is in a decoder lane's register -- 354 instead of 211 instructions per
 // batch, spills --, and the decoding warp itself folding every 256 rows from L2 -- 12.3 against 9.9 + 2.4 ms.)
 constexpr int SPEC_PENDING = -1;             // status of a block that is not decoded yet (set by the host before a fused launch)
