@@ -194,7 +194,37 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
             // zero offset (minus one wraps), fails the one comparison; for the lanes that pass, offr is the offset in words
             const uint32_t offr = __funnelshift_r(off, off, 3);
             const bool okp = tok == tok0 && offr - 1u < opw + lane && opw + lane < lim_w;
-            if (__all_sync(FULL, okp)) {
+            const uint32_t badp = ~__ballot_sync(FULL, okp);
+            // One lane fails, and only because its match is 16 - L0 bytes instead of 8 - L0 -- same stream stride, two output
+            // words, 1 % of the tokens of rand(1:100) and the end of a quarter of its batches --, with both sources before the
+            // batch: the batch stays whole.  Lanes behind it sit one word further on; the owner of an in-batch source word q is
+            // lane q up to it, lane q - 1 behind it, and word z + 1 is that sequence's second word (source: the word after its first).
+            uint32_t z = 32u;
+            if (badp && (badp & (badp - 1u)) == 0) {
+                const uint32_t zz = (uint32_t)__ffs(badp) - 1u;
+                const bool two = lane == zz && tok == tok0 + 8u && offr - 1u < opw + lane && offr >= zz + 2u;
+                if (__ballot_sync(FULL, two) && opw + 33u <= lim_w) z = zz;
+            }
+            if (z < 32u) {
+                // ---- a full batch with one two-word sequence in it ----
+                pendL = 0xffu;
+                const uint64_t nx = advance_stream(32u * (3u + L0), false);
+                const uint32_t myw = opw + lane + (lane > z ? 1u : 0u);
+                uint32_t s = myw - offr;
+                bool inb = s >= opw;                                            // (never lane z)
+                while (__any_sync(FULL, inb)) {
+                    const uint32_t q = s - opw;
+                    const uint32_t t = __shfl_sync(FULL, s, q - (q > z ? 1u : 0u));
+                    if (inb) { s = t + (q == z + 1u ? 1u : 0u); inb = s >= opw; }
+                }
+                const unsigned long long v = source(s, opw);
+                put(myw, (v & kp0) | ((unsigned long long)(x >> 8) & ~kp0));
+                if (lane == z) put(myw + 1u, source(s + 1u, opw));
+                __syncwarp();                                                   // the batch's words are visible to the whole warp
+                op += 264u;
+                x = nx;
+                batch = true;
+            } else if (!badp) {
                 // ---- a full batch of 32 one-word sequences: lane = sequence = output word ----
                 pendL = 0xffu;
                 const uint64_t nx = advance_stream(32u * (3u + L0), false);
@@ -220,7 +250,7 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
                 // measured: 13 % fewer batches, but the bookkeeping (first-word masks, owner lookup, truncation at 32 words) made
                 // every such batch dearer; 5.6 G instead of 4.9 G warp instructions per 1e9 rows.  They close the run like any
                 // other shape.)
-                const uint32_t n = (uint32_t)__ffs(~__ballot_sync(FULL, okp)) - 1u;
+                const uint32_t n = (uint32_t)__ffs(badp) - 1u;
                 const uint32_t myw = opw + lane;
                 // the sequence that ends the run, analysed by its own lane: any "word form" -- L <= 5 literal bytes + match, 8 or 16 bytes in all
                 const uint32_t L = tok >> 4, LM = L + (tok & 15u) + 4u;
