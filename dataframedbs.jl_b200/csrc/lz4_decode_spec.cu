@@ -195,36 +195,7 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
             const uint32_t offr = __funnelshift_r(off, off, 3);
             const bool okp = tok == tok0 && offr - 1u < opw + lane && opw + lane < lim_w;
             const uint32_t badp = ~__ballot_sync(FULL, okp);
-            // One lane fails, and only because its match is 16 - L0 bytes instead of 8 - L0 -- same stream stride, two output
-            // words, 1 % of the tokens of rand(1:100) and the end of a quarter of its batches --, with both sources before the
-            // batch: the batch stays whole.  Lanes behind it sit one word further on; the owner of an in-batch source word q is
-            // lane q up to it, lane q - 1 behind it, and word z + 1 is that sequence's second word (source: the word after its first).
-            uint32_t z = 32u;
-            if (badp && (badp & (badp - 1u)) == 0) {
-                const uint32_t zz = (uint32_t)__ffs(badp) - 1u;
-                const bool two = lane == zz && tok == tok0 + 8u && offr - 1u < opw + lane && offr >= zz + 2u;
-                if (__ballot_sync(FULL, two) && opw + 33u <= lim_w) z = zz;
-            }
-            if (z < 32u) {
-                // ---- a full batch with one two-word sequence in it ----
-                pendL = 0xffu;
-                const uint64_t nx = advance_stream(32u * (3u + L0), false);
-                const uint32_t myw = opw + lane + (lane > z ? 1u : 0u);
-                uint32_t s = myw - offr;
-                bool inb = s >= opw;                                            // (never lane z)
-                while (__any_sync(FULL, inb)) {
-                    const uint32_t q = s - opw;
-                    const uint32_t t = __shfl_sync(FULL, s, q - (q > z ? 1u : 0u));
-                    if (inb) { s = t + (q == z + 1u ? 1u : 0u); inb = s >= opw; }
-                }
-                const unsigned long long v = source(s, opw);
-                put(myw, (v & kp0) | ((unsigned long long)(x >> 8) & ~kp0));
-                if (lane == z) put(myw + 1u, source(s + 1u, opw));
-                __syncwarp();                                                   // the batch's words are visible to the whole warp
-                op += 264u;
-                x = nx;
-                batch = true;
-            } else if (!badp) {
+            if (!badp) {
                 // ---- a full batch of 32 one-word sequences: lane = sequence = output word ----
                 pendL = 0xffu;
                 const uint64_t nx = advance_stream(32u * (3u + L0), false);
@@ -245,59 +216,90 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
                 x = nx;
                 batch = true;
             } else {
-                // ---- the run ends inside the batch: n one-word sequences, then maybe one closing sequence of another word form ----
-                // (Keeping sequences of 16 - L0 match bytes -- two words, same stream stride -- inside the run was built and
-                // measured: 13 % fewer batches, but the bookkeeping (first-word masks, owner lookup, truncation at 32 words) made
-                // every such batch dearer; 5.6 G instead of 4.9 G warp instructions per 1e9 rows.  They close the run like any
-                // other shape.)
-                const uint32_t n = (uint32_t)__ffs(badp) - 1u;
-                const uint32_t myw = opw + lane;
-                // the sequence that ends the run, analysed by its own lane: any "word form" -- L <= 5 literal bytes + match, 8 or 16 bytes in all
-                const uint32_t L = tok >> 4, LM = L + (tok & 15u) + 4u;
-                // (its offset: stream bytes L + 1 and L + 2 of the lane's eight, picked by one PRMT -- a 64-bit variable shift is a dozen instructions)
-                const uint32_t off_s = __byte_perm((uint32_t)x, (uint32_t)(x >> 32), 0x4421u + 0x11u * L) & 0xffffu, offw_s = off_s >> 3;
-                const uint32_t Wc = LM >> 3;
-                const bool sp = lane == n && L <= 5u && (LM == 8u || LM == 16u) && (off_s & 7u) == 0 && off_s != 0 &&
-                                offw_s <= myw && offw_s >= lane + Wc &&                    // sources inside the output and final (before the batch)
-                                myw + Wc <= lim_w;
-                uint32_t hdr_s = 0, W_s = 0;
-                if (__ballot_sync(FULL, sp)) {
-                    const uint32_t pk = __shfl_sync(FULL, (L << 8) | Wc, n);
-                    hdr_s = 3u + (pk >> 8);
-                    W_s = pk & 0xffu;
+                // One lane fails, and only because its match is 16 - L0 bytes instead of 8 - L0 -- same stream stride, two output
+                // words, 1 % of the tokens of rand(1:100) and the end of a quarter of its batches --, with both sources before the
+                // batch: the batch stays whole.  Lanes behind it sit one word further on; the owner of an in-batch source word q is
+                // lane q up to it, lane q - 1 behind it, and word z + 1 is that sequence's second word (source: the word after its first).
+                uint32_t z = 32u;
+                if ((badp & (badp - 1u)) == 0) {
+                    const uint32_t zz = (uint32_t)__ffs(badp) - 1u;
+                    const bool two = lane == zz && tok == tok0 + 8u && offr - 1u < opw + lane && offr >= zz + 2u;
+                    if (__ballot_sync(FULL, two) && opw + 33u <= lim_w) z = zz;
                 }
-                if (n + W_s > 0) {
-                    const uint32_t stride = 3u + L0;
-                    const unsigned long long kp = sp ? ~0ull << (8u * L) : kp0;   // the bytes a word takes from its source (the others are literals)
-                    // a sequence of another one-word shape alone at the head of a batch is just the closing sequence of an empty run;
-                    // two of the same shape in a row are a new run: switch (the bytes requested next use the new stride)
-                    if (n == 0 && W_s == 1u) {
-                        const uint32_t Lh = hdr_s - 3u;
-                        if (Lh == pendL && Lh <= 4u) {
-                            L0 = Lh;
-                            tok0 = (L0 << 4) | (4u - L0); sh0 = 8u + 8u * L0; kp0 = ~0ull << (8u * L0);
-                        }
-                        pendL = Lh;
-                    } else {
-                        pendL = 0xffu;
-                    }
-                    const uint64_t nx = advance_stream(stride * n + hdr_s, stride != 3u + L0);
-                    const bool mine = lane < n;
-                    uint32_t s = myw - (sp ? offw_s : offr);
-                    bool inb = mine && s >= opw;
+                if (z < 32u) {
+                    // ---- a full batch with one two-word sequence in it ----
+                    pendL = 0xffu;
+                    const uint64_t nx = advance_stream(32u * (3u + L0), false);
+                    const uint32_t myw = opw + lane + (lane > z ? 1u : 0u);
+                    uint32_t s = myw - offr;
+                    bool inb = s >= opw;                                            // (never lane z)
                     while (__any_sync(FULL, inb)) {
-                        const uint32_t t = __shfl_sync(FULL, s, s - opw);
-                        if (inb) { s = t; inb = s >= opw; }
+                        const uint32_t q = s - opw;
+                        const uint32_t t = __shfl_sync(FULL, s, q - (q > z ? 1u : 0u));
+                        if (inb) { s = t + (q == z + 1u ? 1u : 0u); inb = s >= opw; }
                     }
-                    if (mine || sp) {
-                        const unsigned long long v = source(s, opw);
-                        put(myw, (v & kp) | ((unsigned long long)(x >> 8) & ~kp));
-                    }
-                    if (W_s == 2u && sp) put(myw + 1u, source(s + 1u, opw));    // a closing sequence of two words
-                    __syncwarp();                                               // the batch's words are visible to the whole warp
-                    op += 8u * (n + W_s);
+                    const unsigned long long v = source(s, opw);
+                    put(myw, (v & kp0) | ((unsigned long long)(x >> 8) & ~kp0));
+                    if (lane == z) put(myw + 1u, source(s + 1u, opw));
+                    __syncwarp();                                                   // the batch's words are visible to the whole warp
+                    op += 264u;
                     x = nx;
                     batch = true;
+                } else {
+                    // ---- the run ends inside the batch: n one-word sequences, then maybe one closing sequence of another word form ----
+                    // (Keeping sequences of 16 - L0 match bytes -- two words, same stream stride -- inside the run was built and
+                    // measured: 13 % fewer batches, but the bookkeeping (first-word masks, owner lookup, truncation at 32 words) made
+                    // every such batch dearer; 5.6 G instead of 4.9 G warp instructions per 1e9 rows.  They close the run like any
+                    // other shape.)
+                    const uint32_t n = (uint32_t)__ffs(badp) - 1u;
+                    const uint32_t myw = opw + lane;
+                    // the sequence that ends the run, analysed by its own lane: any "word form" -- L <= 5 literal bytes + match, 8 or 16 bytes in all
+                    const uint32_t L = tok >> 4, LM = L + (tok & 15u) + 4u;
+                    // (its offset: stream bytes L + 1 and L + 2 of the lane's eight, picked by one PRMT -- a 64-bit variable shift is a dozen instructions)
+                    const uint32_t off_s = __byte_perm((uint32_t)x, (uint32_t)(x >> 32), 0x4421u + 0x11u * L) & 0xffffu, offw_s = off_s >> 3;
+                    const uint32_t Wc = LM >> 3;
+                    const bool sp = lane == n && L <= 5u && (LM == 8u || LM == 16u) && (off_s & 7u) == 0 && off_s != 0 &&
+                                    offw_s <= myw && offw_s >= lane + Wc &&                    // sources inside the output and final (before the batch)
+                                    myw + Wc <= lim_w;
+                    uint32_t hdr_s = 0, W_s = 0;
+                    if (__ballot_sync(FULL, sp)) {
+                        const uint32_t pk = __shfl_sync(FULL, (L << 8) | Wc, n);
+                        hdr_s = 3u + (pk >> 8);
+                        W_s = pk & 0xffu;
+                    }
+                    if (n + W_s > 0) {
+                        const uint32_t stride = 3u + L0;
+                        const unsigned long long kp = sp ? ~0ull << (8u * L) : kp0;   // the bytes a word takes from its source (the others are literals)
+                        // a sequence of another one-word shape alone at the head of a batch is just the closing sequence of an empty run;
+                        // two of the same shape in a row are a new run: switch (the bytes requested next use the new stride)
+                        if (n == 0 && W_s == 1u) {
+                            const uint32_t Lh = hdr_s - 3u;
+                            if (Lh == pendL && Lh <= 4u) {
+                                L0 = Lh;
+                                tok0 = (L0 << 4) | (4u - L0); sh0 = 8u + 8u * L0; kp0 = ~0ull << (8u * L0);
+                            }
+                            pendL = Lh;
+                        } else {
+                            pendL = 0xffu;
+                        }
+                        const uint64_t nx = advance_stream(stride * n + hdr_s, stride != 3u + L0);
+                        const bool mine = lane < n;
+                        uint32_t s = myw - (sp ? offw_s : offr);
+                        bool inb = mine && s >= opw;
+                        while (__any_sync(FULL, inb)) {
+                            const uint32_t t = __shfl_sync(FULL, s, s - opw);
+                            if (inb) { s = t; inb = s >= opw; }
+                        }
+                        if (mine || sp) {
+                            const unsigned long long v = source(s, opw);
+                            put(myw, (v & kp) | ((unsigned long long)(x >> 8) & ~kp));
+                        }
+                        if (W_s == 2u && sp) put(myw + 1u, source(s + 1u, opw));    // a closing sequence of two words
+                        __syncwarp();                                               // the batch's words are visible to the whole warp
+                        op += 8u * (n + W_s);
+                        x = nx;
+                        batch = true;
+                    }
                 }
             }
         }
