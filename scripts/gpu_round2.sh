@@ -5,6 +5,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/gpu.txt 2>&1
 ( time timeout 900 python -m pytest tests -m gpu -x -q ) > $OUT/pytest_gpu.log 2>&1
+( timeout 300 python __graft_entry__.py smoke ) > $OUT/smoke.log 2>&1; tail -1 $OUT/smoke.log
 tail -3 $OUT/pytest_gpu.log
 ( time timeout 900 python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 ) > $OUT/bench_ref.json 2> $OUT/bench_ref.err
 cut -c1-600 $OUT/bench_ref.json
