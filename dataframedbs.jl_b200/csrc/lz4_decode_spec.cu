@@ -13,10 +13,15 @@
 // length extensions, unaligned offsets, the last sequences of the block -- is decoded one sequence at a time by the whole
 // warp (decode_one_sequence, lz4_common.cuh).
 //
+// Three batch shapes, in order of frequency on rand(1:100): 32 one-word sequences (the full batch, compiled on its own: ~71
+// instructions + 6 per jump round for 256 output bytes); a full batch that holds ONE two-word sequence (match of 16 - L0 bytes:
+// same stream stride, the lanes behind it shift by one word); a run that ends inside the batch, with its closing sequence.
 // Against the walker / consumer kernel (lz4_decode_v3.cu, ~350 warp instructions per 32 tokens: ring entries, polls, dependency
-// waves) a batch here is ~50 instructions for ~12-32 tokens, at full occupancy (64 warps per SM).  The kernel is memory-safe
-// on any input (every access is bounds-checked, errors set a per-block status); the accept / reject verdict of damaged streams
-// is the lane decoder's, taken at load (api.cu).
+// waves) this is ~125 instructions per batch on average, 5 CTAs x 8 warps per SM at 48 registers; the kernel is issue-bound
+// (IPC 2.95) and its time follows its instruction count: 5.66 ms per 1e9 rows against 13.1 ms (DESIGN.md has the history).  The
+// kernel is memory-safe on any input (every access is bounds-checked, errors set a per-block status); the accept / reject
+// verdict of damaged streams is the lane decoder's, taken at load (api.cu).  The same file holds the long-sequence decoder
+// (lz4_decode_long_kernel) and the scan warps of the fused launch (an option).
 //
 // Algorithmic bytes per block (roofline): compressed bytes read + origin bytes written.
 #include <cuda_runtime.h>
