@@ -231,7 +231,37 @@ __device__ int decode_block_spec(const uint8_t *__restrict__ src, uint32_t comp_
                     const bool two = lane == zz && tok == tok0 + 8u && offr - 1u < opw + lane && offr >= zz + 2u;
                     if (__ballot_sync(FULL, two) && opw + 33u <= lim_w) z = zz;
                 }
-                if (z < 32u) {
+                // Or the one lane that fails is a (1, 7) sequence in a run of plain matches (L0 = 0: LZ4 missed a value and emitted
+                // its first byte as a literal): one stream byte more, so the lanes behind it find their sequence one byte further on
+                // -- in the eight stream bytes they already hold -- and one output word like everybody else.  The batch stays whole
+                // if they all check out from there and none of them copies that word (its literal byte is not in its source).
+                uint32_t zb = 32u;
+                const uint32_t offr1 = __funnelshift_r((uint32_t)(x >> 16) & 0xffffu, (uint32_t)(x >> 16) & 0xffffu, 3);
+                if (z == 32u && tok0 == 0x04u) {
+                    const uint32_t zz = (uint32_t)__ffs(badp) - 1u;
+                    const bool pos_ok = offr1 - 1u < opw + lane && opw + lane < lim_w;
+                    const bool c = lane < zz || (pos_ok && (lane == zz ? tok == 0x13u : (((uint32_t)(x >> 8) & 0xffu) == 0x04u && offr1 != lane - zz)));
+                    if (__all_sync(FULL, c)) zb = zz;
+                }
+                if (zb < 32u) {
+                    // ---- a full batch with one (1, 7) sequence in it ----
+                    pendL = 0xffu;
+                    const uint64_t nx = advance_stream(32u * 3u + 1u, false);
+                    const uint32_t myw = opw + lane;
+                    uint32_t s = myw - (lane >= zb ? offr1 : offr);
+                    bool inb = s >= opw;
+                    while (__any_sync(FULL, inb)) {
+                        const uint32_t t = __shfl_sync(FULL, s, s - opw);
+                        if (inb) { s = t; inb = s >= opw; }
+                    }
+                    unsigned long long v = source(s, opw);
+                    if (lane == zb) v = (v & ~0xffull) | ((unsigned long long)(x >> 8) & 0xffull);
+                    put(myw, v);
+                    __syncwarp();                                               // the batch's words are visible to the whole warp
+                    op += 256u;
+                    x = nx;
+                    batch = true;
+                } else if (z < 32u) {
                     // ---- a full batch with one two-word sequence in it ----
                     pendL = 0xffu;
                     const uint64_t nx = advance_stream(32u * (3u + L0), false);
