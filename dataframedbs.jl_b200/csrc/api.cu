@@ -1184,7 +1184,7 @@ int run_aggregate(dfdb_scan *s, int32_t proj_idx, bool count_only, AggPartial *h
     int64_t scan_bytes = 0;
     TmaScanArgs ta;
     memset(&ta, 0, sizeof ta);
-    bool use_tma = false, scanned = false, fused_done = false;
+    bool use_tma = false, scanned = false, fused_done = false, finalized = false;
     // the TMA scan of local blocks [b0, b1) on `sms` SMs (partials are per work unit, so parts compose)
     auto scan_part = [&](int b0, int b1, int sms) -> int {
         if (!use_tma || b1 <= b0) return DFDB_OK;
@@ -1198,8 +1198,21 @@ int run_aggregate(dfdb_scan *s, int32_t proj_idx, bool count_only, AggPartial *h
         part.g.nblocks = b1 - b0;
         for (int c = 0; c < part.ncols; c++) part.col[c].blk_off += b0;
         part.partials = static_cast<AggPartial *>(s->d_partials) + (int64_t)b0 * g.segs_per_block;
-        PhaseScope ps(PH_CONSUME, scan_bytes * (b1 - b0) / std::max(g.nblocks, 1));
-        LAUNCH(launch_fused_tma(part, agg, sms, rt.stream));
+        {
+            PhaseScope ps(PH_CONSUME, scan_bytes * (b1 - b0) / std::max(g.nblocks, 1));
+            LAUNCH(launch_fused_tma(part, agg, sms, rt.stream));
+        }
+        if (b1 == g.nblocks && !finalized) {
+            // the last part: the fold of the partials and the copy of the result follow at once, so that they run (and are
+            // covered by the synchronisation of the integrity gate in ensure_decoded) instead of waiting for a host round trip
+            {
+                PhaseScope ps(PH_CONSUME, 0);
+                LAUNCH(launch_agg_finalize(static_cast<AggPartial *>(s->d_partials), nunits, agg == 2 ? VC_FLT : cls, static_cast<AggPartial *>(s->d_result), rt.stream));
+            }
+            PhaseScope ps(PH_D2H, sizeof(AggPartial));
+            CUDA_TRY(cudaMemcpyAsync(s->h_result, s->d_result, sizeof(AggPartial), cudaMemcpyDeviceToHost, rt.stream));
+            finalized = true;
+        }
         return DFDB_OK;
     };
     const PartFn part_fn = scan_part;
@@ -1265,11 +1278,15 @@ int run_aggregate(dfdb_scan *s, int32_t proj_idx, bool count_only, AggPartial *h
             PhaseScope ps(PH_CONSUME, scan_bytes);
             LAUNCH(launch_fused(a, agg, false, wide, rt.sm_count, rt.stream));
         }
-        PhaseScope ps(PH_CONSUME, 0);
-        LAUNCH(launch_agg_finalize(static_cast<AggPartial *>(s->d_partials), nunits, agg == 2 ? VC_FLT : cls, static_cast<AggPartial *>(s->d_result), rt.stream));
+        if (!finalized) {
+            PhaseScope ps(PH_CONSUME, 0);
+            LAUNCH(launch_agg_finalize(static_cast<AggPartial *>(s->d_partials), nunits, agg == 2 ? VC_FLT : cls, static_cast<AggPartial *>(s->d_result), rt.stream));
+        }
     }
-    PhaseScope ps(PH_D2H, sizeof(AggPartial));
-    CUDA_TRY(cudaMemcpyAsync(s->h_result, s->d_result, sizeof(AggPartial), cudaMemcpyDeviceToHost, rt.stream));
+    if (!finalized) {
+        PhaseScope ps(PH_D2H, sizeof(AggPartial));
+        CUDA_TRY(cudaMemcpyAsync(s->h_result, s->d_result, sizeof(AggPartial), cudaMemcpyDeviceToHost, rt.stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(rt.stream));
     *host_out = *static_cast<AggPartial *>(s->h_result);
     *cls_out = cls;
