@@ -574,6 +574,7 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
         }
     }
     const bool fusing = fuse && fused_out && todo.size() == 1 && host_bytes == 0 && nchunks == 1 && !parted && spec_flavour(eff[0]);
+    bool chunk_parts = false;
     for (int k = 0; k < nchunks && !parted; k++) {
         const int b0 = wlo + (int)((int64_t)(whi - wlo) * k / nchunks), b1 = wlo + (int)((int64_t)(whi - wlo) * (k + 1) / nchunks);
         if (!copied.empty()) {
@@ -634,8 +635,14 @@ int ensure_decoded(dfdb_table *t, const std::vector<int64_t> &col_ids, const Par
             }
           }
         }
+        // transfer-inclusive mode: the caller's scan of this chunk follows its decode, beside the copy of the next chunks
+        if (on_part && nchunks > 1) {
+            const int rc = (*on_part)(b0, b1, rt.sm_count);
+            if (rc) return rc;
+            chunk_parts = true;
+        }
     }
-    if (on_part && !parted) {
+    if (on_part && !parted && !chunk_parts) {
         const int rc = (*on_part)(wlo, whi, rt.sm_count);
         if (rc) return rc;
     }
