@@ -2574,7 +2574,7 @@ int32_t dfdb_host_free(void *ptr)
 
 int32_t dfdb_lz4_classify_block(const uint8_t *comp, int64_t comp_len, int64_t origin)
 {
-    if (!comp || comp_len < 0 || origin < 0) return fail(DFDB_ERR_ARGUMENT, "bad block");
+    if (!comp || comp_len < 0 || origin < 0) { fail(DFDB_ERR_ARGUMENT, "bad block"); return -2; }   // (not a DFDB_ERR_* value: those are positive, like the flavours)
     return sample_flavour(comp, comp_len, origin);
 }
 

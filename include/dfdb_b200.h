@@ -244,7 +244,7 @@ DFDB_API int32_t dfdb_lz4_decode_blocks(const uint8_t *comp, const int64_t *comp
 
 /* which K1 decoder dfdb_table_load would pick for a column whose blocks look like this raw LZ4 block (host memory, no device needed;
  * the choice at load is a vote of the first, middle and last block): 1 = walker / consumer, 2 = verified word runs, 3 = long
- * sequences, 4 = match-only byte streams, -1 = too short to tell */
+ * sequences, 4 = match-only byte streams, -1 = too short to tell, -2 = bad arguments (dfdb_last_error says which) */
 DFDB_API int32_t dfdb_lz4_classify_block(const uint8_t *comp, int64_t comp_len, int64_t origin);
 
 #ifdef __cplusplus
