@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(BY_WARPS * 32, 3) lz4_decode_bytes_kernel(cons
         int e;
         if (origin == 0) e = (comp_len == 1 && src[0] == 0) ? E_OK : E_SIZE;
         else if (comp_len == 0) e = E_TRUNCATED;
-        else if ((uintptr_t)src & 3u) e = decode_simple(src, comp_len, dst, origin);
+        else if (((uintptr_t)src & 3u) || ((uintptr_t)dst & 3u)) e = decode_simple(src, comp_len, dst, origin);   // (the batch path loads and stores words)
         else e = decode_block_bytes(src, comp_len, dst, origin, ring_s);
         if (lane == 0) col.status[b] = e;
         __syncwarp();
